@@ -1,0 +1,201 @@
+/*
+ * pgp.h -- C ABI of the B200-native PCS -> LCP -> TrICP hot path (libpgp.so).
+ *
+ * This is the drop-in boundary under the reference's hypothesis-generation stage.  Every entry
+ * point cites the reference interface it replaces.  Paths are relative to the reference tree:
+ *   S4  = src/3rdparty/super4pcs/src/super4pcs
+ *   PPE = src/physim_pose_estimation
+ *
+ * Conventions
+ *   - plain C types, caller-owned buffers, no exceptions cross the boundary;
+ *   - every function returns PGP_OK (0) or a negative pgp_status; pgp_last_error() gives the text;
+ *   - one context per GPU (one process per GPU); all work of a context is ordered on its stream;
+ *   - transforms are ROW-MAJOR 3x4 fp32 in the CENTRED frame the reference scores in
+ *     (Tr(-c_P) . T . Tr(c_Q), S4/algorithms/match4pcsBase.cc:1601-1610); pgp_pose_to_centred /
+ *     pgp_centred_to_pose convert to and from camera-frame 4x4 poses exactly as
+ *     match4pcsBase.cc:1474-1482 does;
+ *   - "host" pointers are ordinary (ideally pinned) CPU memory, "dev" pointers are CUDA device
+ *     memory of the context's device;
+ *   - there is NO CPU fallback: without a CUDA device pgp_create fails.
+ */
+#ifndef PGP_H_
+#define PGP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGP_API __attribute__((visibility("default")))
+
+typedef struct pgp_ctx pgp_ctx;
+
+typedef enum pgp_status {
+  PGP_OK = 0,
+  PGP_E_INVALID = -1,      /* bad argument */
+  PGP_E_CUDA = -2,         /* CUDA runtime error (text in pgp_last_error) */
+  PGP_E_NO_SCENE = -3,     /* pgp_set_scene has not been called */
+  PGP_E_NO_MODEL = -4,     /* pgp_set_model has not been called for this object */
+  PGP_E_NO_SCORES = -5,    /* top-k / chain requested before any scoring call */
+  PGP_E_TOO_LARGE = -6,    /* scene extent / delta needs more grid cells than PGP_MAX_CELLS */
+  PGP_E_NOMEM = -7,
+  PGP_E_CAPACITY = -8      /* an output list overflowed the capacity the caller gave */
+} pgp_status;
+
+/* LCP scoring modes: which reference function a scoring call reproduces. */
+typedef enum pgp_lcp_mode {
+  PGP_LCP_COUNT = 0,       /* Match4PCSBase::Verify          S4/algorithms/match4pcsBase.cc:1699-1731 */
+  PGP_LCP_WEIGHTED = 1     /* Match4PCSBase::WeightedVerify  S4/algorithms/match4pcsBase.cc:1733-1766 */
+} pgp_lcp_mode;
+
+/* One scored hypothesis as it leaves the device (64 bytes; the record the multi-GPU merge moves). */
+typedef struct pgp_hyp {
+  int64_t index;    /* generation index (global, i.e. including the rank's index_base) */
+  uint32_t count;   /* COUNT: inlier count;  WEIGHTED: number of gated in-range points */
+  float score;      /* what the reference stores in allPose[i].second: count/|Qval| or sum(prior)/|Qval| */
+  float T[12];      /* centred-frame row-major 3x4 */
+} pgp_hyp;
+
+/* Options of the congruent-set generator (Match4PCSOptions, S4/shared4pcs.h:146-174, as set by
+ * S4/super4pcs_test.cc:91-99, plus the compile-time caps of match4pcsBase.cc:290-291,1858). */
+typedef struct pgp_pcs_opts {
+  int n_bases;               /* max_number_of_bases_ = 100            match4pcsBase.cc:290  */
+  int max_quads_per_base;    /* max_sampled_csets  = 100              match4pcsBase.cc:1858; <=0: keep all */
+  float max_base_diameter;   /* <=0: estimate like init(), match4pcsBase.cc:274-283 */
+  float overlap;             /* overlap_estimation (only scales the wide-base target), default 0.5 */
+  int base_trials;           /* kNumberOfDiameterTrials = 1000 random triangles per base, :377-410 */
+} pgp_pcs_opts;
+
+/* ---------------------------------------------------------------- context ------------------ */
+
+/* Creates a context on CUDA device `device`.  Returns NULL when no CUDA device is usable (there
+ * is no CPU path).  Replaces the construction of match_4pcs::MatchSuper4PCS
+ * (S4/super4pcs_test.cc:100, S4/algorithms/super4pcs.cc:70-73). */
+PGP_API pgp_ctx* pgp_create(int device);
+PGP_API void pgp_destroy(pgp_ctx* ctx);
+PGP_API const char* pgp_last_error(const pgp_ctx* ctx);   /* ctx may be NULL: error of pgp_create */
+PGP_API const char* pgp_version(void);
+/* Makes later calls of this context run on an externally owned cudaStream_t (e.g. the caller's
+ * current stream).  NULL restores the context's own stream. */
+PGP_API int pgp_set_stream(pgp_ctx* ctx, void* cuda_stream);
+PGP_API int pgp_synchronize(pgp_ctx* ctx);
+
+/* ---------------------------------------------------------------- K1: scene ---------------- */
+
+/* Scene segment "P": centring + kd-tree of Match4PCSBase::init (match4pcsBase.cc:242-270) and
+ * initKdTree (:1046-1056 -> S4/accelerators/kdtree.h:355-370).  xyz: n x 3 camera-frame metres;
+ * nrm: n x 3 or NULL (normalised like Point3D::set_normal, S4/shared4pcs.h:85-87; |n|^2 < 0.01
+ * -> zero, S4/utils/geometry.h:56-82).  Builds the delta-cell voxel grid on the device (K1).
+ * Priors default to 1.0. */
+PGP_API int pgp_set_scene(pgp_ctx* ctx, const float* xyz_host, const float* nrm_host, int n, float delta);
+
+/* Per-scene-point prior from the probability image (match4pcsBase.cc:317-340): value/10000 at the
+ * pin-hole projection of the un-centred point through K (row-major 3x3).  img: rows x cols uint16.
+ * (The reference indexes the image unchecked; here row/col are clamped into the image.) */
+PGP_API int pgp_set_scene_prior_image(pgp_ctx* ctx, const uint16_t* img_host, int rows, int cols, const float* K9);
+/* Or hand the priors over directly (orig_probabilities_, one per scene point). */
+PGP_API int pgp_set_scene_priors(pgp_ctx* ctx, const float* prior_host);
+PGP_API int pgp_get_scene_priors(pgp_ctx* ctx, float* prior_host);
+
+/* Model clouds of object slot `obj` (0..PGP_MAX_OBJECTS-1): "Q" = search sampling
+ * (model_search.ply), "Q_validation" = validation sampling (model_validation.ply); both centred
+ * on the centroid of the SEARCH cloud (match4pcsBase.cc:248-261). */
+PGP_API int pgp_set_model(pgp_ctx* ctx, int obj, const float* search_xyz, const float* search_nrm, int nq,
+                          const float* val_xyz, const float* val_nrm, int nv);
+
+PGP_API int pgp_get_centroids(pgp_ctx* ctx, int obj, float* cP3, float* cQ3);
+/* camera-frame pose (row-major 4x4 double) <-> centred row-major 3x4 float. */
+PGP_API int pgp_pose_to_centred(pgp_ctx* ctx, int obj, const double* pose16, float* T12);
+PGP_API int pgp_centred_to_pose(pgp_ctx* ctx, int obj, const float* T12, double* pose16);
+
+/* Grid facts for reports: dims[3], number of cells, occupied cells, cell size, bytes of the grid. */
+PGP_API int pgp_grid_info(pgp_ctx* ctx, int* dims3, int64_t* n_cells, int64_t* n_occupied, float* cell, int64_t* bytes);
+
+/* ---------------------------------------------------------------- K3: LCP scoring ---------- */
+
+/* Scores n hypotheses (verifyRigidTransform, match4pcsBase.cc:1490-1502, over the loop at
+ * :1888-1901).  T_host: n x 12.  counts_host / scores_host may be NULL.  Copies in, scores,
+ * copies out, and returns after the results are on the host.  The batch stays resident on the
+ * device for pgp_topk / pgp_improving_chain. */
+PGP_API int pgp_score_lcp(pgp_ctx* ctx, int obj, const float* T_host, int64_t n, int mode,
+                          uint32_t* counts_host, float* scores_host);
+/* Same with everything already in device memory; asynchronous on the context's stream.
+ * counts_dev (n x u32) and scores_dev (n x f32) are caller-owned and must stay alive until the
+ * top-k / chain calls that follow. */
+PGP_API int pgp_score_lcp_dev(pgp_ctx* ctx, int obj, const float* T_dev, int64_t n, int mode,
+                              uint32_t* counts_dev, float* scores_dev);
+/* Scene indices matched by ONE pose in WEIGHTED mode, in model-point order (the
+ * registered_indices of match4pcsBase.cc:1760,1894; registered_points of
+ * PPE/src/hypothesis_generation/ObjectPoseCandidateSet.hpp:8-22).  Returns the number written. */
+PGP_API int pgp_registered_points(pgp_ctx* ctx, int obj, const float* T12_host, int32_t* idx_host, int cap);
+/* Nearest in-range scene index (or -1) of every transformed validation point for one pose:
+ * KdTree::doQueryRestrictedClosestIndex (S4/accelerators/kdtree.h:394-459) per point. */
+PGP_API int pgp_nearest_in_range(pgp_ctx* ctx, int obj, const float* T12_host, int32_t* idx_host);
+
+/* Number of my kernels launched by this context so far (bench.py's gpu_launches). */
+PGP_API int64_t pgp_launch_count(const pgp_ctx* ctx);
+
+/* ---------------------------------------------------------------- K4: selection ------------ */
+
+/* Top-k of the last scored batch, ordered by (score desc, index asc); replaces the serial
+ * best-so-far scan of Perform_N_steps (match4pcsBase.cc:1888-1901).  index_base is added to the
+ * local indices (the rank's offset when hypotheses are sharded).  Returns the number written. */
+PGP_API int pgp_topk(pgp_ctx* ctx, int obj, int k, int64_t index_base, pgp_hyp* out_host);
+/* Deterministic merge of per-rank top-k lists (n_lists x k_each records, e.g. the output of an
+ * all-gather): same order as pgp_topk on the union.  Host-side, no context needed. */
+PGP_API int pgp_topk_merge(const pgp_hyp* lists, int n_lists, int k_each, int k, pgp_hyp* out);
+/* The strictly-improving chain in generation order that Perform_N_steps returns as
+ * hypothesisSet (match4pcsBase.cc:1888-1914); its last element is bestHypothesis.
+ * Returns the chain length (<= cap) or PGP_E_CAPACITY. */
+PGP_API int pgp_improving_chain(pgp_ctx* ctx, int obj, int64_t index_base, pgp_hyp* out_host, int cap);
+
+/* ---------------------------------------------------------------- K2: PCS generation ------- */
+
+PGP_API void pgp_pcs_default_opts(pgp_pcs_opts* o);
+/* All ordered pairs (i,j),(j,i) of the centred SEARCH model with | |q_i - q_j| - dist | <= eps:
+ * MatchSuper4PCS::ExtractPairs (S4/algorithms/super4pcs.cc:193-236) with the shipped options,
+ * i.e. the filter of S4/pairCreationFunctor.h:167-253 / brute-force spec S4/algorithms/4pcs.cc:109-192.
+ * pairs_host: cap x 2 int32 (may be NULL to only count).  Returns the number of ordered pairs
+ * through *n_pairs (which may exceed cap; only cap are written). */
+PGP_API int pgp_extract_pairs(pgp_ctx* ctx, int obj, float dist, float eps, int32_t* pairs_host, int64_t cap, int64_t* n_pairs);
+/* Congruent quads for one base (scene ids b[4], invariants inv1/inv2): the join of
+ * MatchSuper4PCS::FindCongruentQuadrilaterals (S4/algorithms/super4pcs.cc:78-187).
+ * pairs1/pairs2: ordered model pairs for base edges (b0,b1) and (b2,b3). quads_host: cap x 4. */
+PGP_API int pgp_find_quads(pgp_ctx* ctx, int obj, const int32_t* base4, float inv1, float inv2, float eps,
+                           const int32_t* pairs1_host, int64_t n1, const int32_t* pairs2_host, int64_t n2,
+                           int32_t* quads_host, int64_t cap, int64_t* n_quads);
+/* Rigid transform of one (base, quad): ComputeRigidTransformFromCongruentPair
+ * (match4pcsBase.cc:1411-1488) + ComputeRigidTransformation (:1504-1614).  n quads of the same
+ * base; T_host: n x 12 centred; ok_host: n flags (0 = rejected: degenerate or non-orthogonal). */
+PGP_API int pgp_rigid_from_quads(pgp_ctx* ctx, int obj, const int32_t* base4, const int32_t* quads_host, int64_t n,
+                                 float* T_host, uint8_t* ok_host);
+/* Full device-side generator: bases from the scene (SelectQuadrilateral, match4pcsBase.cc:507-580),
+ * pairs, quads, transforms -- written straight into the device buffer that pgp_score_generated
+ * scores, no host round trip.  Returns the number of hypotheses generated through *n_hyp. */
+PGP_API int pgp_generate_pcs(pgp_ctx* ctx, int obj, const pgp_pcs_opts* opts, uint64_t seed, int64_t max_hyp, int64_t* n_hyp);
+/* Scores the hypotheses pgp_generate_pcs left on the device. */
+PGP_API int pgp_score_generated(pgp_ctx* ctx, int obj, int mode);
+/* Copies generated transforms / their scores to the host (n x 12, n). */
+PGP_API int pgp_get_generated(pgp_ctx* ctx, int obj, float* T_host, uint32_t* counts_host, float* scores_host, int64_t cap);
+
+/* ---------------------------------------------------------------- K5: trimmed ICP ---------- */
+
+/* Trimmed ICP of k poses of object `obj` against the segment (source) with the model's
+ * VALIDATION cloud as target: UCTState::performTrICP (PPE/src/hypothesis_verification/mcts/
+ * UCTState.cpp:121-204) / utilities::performTrICP (PPE/src/misc/utilities.cpp:651-680) ->
+ * pcl::recognition::TrimmedICP::align.  poses: k x 16 doubles, row-major camera-frame
+ * model->scene poses, refined in place.  seg_xyz: ns x 3 camera frame.  trim: kept fraction
+ * (0.5 at the MCTS call site), ratio: new-to-old energy ratio (0.99), max_iter: safety cap.
+ * iters_out / energy_out (k each) may be NULL. */
+PGP_API int pgp_tricp(pgp_ctx* ctx, int obj, const float* seg_xyz_host, int ns, double* poses16_host, int k,
+                      float trim, float ratio, int max_iter, int* iters_out, float* energy_out);
+
+#define PGP_MAX_OBJECTS 64
+#define PGP_MAX_CELLS (1ll << 29)
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGP_H_ */

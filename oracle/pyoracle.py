@@ -143,9 +143,12 @@ class PortOracle(_Base):
                         _p(self.V, _f32p), _p(self.Vn, _f32p), self.nV, float(delta), _p(K9, _f32p), _p(img, _u16p), rows, cols)
 
     def __del__(self):
-        if getattr(self, "h", None):
-            self._fn("destroy", None, [C.c_void_p])(self.h)
-            self.h = None
+        try:
+            if getattr(self, "h", None):
+                self._fn("destroy", None, [C.c_void_p])(self.h)
+                self.h = None
+        except Exception:      # interpreter shutdown
+            pass
 
     def verify_mt(self, T, nthreads):
         T = _f32(T).reshape(-1, 12)

@@ -1,0 +1,90 @@
+"""ctypes binding of libpgp.so (include/pgp.h).  There is no fallback: if the library is not
+built, or no B200 is present, every entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpgp.so")
+
+PGP_LCP_COUNT = 0
+PGP_LCP_WEIGHTED = 1
+
+STATUS = {0: "PGP_OK", -1: "PGP_E_INVALID", -2: "PGP_E_CUDA", -3: "PGP_E_NO_SCENE", -4: "PGP_E_NO_MODEL",
+          -5: "PGP_E_NO_SCORES", -6: "PGP_E_TOO_LARGE", -7: "PGP_E_NOMEM", -8: "PGP_E_CAPACITY"}
+
+
+class PgpHyp(C.Structure):
+    """pgp_hyp of include/pgp.h (64 bytes)."""
+    _fields_ = [("index", C.c_int64), ("count", C.c_uint32), ("score", C.c_float), ("T", C.c_float * 12)]
+
+
+class PgpPcsOpts(C.Structure):
+    _fields_ = [("n_bases", C.c_int), ("max_quads_per_base", C.c_int), ("max_base_diameter", C.c_float),
+                ("overlap", C.c_float), ("base_trials", C.c_int)]
+
+
+class PgpError(RuntimeError):
+    def __init__(self, code: int, text: str):
+        super().__init__(f"{STATUS.get(code, code)}: {text}")
+        self.code = code
+
+
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_SIGNATURES = {
+    "pgp_create": (_vp, [_i]),
+    "pgp_destroy": (None, [_vp]),
+    "pgp_last_error": (C.c_char_p, [_vp]),
+    "pgp_version": (C.c_char_p, []),
+    "pgp_set_stream": (_i, [_vp, _vp]),
+    "pgp_synchronize": (_i, [_vp]),
+    "pgp_set_scene": (_i, [_vp, _vp, _vp, _i, _f]),
+    "pgp_set_scene_prior_image": (_i, [_vp, _vp, _i, _i, _vp]),
+    "pgp_set_scene_priors": (_i, [_vp, _vp]),
+    "pgp_get_scene_priors": (_i, [_vp, _vp]),
+    "pgp_set_model": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _i]),
+    "pgp_get_centroids": (_i, [_vp, _i, _vp, _vp]),
+    "pgp_pose_to_centred": (_i, [_vp, _i, _vp, _vp]),
+    "pgp_centred_to_pose": (_i, [_vp, _i, _vp, _vp]),
+    "pgp_grid_info": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "pgp_score_lcp": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp]),
+    "pgp_score_lcp_dev": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp]),
+    "pgp_registered_points": (_i, [_vp, _i, _vp, _vp, _i]),
+    "pgp_nearest_in_range": (_i, [_vp, _i, _vp, _vp]),
+    "pgp_launch_count": (_i64, [_vp]),
+    "pgp_topk": (_i, [_vp, _i, _i, _i64, _vp]),
+    "pgp_topk_merge": (_i, [_vp, _i, _i, _i, _vp]),
+    "pgp_improving_chain": (_i, [_vp, _i, _i64, _vp, _i]),
+    "pgp_pcs_default_opts": (None, [_vp]),
+    "pgp_extract_pairs": (_i, [_vp, _i, _f, _f, _vp, _i64, _vp]),
+    "pgp_find_quads": (_i, [_vp, _i, _vp, _f, _f, _f, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
+    "pgp_rigid_from_quads": (_i, [_vp, _i, _vp, _vp, _i64, _vp, _vp]),
+    "pgp_generate_pcs": (_i, [_vp, _i, _vp, C.c_uint64, _i64, _vp]),
+    "pgp_score_generated": (_i, [_vp, _i, _i]),
+    "pgp_get_generated": (_i, [_vp, _i, _vp, _vp, _vp, _i64]),
+    "pgp_tricp": (_i, [_vp, _i, _vp, _i, _vp, _i, _f, _f, _i, _vp, _vp]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads libpgp.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(or `make -C physimglobalpose_b200/csrc`).  There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def exported_symbols() -> list[str]:
+    return sorted(_SIGNATURES)

@@ -1,0 +1,418 @@
+// K3 -- LCP scoring of pose hypotheses on the scene voxel grid.
+//
+// Replaces, per hypothesis, Match4PCSBase::Verify (S4/algorithms/match4pcsBase.cc:1699-1731) and
+// Match4PCSBase::WeightedVerify (:1733-1766), i.e. one KdTree::doQueryRestrictedClosestIndex
+// (S4/accelerators/kdtree.h:394-459) per validation-model point, and the loop over hypotheses of
+// Perform_N_steps (:1888-1901).
+//
+// Mapping: persistent CTAs; the validation model is staged ONCE per CTA into shared memory with a
+// 1-D TMA bulk copy (cp.async.bulk -> SASS UBLKCP) together with the dilated-occupancy bitmap; each
+// warp pulls one hypothesis at a time from a global work counter, keeps its 3x4 transform in
+// registers, and walks the model 32 points per step:
+//   phase 1 (uniform control flow)  exact fp32 transform, cell, one bitmap bit: queries whose 27
+//           cells hold no scene point are done; survivors go to a per-warp shared-memory queue
+//           (warp-ballot compaction);
+//   phase 2 (dense)  whenever 32 survivors are queued, every lane takes one and runs the exact
+//           d2 <= delta^2 test over the 9 contiguous x-rows of the 27 cells.
+// Inlier counts are warp-reduced (REDUX) -- integer, hence order-free and bit-exact.
+// All float math is the reference's association, non-fused (pgp_internal.cuh).
+#include <math.h>
+
+#include "pgp_internal.cuh"
+
+namespace {
+
+constexpr int WARPS = 16;            // warps per CTA
+constexpr int THREADS = WARPS * 32;
+constexpr int QCAP = 64;             // queue slots per warp
+
+struct LcpParams {
+  const float4* model;       // nv x float4 (xyz, w = original index bits)
+  const float4* model_nrm;   // nv x float4
+  int nv;
+  int tile_cap;              // model points per shared-memory tile
+  const float* T;            // n x 12
+  long long n;
+  const float4* pts;
+  const float4* aux;
+  const uint32_t* cell_start;
+  const uint32_t* bitmap;
+  int bitmap_words;          // words staged in smem (0: read the bitmap from global/L1)
+  GridParams g;
+  uint32_t* counts;
+  float* scores;
+  unsigned long long* work;  // one counter per model tile
+  int n_tiles;
+};
+
+// ---- mbarrier + TMA bulk copy (global -> shared), sm_90+/sm_100a PTX ---------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D;\n\tbra W;\n\tD:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+struct Xf { float m[12]; };
+
+__device__ __forceinline__ Xf load_xf(const float* __restrict__ T, long long h) {
+  const float4* t4 = reinterpret_cast<const float4*>(T + 12 * h);
+  float4 a = __ldg(t4), b = __ldg(t4 + 1), c = __ldg(t4 + 2);
+  Xf x;
+  x.m[0] = a.x; x.m[1] = a.y; x.m[2] = a.z; x.m[3] = a.w;
+  x.m[4] = b.x; x.m[5] = b.y; x.m[6] = b.z; x.m[7] = b.w;
+  x.m[8] = c.x; x.m[9] = c.y; x.m[10] = c.z; x.m[11] = c.w;
+  return x;
+}
+
+__device__ __forceinline__ void apply_xf(const Xf& x, float4 q, float& tx, float& ty, float& tz) {
+  tx = xf_row(x.m[0], x.m[1], x.m[2], x.m[3], q.x, q.y, q.z);
+  ty = xf_row(x.m[4], x.m[5], x.m[6], x.m[7], q.x, q.y, q.z);
+  tz = xf_row(x.m[8], x.m[9], x.m[10], x.m[11], q.x, q.y, q.z);
+}
+
+// cell of a query; false when the query is outside the grid (then no scene point is within delta)
+__device__ __forceinline__ bool query_cell(const GridParams& g, float tx, float ty, float tz, int& cx, int& cy, int& cz) {
+  float ux = cell_coord(tx, g.lo[0], g.inv_h), uy = cell_coord(ty, g.lo[1], g.inv_h), uz = cell_coord(tz, g.lo[2], g.inv_h);
+  bool in = (ux >= 1.0f) & (ux < (float)(g.dim[0] - 1)) & (uy >= 1.0f) & (uy < (float)(g.dim[1] - 1)) & (uz >= 1.0f) &
+            (uz < (float)(g.dim[2] - 1));
+  cx = (int)ux; cy = (int)uy; cz = (int)uz;
+  return in;   // NaN compares false
+}
+
+// exact existence test over the 27 cells = 9 contiguous x-rows
+__device__ __forceinline__ bool exists_within(const LcpParams& p, float tx, float ty, float tz, int cx, int cy, int cz) {
+  const int dx = p.g.dim[0], dy = p.g.dim[1];
+  const float r2 = p.g.r2;
+#pragma unroll 1
+  for (int oz = -1; oz <= 1; ++oz) {
+    const int rowz = ((cz + oz) * dy + cy) * dx + cx;
+    uint32_t s[3], e[3];
+#pragma unroll
+    for (int oy = -1; oy <= 1; ++oy) {
+      s[oy + 1] = __ldg(p.cell_start + rowz + oy * dx - 1);
+      e[oy + 1] = __ldg(p.cell_start + rowz + oy * dx + 2);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      for (uint32_t i = s[k]; i < e[k]; ++i) {
+        float4 q = __ldg(p.pts + i);
+        if (sqdist3(tx, ty, tz, q.x, q.y, q.z) <= r2) return true;
+      }
+    }
+  }
+  return false;
+}
+
+// nearest in-range scene point: sorted position (or -1).  Acceptance d2 <= best as kdtree.h:424;
+// exact ties resolve to the smaller original index (the reference: kd-tree visiting order).
+__device__ __forceinline__ int nearest_within(const LcpParams& p, float tx, float ty, float tz, int cx, int cy, int cz) {
+  const int dx = p.g.dim[0], dy = p.g.dim[1];
+  float best = p.g.r2;
+  int best_pos = -1, best_orig = 0x7fffffff;
+#pragma unroll 1
+  for (int oz = -1; oz <= 1; ++oz) {
+    const int rowz = ((cz + oz) * dy + cy) * dx + cx;
+    uint32_t s[3], e[3];
+#pragma unroll
+    for (int oy = -1; oy <= 1; ++oy) {
+      s[oy + 1] = __ldg(p.cell_start + rowz + oy * dx - 1);
+      e[oy + 1] = __ldg(p.cell_start + rowz + oy * dx + 2);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      for (uint32_t i = s[k]; i < e[k]; ++i) {
+        float4 q = __ldg(p.pts + i);
+        float d2 = sqdist3(tx, ty, tz, q.x, q.y, q.z);
+        int orig = __float_as_int(q.w);
+        if (d2 < best || (d2 == best && (best_pos < 0 || orig < best_orig))) { best = d2; best_pos = (int)i; best_orig = orig; }
+      }
+    }
+  }
+  return best_pos;
+}
+
+// The normal gate of WeightedVerify (match4pcsBase.cc:1755-1758):
+//   n_q = R n (tree-order products); angle = float(double(acosf(dot) * 180.f) / pi);
+//   min(angle, |180 - angle|) < 30   with NaN (|dot| > 1) never counted.
+// The decision is taken on the dot product; only inside a guard band around cos 30 deg is the
+// angle evaluated (correctly rounded acos via double), so libm differences cannot matter outside
+// a 1-ulp sliver at exactly 30 / 150 degrees.
+__device__ __forceinline__ bool normal_gate(const Xf& x, float4 nm, float4 ns) {
+  float qx = dot3_tree(x.m[0], x.m[1], x.m[2], nm.x, nm.y, nm.z);
+  float qy = dot3_tree(x.m[4], x.m[5], x.m[6], nm.x, nm.y, nm.z);
+  float qz = dot3_tree(x.m[8], x.m[9], x.m[10], nm.x, nm.y, nm.z);
+  float d = dot3_tree(ns.x, ns.y, ns.z, qx, qy, qz);
+  float a = fabsf(d);
+  if (!(a <= 1.0f)) return false;                 // acos -> NaN -> both min() operands NaN -> not counted
+  const float c30 = 0.8660254f;
+  if (a > c30 + 1e-4f) return true;
+  if (a < c30 - 1e-4f) return false;
+  float ang = (float)((double)__fmul_rn((float)acos((double)d), 180.0f) / 3.14159265358979323846);
+  float other = fabsf(__fsub_rn(180.0f, ang));
+  float m = other < ang ? other : ang;
+  return m < 30.0f;
+}
+
+template <int MODE>   // 0 = count, 1 = weighted with binary priors (order-free integer sums)
+__global__ void __launch_bounds__(THREADS, 2) k3_lcp_kernel(const __grid_constant__ LcpParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  float4* s_model = reinterpret_cast<float4*>(smem);
+  float4* s_nrm = s_model + p.tile_cap;                                   // only MODE 1
+  uint32_t* s_bitmap = reinterpret_cast<uint32_t*>(smem + (size_t)p.tile_cap * 16 * (MODE == 1 ? 2 : 1));
+  uint16_t* s_queue = reinterpret_cast<uint16_t*>(s_bitmap + p.bitmap_words);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint16_t* q = s_queue + warp * QCAP;
+  const uint32_t* bitmap = p.bitmap_words ? s_bitmap : p.bitmap;
+  const unsigned lt_mask = (1u << lane) - 1u;
+
+  if (threadIdx.x == 0) mbar_init(&mbar, 1);
+  __syncthreads();
+
+  for (int tile = 0; tile < p.n_tiles; ++tile) {
+    const int t0 = tile * p.tile_cap;
+    const int tn = min(p.tile_cap, p.nv - t0);
+    if (threadIdx.x == 0) {
+      uint32_t bytes = (uint32_t)tn * 16u;
+      uint32_t total = bytes * (MODE == 1 ? 2u : 1u) + (tile == 0 ? (uint32_t)p.bitmap_words * 4u : 0u);
+      mbar_expect_tx(&mbar, total);
+      tma_bulk_g2s(s_model, p.model + t0, bytes, &mbar);
+      if (MODE == 1) tma_bulk_g2s(s_nrm, p.model_nrm + t0, bytes, &mbar);
+      if (tile == 0 && p.bitmap_words) tma_bulk_g2s(s_bitmap, p.bitmap, (uint32_t)p.bitmap_words * 4u, &mbar);
+    }
+    mbar_wait(&mbar, tile & 1);
+
+    for (;;) {
+      long long h = 0;
+      if (lane == 0) h = (long long)atomicAdd(p.work + tile, 1ull);
+      h = __shfl_sync(0xffffffffu, h, 0);
+      if (h >= p.n) break;
+      const Xf x = load_xf(p.T, h);
+      int good = 0;
+      int qn = 0;
+
+      auto drain = [&](int take) {   // lanes < take each resolve one queued query
+        if (lane < take) {
+          int i = q[qn - take + lane];
+          float tx, ty, tz;
+          int cx, cy, cz;
+          apply_xf(x, s_model[i], tx, ty, tz);
+          query_cell(p.g, tx, ty, tz, cx, cy, cz);
+          if (MODE == 0) {
+            good += exists_within(p, tx, ty, tz, cx, cy, cz) ? 1 : 0;
+          } else {
+            int pos = nearest_within(p, tx, ty, tz, cx, cy, cz);
+            if (pos >= 0) {
+              float4 ns = __ldg(p.aux + pos);
+              if (normal_gate(x, s_nrm[i], ns)) good += (ns.w != 0.f) ? 0x10001 : 0x1;   // hi: prior==1, lo: gated
+            }
+          }
+        }
+        qn -= take;
+      };
+
+      for (int base = 0; base < tn; base += 32) {
+        const int i = base + lane;
+        bool cand = false;
+        if (i < tn) {
+          float tx, ty, tz;
+          int cx, cy, cz;
+          apply_xf(x, s_model[i], tx, ty, tz);
+          if (query_cell(p.g, tx, ty, tz, cx, cy, cz)) {
+            int c = (cz * p.g.dim[1] + cy) * p.g.dim[0] + cx;
+            cand = (bitmap[c >> 5] >> (c & 31)) & 1u;
+          }
+        }
+        unsigned b = __ballot_sync(0xffffffffu, cand);
+        if (cand) q[qn + __popc(b & lt_mask)] = (uint16_t)i;
+        qn += __popc(b);
+        __syncwarp();
+        if (qn >= 32) { drain(32); __syncwarp(); }
+      }
+      if (qn > 0) { drain(qn); __syncwarp(); }
+
+      if (MODE == 0) {
+        int tot = __reduce_add_sync(0xffffffffu, good);
+        if (lane == 0) {
+          if (p.n_tiles == 1) {
+            p.counts[h] = (uint32_t)tot;
+            if (p.scores) p.scores[h] = __fdiv_rn((float)tot, (float)p.nv);   // Scalar(good)/Scalar(n) :1730
+          } else if (tot) {
+            atomicAdd(p.counts + h, (uint32_t)tot);
+          }
+        }
+      } else {
+        int tot = __reduce_add_sync(0xffffffffu, good);   // nv < 65536 per tile keeps the halves apart
+        if (lane == 0) {
+          uint32_t gated = (uint32_t)tot & 0xffffu, w = (uint32_t)tot >> 16;
+          if (p.n_tiles == 1) {
+            p.counts[h] = gated;
+            if (p.scores) p.scores[h] = __fdiv_rn((float)w, (float)p.nv);   // weighted_match / Scalar(n) :1765
+          } else {
+            if (gated) atomicAdd(p.counts + h, gated);
+            if (w && p.scores) atomicAdd(reinterpret_cast<uint32_t*>(p.scores) + h, w);   // integer for now; finalised below
+          }
+        }
+      }
+    }
+    __syncthreads();   // everyone is done with this tile before it is overwritten
+  }
+}
+
+// multi-tile epilogue: counts -> scores
+__global__ void k3_finalise(const uint32_t* __restrict__ counts, float* __restrict__ scores, long long n, int nv, int mode) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t v = mode == 0 ? counts[i] : reinterpret_cast<const uint32_t*>(scores)[i];
+  scores[i] = __fdiv_rn((float)v, (float)nv);
+}
+
+// WeightedVerify with arbitrary priors: the reference adds the priors of the gated matches in
+// model-point order in fp32 (weighted_match += ..., :1759), which is not associative, so the sum is
+// formed in exactly that order: per 32-point step the lanes' contributions are folded in lane order.
+// One warp per hypothesis, model read from global in ORIGINAL order.  Also the kernel behind
+// pgp_registered_points / pgp_nearest_in_range (idx_out != nullptr, one hypothesis).
+__global__ void __launch_bounds__(256) k3_weighted_ordered(const LcpParams p, int32_t* __restrict__ idx_out, int gate) {
+  const int lane = threadIdx.x & 31;
+  const long long h = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (h >= p.n) return;
+  const Xf x = load_xf(p.T, h);
+  float acc = 0.f;
+  int gated = 0;
+  for (int base = 0; base < p.nv; base += 32) {
+    const int i = base + lane;
+    float w = 0.f;
+    bool hit = false;
+    int orig = -1;
+    if (i < p.nv) {
+      float tx, ty, tz;
+      int cx, cy, cz;
+      apply_xf(x, __ldg(p.model + i), tx, ty, tz);
+      if (query_cell(p.g, tx, ty, tz, cx, cy, cz)) {
+        int pos = nearest_within(p, tx, ty, tz, cx, cy, cz);
+        if (pos >= 0) {
+          float4 ns = __ldg(p.aux + pos);
+          if (!gate || normal_gate(x, __ldg(p.model_nrm + i), ns)) {
+            hit = true; w = ns.w; orig = __float_as_int(__ldg(p.pts + pos).w);
+          }
+        }
+      }
+      if (idx_out) idx_out[i] = orig;
+    }
+    unsigned b = __ballot_sync(0xffffffffu, hit);
+    gated += __popc(b);
+    while (b) {
+      int l = __ffs(b) - 1;
+      b &= b - 1;
+      acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, w, l));
+    }
+  }
+  if (lane == 0 && p.counts) {
+    p.counts[h] = (uint32_t)gated;
+    if (p.scores) p.scores[h] = __fdiv_rn(acc, (float)p.nv);
+  }
+}
+
+}  // namespace
+
+static LcpParams make_params(pgp_ctx* ctx, const Model& m, const float* T, int64_t n, uint32_t* counts, float* scores) {
+  const Scene& s = ctx->scene;
+  LcpParams p{};
+  p.nv = m.nv;
+  p.T = T; p.n = n;
+  p.pts = s.pts.as<float4>(); p.aux = s.aux.as<float4>();
+  p.cell_start = s.cell_start.as<uint32_t>(); p.bitmap = s.bitmap.as<uint32_t>();
+  p.g = s.g;
+  p.counts = counts; p.scores = scores;
+  return p;
+}
+
+int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mode, uint32_t* counts_dev, float* scores_dev) {
+  if (n == 0) return PGP_OK;
+  const Scene& s = ctx->scene;
+  LcpParams p = make_params(ctx, m, T_dev, n, counts_dev, scores_dev);
+  cudaStream_t st = ctx->stream;
+
+  if (mode == PGP_LCP_WEIGHTED && !s.priors_binary) {
+    p.model = m.val_orig.as<float4>(); p.model_nrm = m.val_nrm_orig.as<float4>();
+    const int T = 256;
+    long long blocks = (n * 32 + T - 1) / T;
+    k3_weighted_ordered<<<(unsigned)blocks, T, 0, st>>>(p, nullptr, 1);
+    ctx->launches++;
+    PGP_CUDA(ctx, cudaGetLastError());
+    return PGP_OK;
+  }
+
+  p.model = m.val.as<float4>(); p.model_nrm = m.val_nrm.as<float4>();
+  const int per_pt = mode == PGP_LCP_WEIGHTED ? 32 : 16;
+  // shared memory plan: model tile + bitmap (if it fits) + queues
+  const size_t smem_max = 100 * 1024;     // two CTAs per SM
+  const size_t qbytes = (size_t)WARPS * QCAP * 2;
+  size_t bm_bytes = (size_t)s.bitmap_words * 4;
+  int tile_cap = (m.nv + 3) & ~3;
+  if (tile_cap > 8192) tile_cap = 8192;                    // queue entries are u16; one mbarrier tx < 1 MiB
+  if ((size_t)tile_cap * per_pt + qbytes + bm_bytes > smem_max) {
+    // try to keep the bitmap; shrink the tile first, drop the bitmap only if it alone is too big
+    if (bm_bytes + qbytes + 1024 * (size_t)per_pt <= smem_max) {
+      tile_cap = (int)((smem_max - bm_bytes - qbytes) / per_pt) & ~3;
+    } else {
+      bm_bytes = 0;
+      if ((size_t)tile_cap * per_pt + qbytes > smem_max) tile_cap = (int)((smem_max - qbytes) / per_pt) & ~3;
+    }
+  }
+  p.tile_cap = tile_cap;
+  p.bitmap_words = (int)(bm_bytes / 4);
+  p.n_tiles = (m.nv + tile_cap - 1) / tile_cap;
+  const size_t smem = (size_t)tile_cap * per_pt + bm_bytes + qbytes;
+
+  PGP_CUDA(ctx, ctx->work.reserve(4096));
+  if (p.n_tiles > 256) return pgp_fail(ctx, PGP_E_INVALID, "validation model too large (%d points)", m.nv);
+  p.work = reinterpret_cast<unsigned long long*>(ctx->work.as<char>() + 1024);
+  PGP_CUDA(ctx, cudaMemsetAsync(p.work, 0, 8 * (size_t)p.n_tiles, st));
+  if (p.n_tiles > 1) {
+    PGP_CUDA(ctx, cudaMemsetAsync(counts_dev, 0, (size_t)n * 4, st));
+    if (scores_dev) PGP_CUDA(ctx, cudaMemsetAsync(scores_dev, 0, (size_t)n * 4, st));
+  }
+  long long want = (n + WARPS - 1) / WARPS;
+  int grid = (int)std::min<long long>(want, 2ll * ctx->sm_count);
+  if (mode == PGP_LCP_COUNT) {
+    PGP_CUDA(ctx, cudaFuncSetAttribute(k3_lcp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k3_lcp_kernel<0><<<grid, THREADS, smem, st>>>(p);
+  } else {
+    PGP_CUDA(ctx, cudaFuncSetAttribute(k3_lcp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k3_lcp_kernel<1><<<grid, THREADS, smem, st>>>(p);
+  }
+  ctx->launches++;
+  if (p.n_tiles > 1 && scores_dev) {
+    k3_finalise<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(counts_dev, scores_dev, n, m.nv, mode);
+    ctx->launches++;
+  }
+  PGP_CUDA(ctx, cudaGetLastError());
+  return PGP_OK;
+}
+
+// one hypothesis, per-point nearest in-range scene index in ORIGINAL model order (gate: apply the normal gate)
+int k3_nearest(pgp_ctx* ctx, const Model& m, const float* T_dev, int32_t* idx_dev, int gate) {
+  LcpParams p = make_params(ctx, m, T_dev, 1, nullptr, nullptr);
+  p.model = m.val_orig.as<float4>(); p.model_nrm = m.val_nrm_orig.as<float4>();
+  k3_weighted_ordered<<<1, 32, 0, ctx->stream>>>(p, idx_dev, gate);
+  ctx->launches++;
+  PGP_CUDA(ctx, cudaGetLastError());
+  return PGP_OK;
+}

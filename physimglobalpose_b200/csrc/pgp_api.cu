@@ -1,0 +1,487 @@
+// The C ABI of include/pgp.h: context, host-side preparation (the O(n) part of
+// Match4PCSBase::init, S4/algorithms/match4pcsBase.cc:216-345) and the thin wrappers that order
+// the kernels of k1..k5 on the context's stream.  No CPU scoring path exists in this library.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <numeric>
+
+#include "pgp_internal.cuh"
+
+static std::string g_create_error;
+
+int pgp_fail(pgp_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[768];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CHECK_CTX(ctx) do { if (!(ctx)) return PGP_E_INVALID; cudaSetDevice((ctx)->device); } while (0)
+
+namespace {
+
+// centroid exactly as match4pcsBase.cc:242-251: sequential fp32 accumulation, then / Scalar(n)
+void seq_centroid(const float* xyz, int n, float c[3]) {
+  volatile float sx = 0.f, sy = 0.f, sz = 0.f;   // volatile: keep the compiler from re-associating / vectorising the sum
+  for (int i = 0; i < n; ++i) { sx = sx + xyz[3 * i]; sy = sy + xyz[3 * i + 1]; sz = sz + xyz[3 * i + 2]; }
+  const float fn = (float)n;
+  c[0] = sx / fn; c[1] = sy / fn; c[2] = sz / fn;
+}
+
+// Point3D::set_normal (S4/shared4pcs.h:85-87) + CleanInvalidNormals (S4/utils/geometry.h:56-82)
+void unit_normal(const float* n, float out[3]) {
+  out[0] = out[1] = out[2] = 0.f;
+  if (!n) return;
+  volatile float s = n[0] * n[0];
+  s = s + n[1] * n[1];
+  s = s + n[2] * n[2];
+  if (s < 0.01f) return;
+  float len = sqrtf(s);
+  out[0] = n[0] / len; out[1] = n[1] / len; out[2] = n[2] / len;
+}
+
+uint32_t spread10(uint32_t v) {
+  v &= 1023u;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+int upload_cloud4(pgp_ctx* ctx, DevBuf& buf, const std::vector<float>& v4) {
+  PGP_CUDA(ctx, buf.reserve(std::max<size_t>(v4.size() * 4, 64)));
+  if (!v4.empty()) PGP_CUDA(ctx, cudaMemcpyAsync(buf.p, v4.data(), v4.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+  return PGP_OK;
+}
+
+Model* get_model(pgp_ctx* ctx, int obj) {
+  if (obj < 0 || obj >= (int)ctx->models.size() || !ctx->models[obj].ready) return nullptr;
+  return &ctx->models[obj];
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pgp_version(void) { return "pgp-b200 0.1 (sm_100a)"; }
+
+pgp_ctx* pgp_create(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    pgp_fail(nullptr, PGP_E_CUDA, "no CUDA device (%s); this library has no CPU path", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    return nullptr;
+  }
+  if (device < 0 || device >= n) { pgp_fail(nullptr, PGP_E_INVALID, "device %d out of range (%d devices)", device, n); return nullptr; }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { pgp_fail(nullptr, PGP_E_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e)); return nullptr; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major < 10) { pgp_fail(nullptr, PGP_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); return nullptr; }
+  pgp_ctx* ctx = new pgp_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    pgp_fail(nullptr, PGP_E_CUDA, "cudaStreamCreate failed");
+    delete ctx;
+    return nullptr;
+  }
+  for (auto& ev : ctx->ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  ctx->stream = ctx->own_stream;
+  ctx->models.resize(PGP_MAX_OBJECTS);
+  return ctx;
+}
+
+void pgp_destroy(pgp_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  Scene& s = ctx->scene;
+  for (DevBuf* b : {&s.xyz_raw, &s.nrm_raw, &s.unsorted, &s.cursor, &s.pts, &s.aux, &s.cell_start, &s.cell_of, &s.bitmap, &s.tri_index,
+                    &s.tri_blocks, &s.prior, &s.scratch, &ctx->batch_T, &ctx->batch_counts, &ctx->batch_scores, &ctx->work, &ctx->topk_out})
+    b->release();
+  for (Model& m : ctx->models)
+    for (DevBuf* b : {&m.search, &m.search_nrm, &m.val, &m.val_nrm, &m.val_orig, &m.val_nrm_orig, &m.gen_T, &m.gen_counts, &m.gen_scores,
+                      &m.tgrid_pts, &m.tgrid_start})
+      b->release();
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(ctx->own_stream);
+  cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+}
+
+const char* pgp_last_error(const pgp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int pgp_set_stream(pgp_ctx* ctx, void* cuda_stream) {
+  CHECK_CTX(ctx);
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return PGP_OK;
+}
+
+int pgp_synchronize(pgp_ctx* ctx) {
+  CHECK_CTX(ctx);
+  PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PGP_OK;
+}
+
+int64_t pgp_launch_count(const pgp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int pgp_set_scene(pgp_ctx* ctx, const float* xyz, const float* nrm, int n, float delta) {
+  CHECK_CTX(ctx);
+  if (!xyz || n <= 0) return pgp_fail(ctx, PGP_E_INVALID, "pgp_set_scene: empty cloud");
+  if (!(delta > 0.f) || !std::isfinite(delta)) return pgp_fail(ctx, PGP_E_INVALID, "pgp_set_scene: delta must be > 0");
+  Scene& s = ctx->scene;
+  s.ready = false;
+  s.n = n;
+  s.delta = delta;
+  s.has_nrm = nrm != nullptr;
+  seq_centroid(xyz, n, s.cP);
+  PGP_CUDA(ctx, s.xyz_raw.reserve((size_t)n * 12));
+  PGP_CUDA(ctx, cudaMemcpyAsync(s.xyz_raw.p, xyz, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+  if (nrm) {
+    PGP_CUDA(ctx, s.nrm_raw.reserve((size_t)n * 12));
+    PGP_CUDA(ctx, cudaMemcpyAsync(s.nrm_raw.p, nrm, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  PGP_CUDA(ctx, ctx->work.reserve(4096));
+  int rc = k1_fill_priors(ctx, 1.0f);
+  if (rc) return rc;
+  ctx->last = LastBatch();
+  return k1_build_grid(ctx);
+}
+
+int pgp_set_scene_priors(pgp_ctx* ctx, const float* prior) {
+  CHECK_CTX(ctx);
+  Scene& s = ctx->scene;
+  if (!s.ready) return pgp_fail(ctx, PGP_E_NO_SCENE, "pgp_set_scene first");
+  if (!prior) return pgp_fail(ctx, PGP_E_INVALID, "null priors");
+  PGP_CUDA(ctx, cudaMemcpyAsync(s.prior.p, prior, (size_t)s.n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  return k1_refresh_sorted_priors(ctx);
+}
+
+int pgp_get_scene_priors(pgp_ctx* ctx, float* prior) {
+  CHECK_CTX(ctx);
+  Scene& s = ctx->scene;
+  if (!s.ready) return pgp_fail(ctx, PGP_E_NO_SCENE, "pgp_set_scene first");
+  PGP_CUDA(ctx, cudaMemcpyAsync(prior, s.prior.p, (size_t)s.n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PGP_OK;
+}
+
+int pgp_set_scene_prior_image(pgp_ctx* ctx, const uint16_t* img, int rows, int cols, const float* K9) {
+  CHECK_CTX(ctx);
+  Scene& s = ctx->scene;
+  if (!s.ready) return pgp_fail(ctx, PGP_E_NO_SCENE, "pgp_set_scene first");
+  if (!img || rows <= 0 || cols <= 0 || !K9) return pgp_fail(ctx, PGP_E_INVALID, "bad prior image");
+  PGP_CUDA(ctx, s.scratch.reserve((size_t)rows * cols * 2));
+  PGP_CUDA(ctx, cudaMemcpyAsync(s.scratch.p, img, (size_t)rows * cols * 2, cudaMemcpyHostToDevice, ctx->stream));
+  return k1_project_priors(ctx, s.scratch.as<uint16_t>(), rows, cols, K9);
+}
+
+int pgp_set_model(pgp_ctx* ctx, int obj, const float* sx, const float* sn, int nq, const float* vx, const float* vn, int nv) {
+  CHECK_CTX(ctx);
+  if (obj < 0 || obj >= PGP_MAX_OBJECTS) return pgp_fail(ctx, PGP_E_INVALID, "object slot %d out of range", obj);
+  if (!sx || nq <= 0 || !vx || nv <= 0) return pgp_fail(ctx, PGP_E_INVALID, "pgp_set_model: empty cloud");
+  Model& m = ctx->models[obj];
+  m.ready = false;
+  m.nq = nq; m.nv = nv; m.n_gen = 0; m.tgrid_ready = false;
+  seq_centroid(sx, nq, m.cQ);   // centroid of the SEARCH cloud centres both clouds (:248-261)
+  std::vector<float> s4((size_t)nq * 4), sn4((size_t)nq * 4), v4((size_t)nv * 4), vn4((size_t)nv * 4);
+  for (int i = 0; i < nq; ++i) {
+    for (int k = 0; k < 3; ++k) s4[4 * (size_t)i + k] = sx[3 * i + k] - m.cQ[k];
+    int idx = i; memcpy(&s4[4 * (size_t)i + 3], &idx, 4);
+    unit_normal(sn ? sn + 3 * i : nullptr, &sn4[4 * (size_t)i]);
+  }
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = 0; i < nv; ++i) {
+    for (int k = 0; k < 3; ++k) {
+      float c = vx[3 * i + k] - m.cQ[k];
+      v4[4 * (size_t)i + k] = c;
+      lo[k] = std::min(lo[k], c); hi[k] = std::max(hi[k], c);
+    }
+    int idx = i; memcpy(&v4[4 * (size_t)i + 3], &idx, 4);
+    unit_normal(vn ? vn + 3 * i : nullptr, &vn4[4 * (size_t)i]);
+  }
+  // scoring order of the validation cloud: Morton order, so the 32 points a warp handles per step
+  // are neighbours and their queries fall into neighbouring cells (counts are order-free).
+  std::vector<uint32_t> code(nv);
+  std::vector<int> order(nv);
+  for (int i = 0; i < nv; ++i) {
+    uint32_t q[3];
+    for (int k = 0; k < 3; ++k) {
+      float ext = hi[k] - lo[k];
+      float u = ext > 0.f ? (v4[4 * (size_t)i + k] - lo[k]) / ext : 0.f;
+      q[k] = (uint32_t)std::min(1023.f, std::max(0.f, u * 1023.f));
+    }
+    code[i] = spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2);
+  }
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return code[a] < code[b]; });
+  std::vector<float> vs4((size_t)nv * 4), vsn4((size_t)nv * 4);
+  for (int i = 0; i < nv; ++i) {
+    memcpy(&vs4[4 * (size_t)i], &v4[4 * (size_t)order[i]], 16);
+    memcpy(&vsn4[4 * (size_t)i], &vn4[4 * (size_t)order[i]], 16);
+  }
+  int rc;
+  if ((rc = upload_cloud4(ctx, m.search, s4))) return rc;
+  if ((rc = upload_cloud4(ctx, m.search_nrm, sn4))) return rc;
+  if ((rc = upload_cloud4(ctx, m.val_orig, v4))) return rc;
+  if ((rc = upload_cloud4(ctx, m.val_nrm_orig, vn4))) return rc;
+  if ((rc = upload_cloud4(ctx, m.val, vs4))) return rc;
+  if ((rc = upload_cloud4(ctx, m.val_nrm, vsn4))) return rc;
+  PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the staging vectors die here
+  m.ready = true;
+  if (ctx->last.obj == obj) ctx->last = LastBatch();
+  return PGP_OK;
+}
+
+int pgp_get_centroids(pgp_ctx* ctx, int obj, float* cP, float* cQ) {
+  CHECK_CTX(ctx);
+  if (cP) { if (!ctx->scene.ready) return pgp_fail(ctx, PGP_E_NO_SCENE, "pgp_set_scene first"); memcpy(cP, ctx->scene.cP, 12); }
+  if (cQ) { Model* m = get_model(ctx, obj); if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", obj); memcpy(cQ, m->cQ, 12); }
+  return PGP_OK;
+}
+
+// T_c = Tr(-c_P) . T . Tr(c_Q)
+int pgp_pose_to_centred(pgp_ctx* ctx, int obj, const double* P, float* T) {
+  CHECK_CTX(ctx);
+  Model* m = get_model(ctx, obj);
+  if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", obj);
+  if (!ctx->scene.ready) return pgp_fail(ctx, PGP_E_NO_SCENE, "pgp_set_scene first");
+  for (int r = 0; r < 3; ++r) {
+    double t = P[4 * r + 3];
+    for (int c = 0; c < 3; ++c) { T[4 * r + c] = (float)P[4 * r + c]; t += P[4 * r + c] * (double)m->cQ[c]; }
+    T[4 * r + 3] = (float)(t - (double)ctx->scene.cP[r]);
+  }
+  return PGP_OK;
+}
+
+// camera-frame pose of a centred transform: rotation unchanged, translation t_c + c_P - R c_Q, which
+// is what match4pcsBase.cc:1474-1482 builds (c1 + cP - R (c2 + cQ) with t_c = c1 - R c2).
+int pgp_centred_to_pose(pgp_ctx* ctx, int obj, const float* T, double* P) {
+  CHECK_CTX(ctx);
+  Model* m = get_model(ctx, obj);
+  if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", obj);
+  if (!ctx->scene.ready) return pgp_fail(ctx, PGP_E_NO_SCENE, "pgp_set_scene first");
+  for (int r = 0; r < 3; ++r) {
+    double t = (double)T[4 * r + 3] + (double)ctx->scene.cP[r];
+    for (int c = 0; c < 3; ++c) { P[4 * r + c] = (double)T[4 * r + c]; t -= (double)T[4 * r + c] * (double)m->cQ[c]; }
+    P[4 * r + 3] = t;
+  }
+  P[12] = P[13] = P[14] = 0.0; P[15] = 1.0;
+  return PGP_OK;
+}
+
+int pgp_grid_info(pgp_ctx* ctx, int* dims3, int64_t* n_cells, int64_t* n_occupied, float* cell, int64_t* bytes) {
+  CHECK_CTX(ctx);
+  const Scene& s = ctx->scene;
+  if (!s.ready) return pgp_fail(ctx, PGP_E_NO_SCENE, "pgp_set_scene first");
+  if (dims3) memcpy(dims3, s.g.dim, 12);
+  if (n_cells) *n_cells = s.g.n_cells;
+  if (n_occupied) *n_occupied = s.n_occupied;
+  if (cell) *cell = s.g.h;
+  if (bytes) *bytes = (int64_t)s.n * 32 + (s.g.n_cells + 1) * 4 + s.bitmap_words * 4;
+  return PGP_OK;
+}
+
+static int check_score_args(pgp_ctx* ctx, int obj, int64_t n, int mode, Model** m) {
+  if (!ctx->scene.ready) return pgp_fail(ctx, PGP_E_NO_SCENE, "pgp_set_scene first");
+  *m = get_model(ctx, obj);
+  if (!*m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", obj);
+  if (n < 0) return pgp_fail(ctx, PGP_E_INVALID, "negative hypothesis count");
+  if (mode != PGP_LCP_COUNT && mode != PGP_LCP_WEIGHTED) return pgp_fail(ctx, PGP_E_INVALID, "unknown LCP mode %d", mode);
+  if (mode == PGP_LCP_WEIGHTED && !ctx->scene.has_nrm) return pgp_fail(ctx, PGP_E_INVALID, "weighted LCP needs scene normals");
+  return PGP_OK;
+}
+
+int pgp_score_lcp_dev(pgp_ctx* ctx, int obj, const float* T_dev, int64_t n, int mode, uint32_t* counts_dev, float* scores_dev) {
+  CHECK_CTX(ctx);
+  Model* m = nullptr;
+  int rc = check_score_args(ctx, obj, n, mode, &m);
+  if (rc) return rc;
+  if (n > 0 && (!T_dev || !counts_dev)) return pgp_fail(ctx, PGP_E_INVALID, "null device buffer");
+  if (mode == PGP_LCP_WEIGHTED && n > 0 && !scores_dev) return pgp_fail(ctx, PGP_E_INVALID, "weighted LCP needs the score buffer");
+  rc = k3_score(ctx, *m, T_dev, n, mode, counts_dev, scores_dev);
+  if (rc) return rc;
+  ctx->last.T = T_dev; ctx->last.counts = counts_dev; ctx->last.scores = scores_dev; ctx->last.n = n; ctx->last.mode = mode; ctx->last.obj = obj;
+  return PGP_OK;
+}
+
+int pgp_score_lcp(pgp_ctx* ctx, int obj, const float* T, int64_t n, int mode, uint32_t* counts, float* scores) {
+  CHECK_CTX(ctx);
+  Model* m = nullptr;
+  int rc = check_score_args(ctx, obj, n, mode, &m);
+  if (rc) return rc;
+  if (n == 0) { ctx->last = LastBatch(); return PGP_OK; }
+  if (!T) return pgp_fail(ctx, PGP_E_INVALID, "null transforms");
+  PGP_CUDA(ctx, ctx->batch_T.reserve((size_t)n * 48));
+  PGP_CUDA(ctx, ctx->batch_counts.reserve((size_t)n * 4));
+  PGP_CUDA(ctx, ctx->batch_scores.reserve((size_t)n * 4));
+  PGP_CUDA(ctx, cudaMemcpyAsync(ctx->batch_T.p, T, (size_t)n * 48, cudaMemcpyHostToDevice, ctx->stream));
+  rc = pgp_score_lcp_dev(ctx, obj, ctx->batch_T.as<float>(), n, mode, ctx->batch_counts.as<uint32_t>(), ctx->batch_scores.as<float>());
+  if (rc) return rc;
+  if (counts) PGP_CUDA(ctx, cudaMemcpyAsync(counts, ctx->batch_counts.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (scores) PGP_CUDA(ctx, cudaMemcpyAsync(scores, ctx->batch_scores.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PGP_OK;
+}
+
+static int nearest_common(pgp_ctx* ctx, int obj, const float* T12, int32_t* idx_host, int gate) {
+  Model* m = nullptr;
+  int rc = check_score_args(ctx, obj, 1, gate ? PGP_LCP_WEIGHTED : PGP_LCP_COUNT, &m);
+  if (rc) return rc;
+  PGP_CUDA(ctx, ctx->topk_out.reserve((size_t)m->nv * 4 + 64));
+  float* dT = ctx->topk_out.as<float>();
+  int32_t* didx = reinterpret_cast<int32_t*>(ctx->topk_out.as<char>() + 64);
+  PGP_CUDA(ctx, cudaMemcpyAsync(dT, T12, 48, cudaMemcpyHostToDevice, ctx->stream));
+  rc = k3_nearest(ctx, *m, dT, didx, gate);
+  if (rc) return rc;
+  PGP_CUDA(ctx, cudaMemcpyAsync(idx_host, didx, (size_t)m->nv * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PGP_OK;
+}
+
+int pgp_nearest_in_range(pgp_ctx* ctx, int obj, const float* T12, int32_t* idx_host) {
+  CHECK_CTX(ctx);
+  if (!T12 || !idx_host) return pgp_fail(ctx, PGP_E_INVALID, "null argument");
+  return nearest_common(ctx, obj, T12, idx_host, 0);
+}
+
+int pgp_registered_points(pgp_ctx* ctx, int obj, const float* T12, int32_t* idx_host, int cap) {
+  CHECK_CTX(ctx);
+  if (!T12 || !idx_host) return pgp_fail(ctx, PGP_E_INVALID, "null argument");
+  Model* m = get_model(ctx, obj);
+  if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", obj);
+  std::vector<int32_t> tmp(m->nv);
+  int rc = nearest_common(ctx, obj, T12, tmp.data(), 1);
+  if (rc) return rc;
+  int k = 0;
+  for (int i = 0; i < m->nv; ++i)
+    if (tmp[i] >= 0) {
+      if (k >= cap) return pgp_fail(ctx, PGP_E_CAPACITY, "more than %d registered points", cap);
+      idx_host[k++] = tmp[i];
+    }
+  return k;
+}
+
+int pgp_topk(pgp_ctx* ctx, int obj, int k, int64_t index_base, pgp_hyp* out) {
+  CHECK_CTX(ctx);
+  if (ctx->last.obj != obj || ctx->last.n <= 0) return pgp_fail(ctx, PGP_E_NO_SCORES, "no scored batch for object %d", obj);
+  if (k < 0 || (k > 0 && !out)) return pgp_fail(ctx, PGP_E_INVALID, "bad k / output");
+  int n_out = 0;
+  int rc = k4_topk(ctx, ctx->last, k, index_base, out, &n_out);
+  return rc ? rc : n_out;
+}
+
+int pgp_improving_chain(pgp_ctx* ctx, int obj, int64_t index_base, pgp_hyp* out, int cap) {
+  CHECK_CTX(ctx);
+  if (ctx->last.obj != obj || ctx->last.n <= 0) return pgp_fail(ctx, PGP_E_NO_SCORES, "no scored batch for object %d", obj);
+  if (cap <= 0 || !out) return pgp_fail(ctx, PGP_E_INVALID, "bad capacity / output");
+  int n_out = 0;
+  int rc = k4_chain(ctx, ctx->last, index_base, out, cap, &n_out);
+  if (rc) return rc;
+  if (n_out > cap) return pgp_fail(ctx, PGP_E_CAPACITY, "improving chain has %d elements, capacity %d (the last %d were written)", n_out, cap, cap);
+  return n_out;
+}
+
+// (score desc, index asc) over the concatenated lists; records with index < 0 are padding.
+int pgp_topk_merge(const pgp_hyp* lists, int n_lists, int k_each, int k, pgp_hyp* out) {
+  if (!lists || !out || n_lists <= 0 || k_each < 0 || k < 0) return PGP_E_INVALID;
+  std::vector<const pgp_hyp*> v;
+  v.reserve((size_t)n_lists * k_each);
+  for (int i = 0; i < n_lists * k_each; ++i)
+    if (lists[i].index >= 0) v.push_back(lists + i);
+  std::sort(v.begin(), v.end(), [](const pgp_hyp* a, const pgp_hyp* b) {
+    if (a->score != b->score) return a->score > b->score;
+    return a->index < b->index;
+  });
+  int m = std::min<int>(k, (int)v.size());
+  for (int i = 0; i < m; ++i) out[i] = *v[i];
+  return m;
+}
+
+void pgp_pcs_default_opts(pgp_pcs_opts* o) {
+  if (!o) return;
+  o->n_bases = 100; o->max_quads_per_base = 100; o->max_base_diameter = -1.f; o->overlap = 0.5f; o->base_trials = 1000;
+}
+
+int pgp_extract_pairs(pgp_ctx* ctx, int obj, float dist, float eps, int32_t* pairs, int64_t cap, int64_t* n_pairs) {
+  CHECK_CTX(ctx);
+  Model* m = get_model(ctx, obj);
+  if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", obj);
+  if (!n_pairs) return pgp_fail(ctx, PGP_E_INVALID, "null n_pairs");
+  return k2_extract_pairs(ctx, *m, dist, eps, pairs, cap, n_pairs);
+}
+
+int pgp_find_quads(pgp_ctx* ctx, int obj, const int32_t* base4, float inv1, float inv2, float eps, const int32_t* p1, int64_t n1,
+                   const int32_t* p2, int64_t n2, int32_t* quads, int64_t cap, int64_t* n_quads) {
+  CHECK_CTX(ctx);
+  Model* m = get_model(ctx, obj);
+  if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", obj);
+  if (!ctx->scene.ready) return pgp_fail(ctx, PGP_E_NO_SCENE, "pgp_set_scene first");
+  if (!base4 || !n_quads || n1 < 0 || n2 < 0) return pgp_fail(ctx, PGP_E_INVALID, "bad argument");
+  return k2_find_quads(ctx, *m, base4, inv1, inv2, eps, p1, n1, p2, n2, quads, cap, n_quads);
+}
+
+int pgp_rigid_from_quads(pgp_ctx* ctx, int obj, const int32_t* base4, const int32_t* quads, int64_t n, float* T, uint8_t* ok) {
+  CHECK_CTX(ctx);
+  Model* m = get_model(ctx, obj);
+  if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", obj);
+  if (!ctx->scene.ready) return pgp_fail(ctx, PGP_E_NO_SCENE, "pgp_set_scene first");
+  if (!base4 || !quads || !T || !ok || n < 0) return pgp_fail(ctx, PGP_E_INVALID, "bad argument");
+  return k2_rigid_from_quads(ctx, *m, base4, quads, n, T, ok);
+}
+
+int pgp_generate_pcs(pgp_ctx* ctx, int obj, const pgp_pcs_opts* opts, uint64_t seed, int64_t max_hyp, int64_t* n_hyp) {
+  CHECK_CTX(ctx);
+  Model* m = get_model(ctx, obj);
+  if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", obj);
+  if (!ctx->scene.ready) return pgp_fail(ctx, PGP_E_NO_SCENE, "pgp_set_scene first");
+  pgp_pcs_opts o;
+  if (opts) o = *opts; else pgp_pcs_default_opts(&o);
+  if (!n_hyp || max_hyp <= 0) return pgp_fail(ctx, PGP_E_INVALID, "bad argument");
+  return k2_generate(ctx, *m, &o, seed, max_hyp, n_hyp);
+}
+
+int pgp_score_generated(pgp_ctx* ctx, int obj, int mode) {
+  CHECK_CTX(ctx);
+  Model* m = get_model(ctx, obj);
+  if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", obj);
+  if (m->n_gen <= 0) return pgp_fail(ctx, PGP_E_NO_SCORES, "pgp_generate_pcs produced no hypotheses for object %d", obj);
+  PGP_CUDA(ctx, m->gen_counts.reserve((size_t)m->n_gen * 4));
+  PGP_CUDA(ctx, m->gen_scores.reserve((size_t)m->n_gen * 4));
+  return pgp_score_lcp_dev(ctx, obj, m->gen_T.as<float>(), m->n_gen, mode, m->gen_counts.as<uint32_t>(), m->gen_scores.as<float>());
+}
+
+int pgp_get_generated(pgp_ctx* ctx, int obj, float* T, uint32_t* counts, float* scores, int64_t cap) {
+  CHECK_CTX(ctx);
+  Model* m = get_model(ctx, obj);
+  if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", obj);
+  int64_t n = std::min<int64_t>(cap, m->n_gen);
+  if (n > 0) {
+    if (T) PGP_CUDA(ctx, cudaMemcpyAsync(T, m->gen_T.p, (size_t)n * 48, cudaMemcpyDeviceToHost, ctx->stream));
+    if (counts && m->gen_counts.p) PGP_CUDA(ctx, cudaMemcpyAsync(counts, m->gen_counts.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (scores && m->gen_scores.p) PGP_CUDA(ctx, cudaMemcpyAsync(scores, m->gen_scores.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return (int)std::min<int64_t>(n, 0x7fffffff);
+}
+
+int pgp_tricp(pgp_ctx* ctx, int obj, const float* seg, int ns, double* poses, int k, float trim, float ratio, int max_iter, int* iters, float* energy) {
+  CHECK_CTX(ctx);
+  Model* m = get_model(ctx, obj);
+  if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", obj);
+  if (!seg || ns <= 0 || !poses || k < 0) return pgp_fail(ctx, PGP_E_INVALID, "bad argument");
+  if (k == 0) return PGP_OK;
+  return k5_tricp(ctx, *m, seg, ns, poses, k, trim, ratio, max_iter, iters, energy);
+}
+
+}  // extern "C"

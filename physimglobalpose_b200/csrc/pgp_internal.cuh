@@ -1,0 +1,165 @@
+// Internal declarations shared by the translation units of libpgp.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "pgp.h"
+
+#define PGP_WARPS_PER_CTA 8
+#define PGP_THREADS (32 * PGP_WARPS_PER_CTA)
+
+// Device buffer that only ever grows (cudaMalloc is not on any steady-state path).
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+// Scene voxel grid ("K1").  Cell edge h = delta * (1 + 2^-8) so that every scene point that can
+// pass the fp32 test d2 <= delta^2 lies in the 27 cells around the query's cell.
+// Two empty apron cells on every side: a query in cells 1..dim-2 never indexes out of range.
+struct GridParams {
+  float lo[3];        // origin of cell (0,0,0)
+  float inv_h;        // 1 / h
+  float h;
+  int dim[3];
+  int64_t n_cells;
+  float r2;           // fl(fl(delta) * fl(delta)), the reference's sq_eps (match4pcsBase.cc:1710)
+  // fine tri-state classification (K1b): sub-voxels per cell edge
+  int fine;           // 0 = not built
+  float inv_hf;       // fine / h
+};
+
+struct Scene {
+  int n = 0;
+  float delta = 0.f;
+  float cP[3] = {0, 0, 0};
+  GridParams g{};
+  DevBuf xyz_raw;      // n x float3, camera frame (for the prior projection)
+  DevBuf nrm_raw;      // n x float3 as given (original order)
+  bool has_nrm = false;
+  DevBuf unsorted;     // n x float4 centred, original order (staging of the build)
+  DevBuf cursor;       // (n_cells + 1) x u32 scatter cursors
+  int64_t bitmap_words = 0;
+  DevBuf pts;          // n x float4 sorted by cell: x,y,z centred, w = original index (as int bits)
+  DevBuf aux;          // n x float4 sorted by cell: unit normal, prior
+  DevBuf cell_start;   // (n_cells + 1) x u32
+  DevBuf cell_of;      // n x u32 (scratch: cell id per original point)
+  DevBuf bitmap;       // ceil(n_cells/32) x u32: dilated occupancy (any point in the 27 cells)
+  DevBuf tri_index;    // n_cells x u32: per-cell fine-block index (K1b) or sentinel
+  DevBuf tri_blocks;   // fine tri-state blocks
+  DevBuf prior;        // n x f32 in ORIGINAL order
+  DevBuf scratch;      // scan scratch etc.
+  int64_t n_occupied = 0;
+  int64_t n_mixed = 0;
+  bool priors_binary = true;   // every prior is exactly 0 or 1 -> weighted sums are order-free
+  bool ready = false;
+};
+
+struct Model {
+  int nq = 0, nv = 0;
+  float cQ[3] = {0, 0, 0};
+  DevBuf search;       // nq x float4 centred (w = 0)
+  DevBuf search_nrm;   // nq x float4 unit normal
+  DevBuf val;          // nv x float4 centred, in a cache-friendly order; w = original index bits
+  DevBuf val_nrm;      // nv x float4 unit normal, same order
+  DevBuf val_orig;     // nv x float4 centred, ORIGINAL order (weighted mode with general priors, TrICP target)
+  DevBuf val_nrm_orig;
+  // model-space grid for TrICP (K5): nearest validation-model point of any query
+  DevBuf tgrid_pts, tgrid_start;
+  GridParams tg{};
+  bool tgrid_ready = false;
+  bool ready = false;
+  // generated hypotheses (K2)
+  DevBuf gen_T, gen_counts, gen_scores;
+  int64_t n_gen = 0;
+};
+
+struct LastBatch {
+  const float* T = nullptr;         // device
+  const uint32_t* counts = nullptr; // device
+  const float* scores = nullptr;    // device
+  int64_t n = 0;
+  int mode = 0;
+  int obj = -1;
+};
+
+struct pgp_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  Scene scene;
+  std::vector<Model> models;
+  LastBatch last;
+  DevBuf batch_T, batch_counts, batch_scores;   // device residency for the host-buffer API
+  DevBuf work;                                   // counters / select scratch
+  DevBuf topk_out;
+  void* pinned = nullptr; size_t pinned_cap = 0;
+  int64_t launches = 0;
+  std::string err;
+};
+
+int pgp_fail(pgp_ctx* ctx, int code, const char* fmt, ...);
+#define PGP_CUDA(ctx, expr)                                                                     \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return pgp_fail(ctx, PGP_E_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+// k1_grid.cu
+int k1_build_grid(pgp_ctx* ctx);
+int k1_project_priors(pgp_ctx* ctx, const uint16_t* img_dev, int rows, int cols, const float* K9);
+int k1_refresh_sorted_priors(pgp_ctx* ctx);
+int k1_fill_priors(pgp_ctx* ctx, float v);
+// k3_lcp.cu
+int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mode, uint32_t* counts_dev, float* scores_dev);
+int k3_nearest(pgp_ctx* ctx, const Model& m, const float* T_dev, int32_t* idx_dev, int gate);
+// k4_select.cu
+int k4_topk(pgp_ctx* ctx, const LastBatch& b, int k, int64_t index_base, pgp_hyp* out_host, int* n_out);
+int k4_chain(pgp_ctx* ctx, const LastBatch& b, int64_t index_base, pgp_hyp* out_host, int cap, int* n_out);
+// k2_pcs.cu
+int k2_extract_pairs(pgp_ctx* ctx, const Model& m, float dist, float eps, int32_t* pairs_host, int64_t cap, int64_t* n_pairs);
+int k2_find_quads(pgp_ctx* ctx, const Model& m, const int32_t* base4, float inv1, float inv2, float eps,
+                  const int32_t* p1, int64_t n1, const int32_t* p2, int64_t n2, int32_t* quads_host, int64_t cap, int64_t* n_quads);
+int k2_rigid_from_quads(pgp_ctx* ctx, const Model& m, const int32_t* base4, const int32_t* quads_host, int64_t n, float* T_host, uint8_t* ok_host);
+int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, int64_t max_hyp, int64_t* n_hyp);
+// k5_tricp.cu
+int k5_tricp(pgp_ctx* ctx, Model& m, const float* seg_xyz_host, int ns, double* poses16_host, int k, float trim, float ratio,
+             int max_iter, int* iters_out, float* energy_out);
+
+// ---------------------------------------------------------------------------------------------
+// fp32 arithmetic in the reference's association, every operation individually rounded
+// (SURVEY.md 7 "Hard parts"; the library is also compiled with -fmad=false).
+__device__ __forceinline__ float xf_row(float m0, float m1, float m2, float m3, float x, float y, float z) {
+  // (mat * p.homogeneous()).head<3>()  S4/algorithms/match4pcsBase.cc:1717 :  ((m0 x + m1 y) + m2 z) + m3
+  return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m0, x), __fmul_rn(m1, y)), __fmul_rn(m2, z)), m3);
+}
+__device__ __forceinline__ float sqdist3(float ax, float ay, float az, float bx, float by, float bz) {
+  // (q - p).squaredNorm()  S4/accelerators/kdtree.h:423 :  dx^2 + (dy^2 + dz^2)
+  float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  return __fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz)));
+}
+__device__ __forceinline__ float dot3_tree(float a0, float a1, float a2, float b0, float b1, float b2) {
+  // 3-element lazy product / dot: a0 b0 + (a1 b1 + a2 b2)   match4pcsBase.cc:1755-1756
+  return __fadd_rn(__fmul_rn(a0, b0), __fadd_rn(__fmul_rn(a1, b1), __fmul_rn(a2, b2)));
+}
+// cell coordinate of a centred coordinate; the SAME function bins scene points and queries, and
+// it is monotone, which is what the 27-cell completeness argument needs.
+__device__ __forceinline__ float cell_coord(float x, float lo, float inv_h) { return __fmul_rn(__fsub_rn(x, lo), inv_h); }

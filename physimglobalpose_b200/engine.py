@@ -1,0 +1,266 @@
+"""Host-side mirror of the reference's per-object matcher (match_4pcs::MatchSuper4PCS as
+`getProbableTransformsSuper4PCS` drives it, S4/super4pcs_test.cc:39-111) over the C ABI of
+include/pgp.h.  numpy arrays are host buffers; torch CUDA tensors are passed by pointer.
+
+S4 = /root/reference/src/3rdparty/super4pcs/src/super4pcs (citations only; nothing is read from
+the reference tree at run time)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import PGP_LCP_COUNT, PGP_LCP_WEIGHTED, PgpError, PgpHyp, PgpPcsOpts
+
+MODES = {"count": PGP_LCP_COUNT, "weighted": PGP_LCP_WEIGHTED, PGP_LCP_COUNT: PGP_LCP_COUNT, PGP_LCP_WEIGHTED: PGP_LCP_WEIGHTED}
+
+HYP_DTYPE = np.dtype([("index", "<i8"), ("count", "<u4"), ("score", "<f4"), ("T", "<f4", (12,))])
+assert HYP_DTYPE.itemsize == C.sizeof(PgpHyp) == 64
+
+
+def _f32(a, cols=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if cols is not None:
+        a = a.reshape(-1, cols)
+    return a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class PoseEngine:
+    """One context on one GPU.  Scene = the segmented cloud of one object request ("P"); model
+    slots hold the search / validation clouds ("Q", "Q_validation")."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        self._ctx = self._lib.pgp_create(int(device))
+        if not self._ctx:
+            raise PgpError(-2, self._lib.pgp_last_error(None).decode())
+        self.device = int(device)
+        self._nv = {}
+        self._nq = {}
+        self._ns = 0
+        self._keep = {}
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.pgp_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> int:
+        if rc < 0:
+            raise PgpError(rc, self._lib.pgp_last_error(self._ctx).decode())
+        return rc
+
+    def set_stream(self, cuda_stream: Optional[int]):
+        """cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream); None = the context's own
+        stream.  torch's default stream has handle 0, which is passed on as cudaStreamLegacy (0x1)."""
+        if cuda_stream is not None and int(cuda_stream) == 0:
+            cuda_stream = 1
+        self._check(self._lib.pgp_set_stream(self._ctx, cuda_stream))
+
+    def synchronize(self):
+        self._check(self._lib.pgp_synchronize(self._ctx))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.pgp_launch_count(self._ctx))
+
+    # ------------------------------------------------------------------ K1
+    def set_scene(self, xyz, normals=None, delta: float = 0.005):
+        """Match4PCSBase::init for P: centring + spatial index (match4pcsBase.cc:242-270)."""
+        xyz = _f32(xyz, 3)
+        normals = _f32(normals, 3)
+        if normals is not None and len(normals) != len(xyz):
+            raise ValueError("normals / points length mismatch")
+        self._check(self._lib.pgp_set_scene(self._ctx, _ptr(xyz), _ptr(normals), len(xyz), float(delta)))
+        self._ns = len(xyz)
+
+    def set_scene_prior_image(self, img_u16, K):
+        img = np.ascontiguousarray(img_u16, dtype=np.uint16)
+        K = _f32(K).reshape(9)
+        self._check(self._lib.pgp_set_scene_prior_image(self._ctx, _ptr(img), img.shape[0], img.shape[1], _ptr(K)))
+
+    def set_scene_priors(self, prior):
+        prior = _f32(prior).reshape(-1)
+        if len(prior) != self._ns:
+            raise ValueError("one prior per scene point")
+        self._check(self._lib.pgp_set_scene_priors(self._ctx, _ptr(prior)))
+
+    def scene_priors(self) -> np.ndarray:
+        out = np.zeros(self._ns, np.float32)
+        self._check(self._lib.pgp_get_scene_priors(self._ctx, _ptr(out)))
+        return out
+
+    def set_model(self, obj: int, search_xyz, search_normals, val_xyz=None, val_normals=None):
+        sx, sn = _f32(search_xyz, 3), _f32(search_normals, 3)
+        vx = sx if val_xyz is None else _f32(val_xyz, 3)
+        vn = sn if val_xyz is None else _f32(val_normals, 3)
+        self._check(self._lib.pgp_set_model(self._ctx, obj, _ptr(sx), _ptr(sn), len(sx), _ptr(vx), _ptr(vn), len(vx)))
+        self._nq[obj], self._nv[obj] = len(sx), len(vx)
+
+    def centroids(self, obj: int = 0):
+        cP, cQ = np.zeros(3, np.float32), np.zeros(3, np.float32)
+        self._check(self._lib.pgp_get_centroids(self._ctx, obj, _ptr(cP), _ptr(cQ)))
+        return cP, cQ
+
+    def pose_to_centred(self, obj: int, pose44) -> np.ndarray:
+        P = np.ascontiguousarray(pose44, dtype=np.float64).reshape(-1, 16)
+        out = np.zeros((len(P), 12), np.float32)
+        for i in range(len(P)):
+            self._check(self._lib.pgp_pose_to_centred(self._ctx, obj, P[i].ctypes.data, out[i].ctypes.data))
+        return out.reshape(-1, 3, 4)
+
+    def centred_to_pose(self, obj: int, T) -> np.ndarray:
+        T = _f32(T).reshape(-1, 12)
+        out = np.zeros((len(T), 16), np.float64)
+        for i in range(len(T)):
+            self._check(self._lib.pgp_centred_to_pose(self._ctx, obj, T[i].ctypes.data, out[i].ctypes.data))
+        return out.reshape(-1, 4, 4)
+
+    def grid_info(self) -> dict:
+        dims = (C.c_int * 3)()
+        nc, no, b = C.c_int64(), C.c_int64(), C.c_int64()
+        cell = C.c_float()
+        self._check(self._lib.pgp_grid_info(self._ctx, dims, C.byref(nc), C.byref(no), C.byref(cell), C.byref(b)))
+        return dict(dims=tuple(dims), n_cells=nc.value, n_occupied=no.value, cell=cell.value, bytes=b.value)
+
+    # ------------------------------------------------------------------ K3
+    def score_lcp(self, obj: int, T, mode="count"):
+        """Host buffers in, host buffers out (counts u32, scores f32); copies are inside the call."""
+        T = _f32(T).reshape(-1, 12)
+        n = len(T)
+        counts = np.zeros(n, np.uint32)
+        scores = np.zeros(n, np.float32)
+        self._check(self._lib.pgp_score_lcp(self._ctx, obj, _ptr(T), n, MODES[mode], _ptr(counts), _ptr(scores)))
+        return counts, scores
+
+    def score_lcp_into(self, obj: int, T: np.ndarray, counts: np.ndarray, scores: Optional[np.ndarray], mode="count"):
+        """Same, with caller-owned (ideally pinned) host buffers -- the bench's e2e call."""
+        n = T.size // 12
+        self._check(self._lib.pgp_score_lcp(self._ctx, obj, T.ctypes.data, n, MODES[mode], counts.ctypes.data,
+                                            None if scores is None else scores.ctypes.data))
+
+    def score_lcp_ptr(self, obj: int, T_ptr: int, n: int, counts_ptr: int, scores_ptr: int, mode="count", host: bool = True):
+        """Raw-pointer form (pinned torch tensors / device tensors)."""
+        fn = self._lib.pgp_score_lcp if host else self._lib.pgp_score_lcp_dev
+        self._check(fn(self._ctx, obj, T_ptr, n, MODES[mode], counts_ptr, scores_ptr))
+
+    def score_lcp_device(self, obj: int, T_dev, counts_dev, scores_dev, mode="count"):
+        """torch CUDA tensors: T (n,12) f32, counts (n,) i32/u32-as-int32, scores (n,) f32.  Asynchronous."""
+        n = T_dev.shape[0]
+        assert T_dev.is_cuda and T_dev.is_contiguous() and counts_dev.is_cuda and scores_dev.is_cuda
+        self._keep[obj] = (T_dev, counts_dev, scores_dev)
+        self._check(self._lib.pgp_score_lcp_dev(self._ctx, obj, T_dev.data_ptr(), n, MODES[mode], counts_dev.data_ptr(), scores_dev.data_ptr()))
+
+    def registered_points(self, obj: int, T) -> np.ndarray:
+        T = _f32(T).reshape(12)
+        out = np.zeros(self._nv[obj], np.int32)
+        k = self._check(self._lib.pgp_registered_points(self._ctx, obj, _ptr(T), _ptr(out), len(out)))
+        return out[:k].copy()
+
+    def nearest_in_range(self, obj: int, T) -> np.ndarray:
+        T = _f32(T).reshape(12)
+        out = np.zeros(self._nv[obj], np.int32)
+        self._check(self._lib.pgp_nearest_in_range(self._ctx, obj, _ptr(T), _ptr(out)))
+        return out
+
+    # ------------------------------------------------------------------ K4
+    def topk(self, obj: int, k: int, index_base: int = 0) -> np.ndarray:
+        out = np.zeros(max(k, 1), HYP_DTYPE)
+        m = self._check(self._lib.pgp_topk(self._ctx, obj, k, index_base, _ptr(out)))
+        return out[:m].copy()
+
+    def improving_chain(self, obj: int, index_base: int = 0, cap: int = 4096) -> np.ndarray:
+        out = np.zeros(cap, HYP_DTYPE)
+        m = self._check(self._lib.pgp_improving_chain(self._ctx, obj, index_base, _ptr(out), cap))
+        return out[:m].copy()
+
+    # ------------------------------------------------------------------ K2
+    def extract_pairs(self, obj: int, dist: float, eps: float, cap: int = 1 << 22) -> np.ndarray:
+        out = np.zeros((cap, 2), np.int32)
+        n = C.c_int64(0)
+        self._check(self._lib.pgp_extract_pairs(self._ctx, obj, float(dist), float(eps), _ptr(out), cap, C.byref(n)))
+        if n.value > cap:
+            return self.extract_pairs(obj, dist, eps, cap=int(n.value))
+        return out[: n.value].copy()
+
+    def find_quads(self, obj: int, base4, inv1, inv2, eps, pairs1, pairs2, cap: int = 1 << 20) -> np.ndarray:
+        b = np.ascontiguousarray(base4, np.int32)
+        p1 = np.ascontiguousarray(pairs1, np.int32).reshape(-1, 2)
+        p2 = np.ascontiguousarray(pairs2, np.int32).reshape(-1, 2)
+        out = np.zeros((cap, 4), np.int32)
+        n = C.c_int64(0)
+        self._check(self._lib.pgp_find_quads(self._ctx, obj, _ptr(b), float(inv1), float(inv2), float(eps), _ptr(p1), len(p1),
+                                             _ptr(p2), len(p2), _ptr(out), cap, C.byref(n)))
+        if n.value > cap:
+            return self.find_quads(obj, base4, inv1, inv2, eps, pairs1, pairs2, cap=int(n.value))
+        return out[: n.value].copy()
+
+    def rigid_from_quads(self, obj: int, base4, quads):
+        b = np.ascontiguousarray(base4, np.int32)
+        q = np.ascontiguousarray(quads, np.int32).reshape(-1, 4)
+        T = np.zeros((len(q), 12), np.float32)
+        ok = np.zeros(len(q), np.uint8)
+        self._check(self._lib.pgp_rigid_from_quads(self._ctx, obj, _ptr(b), _ptr(q), len(q), _ptr(T), _ptr(ok)))
+        return T.reshape(-1, 3, 4), ok.astype(bool)
+
+    def generate_pcs(self, obj: int, seed: int = 1, max_hyp: int = 10000, **opts) -> int:
+        o = PgpPcsOpts()
+        self._lib.pgp_pcs_default_opts(C.byref(o))
+        for k, v in opts.items():
+            setattr(o, k, v)
+        n = C.c_int64(0)
+        self._check(self._lib.pgp_generate_pcs(self._ctx, obj, C.byref(o), int(seed), int(max_hyp), C.byref(n)))
+        self._ngen = getattr(self, "_ngen", {})
+        self._ngen[obj] = n.value
+        return n.value
+
+    def score_generated(self, obj: int, mode="count"):
+        self._check(self._lib.pgp_score_generated(self._ctx, obj, MODES[mode]))
+
+    def get_generated(self, obj: int):
+        n = self._ngen.get(obj, 0)
+        T = np.zeros((n, 12), np.float32)
+        counts = np.zeros(n, np.uint32)
+        scores = np.zeros(n, np.float32)
+        self._check(self._lib.pgp_get_generated(self._ctx, obj, _ptr(T), _ptr(counts), _ptr(scores), n))
+        return T.reshape(-1, 3, 4), counts, scores
+
+    # ------------------------------------------------------------------ K5
+    def tricp(self, obj: int, segment_xyz, poses44, trim: float = 0.5, ratio: float = 0.99, max_iter: int = 100):
+        seg = _f32(segment_xyz, 3)
+        P = np.ascontiguousarray(poses44, dtype=np.float64).reshape(-1, 16).copy()
+        iters = np.zeros(len(P), np.int32)
+        energy = np.zeros(len(P), np.float32)
+        self._check(self._lib.pgp_tricp(self._ctx, obj, _ptr(seg), len(seg), _ptr(P), len(P), float(trim), float(ratio), int(max_iter),
+                                        _ptr(iters), _ptr(energy)))
+        return P.reshape(-1, 4, 4), iters, energy
+
+
+def topk_merge(lists: Sequence[np.ndarray], k: int) -> np.ndarray:
+    """Deterministic merge of per-rank top-k record arrays (pgp_topk_merge)."""
+    lib = _lib.load()
+    k_each = max((len(a) for a in lists), default=0)
+    buf = np.zeros((len(lists), max(k_each, 1)), HYP_DTYPE)
+    buf["index"] = -1
+    for i, a in enumerate(lists):
+        buf[i, : len(a)] = a
+    out = np.zeros(max(k, 1), HYP_DTYPE)
+    m = lib.pgp_topk_merge(buf.ctypes.data, len(lists), max(k_each, 1), k, out.ctypes.data)
+    if m < 0:
+        raise PgpError(m, "pgp_topk_merge")
+    return out[:m].copy()

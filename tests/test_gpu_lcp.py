@@ -1,0 +1,84 @@
+"""GPU parity of K1 + K3 + K4 against the CPU oracle, through the C ABI (libpgp.so)."""
+import numpy as np
+import pytest
+
+from physimglobalpose_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle(port_lib, prob, **kw):
+    return port_lib.PortOracle(prob.scene_xyz, prob.scene_nrm, prob.model_xyz, prob.model_nrm, prob.model_xyz, prob.model_nrm, prob.delta, **kw)
+
+
+def _setup(engine, prob, obj=0):
+    engine.set_scene(prob.scene_xyz, prob.scene_nrm, prob.delta)
+    engine.set_model(obj, prob.model_xyz, prob.model_nrm)
+
+
+def test_centroids_and_conversion(engine, port_lib, small_problem):
+    prob, T = small_problem
+    _setup(engine, prob)
+    o = _oracle(port_lib, prob)
+    cP, cQ = engine.centroids(0)
+    oP, oQ = o.centroids()
+    assert np.array_equal(cP, oP) and np.array_equal(cQ, oQ)      # bit-exact sequential fp32 sums
+    pose = engine.centred_to_pose(0, T[:5])
+    back = engine.pose_to_centred(0, pose)
+    assert np.allclose(back, T[:5], atol=1e-6)
+
+
+def test_count_parity_small(engine, port_lib, small_problem):
+    prob, T = small_problem
+    _setup(engine, prob)
+    want = _oracle(port_lib, prob).verify(T)
+    counts, scores = engine.score_lcp(0, T, "count")
+    assert np.array_equal(counts, want)                            # integer inlier counts: bit-exact
+    assert counts[0] == len(prob.model_xyz) and counts.argmax() == want.argmax() == 0
+    assert np.array_equal(scores, (want.astype(np.float32) / np.float32(len(prob.model_xyz))))
+
+
+def test_weighted_parity_small(engine, port_lib, small_problem):
+    prob, T = small_problem
+    _setup(engine, prob)
+    o = _oracle(port_lib, prob)
+    ws, wn, reg = o.weighted_verify(T, reg_of=1)
+    counts, scores = engine.score_lcp(0, T, "weighted")
+    assert np.array_equal(counts, wn.astype(np.uint32))
+    assert np.array_equal(scores, ws)
+    assert np.array_equal(engine.registered_points(0, T[1]), reg)
+    assert np.array_equal(engine.nearest_in_range(0, T[3]), o.nn_ids(T[3]))
+
+
+def test_weighted_general_priors_bit_exact(engine, port_lib, small_problem):
+    prob, T = small_problem
+    _setup(engine, prob)
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 10001, size=(480, 640)).astype(np.uint16)
+    K = np.array([[600.0, 0, 320], [0, 600.0, 240], [0, 0, 1]], np.float32)
+    o = _oracle(port_lib, prob, K=K, prior_img=img)
+    engine.set_scene_prior_image(img, K)
+    assert np.array_equal(engine.scene_priors(), o.priors())
+    ws, wn = o.weighted_verify(T[:200])
+    counts, scores = engine.score_lcp(0, T[:200], "weighted")
+    assert np.array_equal(counts, wn.astype(np.uint32))
+    assert np.array_equal(scores, ws)                               # ordered fp32 accumulation: bit-exact
+
+
+def test_topk_and_chain(engine, port_lib, small_problem):
+    prob, T = small_problem
+    _setup(engine, prob)
+    o = _oracle(port_lib, prob)
+    want = o.verify(T)
+    counts, scores = engine.score_lcp(0, T, "count")
+    top = engine.topk(0, 16)
+    order = np.lexsort((np.arange(len(want)), -want.astype(np.int64)))[:16]
+    assert np.array_equal(top["index"], order)
+    assert np.array_equal(top["count"], want[order])
+    assert np.array_equal(top["T"].reshape(-1, 3, 4), T[order])
+    # improving chain in a shuffled generation order (so it is longer than one element)
+    perm = np.random.default_rng(5).permutation(len(T))
+    counts, scores = engine.score_lcp(0, T[perm], "count")
+    chain = engine.improving_chain(0)
+    assert np.array_equal(chain["index"], o.improving_chain(scores))
+    assert chain["score"][-1] == scores.max() and np.all(np.diff(chain["score"]) > 0)

@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""Benchmark of the LCP hot path: hypotheses scored per second (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (CUDA, libpgp.so)
+  python bench.py --impl reference [...]                       the reference's CPU LCP on the host cores
+
+One step = one pass of the hot path over one batch: K3 scores H = 100 000 hypotheses of a 2k-point
+model against the 100k-point scene grid, K4 selects the top 64 and (N > 1) the per-rank lists are
+all-gathered over NCCL and merged.  N > 1 is launched by torchrun, one rank per GPU; every rank
+scores its own H hypotheses (weak scaling), the scene grid and model are replicated.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_MODEL, N_SCENE, N_HYP, DELTA, TOPK = 2000, 100_000, 100_000, 0.01, 64
+METRIC = "LCP hypotheses scored/sec at 1/2/4/8 B200 (2k-pt model, 100k-pt scene)"
+UNIT = "hyp/s"
+WORKLOAD = "configs[1]: synthetic LCP scoring, 2k-pt model, 100k-pt scene, 100k hypotheses per GPU, delta=1 cm"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, uuid: str | None):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        cmd = ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"]
+        if uuid:
+            cmd += ["-i", uuid]
+        try:
+            self.p = subprocess.Popen(cmd, stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self) -> dict:
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(rank: int):
+    from physimglobalpose_b200 import synth
+    prob = synth.make_problem(N_MODEL, N_SCENE, DELTA, seed=1234)
+    T = synth.make_hypotheses(prob, N_HYP, seed=4321 + rank)
+    return prob, T
+
+
+def algorithmic_bytes_per_hyp(prob, T) -> tuple[float, float, float]:
+    """B_hyp = 48 + 4 + N_m (27*8 + 16 k-bar)   (SURVEY.md 8(d)); k-bar from the actual inputs."""
+    from physimglobalpose_b200 import synth
+    kbar, nonempty = synth.kbar_27(prob, T, max_hyp=512)
+    return 52.0 + N_MODEL * (27 * 8 + 16.0 * kbar), kbar, nonempty
+
+
+# ------------------------------------------------------------------------------------------ CPU
+def cpu_reference_run(prob, T, seconds_per_step: float, steps: int, warmup: int):
+    """Times the reference's own CPU LCP (Match4PCSBase::Verify through oracle/_ref when that .so
+    was built from /root/reference, else the C restatement) on all host threads."""
+    from oracle import pyoracle
+    cores = os.cpu_count() or 1
+    args = (prob.scene_xyz, prob.scene_nrm, prob.model_xyz, prob.model_nrm, prob.model_xyz, prob.model_nrm, prob.delta)
+    if pyoracle.have_ref():
+        o, kind = pyoracle.RefOracle(*args), "reference"
+    else:
+        pyoracle.build_port()
+        o, kind = pyoracle.PortOracle(*args), "port"
+    probe = min(len(T), 64 * cores)
+    _, s = o.verify_mt(T[:probe], cores)
+    rate = probe / max(s, 1e-6)
+    sample = int(max(cores, min(len(T), rate * seconds_per_step)))
+    times = []
+    counts = None
+    for i in range(warmup + steps):
+        counts, s = o.verify_mt(T[:sample], cores)
+        if i >= warmup:
+            times.append(s)
+    total = sum(times)
+    return dict(value=sample * steps / total, unit=UNIT, cores=cores, kind=kind,
+                sample=f"first {sample} of the {len(T)} hypotheses per step, {steps} steps, Verify with full counts, {cores} threads"), \
+        total / steps * 1e3, counts, sample
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    prob, T = make_inputs(0)
+    base, ms_per_step, _, sample = cpu_reference_run(prob, T, seconds_per_step=2.0, steps=args.steps, warmup=args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "hypotheses_per_step": sample, "device": "host CPU"},
+            "cpu_baseline": base, "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    from physimglobalpose_b200.engine import PoseEngine
+    from physimglobalpose_b200.sharding import DeviceTopkGather
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    prob, T = make_inputs(rank)
+    peaks, peak_kind = measured_peaks()
+
+    eng = PoseEngine(local_rank)          # no fallback: raises without libpgp.so / a B200
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_scene(prob.scene_xyz, prob.scene_nrm, prob.delta)
+    eng.set_model(0, prob.model_xyz, prob.model_nrm)
+    grid = eng.grid_info()
+
+    T_host = torch.from_numpy(T.reshape(-1, 12).copy()).pin_memory()
+    counts_host = torch.zeros(N_HYP, dtype=torch.int32).pin_memory()
+    scores_host = torch.zeros(N_HYP, dtype=torch.float32).pin_memory()
+    T_dev = T_host.cuda(non_blocking=True)
+    counts_dev = torch.zeros(N_HYP, dtype=torch.int32, device="cuda")
+    scores_dev = torch.zeros(N_HYP, dtype=torch.float32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+    gather = DeviceTopkGather(eng, TOPK)
+    index_base = rank * N_HYP
+
+    def step_resident():
+        eng.score_lcp_device(0, T_dev, counts_dev, scores_dev, "count")
+        return gather(0, index_base)
+
+    def step_e2e():
+        eng.score_lcp_ptr(0, T_host.data_ptr(), N_HYP, counts_host.data_ptr(), scores_host.data_ptr(), "count", host=True)
+        return gather(0, index_base)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up, then the timed region: K steps, device-timed, L2 flushed between steps
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        top = step_resident()
+    uuid = None
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        pass
+    barrier()
+    sampler = ClockSampler(uuid) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = eng.launch_count
+    for a, b in ev:
+        flush.zero_()
+        a.record(stream)
+        top = step_resident()
+        b.record(stream)
+    barrier()
+    launches = eng.launch_count - launches0
+    total_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+    value = world * N_HYP * args.steps / (total_ms * 1e-3)
+
+    # ---- the dominant kernel alone (K3), for the roofline
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(min(args.steps, 10))]
+    for a, b in kev:
+        flush.zero_()
+        a.record(stream)
+        eng.score_lcp_device(0, T_dev, counts_dev, scores_dev, "count")
+        b.record(stream)
+    torch.cuda.synchronize()
+    kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end to end through the host-buffer API (H2D of the transforms + D2H of counts/scores/top-k inside)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()
+        top_e2e = step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * N_HYP * args.steps / e2e_s
+
+    if rank == 0:
+        b_hyp, kbar, nonempty = algorithmic_bytes_per_hyp(prob, T)
+        achieved = b_hyp * N_HYP / (kernel_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "n_model": N_MODEL, "n_scene": N_SCENE, "hypotheses_per_gpu": N_HYP, "delta": DELTA,
+                       "topk": TOPK, "mode": "count (Match4PCSBase::Verify, full counts)", "grid_dims": grid["dims"],
+                       "l2": "256 MiB device memset between timed steps (outside the timed events)",
+                       "parallelism": f"hypotheses sharded over {world} GPU(s), scene grid replicated"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_HYP * 48, "d2h_bytes_per_step": N_HYP * 8 + world * TOPK * 64},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                         "traffic": None, "peak_kind": peak_kind, "kernel": "k3_lcp_kernel<0>", "kernel_ms": kernel_ms,
+                         "algorithmic_bytes_per_hyp": b_hyp, "kbar_27": kbar, "nonempty_query_fraction": nonempty,
+                         "note": "algorithmic bytes of the canonical 27-cell probe (SURVEY.md 8d); the working set is L2-resident and "
+                                 "the bitmap cull skips empty queries, so this fraction is not capped at 1"},
+            "best": {"index": int(top["index"][0]), "count": int(top["count"][0])},
+        }
+        if world == 1:
+            base, _, cpu_counts, sample = cpu_reference_run(prob, T, seconds_per_step=12.0, steps=1, warmup=0)
+            line["cpu_baseline"] = base
+            got = counts_host.numpy()[:sample].astype(np.uint32)
+            line["parity"] = {"checked": int(sample), "mismatches": int((got != cpu_counts).sum())}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -143,6 +143,9 @@ PGP_API int64_t pgp_launch_count(const pgp_ctx* ctx);
  * best-so-far scan of Perform_N_steps (match4pcsBase.cc:1888-1901).  index_base is added to the
  * local indices (the rank's offset when hypotheses are sharded).  Returns the number written. */
 PGP_API int pgp_topk(pgp_ctx* ctx, int obj, int k, int64_t index_base, pgp_hyp* out_host);
+/* Same, asynchronous, with the k records written straight into caller-owned DEVICE memory (the
+ * send buffer of the multi-GPU all-gather); slots beyond the batch size get index = -1. */
+PGP_API int pgp_topk_dev(pgp_ctx* ctx, int obj, int k, int64_t index_base, pgp_hyp* out_dev);
 /* Deterministic merge of per-rank top-k lists (n_lists x k_each records, e.g. the output of an
  * all-gather): same order as pgp_topk on the union.  Host-side, no context needed. */
 PGP_API int pgp_topk_merge(const pgp_hyp* lists, int n_lists, int k_each, int k, pgp_hyp* out);

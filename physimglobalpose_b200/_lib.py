@@ -54,6 +54,7 @@ _SIGNATURES = {
     "pgp_nearest_in_range": (_i, [_vp, _i, _vp, _vp]),
     "pgp_launch_count": (_i64, [_vp]),
     "pgp_topk": (_i, [_vp, _i, _i, _i64, _vp]),
+    "pgp_topk_dev": (_i, [_vp, _i, _i, _i64, _vp]),
     "pgp_topk_merge": (_i, [_vp, _i, _i, _i, _vp]),
     "pgp_improving_chain": (_i, [_vp, _i, _i64, _vp, _i]),
     "pgp_pcs_default_opts": (None, [_vp]),

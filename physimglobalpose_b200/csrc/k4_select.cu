@@ -160,6 +160,13 @@ __global__ void __launch_bounds__(ST, 1) k4_select_kernel(const SelParams p) {
       __syncthreads();
       bitonic_desc(s_keys, m);
       for (int t = threadIdx.x; t < k; t += ST) write_record(p, t, s_keys[t]);
+      for (int t = k + threadIdx.x; t < p.k; t += ST) {      // pad: the merge skips index < 0
+        pgp_hyp r;
+        r.index = -1; r.count = 0; r.score = 0.f;
+#pragma unroll
+        for (int c = 0; c < 12; ++c) r.T[c] = 0.f;
+        p.out[t] = r;
+      }
       if (threadIdx.x == 0) *p.n_out = k;
     }
   } else {
@@ -219,8 +226,8 @@ __global__ void __launch_bounds__(ST, 1) k4_select_kernel(const SelParams p) {
 
 int bits_for(unsigned long long v) { int b = 1; while (b < 64 && (v >> b)) ++b; return b; }
 
-int run_select(pgp_ctx* ctx, const LastBatch& b, int k, int64_t index_base, pgp_hyp* out_host, int mode, int* n_out) {
-  *n_out = 0;
+int run_select(pgp_ctx* ctx, const LastBatch& b, int k, int64_t index_base, pgp_hyp* out_host, int mode, int* n_out, pgp_hyp* out_dev = nullptr) {
+  if (n_out) *n_out = 0;
   if (b.n <= 0 || k <= 0) return PGP_OK;
   if (k > KMAX) return pgp_fail(ctx, PGP_E_INVALID, "k = %d exceeds %d", k, KMAX);
   if (b.n > (1ll << 40)) return pgp_fail(ctx, PGP_E_INVALID, "batch too large for selection");
@@ -236,6 +243,7 @@ int run_select(pgp_ctx* ctx, const LastBatch& b, int k, int64_t index_base, pgp_
     p.key32 = reinterpret_cast<const uint32_t*>(b.scores); p.kbits = 32;
   }
   (void)binary_weight;
+  if (p.ibits + p.kbits > 63) return pgp_fail(ctx, PGP_E_INVALID, "batch too large for a 64-bit selection key");
   const size_t off_hist = 2048, off_bar = off_hist + (size_t)MAX_PASSES * BINS * 4, off_ncand = off_bar + 64, off_nout = off_ncand + 64,
                off_cand = off_nout + 64, off_seg = off_cand + (size_t)KMAX * 8, off_out = off_seg + 8 * 1024, total = off_out + (size_t)KMAX * sizeof(pgp_hyp);
   PGP_CUDA(ctx, ctx->work.reserve(total));
@@ -246,13 +254,15 @@ int run_select(pgp_ctx* ctx, const LastBatch& b, int k, int64_t index_base, pgp_
   p.n_out = reinterpret_cast<int*>(w + off_nout);
   p.cand = reinterpret_cast<unsigned long long*>(w + off_cand);
   p.seg_max = reinterpret_cast<unsigned long long*>(w + off_seg);
-  p.out = reinterpret_cast<pgp_hyp*>(w + off_out);
+  p.out = out_dev ? out_dev : reinterpret_cast<pgp_hyp*>(w + off_out);
   PGP_CUDA(ctx, cudaMemsetAsync(w + off_hist, 0, off_cand - off_hist, ctx->stream));
   int grid = (int)std::min<long long>(ctx->sm_count, (b.n + ST - 1) / ST);
   if (grid > 1024) grid = 1024;
   void* args[] = {(void*)&p};
   PGP_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k4_select_kernel, dim3(grid), dim3(ST), args, 0, ctx->stream));
   ctx->launches++;
+  PGP_CUDA(ctx, cudaGetLastError());
+  if (out_dev) return PGP_OK;      // asynchronous: the records stay on the device (e.g. an NCCL send buffer)
   int n_found = 0;
   PGP_CUDA(ctx, cudaMemcpyAsync(&n_found, p.n_out, 4, cudaMemcpyDeviceToHost, ctx->stream));
   PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -266,6 +276,9 @@ int run_select(pgp_ctx* ctx, const LastBatch& b, int k, int64_t index_base, pgp_
 
 int k4_topk(pgp_ctx* ctx, const LastBatch& b, int k, int64_t index_base, pgp_hyp* out_host, int* n_out) {
   return run_select(ctx, b, k, index_base, out_host, 0, n_out);
+}
+int k4_topk_dev(pgp_ctx* ctx, const LastBatch& b, int k, int64_t index_base, pgp_hyp* out_dev) {
+  return run_select(ctx, b, k, index_base, nullptr, 0, nullptr, out_dev);
 }
 int k4_chain(pgp_ctx* ctx, const LastBatch& b, int64_t index_base, pgp_hyp* out_host, int cap, int* n_out) {
   return run_select(ctx, b, cap, index_base, out_host, 1, n_out);

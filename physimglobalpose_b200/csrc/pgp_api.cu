@@ -381,6 +381,13 @@ int pgp_topk(pgp_ctx* ctx, int obj, int k, int64_t index_base, pgp_hyp* out) {
   return rc ? rc : n_out;
 }
 
+int pgp_topk_dev(pgp_ctx* ctx, int obj, int k, int64_t index_base, pgp_hyp* out_dev) {
+  CHECK_CTX(ctx);
+  if (ctx->last.obj != obj || ctx->last.n <= 0) return pgp_fail(ctx, PGP_E_NO_SCORES, "no scored batch for object %d", obj);
+  if (k <= 0 || !out_dev) return pgp_fail(ctx, PGP_E_INVALID, "bad k / output");
+  return k4_topk_dev(ctx, ctx->last, k, index_base, out_dev);
+}
+
 int pgp_improving_chain(pgp_ctx* ctx, int obj, int64_t index_base, pgp_hyp* out, int cap) {
   CHECK_CTX(ctx);
   if (ctx->last.obj != obj || ctx->last.n <= 0) return pgp_fail(ctx, PGP_E_NO_SCORES, "no scored batch for object %d", obj);

@@ -184,6 +184,11 @@ class PoseEngine:
         m = self._check(self._lib.pgp_topk(self._ctx, obj, k, index_base, _ptr(out)))
         return out[:m].copy()
 
+    def topk_device(self, obj: int, k: int, index_base: int, out_dev):
+        """Asynchronous: k 64-byte records into a torch CUDA uint8 tensor of k*64 bytes (an all-gather send buffer)."""
+        assert out_dev.is_cuda and out_dev.numel() * out_dev.element_size() >= 64 * k
+        self._check(self._lib.pgp_topk_dev(self._ctx, obj, k, index_base, out_dev.data_ptr()))
+
     def improving_chain(self, obj: int, index_base: int = 0, cap: int = 4096) -> np.ndarray:
         out = np.zeros(cap, HYP_DTYPE)
         m = self._check(self._lib.pgp_improving_chain(self._ctx, obj, index_base, _ptr(out), cap))

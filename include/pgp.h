@@ -134,6 +134,9 @@ PGP_API int pgp_registered_points(pgp_ctx* ctx, int obj, const float* T12_host, 
  * KdTree::doQueryRestrictedClosestIndex (S4/accelerators/kdtree.h:394-459) per point. */
 PGP_API int pgp_nearest_in_range(pgp_ctx* ctx, int obj, const float* T12_host, int32_t* idx_host);
 
+/* Tuning / test switches.  "force_coarse" = 1: score on the plain 27-cell path even when the
+ * fine tri-state grid exists (used by the tests to cross-check the two paths). */
+PGP_API int pgp_set_option(pgp_ctx* ctx, const char* name, int value);
 /* Number of my kernels launched by this context so far (bench.py's gpu_launches). */
 PGP_API int64_t pgp_launch_count(const pgp_ctx* ctx);
 

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "pgp_score_lcp_dev": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp]),
     "pgp_registered_points": (_i, [_vp, _i, _vp, _vp, _i]),
     "pgp_nearest_in_range": (_i, [_vp, _i, _vp, _vp]),
+    "pgp_set_option": (_i, [_vp, C.c_char_p, _i]),
     "pgp_launch_count": (_i64, [_vp]),
     "pgp_topk": (_i, [_vp, _i, _i, _i64, _vp]),
     "pgp_topk_dev": (_i, [_vp, _i, _i, _i64, _vp]),

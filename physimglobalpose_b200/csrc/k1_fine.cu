@@ -1,0 +1,146 @@
+// K1b -- fine tri-state classification of the scene grid.
+//
+// The reference decides "is some scene point within delta of T q" with a kd-tree descent per
+// query (S4/accelerators/kdtree.h:394-459, called from Verify, S4/algorithms/match4pcsBase.cc:
+// 1713-1718).  Here the decision is tabulated once per scene for (almost) all of space: every cell
+// whose 27-neighbourhood holds scene points is cut into 8x8x8 sub-voxels and each sub-voxel is
+// labelled
+//     OUT    no scene point can pass d2 <= delta^2 for ANY query that lands in the voxel,
+//     IN     one scene point passes it for EVERY query that lands in the voxel,
+//     AMBIG  neither could be proven (the voxel straddles the surface of the union of delta-balls).
+// Only AMBIG queries (a few %) still run the exact fp32 test in K3, so the labels must be
+// conservative under every rounding the scoring kernel can commit; see DESIGN.md "Exactness of the
+// tri-state labels" for the bounds behind `inflate`, dlo2 and dhi2.
+#include <math.h>
+
+#include "pgp_internal.cuh"
+
+namespace {
+
+constexpr int F = 8;
+constexpr int CLS_THREADS = 128;
+constexpr int CLS_CHUNK = 512;
+
+__global__ void k1f_popc(const uint32_t* __restrict__ bitmap, int64_t n_words, uint32_t* __restrict__ out) {
+  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < n_words) out[w] = __popc(bitmap[w]);
+}
+__global__ void k1f_bmrank(const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ prefix, int64_t n_words, int64_t n_cells,
+                           uint2* __restrict__ bmrank, uint32_t* __restrict__ block_cell) {
+  int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_words * 32) return;
+  const int64_t w = c >> 5;
+  const uint32_t bits = bitmap[w], pre = prefix[w];
+  if ((c & 31) == 0) bmrank[w] = make_uint2(bits, pre);
+  if (c < n_cells && ((bits >> (c & 31)) & 1u)) block_cell[pre + __popc(bits & ((1u << (c & 31)) - 1u))] = (uint32_t)c;
+}
+
+// one CTA per block (= per cell with an occupied 27-neighbourhood): 4 sub-voxels per thread.
+__global__ void __launch_bounds__(CLS_THREADS) k1f_classify(const uint32_t* __restrict__ block_cell, const uint32_t* __restrict__ cell_start,
+                                                            const float4* __restrict__ pts, GridParams g, uint32_t* __restrict__ codes) {
+  __shared__ float4 s_p[CLS_CHUNK];
+  __shared__ unsigned char s_code[F * F * F];
+  const int b = blockIdx.x;
+  const uint32_t c = block_cell[b];
+  const int cx = (int)(c % g.dim[0]), cy = (int)((c / g.dim[0]) % g.dim[1]), cz = (int)(c / ((uint32_t)g.dim[0] * g.dim[1]));
+  const float hs = 0.5f * g.hf + g.inflate;
+  float vx[4], vy[4], vz[4];
+  bool in[4] = {false, false, false, false};
+  bool near[4] = {false, false, false, false};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int v = threadIdx.x + CLS_THREADS * j;
+    vx[j] = __fmaf_rn((float)(cx * F + (v & 7)) + 0.5f, g.hf, g.lo[0]);
+    vy[j] = __fmaf_rn((float)(cy * F + ((v >> 3) & 7)) + 0.5f, g.hf, g.lo[1]);
+    vz[j] = __fmaf_rn((float)(cz * F + (v >> 6)) + 0.5f, g.hf, g.lo[2]);
+  }
+  for (int row = 0; row < 9; ++row) {
+    const int oy = row % 3 - 1, oz = row / 3 - 1;
+    const int r = ((cz + oz) * g.dim[1] + (cy + oy)) * g.dim[0] + cx;
+    const uint32_t s = cell_start[r - 1], e = cell_start[r + 2];
+    for (uint32_t base = s; base < e; base += CLS_CHUNK) {
+      const int m = (int)min((uint32_t)CLS_CHUNK, e - base);
+      __syncthreads();
+      for (int t = threadIdx.x; t < m; t += CLS_THREADS) s_p[t] = pts[base + t];
+      __syncthreads();
+      for (int t = 0; t < m; ++t) {
+        const float4 p = s_p[t];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float ax = fabsf(p.x - vx[j]), ay = fabsf(p.y - vy[j]), az = fabsf(p.z - vz[j]);
+          const float lx = fmaxf(ax - hs, 0.f), ly = fmaxf(ay - hs, 0.f), lz = fmaxf(az - hs, 0.f);
+          const float hx = ax + hs, hy = ay + hs, hz = az + hs;
+          const float mind2 = __fmaf_rn(lx, lx, __fmaf_rn(ly, ly, lz * lz));
+          const float maxd2 = __fmaf_rn(hx, hx, __fmaf_rn(hy, hy, hz * hz));
+          near[j] |= mind2 <= g.dhi2;
+          in[j] |= maxd2 <= g.dlo2;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) s_code[threadIdx.x + CLS_THREADS * j] = in[j] ? 1 : (near[j] ? 2 : 0);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) w |= (uint32_t)s_code[threadIdx.x * 16 + k] << (2 * k);
+    codes[(size_t)b * 32 + threadIdx.x] = w;
+  }
+}
+
+}  // namespace
+
+int k1_build_fine(pgp_ctx* ctx) {
+  Scene& s = ctx->scene;
+  GridParams& g = s.g;
+  cudaStream_t st = ctx->stream;
+  const int64_t nw = s.bitmap_words;
+  g.fine = 0; g.n_blocks = 0;
+  // rank structure over the dilated-occupancy bitmap
+  PGP_CUDA(ctx, s.bmrank.reserve((size_t)nw * 8 + 16));
+  PGP_CUDA(ctx, s.cursor.reserve((size_t)(nw + 1) * 4));
+  PGP_CUDA(ctx, s.scratch.reserve((size_t)((nw + 1) / 2048 + 4096) * 4));
+  uint32_t* pre = s.cursor.as<uint32_t>();
+  PGP_CUDA(ctx, cudaMemsetAsync(pre, 0, (size_t)(nw + 1) * 4, st));
+  k1f_popc<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(s.bitmap.as<uint32_t>(), nw, pre);
+  ctx->launches++;
+  int rc = pgp_scan_exclusive_u32(ctx, pre, nw + 1, s.scratch.as<uint32_t>());
+  if (rc) return rc;
+  uint32_t nb = 0;
+  PGP_CUDA(ctx, cudaMemcpyAsync(&nb, pre + nw, 4, cudaMemcpyDeviceToHost, st));
+  PGP_CUDA(ctx, cudaStreamSynchronize(st));
+  if ((size_t)nb * 128 > ((size_t)24 << 30)) return PGP_OK;     // absurdly large: stay on the 27-cell path
+  PGP_CUDA(ctx, s.block_cell.reserve((size_t)nb * 4 + 16));
+  PGP_CUDA(ctx, s.codes.reserve((size_t)nb * 128 + 16));
+  k1f_bmrank<<<(unsigned)((nw * 32 + 255) / 256), 256, 0, st>>>(s.bitmap.as<uint32_t>(), pre, nw, g.n_cells, s.bmrank.as<uint2>(),
+                                                              s.block_cell.as<uint32_t>());
+  ctx->launches++;
+
+  // conservative margins: positions are uncertain by eps_pos (fast FMA transform vs the
+  // reference's rounding sequence) plus the rounding of the voxel index itself.
+  float maxabs = 0.f;
+  int dmax = 0;
+  for (int k = 0; k < 3; ++k) {
+    maxabs = fmaxf(maxabs, fmaxf(fabsf(g.lo[k]), fabsf(g.lo[k] + g.h * (float)g.dim[k])));
+    dmax = g.dim[k] > dmax ? g.dim[k] : dmax;
+  }
+  g.hf = g.h / (float)F;
+  g.inv_hf = g.inv_h * (float)F;
+  g.pos_bound = 3.0f * maxabs;
+  const float eps_pos = 32.0f * 5.9604645e-8f * (g.pos_bound + maxabs);
+  g.inflate = g.hf * (2e-3f + 16.0f * 5.9604645e-8f * (float)(dmax * F)) + eps_pos;
+  const double d = (double)s.delta;
+  g.dlo2 = (float)((d * (1.0 - 1e-5)) * (d * (1.0 - 1e-5)));
+  g.dhi2 = (float)((d * (1.0 + 1e-5)) * (d * (1.0 + 1e-5)));
+  // the OUT label also needs: everything within delta(1+1e-5) + inflate of a cell lies in its 27 cells
+  if (!((double)g.h * (1.0 - 4e-4) >= d * (1.0 + 1e-5) + (double)g.inflate)) return PGP_OK;   // margins do not close: no fine grid
+  if (nb > 0) {
+    k1f_classify<<<nb, CLS_THREADS, 0, st>>>(s.block_cell.as<uint32_t>(), s.cell_start.as<uint32_t>(), s.pts.as<float4>(), g, s.codes.as<uint32_t>());
+    ctx->launches++;
+  }
+  PGP_CUDA(ctx, cudaGetLastError());
+  g.n_blocks = (int)nb;
+  g.fine = F;
+  return PGP_OK;
+}

@@ -91,13 +91,15 @@ __global__ void k1_scan_add(uint32_t* __restrict__ data, int64_t n, const uint32
   for (int k = 0; k < SCAN_ITEMS; ++k, i += SCAN_T) if (i < n) data[i] += off;
 }
 
-int scan_exclusive(pgp_ctx* ctx, uint32_t* data, int64_t n, uint32_t* scratch) {
-  // scratch must hold ceil(n/2048) + ceil(n/2048^2) + 8 words
+}  // namespace
+
+// in-place exclusive scan; scratch must hold ceil(n/2048) + ceil(n/2048^2) + 8 words
+int pgp_scan_exclusive_u32(pgp_ctx* ctx, uint32_t* data, int64_t n, uint32_t* scratch) {
   int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
   k1_scan_block<<<(unsigned)nb, SCAN_T, 0, ctx->stream>>>(data, n, nb > 1 ? scratch : nullptr);
   ctx->launches++;
   if (nb > 1) {
-    int rc = scan_exclusive(ctx, scratch, nb, scratch + nb);
+    int rc = pgp_scan_exclusive_u32(ctx, scratch, nb, scratch + nb);
     if (rc) return rc;
     k1_scan_add<<<(unsigned)nb, SCAN_T, 0, ctx->stream>>>(data, n, scratch);
     ctx->launches++;
@@ -105,6 +107,8 @@ int scan_exclusive(pgp_ctx* ctx, uint32_t* data, int64_t n, uint32_t* scratch) {
   PGP_CUDA(ctx, cudaGetLastError());
   return PGP_OK;
 }
+
+namespace {
 
 __global__ void k1_scatter(const float4* __restrict__ in, int n, const uint32_t* __restrict__ cell_of,
                            uint32_t* __restrict__ cursor, float4* __restrict__ out) {
@@ -273,7 +277,7 @@ int k1_build_grid(pgp_ctx* ctx) {
   PGP_CUDA(ctx, cudaMemsetAsync(cs, 0, (size_t)(nc + 1) * 4, st));
   k1_count<<<B, T, 0, st>>>(s.unsorted.as<float4>(), n, g, s.cell_of.as<uint32_t>(), cs);
   ctx->launches++;
-  int rc = scan_exclusive(ctx, cs, nc + 1, s.scratch.as<uint32_t>());
+  int rc = pgp_scan_exclusive_u32(ctx, cs, nc + 1, s.scratch.as<uint32_t>());
   if (rc) return rc;
   PGP_CUDA(ctx, cudaMemcpyAsync(s.cursor.p, cs, (size_t)(nc + 1) * 4, cudaMemcpyDeviceToDevice, st));
   k1_scatter<<<B, T, 0, st>>>(s.unsorted.as<float4>(), n, s.cell_of.as<uint32_t>(), s.cursor.as<uint32_t>(), s.pts.as<float4>());
@@ -295,6 +299,8 @@ int k1_build_grid(pgp_ctx* ctx) {
   PGP_CUDA(ctx, cudaStreamSynchronize(st));
   PGP_CUDA(ctx, cudaGetLastError());
   s.n_occupied = (int64_t)occ;
+  rc = k1_build_fine(ctx);
+  if (rc) return rc;
   s.ready = true;
   return PGP_OK;
 }

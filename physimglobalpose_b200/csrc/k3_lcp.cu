@@ -43,6 +43,11 @@ struct LcpParams {
   float* scores;
   unsigned long long* work;  // one counter per model tile
   int n_tiles;
+  // fine tri-state path (K1b)
+  const uint2* bmrank;       // per bitmap word {bits, rank prefix}
+  const uint32_t* codes;     // n_blocks x 32 words
+  int bmrank_words;          // words staged in smem (0: read from global/L1)
+  float model_rinf;          // max |coordinate| of the validation model (bounds the transform's intermediates)
 };
 
 // ---- mbarrier + TMA bulk copy (global -> shared), sm_90+/sm_100a PTX ---------------------------
@@ -275,6 +280,130 @@ __global__ void __launch_bounds__(THREADS, 2) k3_lcp_kernel(const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Count mode on the fine tri-state grid (K1b).  Phase 1 computes the query's SUB-VOXEL directly
+// with 9 FMAs (transform pre-scaled to voxel units), looks the cell up in the shared-memory
+// bitmap+rank table and fetches the 2-bit label; OUT/IN finish the query, AMBIG queries are queued
+// and resolved by the exact, non-fused test of the reference in phase 2.  The labels are
+// conservative with respect to the difference between the fast transform and the reference's
+// rounding sequence (GridParams::inflate), so counts stay bit-exact.
+constexpr int FWARPS = 32;
+constexpr int FTHREADS = FWARPS * 32;
+
+__global__ void __launch_bounds__(FTHREADS, 1) k3_count_fine_kernel(const __grid_constant__ LcpParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t mbar;
+  float4* s_model = reinterpret_cast<float4*>(smem);
+  uint2* s_bmrank = reinterpret_cast<uint2*>(smem + (size_t)p.tile_cap * 16);
+  uint16_t* s_queue = reinterpret_cast<uint16_t*>(s_bmrank + p.bmrank_words);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint16_t* q = s_queue + warp * QCAP;
+  const uint2* bmrank = p.bmrank_words ? s_bmrank : p.bmrank;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int dimx = p.g.dim[0], dimy = p.g.dim[1];
+  const unsigned rx = (unsigned)(p.g.dim[0] - 2) * 8u, ry = (unsigned)(p.g.dim[1] - 2) * 8u, rz = (unsigned)(p.g.dim[2] - 2) * 8u;
+
+  if (threadIdx.x == 0) mbar_init(&mbar, 1);
+  __syncthreads();
+
+  for (int tile = 0; tile < p.n_tiles; ++tile) {
+    const int t0 = tile * p.tile_cap;
+    const int tn = min(p.tile_cap, p.nv - t0);
+    if (threadIdx.x == 0) {
+      uint32_t bytes = (uint32_t)tn * 16u;
+      uint32_t bm = tile == 0 ? (uint32_t)p.bmrank_words * 8u : 0u;
+      mbar_expect_tx(&mbar, bytes + bm);
+      tma_bulk_g2s(s_model, p.model + t0, bytes, &mbar);
+      // one bulk copy moves at most 2^20 - 16 bytes; the table is far below that
+      if (bm) tma_bulk_g2s(s_bmrank, p.bmrank, bm, &mbar);
+    }
+    mbar_wait(&mbar, tile & 1);
+
+    for (;;) {
+      long long h = 0;
+      if (lane == 0) h = (long long)atomicAdd(p.work + tile, 1ull);
+      h = __shfl_sync(0xffffffffu, h, 0);
+      if (h >= p.n) break;
+      const Xf x = load_xf(p.T, h);
+      // voxel-unit transform: u = (T q - lo) / hf, folded into the matrix
+      float a[12];
+      float bound = 0.f;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        a[4 * r + 0] = x.m[4 * r + 0] * p.g.inv_hf;
+        a[4 * r + 1] = x.m[4 * r + 1] * p.g.inv_hf;
+        a[4 * r + 2] = x.m[4 * r + 2] * p.g.inv_hf;
+        a[4 * r + 3] = (x.m[4 * r + 3] - p.g.lo[r]) * p.g.inv_hf;
+        bound = fmaxf(bound, (fabsf(x.m[4 * r]) + fabsf(x.m[4 * r + 1]) + fabsf(x.m[4 * r + 2])) * p.model_rinf + fabsf(x.m[4 * r + 3]));
+      }
+      const bool fast = bound <= p.g.pos_bound;     // false for NaN / huge matrices: those take the reference's arithmetic
+      int good = 0;
+      int qn = 0;
+
+      auto drain = [&](int take) {
+        if (lane < take) {
+          int i = q[qn - take + lane];
+          float tx, ty, tz;
+          int cx, cy, cz;
+          apply_xf(x, s_model[i], tx, ty, tz);
+          if (query_cell(p.g, tx, ty, tz, cx, cy, cz)) good += exists_within(p, tx, ty, tz, cx, cy, cz) ? 1 : 0;
+        }
+        qn -= take;
+      };
+
+      for (int base = 0; base < tn; base += 32) {
+        const int i = base + lane;
+        bool amb = false;
+        if (i < tn) {
+          const float4 m = s_model[i];
+          float ux, uy, uz;
+          if (fast) {
+            ux = __fmaf_rn(a[0], m.x, __fmaf_rn(a[1], m.y, __fmaf_rn(a[2], m.z, a[3])));
+            uy = __fmaf_rn(a[4], m.x, __fmaf_rn(a[5], m.y, __fmaf_rn(a[6], m.z, a[7])));
+            uz = __fmaf_rn(a[8], m.x, __fmaf_rn(a[9], m.y, __fmaf_rn(a[10], m.z, a[11])));
+          } else {
+            float tx, ty, tz;
+            apply_xf(x, m, tx, ty, tz);
+            ux = cell_coord(tx, p.g.lo[0], p.g.inv_hf); uy = cell_coord(ty, p.g.lo[1], p.g.inv_hf); uz = cell_coord(tz, p.g.lo[2], p.g.inv_hf);
+          }
+          const int ix = __float2int_rz(ux), iy = __float2int_rz(uy), iz = __float2int_rz(uz);   // saturating, NaN -> 0
+          if ((unsigned)(ix - 8) < rx && (unsigned)(iy - 8) < ry && (unsigned)(iz - 8) < rz) {   // cells 1 .. dim-2
+            const int c = ((iz >> 3) * dimy + (iy >> 3)) * dimx + (ix >> 3);
+            const uint2 wr = bmrank[c >> 5];
+            const unsigned bit = 1u << (c & 31);
+            if (wr.x & bit) {
+              const unsigned blk = wr.y + __popc(wr.x & (bit - 1u));
+              const int v = ((iz & 7) << 6) | ((iy & 7) << 3) | (ix & 7);
+              const uint32_t code = (__ldg(p.codes + (size_t)blk * 32 + (v >> 4)) >> ((v & 15) * 2)) & 3u;
+              good += (code == 1u);
+              amb = (code == 2u);
+            }
+          }
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, amb);
+        if (b) {
+          if (amb) q[qn + __popc(b & lt_mask)] = (uint16_t)i;
+          qn += __popc(b);
+          __syncwarp();
+          if (qn >= 32) { drain(32); __syncwarp(); }
+        }
+      }
+      if (qn > 0) { drain(qn); __syncwarp(); }
+
+      const int tot = __reduce_add_sync(0xffffffffu, good);
+      if (lane == 0) {
+        if (p.n_tiles == 1) {
+          p.counts[h] = (uint32_t)tot;
+          if (p.scores) p.scores[h] = __fdiv_rn((float)tot, (float)p.nv);
+        } else if (tot) {
+          atomicAdd(p.counts + h, (uint32_t)tot);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // multi-tile epilogue: counts -> scores
 __global__ void k3_finalise(const uint32_t* __restrict__ counts, float* __restrict__ scores, long long n, int nv, int mode) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -360,6 +489,36 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
   }
 
   p.model = m.val.as<float4>(); p.model_nrm = m.val_nrm.as<float4>();
+  PGP_CUDA(ctx, ctx->work.reserve(4096));
+  p.work = reinterpret_cast<unsigned long long*>(ctx->work.as<char>() + 1024);
+
+  if (mode == PGP_LCP_COUNT && s.g.fine == 8 && !ctx->force_coarse) {
+    const size_t smem_max = 200 * 1024, qb = (size_t)FWARPS * QCAP * 2;
+    size_t bm = (size_t)s.bitmap_words * 8;
+    int tile_cap = std::min((m.nv + 3) & ~3, 8192);
+    if (bm + qb + (size_t)std::min(tile_cap, 2048) * 16 > smem_max) bm = 0;          // table too big for smem: read it through L1
+    if ((size_t)tile_cap * 16 + bm + qb > smem_max) tile_cap = (int)((smem_max - bm - qb) / 16) & ~3;
+    p.tile_cap = tile_cap;
+    p.n_tiles = (m.nv + tile_cap - 1) / tile_cap;
+    if (p.n_tiles > 256) return pgp_fail(ctx, PGP_E_INVALID, "validation model too large (%d points)", m.nv);
+    p.bmrank = s.bmrank.as<uint2>(); p.codes = s.codes.as<uint32_t>();
+    p.bmrank_words = (int)(bm / 8);
+    p.model_rinf = m.val_rinf;
+    const size_t smem = (size_t)tile_cap * 16 + bm + qb;
+    PGP_CUDA(ctx, cudaMemsetAsync(p.work, 0, 8 * (size_t)p.n_tiles, st));
+    if (p.n_tiles > 1) PGP_CUDA(ctx, cudaMemsetAsync(counts_dev, 0, (size_t)n * 4, st));
+    int grid = (int)std::min<long long>((n + FWARPS - 1) / FWARPS, ctx->sm_count);
+    PGP_CUDA(ctx, cudaFuncSetAttribute(k3_count_fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k3_count_fine_kernel<<<grid, FTHREADS, smem, st>>>(p);
+    ctx->launches++;
+    if (p.n_tiles > 1 && scores_dev) {
+      k3_finalise<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(counts_dev, scores_dev, n, m.nv, mode);
+      ctx->launches++;
+    }
+    PGP_CUDA(ctx, cudaGetLastError());
+    return PGP_OK;
+  }
+
   const int per_pt = mode == PGP_LCP_WEIGHTED ? 32 : 16;
   // shared memory plan: model tile + bitmap (if it fits) + queues
   const size_t smem_max = 100 * 1024;     // two CTAs per SM
@@ -381,9 +540,7 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
   p.n_tiles = (m.nv + tile_cap - 1) / tile_cap;
   const size_t smem = (size_t)tile_cap * per_pt + bm_bytes + qbytes;
 
-  PGP_CUDA(ctx, ctx->work.reserve(4096));
   if (p.n_tiles > 256) return pgp_fail(ctx, PGP_E_INVALID, "validation model too large (%d points)", m.nv);
-  p.work = reinterpret_cast<unsigned long long*>(ctx->work.as<char>() + 1024);
   PGP_CUDA(ctx, cudaMemsetAsync(p.work, 0, 8 * (size_t)p.n_tiles, st));
   if (p.n_tiles > 1) {
     PGP_CUDA(ctx, cudaMemsetAsync(counts_dev, 0, (size_t)n * 4, st));

@@ -105,8 +105,8 @@ void pgp_destroy(pgp_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   Scene& s = ctx->scene;
-  for (DevBuf* b : {&s.xyz_raw, &s.nrm_raw, &s.unsorted, &s.cursor, &s.pts, &s.aux, &s.cell_start, &s.cell_of, &s.bitmap, &s.tri_index,
-                    &s.tri_blocks, &s.prior, &s.scratch, &ctx->batch_T, &ctx->batch_counts, &ctx->batch_scores, &ctx->work, &ctx->topk_out})
+  for (DevBuf* b : {&s.xyz_raw, &s.nrm_raw, &s.unsorted, &s.cursor, &s.pts, &s.aux, &s.cell_start, &s.cell_of, &s.bitmap, &s.bmrank,
+                    &s.block_cell, &s.codes, &s.prior, &s.scratch, &ctx->batch_T, &ctx->batch_counts, &ctx->batch_scores, &ctx->work, &ctx->topk_out})
     b->release();
   for (Model& m : ctx->models)
     for (DevBuf* b : {&m.search, &m.search_nrm, &m.val, &m.val_nrm, &m.val_orig, &m.val_nrm_orig, &m.gen_T, &m.gen_counts, &m.gen_scores,
@@ -134,6 +134,12 @@ int pgp_synchronize(pgp_ctx* ctx) {
 }
 
 int64_t pgp_launch_count(const pgp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int pgp_set_option(pgp_ctx* ctx, const char* name, int value) {
+  CHECK_CTX(ctx);
+  if (name && !strcmp(name, "force_coarse")) { ctx->force_coarse = value; return PGP_OK; }
+  return pgp_fail(ctx, PGP_E_INVALID, "unknown option %s", name ? name : "(null)");
+}
 
 int pgp_set_scene(pgp_ctx* ctx, const float* xyz, const float* nrm, int n, float delta) {
   CHECK_CTX(ctx);
@@ -192,7 +198,7 @@ int pgp_set_model(pgp_ctx* ctx, int obj, const float* sx, const float* sn, int n
   if (!sx || nq <= 0 || !vx || nv <= 0) return pgp_fail(ctx, PGP_E_INVALID, "pgp_set_model: empty cloud");
   Model& m = ctx->models[obj];
   m.ready = false;
-  m.nq = nq; m.nv = nv; m.n_gen = 0; m.tgrid_ready = false;
+  m.nq = nq; m.nv = nv; m.n_gen = 0; m.tgrid_ready = false; m.val_rinf = 0.f;
   seq_centroid(sx, nq, m.cQ);   // centroid of the SEARCH cloud centres both clouds (:248-261)
   std::vector<float> s4((size_t)nq * 4), sn4((size_t)nq * 4), v4((size_t)nv * 4), vn4((size_t)nv * 4);
   for (int i = 0; i < nq; ++i) {
@@ -206,6 +212,7 @@ int pgp_set_model(pgp_ctx* ctx, int obj, const float* sx, const float* sn, int n
       float c = vx[3 * i + k] - m.cQ[k];
       v4[4 * (size_t)i + k] = c;
       lo[k] = std::min(lo[k], c); hi[k] = std::max(hi[k], c);
+      m.val_rinf = std::max(m.val_rinf, fabsf(c));
     }
     int idx = i; memcpy(&v4[4 * (size_t)i + 3], &idx, 4);
     unit_normal(vn ? vn + 3 * i : nullptr, &vn4[4 * (size_t)i]);

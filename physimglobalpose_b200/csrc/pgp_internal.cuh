@@ -38,9 +38,16 @@ struct GridParams {
   int dim[3];
   int64_t n_cells;
   float r2;           // fl(fl(delta) * fl(delta)), the reference's sq_eps (match4pcsBase.cc:1710)
-  // fine tri-state classification (K1b): sub-voxels per cell edge
-  int fine;           // 0 = not built
-  float inv_hf;       // fine / h
+  // fine tri-state classification (K1b): every cell whose 27-neighbourhood is occupied owns a
+  // block of 8x8x8 sub-voxels, 2 bits each: 0 = no scene point can be within delta of ANY query that
+  // lands in the voxel, 1 = some scene point is within delta of EVERY such query, 2 = undecided.
+  int fine;           // sub-voxels per cell edge (8), 0 = not built
+  float inv_hf;       // fine * inv_h  (exact: power-of-two scaling)
+  float hf;           // h / fine
+  float inflate;      // how far outside its ideal box a voxel's queries may lie (rounding of the fast path)
+  float pos_bound;    // the fast (FMA) transform path is valid for hypotheses whose intermediates stay below this
+  float dlo2, dhi2;   // (delta (1 -+ 1e-5))^2: certainly-inside / certainly-outside thresholds
+  int n_blocks;
 };
 
 struct Scene {
@@ -59,8 +66,9 @@ struct Scene {
   DevBuf cell_start;   // (n_cells + 1) x u32
   DevBuf cell_of;      // n x u32 (scratch: cell id per original point)
   DevBuf bitmap;       // ceil(n_cells/32) x u32: dilated occupancy (any point in the 27 cells)
-  DevBuf tri_index;    // n_cells x u32: per-cell fine-block index (K1b) or sentinel
-  DevBuf tri_blocks;   // fine tri-state blocks
+  DevBuf bmrank;       // per bitmap word: {bits, number of set bits in all earlier words} -> block id of a cell
+  DevBuf block_cell;   // n_blocks x u32: cell of block b
+  DevBuf codes;        // n_blocks x 32 words: 512 2-bit voxel states, voxel v = (sz*8+sy)*8+sx at bits 2(v&15) of word v>>4
   DevBuf prior;        // n x f32 in ORIGINAL order
   DevBuf scratch;      // scan scratch etc.
   int64_t n_occupied = 0;
@@ -72,6 +80,7 @@ struct Scene {
 struct Model {
   int nq = 0, nv = 0;
   float cQ[3] = {0, 0, 0};
+  float val_rinf = 0.f;  // max |coordinate| of the centred validation cloud
   DevBuf search;       // nq x float4 centred (w = 0)
   DevBuf search_nrm;   // nq x float4 unit normal
   DevBuf val;          // nv x float4 centred, in a cache-friendly order; w = original index bits
@@ -112,6 +121,7 @@ struct pgp_ctx {
   DevBuf topk_out;
   void* pinned = nullptr; size_t pinned_cap = 0;
   int64_t launches = 0;
+  int force_coarse = 0;   // test hook: score on the 27-cell path even when the fine grid exists
   std::string err;
 };
 
@@ -128,6 +138,8 @@ int k1_build_grid(pgp_ctx* ctx);
 int k1_project_priors(pgp_ctx* ctx, const uint16_t* img_dev, int rows, int cols, const float* K9);
 int k1_refresh_sorted_priors(pgp_ctx* ctx);
 int k1_fill_priors(pgp_ctx* ctx, float v);
+int k1_build_fine(pgp_ctx* ctx);
+int pgp_scan_exclusive_u32(pgp_ctx* ctx, uint32_t* data, int64_t n, uint32_t* scratch);
 // k3_lcp.cu
 int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mode, uint32_t* counts_dev, float* scores_dev);
 int k3_nearest(pgp_ctx* ctx, const Model& m, const float* T_dev, int32_t* idx_dev, int gate);

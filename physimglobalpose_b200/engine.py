@@ -72,6 +72,9 @@ class PoseEngine:
             cuda_stream = 1
         self._check(self._lib.pgp_set_stream(self._ctx, cuda_stream))
 
+    def set_option(self, name: str, value: int):
+        self._check(self._lib.pgp_set_option(self._ctx, name.encode(), int(value)))
+
     def synchronize(self):
         self._check(self._lib.pgp_synchronize(self._ctx))
 

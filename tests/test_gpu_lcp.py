@@ -82,3 +82,27 @@ def test_topk_and_chain(engine, port_lib, small_problem):
     chain = engine.improving_chain(0)
     assert np.array_equal(chain["index"], o.improving_chain(scores))
     assert chain["score"][-1] == scores.max() and np.all(np.diff(chain["score"]) > 0)
+
+
+def test_fine_grid_equals_coarse_path_and_oracle(engine, port_lib):
+    """The tri-state fast path (K1b labels + FMA voxel transform) must give the same integer counts as
+    the plain 27-cell exact path and as the oracle, including for degenerate / huge / NaN matrices."""
+    prob = synth.make_problem(800, 30000, 0.01, seed=21)
+    T = synth.make_hypotheses(prob, 3000, seed=22).copy()
+    rng = np.random.default_rng(0)
+    T[5] = 0.0                                   # collapses the model onto one point
+    T[6] = T[1] * 1e4                            # huge entries: intermediates beyond pos_bound -> exact path
+    T[7, 0, 0] = np.nan
+    T[8, :, 3] = np.inf
+    T[9] = rng.normal(size=(3, 4)).astype(np.float32)        # not a rotation
+    T[10, :, :3] *= 1.5                          # scaled
+    _setup(engine, prob)
+    want = _oracle(port_lib, prob).verify(T)
+    fine, _ = engine.score_lcp(0, T, "count")
+    engine.set_option("force_coarse", 1)
+    try:
+        coarse, _ = engine.score_lcp(0, T, "count")
+    finally:
+        engine.set_option("force_coarse", 0)
+    assert np.array_equal(coarse, want)
+    assert np.array_equal(fine, want)

@@ -36,17 +36,23 @@ __global__ void k1f_bmrank(const uint32_t* __restrict__ bitmap, const uint32_t* 
 }
 
 // one CTA per block (= per cell with an occupied 27-neighbourhood): 4 sub-voxels per thread.
+// Pass A: labels + per-voxel number of "near" points (candidates of the exact test) + block header.
 __global__ void __launch_bounds__(CLS_THREADS) k1f_classify(const uint32_t* __restrict__ block_cell, const uint32_t* __restrict__ cell_start,
-                                                            const float4* __restrict__ pts, GridParams g, uint32_t* __restrict__ codes) {
+                                                            const float4* __restrict__ pts, GridParams g, uint32_t* __restrict__ codes,
+                                                            uint16_t* __restrict__ near_cnt, uint32_t* __restrict__ hdr,
+                                                            uint32_t* __restrict__ region_words, int* __restrict__ overflow) {
   __shared__ float4 s_p[CLS_CHUNK];
   __shared__ unsigned char s_code[F * F * F];
+  __shared__ uint32_t s_words[32];
+  __shared__ uint32_t s_tot;
   const int b = blockIdx.x;
   const uint32_t c = block_cell[b];
   const int cx = (int)(c % g.dim[0]), cy = (int)((c / g.dim[0]) % g.dim[1]), cz = (int)(c / ((uint32_t)g.dim[0] * g.dim[1]));
   const float hs = 0.5f * g.hf + g.inflate;
   float vx[4], vy[4], vz[4];
   bool in[4] = {false, false, false, false};
-  bool near[4] = {false, false, false, false};
+  int near[4] = {0, 0, 0, 0};
+  if (threadIdx.x == 0) s_tot = 0;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int v = threadIdx.x + CLS_THREADS * j;
@@ -72,20 +78,133 @@ __global__ void __launch_bounds__(CLS_THREADS) k1f_classify(const uint32_t* __re
           const float hx = ax + hs, hy = ay + hs, hz = az + hs;
           const float mind2 = __fmaf_rn(lx, lx, __fmaf_rn(ly, ly, lz * lz));
           const float maxd2 = __fmaf_rn(hx, hx, __fmaf_rn(hy, hy, hz * hz));
-          near[j] |= mind2 <= g.dhi2;
+          near[j] += (mind2 <= g.dhi2) ? 1 : 0;
           in[j] |= maxd2 <= g.dlo2;
         }
       }
     }
   }
+  uint32_t my_list = 0;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) s_code[threadIdx.x + CLS_THREADS * j] = in[j] ? 1 : (near[j] ? 2 : 0);
+  for (int j = 0; j < 4; ++j) {
+    const int v = threadIdx.x + CLS_THREADS * j;
+    const int code = in[j] ? 1 : (near[j] > 0 ? 2 : 0);
+    s_code[v] = (unsigned char)code;
+    if (code == 2 && near[j] > 65535) atomicOr(overflow, 1);      // absurd density: the host drops the fine grid
+    const int nn = code == 2 ? min(near[j], 65535) : 0;
+    near_cnt[(size_t)b * 512 + v] = (uint16_t)nn;
+    my_list += (uint32_t)nn;
+  }
+  my_list = __reduce_add_sync(0xffffffffu, my_list);
+  if ((threadIdx.x & 31) == 0 && my_list) atomicAdd(&s_tot, my_list);
   __syncthreads();
   if (threadIdx.x < 32) {
     uint32_t w = 0;
 #pragma unroll
     for (int k = 0; k < 16; ++k) w |= (uint32_t)s_code[threadIdx.x * 16 + k] << (2 * k);
     codes[(size_t)b * 32 + threadIdx.x] = w;
+    s_words[threadIdx.x] = w;
+    __syncwarp();
+    // header: ambig-rank prefix per group of 64 voxels (4 words), number of ambig voxels, list words
+    const uint32_t amb = __popc(w & 0xAAAAAAAAu);
+    uint32_t incl = amb;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += t; }
+    const uint32_t excl = incl - amb;
+    const uint32_t n_amb = __shfl_sync(0xffffffffu, incl, 31);
+    // gp[k] = ambig voxels before group k = excl at word 4k
+    const uint32_t g_lo = __shfl_sync(0xffffffffu, excl, (threadIdx.x & 3) * 8);       // groups 0,2,4,6
+    const uint32_t g_hi = __shfl_sync(0xffffffffu, excl, (threadIdx.x & 3) * 8 + 4);   // groups 1,3,5,7
+    if (threadIdx.x < 4) hdr[(size_t)b * 8 + threadIdx.x] = g_lo | (g_hi << 16);
+    if (threadIdx.x == 0) {
+      hdr[(size_t)b * 8 + 4] = 0;                 // region base, filled after the scan
+      hdr[(size_t)b * 8 + 5] = n_amb;
+      hdr[(size_t)b * 8 + 6] = s_tot;
+      hdr[(size_t)b * 8 + 7] = 0;
+      region_words[b] = n_amb ? n_amb + 1 + s_tot : 0;
+    }
+  }
+}
+
+// Pass B: candidate lists of the AMBIG voxels.  Region of block b in `lists` (u32 words):
+//   [n_amb + 1 offsets relative to the region][ids...]; offsets[r] .. offsets[r+1] delimit the ids
+// (positions in the cell-sorted point array) of the r-th AMBIG voxel of the block.
+__global__ void __launch_bounds__(CLS_THREADS) k1f_fill_lists(const uint32_t* __restrict__ block_cell, const uint32_t* __restrict__ cell_start,
+                                                              const float4* __restrict__ pts, GridParams g, const uint32_t* __restrict__ codes,
+                                                              const uint16_t* __restrict__ near_cnt, uint32_t* __restrict__ hdr,
+                                                              const uint32_t* __restrict__ region_base, uint32_t* __restrict__ lists) {
+  __shared__ float4 s_p[CLS_CHUNK];
+  __shared__ uint16_t s_av[F * F * F];       // AMBIG voxels in rank order
+  __shared__ uint32_t s_off[F * F * F + 1];  // their list offsets
+  __shared__ uint32_t s_wpre[33];
+  const int b = blockIdx.x;
+  const uint32_t n_amb = hdr[(size_t)b * 8 + 5];
+  if (threadIdx.x == 0) hdr[(size_t)b * 8 + 4] = region_base[b];
+  if (n_amb == 0) return;
+  const uint32_t base_w = region_base[b];
+  const uint32_t c = block_cell[b];
+  const int cx = (int)(c % g.dim[0]), cy = (int)((c / g.dim[0]) % g.dim[1]), cz = (int)(c / ((uint32_t)g.dim[0] * g.dim[1]));
+  const float hs = 0.5f * g.hf + g.inflate;
+  // rank order = voxel order; build the compact voxel list from the code words
+  if (threadIdx.x < 32) {
+    const uint32_t w = codes[(size_t)b * 32 + threadIdx.x] & 0xAAAAAAAAu;
+    uint32_t cnt = __popc(w), incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += t; }
+    uint32_t r = incl - cnt, ww = w;
+    while (ww) { int bit = __ffs(ww) - 1; ww &= ww - 1; s_av[r++] = (uint16_t)(threadIdx.x * 16 + (bit >> 1)); }
+  }
+  __syncthreads();
+  // offsets: serial scan by one warp over <= 512 entries (tiny)
+  if (threadIdx.x < 32) {
+    uint32_t run = n_amb + 1;     // ids start after the offset table
+    for (uint32_t r0 = 0; r0 < n_amb; r0 += 32) {
+      const uint32_t r = r0 + threadIdx.x;
+      uint32_t cnt = r < n_amb ? near_cnt[(size_t)b * 512 + s_av[r]] : 0u, incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += t; }
+      if (r < n_amb) s_off[r] = run + incl - cnt;
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (threadIdx.x == 0) s_off[n_amb] = run;
+  }
+  __syncthreads();
+  for (uint32_t r = threadIdx.x; r <= n_amb; r += CLS_THREADS) lists[base_w + r] = s_off[r];
+  // fill: thread t owns AMBIG voxels t, t+128, ... (up to 4)
+  float vx[4], vy[4], vz[4];
+  uint32_t wr[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t r = threadIdx.x + CLS_THREADS * j;
+    const int v = r < n_amb ? s_av[r] : 0;
+    vx[j] = __fmaf_rn((float)(cx * F + (v & 7)) + 0.5f, g.hf, g.lo[0]);
+    vy[j] = __fmaf_rn((float)(cy * F + ((v >> 3) & 7)) + 0.5f, g.hf, g.lo[1]);
+    vz[j] = __fmaf_rn((float)(cz * F + (v >> 6)) + 0.5f, g.hf, g.lo[2]);
+    wr[j] = r < n_amb ? base_w + s_off[r] : 0xffffffffu;
+  }
+  const uint32_t active_j = (n_amb + CLS_THREADS - 1) / CLS_THREADS;
+  for (int row = 0; row < 9; ++row) {
+    const int oy = row % 3 - 1, oz = row / 3 - 1;
+    const int rr = ((cz + oz) * g.dim[1] + (cy + oy)) * g.dim[0] + cx;
+    const uint32_t s = cell_start[rr - 1], e = cell_start[rr + 2];
+    for (uint32_t base = s; base < e; base += CLS_CHUNK) {
+      const int m = (int)min((uint32_t)CLS_CHUNK, e - base);
+      __syncthreads();
+      for (int t = threadIdx.x; t < m; t += CLS_THREADS) s_p[t] = pts[base + t];
+      __syncthreads();
+      for (int t = 0; t < m; ++t) {
+        const float4 p = s_p[t];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if ((uint32_t)j < active_j && wr[j] != 0xffffffffu) {
+            const float ax = fabsf(p.x - vx[j]), ay = fabsf(p.y - vy[j]), az = fabsf(p.z - vz[j]);
+            const float lx = fmaxf(ax - hs, 0.f), ly = fmaxf(ay - hs, 0.f), lz = fmaxf(az - hs, 0.f);
+            const float mind2 = __fmaf_rn(lx, lx, __fmaf_rn(ly, ly, lz * lz));
+            if (mind2 <= g.dhi2) lists[wr[j]++] = base + (uint32_t)t;
+          }
+        }
+      }
+    }
   }
 }
 
@@ -135,9 +254,31 @@ int k1_build_fine(pgp_ctx* ctx) {
   g.dhi2 = (float)((d * (1.0 + 1e-5)) * (d * (1.0 + 1e-5)));
   // the OUT label also needs: everything within delta(1+1e-5) + inflate of a cell lies in its 27 cells
   if (!((double)g.h * (1.0 - 4e-4) >= d * (1.0 + 1e-5) + (double)g.inflate)) return PGP_OK;   // margins do not close: no fine grid
+  s.n_list_words = 0;
   if (nb > 0) {
-    k1f_classify<<<nb, CLS_THREADS, 0, st>>>(s.block_cell.as<uint32_t>(), s.cell_start.as<uint32_t>(), s.pts.as<float4>(), g, s.codes.as<uint32_t>());
+    PGP_CUDA(ctx, s.near_cnt.reserve((size_t)nb * 512 * 2));
+    PGP_CUDA(ctx, s.hdr.reserve((size_t)nb * 32));
+    PGP_CUDA(ctx, s.region.reserve((size_t)(nb + 1) * 4));
+    PGP_CUDA(ctx, s.scratch.reserve((size_t)((nb + 1) / 2048 + 4096) * 4));
+    uint32_t* region = s.region.as<uint32_t>();
+    PGP_CUDA(ctx, cudaMemsetAsync(region, 0, (size_t)(nb + 1) * 4, st));
+    PGP_CUDA(ctx, cudaMemsetAsync(ctx->work.as<int>() + 40, 0, 4, st));
+    k1f_classify<<<nb, CLS_THREADS, 0, st>>>(s.block_cell.as<uint32_t>(), s.cell_start.as<uint32_t>(), s.pts.as<float4>(), g, s.codes.as<uint32_t>(),
+                                             s.near_cnt.as<uint16_t>(), s.hdr.as<uint32_t>(), region, ctx->work.as<int>() + 40);
     ctx->launches++;
+    rc = pgp_scan_exclusive_u32(ctx, region, (int64_t)nb + 1, s.scratch.as<uint32_t>());
+    if (rc) return rc;
+    uint32_t total = 0;
+    int overflow = 0;
+    PGP_CUDA(ctx, cudaMemcpyAsync(&total, region + nb, 4, cudaMemcpyDeviceToHost, st));
+    PGP_CUDA(ctx, cudaMemcpyAsync(&overflow, ctx->work.as<int>() + 40, 4, cudaMemcpyDeviceToHost, st));
+    PGP_CUDA(ctx, cudaStreamSynchronize(st));
+    if (overflow) return PGP_OK;     // g.fine stays 0: scoring uses the 27-cell path
+    PGP_CUDA(ctx, s.lists.reserve((size_t)total * 4 + 16));
+    k1f_fill_lists<<<nb, CLS_THREADS, 0, st>>>(s.block_cell.as<uint32_t>(), s.cell_start.as<uint32_t>(), s.pts.as<float4>(), g, s.codes.as<uint32_t>(),
+                                               s.near_cnt.as<uint16_t>(), s.hdr.as<uint32_t>(), region, s.lists.as<uint32_t>());
+    ctx->launches++;
+    s.n_list_words = total;
   }
   PGP_CUDA(ctx, cudaGetLastError());
   g.n_blocks = (int)nb;

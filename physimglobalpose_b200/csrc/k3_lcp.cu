@@ -47,6 +47,8 @@ struct LcpParams {
   const uint2* bmrank;       // per bitmap word {bits, rank prefix}
   const uint32_t* codes;     // n_blocks x 32 words
   int bmrank_words;          // words staged in smem (0: read from global/L1)
+  const uint4* hdr;          // n_blocks x 2 uint4: {u16 ambig-rank prefix per 64-voxel group x 8}, {list region base, #ambig, #ids, 0}
+  const uint32_t* lists;     // candidate ids of the AMBIG voxels (K1b pass B)
   float model_rinf;          // max |coordinate| of the validation model (bounds the transform's intermediates)
 };
 
@@ -340,13 +342,53 @@ __global__ void __launch_bounds__(FTHREADS, 1) k3_count_fine_kernel(const __grid
       int good = 0;
       int qn = 0;
 
+      // voxel of model point m under this hypothesis -- the SAME arithmetic in phase 1 and phase 2
+      auto voxel_of = [&](const float4 m, int& ix, int& iy, int& iz) {
+        float ux, uy, uz;
+        if (fast) {
+          ux = __fmaf_rn(a[0], m.x, __fmaf_rn(a[1], m.y, __fmaf_rn(a[2], m.z, a[3])));
+          uy = __fmaf_rn(a[4], m.x, __fmaf_rn(a[5], m.y, __fmaf_rn(a[6], m.z, a[7])));
+          uz = __fmaf_rn(a[8], m.x, __fmaf_rn(a[9], m.y, __fmaf_rn(a[10], m.z, a[11])));
+        } else {
+          float tx, ty, tz;
+          apply_xf(x, m, tx, ty, tz);
+          ux = cell_coord(tx, p.g.lo[0], p.g.inv_hf); uy = cell_coord(ty, p.g.lo[1], p.g.inv_hf); uz = cell_coord(tz, p.g.lo[2], p.g.inv_hf);
+        }
+        ix = __float2int_rz(ux); iy = __float2int_rz(uy); iz = __float2int_rz(uz);   // saturating, NaN -> 0
+      };
+
+      // phase 2: the reference's exact test, restricted to the candidate list of the query's AMBIG voxel
       auto drain = [&](int take) {
         if (lane < take) {
-          int i = q[qn - take + lane];
+          const int i = q[qn - take + lane];
+          const float4 m = s_model[i];
+          int ix, iy, iz;
+          voxel_of(m, ix, iy, iz);
+          const int c = ((iz >> 3) * dimy + (iy >> 3)) * dimx + (ix >> 3);
+          const uint2 wr = bmrank[c >> 5];
+          const unsigned blk = wr.y + __popc(wr.x & ((1u << (c & 31)) - 1u));
+          const int v = ((iz & 7) << 6) | ((iy & 7) << 3) | (ix & 7);
+          const uint4 gp = __ldg(p.hdr + (size_t)blk * 2);
+          const uint4 h1 = __ldg(p.hdr + (size_t)blk * 2 + 1);
+          const uint4 grp = __ldg(reinterpret_cast<const uint4*>(p.codes) + (size_t)blk * 8 + (v >> 6));
           float tx, ty, tz;
-          int cx, cy, cz;
-          apply_xf(x, s_model[i], tx, ty, tz);
-          if (query_cell(p.g, tx, ty, tz, cx, cy, cz)) good += exists_within(p, tx, ty, tz, cx, cy, cz) ? 1 : 0;
+          apply_xf(x, m, tx, ty, tz);
+          const int g8 = v >> 6, wi = (v >> 4) & 3;
+          const uint32_t gw = g8 < 2 ? gp.x : g8 < 4 ? gp.y : g8 < 6 ? gp.z : gp.w;
+          uint32_t r = (gw >> ((g8 & 1) * 16)) & 0xffffu;
+          const uint32_t A = 0xAAAAAAAAu;
+          r += (wi > 0 ? __popc(grp.x & A) : 0) + (wi > 1 ? __popc(grp.y & A) : 0) + (wi > 2 ? __popc(grp.z & A) : 0);
+          const uint32_t word = wi == 0 ? grp.x : wi == 1 ? grp.y : wi == 2 ? grp.z : grp.w;
+          r += __popc(word & A & ((1u << ((v & 15) * 2)) - 1u));
+          const uint32_t* reg = p.lists + h1.x;
+          const uint32_t s0 = __ldg(reg + r), s1 = __ldg(reg + r + 1);
+          const float r2 = p.g.r2;
+          bool hit = false;
+          for (uint32_t j = s0; j < s1; ++j) {
+            const float4 sp = __ldg(p.pts + __ldg(reg + j));
+            if (sqdist3(tx, ty, tz, sp.x, sp.y, sp.z) <= r2) { hit = true; break; }
+          }
+          good += hit ? 1 : 0;
         }
         qn -= take;
       };
@@ -355,18 +397,8 @@ __global__ void __launch_bounds__(FTHREADS, 1) k3_count_fine_kernel(const __grid
         const int i = base + lane;
         bool amb = false;
         if (i < tn) {
-          const float4 m = s_model[i];
-          float ux, uy, uz;
-          if (fast) {
-            ux = __fmaf_rn(a[0], m.x, __fmaf_rn(a[1], m.y, __fmaf_rn(a[2], m.z, a[3])));
-            uy = __fmaf_rn(a[4], m.x, __fmaf_rn(a[5], m.y, __fmaf_rn(a[6], m.z, a[7])));
-            uz = __fmaf_rn(a[8], m.x, __fmaf_rn(a[9], m.y, __fmaf_rn(a[10], m.z, a[11])));
-          } else {
-            float tx, ty, tz;
-            apply_xf(x, m, tx, ty, tz);
-            ux = cell_coord(tx, p.g.lo[0], p.g.inv_hf); uy = cell_coord(ty, p.g.lo[1], p.g.inv_hf); uz = cell_coord(tz, p.g.lo[2], p.g.inv_hf);
-          }
-          const int ix = __float2int_rz(ux), iy = __float2int_rz(uy), iz = __float2int_rz(uz);   // saturating, NaN -> 0
+          int ix, iy, iz;
+          voxel_of(s_model[i], ix, iy, iz);
           if ((unsigned)(ix - 8) < rx && (unsigned)(iy - 8) < ry && (unsigned)(iz - 8) < rz) {   // cells 1 .. dim-2
             const int c = ((iz >> 3) * dimy + (iy >> 3)) * dimx + (ix >> 3);
             const uint2 wr = bmrank[c >> 5];
@@ -502,6 +534,7 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     p.n_tiles = (m.nv + tile_cap - 1) / tile_cap;
     if (p.n_tiles > 256) return pgp_fail(ctx, PGP_E_INVALID, "validation model too large (%d points)", m.nv);
     p.bmrank = s.bmrank.as<uint2>(); p.codes = s.codes.as<uint32_t>();
+    p.hdr = s.hdr.as<uint4>(); p.lists = s.lists.as<uint32_t>();
     p.bmrank_words = (int)(bm / 8);
     p.model_rinf = m.val_rinf;
     const size_t smem = (size_t)tile_cap * 16 + bm + qb;

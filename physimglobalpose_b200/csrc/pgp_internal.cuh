@@ -69,6 +69,11 @@ struct Scene {
   DevBuf bmrank;       // per bitmap word: {bits, number of set bits in all earlier words} -> block id of a cell
   DevBuf block_cell;   // n_blocks x u32: cell of block b
   DevBuf codes;        // n_blocks x 32 words: 512 2-bit voxel states, voxel v = (sz*8+sy)*8+sx at bits 2(v&15) of word v>>4
+  DevBuf near_cnt;     // build scratch: n_blocks x 512 u16 candidate counts
+  DevBuf hdr;          // n_blocks x 8 u32: {4 words of u16 ambig-rank prefixes per 64-voxel group, list region base, #ambig, #ids, 0}
+  DevBuf region;       // build scratch: region sizes / bases
+  DevBuf lists;        // per-block regions: offsets + candidate ids of the AMBIG voxels
+  int64_t n_list_words = 0;
   DevBuf prior;        // n x f32 in ORIGINAL order
   DevBuf scratch;      // scan scratch etc.
   int64_t n_occupied = 0;

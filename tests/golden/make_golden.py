@@ -1,0 +1,84 @@
+#!/usr/bin/env python
+"""Mints golden vectors for the PCS -> LCP path FROM THE REFERENCE ENGINE ITSELF
+(oracle/_ref/libs4ref.so = the reference sources compiled in place from /root/reference by
+oracle/Makefile).  Run in the build container (where /root/reference exists):
+
+    make -C oracle ref && python tests/golden/make_golden.py
+
+The reference's own test-suite holds no golden vectors for this path, so these
+files are what pins the oracle restatement (oracle/lcp_oracle.c) and the CUDA path on machines
+that do not have the reference tree.  Inputs are stored next to the outputs, so nothing has to be
+regenerated bit-identically elsewhere."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle.pyoracle import RefOracle  # noqa: E402
+from physimglobalpose_b200 import synth  # noqa: E402
+
+
+def main():
+    # ---- LCP: count + weighted (with and without a prior image), centring, chain
+    prob = synth.make_problem(300, 6000, 0.01, seed=101)
+    T = synth.make_hypotheses(prob, 96, seed=102)
+    rng = np.random.default_rng(103)
+    perm = rng.permutation(len(T))
+    T = T[perm]                                   # GT not first: the improving chain gets longer
+    args = (prob.scene_xyz, prob.scene_nrm, prob.model_xyz, prob.model_nrm, prob.model_xyz, prob.model_nrm, prob.delta)
+    ref = RefOracle(*args)
+    counts = ref.verify(T)
+    frac, best_index = ref.verify_running_best(T)
+    ws, wn, reg = ref.weighted_verify(T, reg_of=int(np.argmax(counts)))
+    cP, cQ = ref.centroids()
+    img = rng.integers(0, 10001, size=(480, 640)).astype(np.uint16)
+    K = np.array([[600.0, 0, 320.0], [0, 600.0, 240.0], [0, 0, 1.0]], np.float32)
+    ref_img = RefOracle(*args, K=K, prior_img=img)
+    priors = ref_img.priors()
+    ws_img, wn_img = ref_img.weighted_verify(T)
+    np.savez_compressed(os.path.join(HERE, "lcp_small.npz"), scene_xyz=prob.scene_xyz, scene_nrm=prob.scene_nrm, model_xyz=prob.model_xyz,
+                        model_nrm=prob.model_nrm, delta=np.float64(prob.delta), T=T, counts=counts, running_frac=frac,
+                        running_best=np.int64(best_index), weighted_score=ws, weighted_nreg=wn, registered_of=np.int64(np.argmax(counts)),
+                        registered=reg, cP=cP, cQ=cQ, prior_img=img, K=K, priors=priors, weighted_score_img=ws_img, weighted_nreg_img=wn_img)
+
+    # ---- a second delta (the shipped default 5 mm) on the same clouds
+    ref5 = RefOracle(*args[:-1], 0.005)
+    np.savez_compressed(os.path.join(HERE, "lcp_small_d5.npz"), counts=ref5.verify(T), weighted_score=ref5.weighted_verify(T)[0])
+
+    # ---- PCS: pair extraction, quad join, rigid transforms for a few bases (operMode 0 pieces)
+    pairs_out, quads_out, rigid_out = {}, {}, {}
+    bases, invs = [], []
+    for seed in range(1, 40):
+        ok, b, inv = ref.select_quadrilateral(seed)
+        if ok:
+            bases.append(b.copy()); invs.append(inv.copy())
+        if len(bases) == 4:
+            break
+    cP_xyz, _ = ref.centred(0)
+    for k, (b, inv) in enumerate(zip(bases, invs)):
+        d1 = float(np.linalg.norm(cP_xyz[b[0]] - cP_xyz[b[1]]))
+        d2 = float(np.linalg.norm(cP_xyz[b[2]] - cP_xyz[b[3]]))
+        p1 = ref.extract_pairs(np.float32(d1), np.float32(prob.delta))
+        p2 = ref.extract_pairs(np.float32(d2), np.float32(prob.delta))
+        q = ref.find_quads(b, inv[0], inv[1], np.float32(prob.delta), p1, p2)
+        q = q[:64]
+        Ts, oks, poses = [], [], []
+        for quad in q:
+            ok, T4, P4 = ref.rigid_from_quad(b, quad)
+            oks.append(ok); Ts.append(T4[:3]); poses.append(P4)
+        pairs_out[f"b{k}_d1"] = np.float32(d1); pairs_out[f"b{k}_d2"] = np.float32(d2)
+        pairs_out[f"b{k}_p1"] = p1; pairs_out[f"b{k}_p2"] = p2
+        quads_out[f"b{k}_quads"] = q
+        rigid_out[f"b{k}_T"] = np.array(Ts, np.float32).reshape(-1, 3, 4); rigid_out[f"b{k}_ok"] = np.array(oks, bool)
+        rigid_out[f"b{k}_pose"] = np.array(poses, np.float64).reshape(-1, 4, 4)
+    np.savez_compressed(os.path.join(HERE, "pcs_small.npz"), bases=np.array(bases, np.int32), invariants=np.array(invs, np.float32),
+                        **pairs_out, **quads_out, **rigid_out)
+    print("golden vectors written:", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
+
+
+if __name__ == "__main__":
+    main()

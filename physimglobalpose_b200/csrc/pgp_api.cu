@@ -109,8 +109,8 @@ void pgp_destroy(pgp_ctx* ctx) {
                     &s.block_cell, &s.codes, &s.near_cnt, &s.hdr, &s.region, &s.lists, &s.prior, &s.scratch, &ctx->batch_T, &ctx->batch_counts, &ctx->batch_scores, &ctx->work, &ctx->topk_out})
     b->release();
   for (Model& m : ctx->models)
-    for (DevBuf* b : {&m.search, &m.search_nrm, &m.val, &m.val_nrm, &m.val_orig, &m.val_nrm_orig, &m.gen_T, &m.gen_counts, &m.gen_scores,
-                      &m.tgrid_pts, &m.tgrid_start})
+    for (DevBuf* b : {&m.search, &m.search_nrm, &m.search_unit, &m.val, &m.val_nrm, &m.val_orig, &m.val_nrm_orig, &m.gen_T, &m.gen_counts, &m.gen_scores,
+                      &m.tgrid_pts, &m.tgrid_start, &m.val_raw})
       b->release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -206,6 +206,39 @@ int pgp_set_model(pgp_ctx* ctx, int obj, const float* sx, const float* sn, int n
     int idx = i; memcpy(&s4[4 * (size_t)i + 3], &idx, 4);
     unit_normal(sn ? sn + 3 * i : nullptr, &sn4[4 * (size_t)i]);
   }
+  // unit-cube copy of the search cloud for the quad join: bbox centre and ratio as synch3DContent
+  // (pairCreationFunctor.h:102-138; AABB::center = min + (max - min)/2, accelerators/bbox.h:91-92)
+  {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = 0; i < nq; ++i)
+      for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], s4[4 * (size_t)i + k]); mx[k] = std::max(mx[k], s4[4 * (size_t)i + k]); }
+    double ratio = 0.0;
+    for (int k = 0; k < 3; ++k) {
+      m.unit_center[k] = mn[k] + ((mx[k] - mn[k]) / 2.0f);
+      ratio = std::max(ratio, (double)(mx[k] - mn[k]) + 0.001);
+    }
+    m.unit_ratio = (float)ratio;
+    std::vector<float> u4((size_t)nq * 4, 0.f);
+    for (int i = 0; i < nq; ++i)
+      for (int k = 0; k < 3; ++k) {
+        volatile float t = s4[4 * (size_t)i + k] - m.unit_center[k];
+        t = t / m.unit_ratio;
+        u4[4 * (size_t)i + k] = t + 0.5f;
+      }
+    int rc0 = upload_cloud4(ctx, m.search_unit, u4);
+    if (rc0) return rc0;
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // diameter estimate from 1000 pseudo-random pairs, like init() (:274-283) but with a fixed hash instead of rand()
+    m.search_diameter = 0.f;
+    uint64_t st = 0x1234567ull;
+    for (int t = 0; t < 1000; ++t) {
+      st = st * 6364136223846793005ull + 1442695040888963407ull; const int a = (int)((st >> 33) % (uint64_t)nq);
+      st = st * 6364136223846793005ull + 1442695040888963407ull; const int b = (int)((st >> 33) % (uint64_t)nq);
+      float d2 = 0.f;
+      for (int k = 0; k < 3; ++k) { float d = s4[4 * (size_t)b + k] - s4[4 * (size_t)a + k]; d2 += d * d; }
+      m.search_diameter = std::max(m.search_diameter, sqrtf(d2));
+    }
+  }
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
   for (int i = 0; i < nv; ++i) {
     for (int k = 0; k < 3; ++k) {
@@ -240,6 +273,17 @@ int pgp_set_model(pgp_ctx* ctx, int obj, const float* sx, const float* sn, int n
   int rc;
   if ((rc = upload_cloud4(ctx, m.search, s4))) return rc;
   if ((rc = upload_cloud4(ctx, m.search_nrm, sn4))) return rc;
+  {
+    std::vector<float> raw4((size_t)nv * 4, 0.f);
+    for (int k = 0; k < 3; ++k) { m.val_raw_lo[k] = INFINITY; m.val_raw_hi[k] = -INFINITY; }
+    for (int i = 0; i < nv; ++i)
+      for (int k = 0; k < 3; ++k) {
+        raw4[4 * (size_t)i + k] = vx[3 * i + k];
+        m.val_raw_lo[k] = std::min(m.val_raw_lo[k], vx[3 * i + k]); m.val_raw_hi[k] = std::max(m.val_raw_hi[k], vx[3 * i + k]);
+      }
+    if ((rc = upload_cloud4(ctx, m.val_raw, raw4))) return rc;
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
   if ((rc = upload_cloud4(ctx, m.val_orig, v4))) return rc;
   if ((rc = upload_cloud4(ctx, m.val_nrm_orig, vn4))) return rc;
   if ((rc = upload_cloud4(ctx, m.val, vs4))) return rc;

@@ -88,13 +88,19 @@ struct Model {
   float val_rinf = 0.f;  // max |coordinate| of the centred validation cloud
   DevBuf search;       // nq x float4 centred (w = 0)
   DevBuf search_nrm;   // nq x float4 unit normal
+  DevBuf search_unit;  // nq x float4: search cloud in the unit cube (PairCreationFunctor::synch3DContent, pairCreationFunctor.h:102-138)
+  float unit_ratio = 1.f;      // _ratio
+  float unit_center[3] = {0, 0, 0};   // _gcenter
+  float search_diameter = 0.f; // P_diameter_ estimate (match4pcsBase.cc:274-283)
   DevBuf val;          // nv x float4 centred, in a cache-friendly order; w = original index bits
   DevBuf val_nrm;      // nv x float4 unit normal, same order
   DevBuf val_orig;     // nv x float4 centred, ORIGINAL order (weighted mode with general priors, TrICP target)
   DevBuf val_nrm_orig;
   // model-space grid for TrICP (K5): nearest validation-model point of any query
+  DevBuf val_raw;        // nv x float4, model frame as given (un-centred): the TrICP target
+  float val_raw_lo[3] = {0, 0, 0}, val_raw_hi[3] = {0, 0, 0};
   DevBuf tgrid_pts, tgrid_start;
-  GridParams tg{};
+  float tg_lo[3] = {0, 0, 0}, tg_g = 1.f; int tg_dim[3] = {1, 1, 1};
   bool tgrid_ready = false;
   bool ready = false;
   // generated hypotheses (K2)

@@ -114,6 +114,45 @@ def make_problem(n_model: int = 2000, n_scene: int = 100_000, delta: float = 0.0
     )
 
 
+def make_segment_problem(n_model: int = 1000, n_segment: int = 2000, delta: float = 0.005, seed: int = 77,
+                         noise: float = 0.001) -> Problem:
+    """Test-scene-sized object request: the scene is ONE object's segment -- the camera-visible part
+    of the model surface at the GT pose (camera at the origin), jittered by +-noise -- as
+    CongruentSetMatching::generate hands it to the matcher
+    (/root/reference/src/physim_pose_estimation/src/hypothesis_generation/ObjectPoseCandidateSet.cpp:23-74)."""
+    rng = np.random.default_rng(seed)
+    mp, mn = sample_box(rng, n_model, BOX)
+    R = rot_axis_angle(GT_AXIS, GT_ANGLE)
+    t = np.array(GT_T)
+    gt = np.eye(4)
+    gt[:3, :3] = R
+    gt[:3, 3] = t
+    pts, nrm = [], []
+    while sum(len(p) for p in pts) < n_segment:
+        sp, sn = sample_box(rng, 4 * n_segment, BOX)
+        sp = sp @ R.T + t
+        sn = sn @ R.T
+        vis = np.einsum("ij,ij->i", sn, sp) < 0          # normal faces the camera at the origin
+        pts.append(sp[vis]); nrm.append(sn[vis])
+    sp = np.concatenate(pts)[:n_segment]
+    sn = np.concatenate(nrm)[:n_segment]
+    sp = sp + rng.uniform(-noise, noise, size=sp.shape)
+    scene_xyz = np.ascontiguousarray(sp, dtype=np.float32)
+    model_xyz = np.ascontiguousarray(mp, dtype=np.float32)
+    return Problem(scene_xyz=scene_xyz, scene_nrm=np.ascontiguousarray(sn, dtype=np.float32),
+                   scene_prior=np.ones(len(scene_xyz), np.float32), model_xyz=model_xyz,
+                   model_nrm=np.ascontiguousarray(mn, dtype=np.float32), delta=float(delta), gt_pose=gt,
+                   c_scene=seq_centroid_f32(scene_xyz), c_model=seq_centroid_f32(model_xyz))
+
+
+def pose_error(pose_a: np.ndarray, pose_b: np.ndarray) -> tuple[float, float]:
+    """(translation distance in metres, rotation angle in radians) between two 4x4 poses."""
+    dt = float(np.linalg.norm(pose_a[:3, 3] - pose_b[:3, 3]))
+    Rr = pose_a[:3, :3].T @ pose_b[:3, :3]
+    ang = float(np.arccos(np.clip((np.trace(Rr) - 1) / 2, -1, 1)))
+    return dt, ang
+
+
 def centre_pose(pose: np.ndarray, c_scene: np.ndarray, c_model: np.ndarray) -> np.ndarray:
     """World pose(s) (…,4,4) f64 -> centred-frame row-major 3x4 fp32: Tr(-c_P) . T . Tr(c_Q)."""
     pose = np.asarray(pose, dtype=np.float64)

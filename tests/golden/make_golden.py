@@ -49,33 +49,44 @@ def main():
     ref5 = RefOracle(*args[:-1], 0.005)
     np.savez_compressed(os.path.join(HERE, "lcp_small_d5.npz"), counts=ref5.verify(T), weighted_score=ref5.weighted_verify(T)[0])
 
-    # ---- PCS: pair extraction, quad join, rigid transforms for a few bases (operMode 0 pieces)
+    # ---- PCS: pair extraction, quad join, rigid transforms for a few bases (operMode 0 pieces) on a
+    # segment-sized request (the scene is one object's visible surface)
+    seg = synth.make_segment_problem(600, 1500, 0.005, seed=201)
+    sargs = (seg.scene_xyz, seg.scene_nrm, seg.model_xyz, seg.model_nrm, seg.model_xyz, seg.model_nrm, seg.delta)
+    ref = RefOracle(*sargs)
     pairs_out, quads_out, rigid_out = {}, {}, {}
     bases, invs = [], []
-    for seed in range(1, 40):
+    for seed in range(1, 400):
         ok, b, inv = ref.select_quadrilateral(seed)
-        if ok:
-            bases.append(b.copy()); invs.append(inv.copy())
-        if len(bases) == 4:
-            break
-    cP_xyz, _ = ref.centred(0)
-    for k, (b, inv) in enumerate(zip(bases, invs)):
-        d1 = float(np.linalg.norm(cP_xyz[b[0]] - cP_xyz[b[1]]))
-        d2 = float(np.linalg.norm(cP_xyz[b[2]] - cP_xyz[b[3]]))
-        p1 = ref.extract_pairs(np.float32(d1), np.float32(prob.delta))
-        p2 = ref.extract_pairs(np.float32(d2), np.float32(prob.delta))
-        q = ref.find_quads(b, inv[0], inv[1], np.float32(prob.delta), p1, p2)
-        q = q[:64]
+        if not ok:
+            continue
+        cP_xyz, _ = ref.centred(0)
+        d1 = np.float32(np.linalg.norm(cP_xyz[b[0]] - cP_xyz[b[1]]))
+        d2 = np.float32(np.linalg.norm(cP_xyz[b[2]] - cP_xyz[b[3]]))
+        p1 = ref.extract_pairs(d1, np.float32(seg.delta))
+        p2 = ref.extract_pairs(d2, np.float32(seg.delta))
+        if len(p1) == 0 or len(p2) == 0:
+            continue
+        q = ref.find_quads(b, inv[0], inv[1], np.float32(seg.delta), p1, p2)
+        if len(q) == 0:
+            continue
+        k = len(bases)
+        bases.append(b.copy()); invs.append(inv.copy())
+        qs = q[:256]
         Ts, oks, poses = [], [], []
-        for quad in q:
-            ok, T4, P4 = ref.rigid_from_quad(b, quad)
-            oks.append(ok); Ts.append(T4[:3]); poses.append(P4)
-        pairs_out[f"b{k}_d1"] = np.float32(d1); pairs_out[f"b{k}_d2"] = np.float32(d2)
+        for quad in qs:
+            ok2, T4, P4 = ref.rigid_from_quad(b, quad)
+            oks.append(ok2); Ts.append(T4[:3]); poses.append(P4)
+        pairs_out[f"b{k}_d1"] = d1; pairs_out[f"b{k}_d2"] = d2
         pairs_out[f"b{k}_p1"] = p1; pairs_out[f"b{k}_p2"] = p2
         quads_out[f"b{k}_quads"] = q
         rigid_out[f"b{k}_T"] = np.array(Ts, np.float32).reshape(-1, 3, 4); rigid_out[f"b{k}_ok"] = np.array(oks, bool)
         rigid_out[f"b{k}_pose"] = np.array(poses, np.float64).reshape(-1, 4, 4)
-    np.savez_compressed(os.path.join(HERE, "pcs_small.npz"), bases=np.array(bases, np.int32), invariants=np.array(invs, np.float32),
+        if len(bases) == 4:
+            break
+    scP, scQ = ref.centroids()
+    np.savez_compressed(os.path.join(HERE, "pcs_small.npz"), scene_xyz=seg.scene_xyz, scene_nrm=seg.scene_nrm, model_xyz=seg.model_xyz,
+                        model_nrm=seg.model_nrm, delta=np.float64(seg.delta), cP=scP, cQ=scQ, bases=np.array(bases, np.int32), invariants=np.array(invs, np.float32),
                         **pairs_out, **quads_out, **rigid_out)
     print("golden vectors written:", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 

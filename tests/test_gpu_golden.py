@@ -1,0 +1,92 @@
+"""CUDA path vs the golden vectors minted from the compiled reference engine (tests/golden/*.npz).
+These run on the GPU box, where /root/reference does not exist."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def lcp():
+    return np.load(os.path.join(G, "lcp_small.npz"))
+
+
+def test_lcp_count_golden(engine, lcp):
+    engine.set_scene(lcp["scene_xyz"], lcp["scene_nrm"], float(lcp["delta"]))
+    engine.set_model(0, lcp["model_xyz"], lcp["model_nrm"])
+    cP, cQ = engine.centroids(0)
+    assert np.array_equal(cP, lcp["cP"]) and np.array_equal(cQ, lcp["cQ"])
+    counts, scores = engine.score_lcp(0, lcp["T"], "count")
+    assert np.array_equal(counts, lcp["counts"])                       # bit-exact vs Match4PCSBase::Verify
+    chain = engine.improving_chain(0)
+    # the reference's running-best scan with early termination ends on the same hypothesis with the same score
+    assert chain["index"][-1] == int(lcp["running_best"])
+    assert chain["score"][-1] == lcp["running_frac"][int(lcp["running_best"])]
+    engine.set_option("force_coarse", 1)
+    try:
+        c2, _ = engine.score_lcp(0, lcp["T"], "count")
+    finally:
+        engine.set_option("force_coarse", 0)
+    assert np.array_equal(c2, lcp["counts"])
+
+
+def test_lcp_weighted_golden(engine, lcp):
+    engine.set_scene(lcp["scene_xyz"], lcp["scene_nrm"], float(lcp["delta"]))
+    engine.set_model(0, lcp["model_xyz"], lcp["model_nrm"])
+    counts, scores = engine.score_lcp(0, lcp["T"], "weighted")
+    assert np.array_equal(scores, lcp["weighted_score"])               # bit-exact vs WeightedVerify
+    assert np.array_equal(counts, lcp["weighted_nreg"].astype(np.uint32))
+    reg = engine.registered_points(0, lcp["T"][int(lcp["registered_of"])])
+    assert np.array_equal(reg, lcp["registered"])
+    # probability image -> per-point priors -> ordered fp32 accumulation
+    engine.set_scene_prior_image(lcp["prior_img"], lcp["K"])
+    assert np.array_equal(engine.scene_priors(), lcp["priors"])
+    counts, scores = engine.score_lcp(0, lcp["T"], "weighted")
+    assert np.array_equal(scores, lcp["weighted_score_img"])
+    assert np.array_equal(counts, lcp["weighted_nreg_img"].astype(np.uint32))
+
+
+def test_lcp_delta_5mm_golden(engine, lcp):
+    d5 = np.load(os.path.join(G, "lcp_small_d5.npz"))
+    engine.set_scene(lcp["scene_xyz"], lcp["scene_nrm"], 0.005)
+    engine.set_model(0, lcp["model_xyz"], lcp["model_nrm"])
+    counts, _ = engine.score_lcp(0, lcp["T"], "count")
+    assert np.array_equal(counts, d5["counts"])
+    _, ws = engine.score_lcp(0, lcp["T"], "weighted")
+    assert np.array_equal(ws, d5["weighted_score"])
+
+
+def _pairset(a):
+    a = np.asarray(a).reshape(-1, a.shape[-1])
+    return set(map(tuple, a.tolist()))
+
+
+def test_pcs_golden(engine):
+    g = np.load(os.path.join(G, "pcs_small.npz"))
+    delta = float(g["delta"])
+    engine.set_scene(g["scene_xyz"], g["scene_nrm"], delta)
+    engine.set_model(0, g["model_xyz"], g["model_nrm"])
+    total_ref = total_common = total_ours = 0
+    for k, (b, inv) in enumerate(zip(g["bases"], g["invariants"])):
+        p1 = engine.extract_pairs(0, float(g[f"b{k}_d1"]), delta)
+        p2 = engine.extract_pairs(0, float(g[f"b{k}_d2"]), delta)
+        assert _pairset(p1) == _pairset(g[f"b{k}_p1"])                 # pair SETS equal MatchSuper4PCS::ExtractPairs
+        assert _pairset(p2) == _pairset(g[f"b{k}_p2"])
+        # the join is fed the reference's own pair lists so that only the join is under test
+        q = engine.find_quads(0, b, inv[0], inv[1], delta, g[f"b{k}_p1"], g[f"b{k}_p2"])
+        ours, ref = _pairset(q), _pairset(g[f"b{k}_quads"])
+        total_ref += len(ref); total_ours += len(ours); total_common += len(ours & ref)
+        # rigid transforms of the reference's first quads
+        nq = len(g[f"b{k}_T"])
+        T, ok = engine.rigid_from_quads(0, b, g[f"b{k}_quads"][:nq])
+        assert np.array_equal(ok, g[f"b{k}_ok"])
+        assert np.allclose(T, g[f"b{k}_T"], atol=5e-6)                 # fp32 frame alignment, not bit-pinned (Eigen association)
+        pose = engine.centred_to_pose(0, T)
+        assert np.allclose(pose, g[f"b{k}_pose"], atol=1e-5)
+    # quad sets: the reference's quantised join (power-of-two position grid, 7^3 direction grid, rasterised
+    # cone) is reproduced cell for cell; only samples that land within rounding of a cell border may differ.
+    assert total_common >= 0.995 * total_ref, (total_common, total_ref, total_ours)
+    assert total_ours <= 1.005 * total_ref + 2, (total_common, total_ref, total_ours)

@@ -1,0 +1,74 @@
+"""K2 (device-side congruent-set generation) and K5 (trimmed ICP) against the oracle."""
+import numpy as np
+import pytest
+
+from physimglobalpose_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_generate_pcs_finds_the_pose(engine, port_lib):
+    prob = synth.make_segment_problem(1000, 2000, 0.005, seed=5)
+    engine.set_scene(prob.scene_xyz, prob.scene_nrm, prob.delta)
+    engine.set_model(0, prob.model_xyz, prob.model_nrm)
+    n = engine.generate_pcs(0, seed=3, max_hyp=20000)                  # 100 bases x <= 100 quads, as the reference
+    assert 100 < n <= 10000
+    engine.score_generated(0, "count")
+    T, counts, scores = engine.get_generated(0)
+    # generated transforms are rigid
+    R = T[:, :, :3].astype(np.float64)
+    assert np.allclose(R @ R.transpose(0, 2, 1), np.eye(3), atol=1e-4)
+    # scoring of the generated batch == oracle on the same transforms
+    o = port_lib.PortOracle(prob.scene_xyz, prob.scene_nrm, prob.model_xyz, prob.model_nrm, prob.model_xyz, prob.model_nrm, prob.delta)
+    assert np.array_equal(counts[:500], o.verify(T[:500]))
+    # determinism: same seed -> same hypotheses
+    n2 = engine.generate_pcs(0, seed=3, max_hyp=20000)
+    T2, _, _ = engine.get_generated(0)
+    assert n2 == n and np.array_equal(T2, T)
+    # the best-LCP hypothesis is the GT pose up to the box's symmetry
+    engine.score_generated(0, "count")
+    top = engine.topk(0, 1)
+    pose = engine.centred_to_pose(0, top["T"][0])[0]
+    errs = []
+    for flip in (np.eye(3), np.diag([-1.0, -1, 1]), np.diag([-1.0, 1, -1]), np.diag([1.0, -1, -1])):   # box symmetries
+        gt = prob.gt_pose.copy(); gt[:3, :3] = gt[:3, :3] @ flip
+        errs.append(synth.pose_error(pose, gt))
+    dt, ang = min(errs, key=lambda e: e[0] + e[1])
+    assert top["score"][0] > 0.3
+    assert dt < 0.01 and ang < 0.1, (dt, ang, top["score"][0])
+    # the improving chain is what hypothesisSet would hold; its last element is bestHypothesis
+    chain = engine.improving_chain(0)
+    assert chain["index"][-1] == top["index"][0] and np.all(np.diff(chain["score"]) > 0)
+
+
+def test_tricp_matches_oracle(engine, port_lib):
+    prob = synth.make_segment_problem(1500, 1200, 0.005, seed=9)
+    engine.set_scene(prob.scene_xyz, prob.scene_nrm, prob.delta)
+    engine.set_model(0, prob.model_xyz, prob.model_nrm)
+    rng = np.random.default_rng(1)
+    poses = []
+    for _ in range(6):
+        axis = rng.normal(size=3)
+        dR = synth.rot_axis_angle(axis, rng.normal(0, 0.08))
+        P = prob.gt_pose.copy()
+        P[:3, :3] = P[:3, :3] @ dR
+        P[:3, 3] += rng.normal(0, 0.006, size=3)
+        poses.append(P)
+    poses = np.array(poses)
+    refined, iters, energy = engine.tricp(0, prob.scene_xyz, poses, trim=0.5, ratio=0.99, max_iter=100)
+    for k in range(len(poses)):
+        T0 = np.linalg.inv(poses[k])[:3].astype(np.float32)             # guess = inverse(pose): scene -> model
+        Tref, it_ref, e_ref = _oracle_tricp(port_lib, prob, T0)
+        M = np.eye(4); M[:3] = Tref
+        want = np.linalg.inv(M)
+        dt, ang = synth.pose_error(refined[k], want)
+        assert dt < 1e-4 and ang < 1e-4, (k, dt, ang, iters[k], it_ref)  # north_star tolerance: 1e-4 m / 1e-4 rad
+        assert iters[k] == it_ref
+        assert abs(energy[k] - e_ref) <= 1e-4 * max(e_ref, 1e-12) + 1e-12
+        # and refinement helps: closer to GT than the start (up to symmetry the start is already near GT)
+        assert synth.pose_error(refined[k], prob.gt_pose)[0] <= synth.pose_error(poses[k], prob.gt_pose)[0] + 1e-3
+
+
+def _oracle_tricp(port_lib, prob, T0):
+    o = port_lib.PortOracle(prob.scene_xyz[:10], prob.scene_nrm[:10], prob.model_xyz, prob.model_nrm, prob.model_xyz, prob.model_nrm, prob.delta)
+    return o.tricp(prob.scene_xyz, prob.model_xyz, T0, trim=0.5, ratio=0.99, max_iter=100)

@@ -6,7 +6,7 @@
 // utilities::performTrICP (PPE/src/misc/utilities.cpp:651-680): target = model cloud, source = scene
 // segment, guess = inverse(pose), n_keep = |trim * N_src| truncated, loop while
 // energy/old_energy < ratio.  PCL is not vendored in the reference tree: the algorithm follows the
-// call sites and PCL's published TrimmedICP (see oracle/lcp_oracle.c lo_tricp; PARITY UNPINNED).
+// call sites and PCL's published TrimmedICP (the CPU checker restates the same algorithm; PARITY UNPINNED).
 //
 // Per iteration and pose: exact 1-NN of every transformed source point in a model-space grid
 // (ring search with a proven stop bound), radix-select of the n_keep-th smallest squared distance,

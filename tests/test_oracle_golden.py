@@ -1,0 +1,104 @@
+"""The CPU oracle (oracle/lcp_oracle.c, a plain-C restatement) against the golden vectors minted
+from the reference engine itself (tests/golden/make_golden.py), and -- where the reference build
+exists (this container) -- against the reference live.  This is what pins the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from physimglobalpose_b200 import synth
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def lcp():
+    return np.load(os.path.join(G, "lcp_small.npz"))
+
+
+def _port(port_lib, g, delta=None, **kw):
+    return port_lib.PortOracle(g["scene_xyz"], g["scene_nrm"], g["model_xyz"], g["model_nrm"], g["model_xyz"], g["model_nrm"],
+                               float(g["delta"]) if delta is None else delta, **kw)
+
+
+def test_port_lcp_matches_reference_golden(port_lib, lcp):
+    o = _port(port_lib, lcp)
+    cP, cQ = o.centroids()
+    assert np.array_equal(cP, lcp["cP"]) and np.array_equal(cQ, lcp["cQ"])
+    assert np.array_equal(o.verify(lcp["T"]), lcp["counts"])
+    frac, best = o.verify_running_best(lcp["T"])
+    assert best == int(lcp["running_best"]) and np.array_equal(frac, lcp["running_frac"])
+    ws, wn, reg = o.weighted_verify(lcp["T"], reg_of=int(lcp["registered_of"]))
+    assert np.array_equal(ws, lcp["weighted_score"]) and np.array_equal(wn, lcp["weighted_nreg"])
+    assert np.array_equal(reg, lcp["registered"])
+    # the improving chain ends at the running best
+    chain = o.improving_chain(lcp["counts"].astype(np.float32) / np.float32(len(lcp["model_xyz"])))
+    assert chain[-1] == int(lcp["running_best"])
+
+
+def test_port_priors_and_weighted_with_image(port_lib, lcp):
+    o = _port(port_lib, lcp, K=lcp["K"], prior_img=lcp["prior_img"])
+    assert np.array_equal(o.priors(), lcp["priors"])
+    ws, wn = o.weighted_verify(lcp["T"])
+    assert np.array_equal(ws, lcp["weighted_score_img"]) and np.array_equal(wn, lcp["weighted_nreg_img"])
+
+
+def test_port_delta_5mm(port_lib, lcp):
+    d5 = np.load(os.path.join(G, "lcp_small_d5.npz"))
+    o = _port(port_lib, lcp, delta=0.005)
+    assert np.array_equal(o.verify(lcp["T"]), d5["counts"])
+    assert np.array_equal(o.weighted_verify(lcp["T"])[0], d5["weighted_score"])
+
+
+def test_port_pcs_pieces_match_reference_golden(port_lib):
+    g = np.load(os.path.join(G, "pcs_small.npz"))
+    o = _port(port_lib, g)
+    for k, b in enumerate(g["bases"]):
+        for which in ("1", "2"):
+            got = o.extract_pairs(float(g[f"b{k}_d{which}"]), float(g["delta"]))
+            assert set(map(tuple, got.tolist())) == set(map(tuple, g[f"b{k}_p{which}"].tolist()))
+        for quad, T, ok, pose in zip(g[f"b{k}_quads"], g[f"b{k}_T"], g[f"b{k}_ok"], g[f"b{k}_pose"]):
+            ok2, T4, P4 = o.rigid_from_quad(b, quad)
+            assert ok2 == bool(ok)
+            assert np.allclose(T4[:3], T, atol=5e-6) and np.allclose(P4, pose, atol=1e-5)
+
+
+def test_lcp_invariants(port_lib):
+    """Properties the reference's (disabled) tests would assert: identity on a copy -> full count; far
+    translation -> 0; monotone in delta."""
+    prob = synth.make_segment_problem(300, 600, 0.005, seed=4)
+    args = (prob.model_xyz, prob.model_nrm, prob.model_xyz, prob.model_nrm, prob.model_xyz, prob.model_nrm)   # scene := model
+    I = np.eye(4)
+    T_id = synth.centre_pose(I, synth.seq_centroid_f32(prob.model_xyz), synth.seq_centroid_f32(prob.model_xyz))
+    far = I.copy(); far[:3, 3] = 5.0
+    T_far = synth.centre_pose(far, synth.seq_centroid_f32(prob.model_xyz), synth.seq_centroid_f32(prob.model_xyz))
+    last = None
+    for d in (0.001, 0.005, 0.02):
+        o = port_lib.PortOracle(*args, d)
+        c = o.verify(np.stack([T_id, T_far]))
+        assert c[0] == len(prob.model_xyz) and c[1] == 0
+        T = synth.make_hypotheses(prob, 32, seed=1)
+        cur = port_lib.PortOracle(prob.scene_xyz, prob.scene_nrm, prob.model_xyz, prob.model_nrm, prob.model_xyz, prob.model_nrm, d).verify(T)
+        if last is not None:
+            assert np.all(cur >= last)
+        last = cur
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference tree (build container only)")
+def test_port_equals_reference_live(port_lib):
+    """Fresh seeded inputs, reference engine compiled in place (oracle/_ref) vs the C restatement."""
+    port_lib.build_ref()
+    prob = synth.make_problem(400, 9000, 0.01, seed=31)
+    T = synth.make_hypotheses(prob, 200, seed=32)
+    args = (prob.scene_xyz, prob.scene_nrm, prob.model_xyz, prob.model_nrm, prob.model_xyz, prob.model_nrm, prob.delta)
+    ref, port = port_lib.RefOracle(*args), port_lib.PortOracle(*args)
+    assert np.array_equal(ref.verify(T), port.verify(T))
+    a, b = ref.weighted_verify(T), port.weighted_verify(T)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    fa, ba = ref.verify_running_best(T)
+    fb, bb = port.verify_running_best(T)
+    assert ba == bb and np.array_equal(fa, fb)
+    cm, _ = ref.verify_mt(T, 3)
+    assert np.array_equal(cm, ref.verify(T))                       # the multi-thread CPU baseline driver is consistent
+    cp, _ = port.verify_mt(T, 3)
+    assert np.array_equal(cp, cm)

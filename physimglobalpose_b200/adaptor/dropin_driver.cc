@@ -1,0 +1,37 @@
+// Test driver: calls the drop-in exactly as CongruentSetMatching::generate does
+// (PPE/src/hypothesis_generation/ObjectPoseCandidateSet.cpp:66-68) and prints the outputs as JSON.
+#include <cstdio>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "eigen_abi.h"
+
+void getProbableTransformsSuper4PCS(std::string input1, std::string input2, std::string input3,
+                                    std::pair<Eigen::Isometry3d, float>& bestHypothesis,
+                                    std::vector<std::pair<Eigen::Isometry3d, float>>& hypothesisSet,
+                                    std::string probImagePath,
+                                    std::map<std::vector<int>, std::vector<std::pair<int, int>>>& PPFMap,
+                                    int max_count_ppf, Eigen::Matrix3f camIntrinsic, std::string objName, std::string scenePath,
+                                    std::vector<int>& registered_points);
+
+int main(int argc, char** argv) {
+  if (argc < 4) { fprintf(stderr, "usage: %s segment.ply model_validation.ply model_search.ply [prob.png fx fy cx cy]\n", argv[0]); return 2; }
+  std::pair<Eigen::Isometry3d, float> best;
+  std::vector<std::pair<Eigen::Isometry3d, float>> set;
+  std::map<std::vector<int>, std::vector<std::pair<int, int>>> ppf;
+  std::vector<int> reg;
+  Eigen::Matrix3f K;
+  std::string png = argc > 4 ? argv[4] : "";
+  if (argc > 8) { K(0, 0) = atof(argv[5]); K(1, 1) = atof(argv[6]); K(0, 2) = atof(argv[7]); K(1, 2) = atof(argv[8]); K(2, 2) = 1.f; }
+  getProbableTransformsSuper4PCS(argv[1], argv[2], argv[3], best, set, png, ppf, 0, K, "obj", "/tmp/", reg);
+  printf("{\"best_score\": %.9g, \"n_hypotheses\": %zu, \"n_registered\": %zu, \"best_pose\": [", best.second, set.size(), reg.size());
+  for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) printf("%s%.17g", (r || c) ? ", " : "", best.first(r, c));
+  printf("], \"scores\": [");
+  for (size_t i = 0; i < set.size(); ++i) printf("%s%.9g", i ? ", " : "", set[i].second);
+  printf("], \"registered_head\": [");
+  for (size_t i = 0; i < reg.size() && i < 8; ++i) printf("%s%d", i ? ", " : "", reg[i]);
+  printf("]}\n");
+  return 0;
+}

@@ -1,0 +1,252 @@
+// Drop-in replacement for the reference's libsuper4pcs.so entry point: exports the SAME mangled
+// C++ symbol the ROS node resolves (declared at PPE/src/hypothesis_generation/
+// ObjectPoseCandidateSet.cpp:5-9, defined at S4/super4pcs_test.cc:39-111, linked through
+// PPE/CMakeLists.txt:116), reads the same files, fills the same outputs -- and does all the work on
+// the B200 through the C ABI of include/pgp.h.  Host-only C++; no CUDA, no Eigen, no PCL needed.
+//
+//   in : segment / model_validation / model_search PLY paths (as PCL's savePLYFile writes them),
+//        16-bit probability PNG path, PPFMap (accepted, not used: pairs come from the device-side
+//        pair extraction), intrinsics, object name, scene path
+//   out: bestHypothesis (pose, score), hypothesisSet = the strictly-improving chain in generation
+//        order (match4pcsBase.cc:1888-1914), registered_points (scene indices matched by the best pose)
+// Failure behaviour: never throws across the boundary; on any error the outputs are identity / 0 /
+// empty (the reference: exit(-1) on unreadable input, uninitialised outputs on exceptions).
+//
+// Environment: PGP_DEVICE (CUDA device, default 0), PGP_LCP_MODE = weighted (default, the shipped
+// WeightedVerify) | count, PGP_DELTA (default 0.005 = S4/super4pcs_test.cc:20), PGP_SEED.
+#include <zlib.h>
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "eigen_abi.h"
+#include "pgp.h"
+
+namespace {
+
+struct Cloud { std::vector<float> xyz, nrm; };
+
+// ---- PLY: vertex element with named properties, ascii or binary_little_endian; other elements skipped
+bool read_ply(const std::string& path, Cloud& out) {
+  std::ifstream in(path, std::ios::binary);
+  if (!in) return false;
+  std::string tok;
+  in >> tok;
+  if (tok != "ply") return false;
+  struct Prop { std::string type, name; };
+  std::vector<Prop> props;
+  bool ascii = true, in_vertex = false;
+  size_t n_vertex = 0;
+  std::string line;
+  std::getline(in, line);
+  while (std::getline(in, line)) {
+    if (!line.empty() && line.back() == '\r') line.pop_back();
+    std::istringstream ls(line);
+    std::string key;
+    ls >> key;
+    if (key == "end_header") break;
+    if (key == "format") { std::string f; ls >> f; if (f == "ascii") ascii = true; else if (f == "binary_little_endian") ascii = false; else return false; }
+    else if (key == "element") { std::string name; size_t cnt; ls >> name >> cnt; in_vertex = (name == "vertex"); if (in_vertex) n_vertex = cnt; }
+    else if (key == "property" && in_vertex) { Prop p; ls >> p.type; if (p.type == "list") return false; ls >> p.name; props.push_back(p); }
+  }
+  auto find = [&](std::initializer_list<const char*> names) { for (size_t i = 0; i < props.size(); ++i) for (const char* n : names) if (props[i].name == n) return (int)i; return -1; };
+  const int ix = find({"x"}), iy = find({"y"}), iz = find({"z"});
+  const int inx = find({"nx", "normal_x"}), iny = find({"ny", "normal_y"}), inz = find({"nz", "normal_z"});
+  if (ix < 0 || iy < 0 || iz < 0) return false;
+  const bool has_n = inx >= 0 && iny >= 0 && inz >= 0;
+  out.xyz.resize(n_vertex * 3);
+  out.nrm.assign(has_n ? n_vertex * 3 : 0, 0.f);
+  auto size_of = [](const std::string& t) -> int {
+    if (t == "float" || t == "float32" || t == "int" || t == "int32" || t == "uint" || t == "uint32") return 4;
+    if (t == "double" || t == "float64") return 8;
+    if (t == "uchar" || t == "uint8" || t == "char" || t == "int8") return 1;
+    if (t == "short" || t == "int16" || t == "ushort" || t == "uint16") return 2;
+    return -1;
+  };
+  std::vector<double> v(props.size());
+  for (size_t i = 0; i < n_vertex; ++i) {
+    if (ascii) {
+      for (size_t k = 0; k < props.size(); ++k) if (!(in >> v[k])) return false;
+    } else {
+      for (size_t k = 0; k < props.size(); ++k) {
+        const int sz = size_of(props[k].type);
+        char b[8];
+        if (sz < 0 || !in.read(b, sz)) return false;
+        const std::string& t = props[k].type;
+        if (t == "float" || t == "float32") { float f; memcpy(&f, b, 4); v[k] = f; }
+        else if (t == "double" || t == "float64") { double d; memcpy(&d, b, 8); v[k] = d; }
+        else if (sz == 1) v[k] = (unsigned char)b[0];
+        else if (sz == 2) { uint16_t u; memcpy(&u, b, 2); v[k] = u; }
+        else { int32_t q; memcpy(&q, b, 4); v[k] = q; }
+      }
+    }
+    out.xyz[3 * i] = (float)v[ix]; out.xyz[3 * i + 1] = (float)v[iy]; out.xyz[3 * i + 2] = (float)v[iz];
+    if (has_n) { out.nrm[3 * i] = (float)v[inx]; out.nrm[3 * i + 1] = (float)v[iny]; out.nrm[3 * i + 2] = (float)v[inz]; }
+  }
+  return n_vertex > 0;
+}
+
+// ---- PNG: 8/16-bit grayscale, non-interlaced (what cv::imwrite produces for the CV_16UC1 prior image)
+bool read_png_gray16(const std::string& path, std::vector<uint16_t>& img, int& rows, int& cols) {
+  std::ifstream in(path, std::ios::binary);
+  if (!in) return false;
+  std::vector<unsigned char> f((std::istreambuf_iterator<char>(in)), std::istreambuf_iterator<char>());
+  static const unsigned char sig[8] = {137, 80, 78, 71, 13, 10, 26, 10};
+  if (f.size() < 8 || memcmp(f.data(), sig, 8)) return false;
+  auto be32 = [&](size_t o) { return (uint32_t)f[o] << 24 | (uint32_t)f[o + 1] << 16 | (uint32_t)f[o + 2] << 8 | f[o + 3]; };
+  size_t o = 8;
+  int depth = 0, ctype = -1, interlace = 0;
+  std::vector<unsigned char> z;
+  while (o + 8 <= f.size()) {
+    const uint32_t len = be32(o);
+    const std::string type((const char*)&f[o + 4], 4);
+    if (o + 12 + len > f.size()) return false;
+    if (type == "IHDR") { cols = (int)be32(o + 8); rows = (int)be32(o + 12); depth = f[o + 16]; ctype = f[o + 17]; interlace = f[o + 20]; }
+    else if (type == "IDAT") z.insert(z.end(), f.begin() + o + 8, f.begin() + o + 8 + len);
+    else if (type == "IEND") break;
+    o += 12 + len;
+  }
+  if (ctype != 0 || interlace != 0 || (depth != 8 && depth != 16) || rows <= 0 || cols <= 0) return false;
+  const size_t bpp = depth / 8, stride = (size_t)cols * bpp;
+  std::vector<unsigned char> raw((stride + 1) * rows);
+  uLongf rl = raw.size();
+  if (uncompress(raw.data(), &rl, z.data(), z.size()) != Z_OK || rl != raw.size()) return false;
+  std::vector<unsigned char> cur(stride), prev(stride, 0);
+  img.resize((size_t)rows * cols);
+  for (int r = 0; r < rows; ++r) {
+    const unsigned char* line = &raw[(stride + 1) * r];
+    const int ft = line[0];
+    for (size_t i = 0; i < stride; ++i) {
+      const int a = i >= bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0;
+      int x = line[1 + i];
+      switch (ft) {
+        case 1: x += a; break;
+        case 2: x += b; break;
+        case 3: x += (a + b) / 2; break;
+        case 4: { const int p = a + b - c, pa = std::abs(p - a), pb = std::abs(p - b), pc = std::abs(p - c); x += (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); break; }
+        default: break;
+      }
+      cur[i] = (unsigned char)x;
+    }
+    for (int cidx = 0; cidx < cols; ++cidx)
+      img[(size_t)r * cols + cidx] = depth == 16 ? (uint16_t)(cur[2 * cidx] << 8 | cur[2 * cidx + 1]) : (uint16_t)cur[cidx];
+    prev = cur;
+  }
+  return true;
+}
+
+struct CtxHolder {
+  pgp_ctx* ctx = nullptr;
+  ~CtxHolder() { if (ctx) pgp_destroy(ctx); }
+};
+pgp_ctx* shared_ctx() {
+  static CtxHolder h;
+  if (!h.ctx) {
+    const char* d = getenv("PGP_DEVICE");
+    h.ctx = pgp_create(d ? atoi(d) : 0);
+    if (!h.ctx) fprintf(stderr, "[pgp] %s\n", pgp_last_error(nullptr));
+  }
+  return h.ctx;
+}
+
+void to_isometry(const double* P16, Eigen::Isometry3d& iso) {
+#ifdef PGP_USE_REAL_EIGEN
+  for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) iso.matrix()(r, c) = P16[4 * r + c];
+#else
+  for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) iso(r, c) = P16[4 * r + c];
+#endif
+}
+
+}  // namespace
+
+// NB: C++ linkage on purpose -- this must mangle exactly like the reference's definition.
+void getProbableTransformsSuper4PCS(std::string input1, std::string input2, std::string input3,
+                                    std::pair<Eigen::Isometry3d, float>& bestHypothesis,
+                                    std::vector<std::pair<Eigen::Isometry3d, float>>& hypothesisSet,
+                                    std::string probImagePath,
+                                    std::map<std::vector<int>, std::vector<std::pair<int, int>>>& PPFMap,
+                                    int max_count_ppf, Eigen::Matrix3f camIntrinsic, std::string objName, std::string scenePath,
+                                    std::vector<int>& registered_points) __attribute__((visibility("default")));
+
+void getProbableTransformsSuper4PCS(std::string input1, std::string input2, std::string input3,
+                                    std::pair<Eigen::Isometry3d, float>& bestHypothesis,
+                                    std::vector<std::pair<Eigen::Isometry3d, float>>& hypothesisSet,
+                                    std::string probImagePath,
+                                    std::map<std::vector<int>, std::vector<std::pair<int, int>>>& PPFMap,
+                                    int max_count_ppf, Eigen::Matrix3f camIntrinsic, std::string objName, std::string scenePath,
+                                    std::vector<int>& registered_points) {
+  (void)PPFMap; (void)max_count_ppf; (void)objName; (void)scenePath;
+  Eigen::Isometry3d identity;
+#ifdef PGP_USE_REAL_EIGEN
+  identity.setIdentity();
+#endif
+  bestHypothesis.first = identity;                  // "no pose" -> identity + 0 (match4pcsBase.cc:1791-1796)
+  bestHypothesis.second = 0.f;
+  registered_points.clear();
+  try {
+    pgp_ctx* ctx = shared_ctx();
+    if (!ctx) return;
+    Cloud seg, val, search;
+    // argument order of the reference: set1 = segment (P), set2 = input2 = model_validation copy (Q_validation),
+    // set3 = input3 = model_search copy (Q)   (S4/super4pcs_test.cc:58-74,103)
+    if (!read_ply(input1, seg) || !read_ply(input2, val) || !read_ply(input3, search)) {
+      fprintf(stderr, "[pgp] cannot read the input PLY files\n");
+      return;
+    }
+    const char* de = getenv("PGP_DELTA");
+    const float delta = de ? (float)atof(de) : 0.005f;
+    const char* me = getenv("PGP_LCP_MODE");
+    int mode = (me && !strcmp(me, "count")) ? PGP_LCP_COUNT : PGP_LCP_WEIGHTED;
+    if (seg.nrm.empty() || val.nrm.empty()) mode = PGP_LCP_COUNT;      // the normal gate needs normals on both sides
+    const char* se = getenv("PGP_SEED");
+    const uint64_t seed = se ? strtoull(se, nullptr, 10) : 1;
+    const int ns = (int)(seg.xyz.size() / 3), nv = (int)(val.xyz.size() / 3), nq = (int)(search.xyz.size() / 3);
+    auto fail = [&](const char* what) { fprintf(stderr, "[pgp] %s: %s\n", what, pgp_last_error(ctx)); };
+    if (pgp_set_scene(ctx, seg.xyz.data(), seg.nrm.empty() ? nullptr : seg.nrm.data(), ns, delta)) return fail("set_scene");
+    std::vector<uint16_t> img;
+    int rows = 0, cols = 0;
+    if (mode == PGP_LCP_WEIGHTED && !probImagePath.empty() && read_png_gray16(probImagePath, img, rows, cols)) {
+      float K[9];
+      for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) K[3 * r + c] = camIntrinsic(r, c);
+      if (pgp_set_scene_prior_image(ctx, img.data(), rows, cols, K)) return fail("set_scene_prior_image");
+    }
+    if (pgp_set_model(ctx, 0, search.xyz.data(), search.nrm.empty() ? nullptr : search.nrm.data(), nq, val.xyz.data(),
+                      val.nrm.empty() ? nullptr : val.nrm.data(), nv))
+      return fail("set_model");
+    pgp_pcs_opts opts;
+    pgp_pcs_default_opts(&opts);                    // 100 bases x <= 100 congruent quads (match4pcsBase.cc:290,1858)
+    int64_t n_hyp = 0;
+    if (pgp_generate_pcs(ctx, 0, &opts, seed, 10000, &n_hyp)) return fail("generate_pcs");
+    if (n_hyp == 0) return;
+    if (pgp_score_generated(ctx, 0, mode)) return fail("score_generated");
+    std::vector<pgp_hyp> chain(4096);
+    int n_chain = pgp_improving_chain(ctx, 0, 0, chain.data(), (int)chain.size());
+    if (n_chain == PGP_E_CAPACITY) n_chain = (int)chain.size();
+    if (n_chain <= 0) return;
+    for (int i = 0; i < n_chain; ++i) {
+      double P[16];
+      if (pgp_centred_to_pose(ctx, 0, chain[i].T, P)) return fail("centred_to_pose");
+      std::pair<Eigen::Isometry3d, float> e;
+      to_isometry(P, e.first);
+      e.second = chain[i].score;
+      hypothesisSet.push_back(e);
+    }
+    bestHypothesis = hypothesisSet.back();          // == allPose[best_lcp_index], best_LCP_
+    if (mode == PGP_LCP_WEIGHTED) {
+      registered_points.resize(nv);
+      const int k = pgp_registered_points(ctx, 0, chain[n_chain - 1].T, registered_points.data(), nv);
+      registered_points.resize(k > 0 ? k : 0);
+    }
+  } catch (...) {
+    // swallow everything, like S4/super4pcs_test.cc:101-108 -- but with defined outputs
+  }
+}

@@ -291,7 +291,134 @@ __global__ void __launch_bounds__(THREADS, 2) k3_lcp_kernel(const __grid_constan
 // rounding sequence (GridParams::inflate), so counts stay bit-exact.
 constexpr int FWARPS = 32;
 constexpr int FTHREADS = FWARPS * 32;
+constexpr int FQCAP = 96;            // queue slots per warp: < 32 left over + 64 new per step
 
+struct FineCtx {
+  const float4* s_model;
+  const uint2* table;        // bmrank: shared (SMEM_TABLE) or global
+  uint16_t* q;
+  int dimx, dimy;
+  unsigned rx, ry, rz;
+  int lane;
+  unsigned lt_mask;
+};
+
+template <bool SMEM_TABLE>
+__device__ __forceinline__ uint2 table_word(const FineCtx& f, int w) {
+  if (SMEM_TABLE) return f.table[w];            // LDS.64
+  return __ldg(f.table + w);
+}
+
+// label of the voxel (ix,iy,iz): 0 OUT (or outside the grid / empty neighbourhood), 1 IN, 2 AMBIG
+template <bool SMEM_TABLE>
+__device__ __forceinline__ uint32_t voxel_label(const LcpParams& p, const FineCtx& f, int ix, int iy, int iz) {
+  uint32_t code = 0;
+  if ((unsigned)(ix - 8) < f.rx && (unsigned)(iy - 8) < f.ry && (unsigned)(iz - 8) < f.rz) {   // cells 1 .. dim-2
+    const int c = ((iz >> 3) * f.dimy + (iy >> 3)) * f.dimx + (ix >> 3);
+    const uint2 wr = table_word<SMEM_TABLE>(f, c >> 5);
+    const unsigned bit = 1u << (c & 31);
+    if (wr.x & bit) {
+      const unsigned blk = wr.y + __popc(wr.x & (bit - 1u));
+      const int v = ((iz & 7) << 6) | ((iy & 7) << 3) | (ix & 7);
+      code = (__ldg(p.codes + ((size_t)blk * 32 + (v >> 4))) >> ((v & 15) * 2)) & 3u;
+    }
+  }
+  return code;
+}
+
+// phase 2 for one queued query: the reference's exact test against the voxel's candidate list
+template <bool SMEM_TABLE>
+__device__ __forceinline__ int resolve_ambiguous(const LcpParams& p, const FineCtx& f, const Xf& x, const float4 m, int ix, int iy, int iz) {
+  const int c = ((iz >> 3) * f.dimy + (iy >> 3)) * f.dimx + (ix >> 3);
+  const uint2 wr = table_word<SMEM_TABLE>(f, c >> 5);
+  const unsigned blk = wr.y + __popc(wr.x & ((1u << (c & 31)) - 1u));
+  const int v = ((iz & 7) << 6) | ((iy & 7) << 3) | (ix & 7);
+  const uint4 gp = __ldg(p.hdr + (size_t)blk * 2);
+  const uint4 h1 = __ldg(p.hdr + (size_t)blk * 2 + 1);
+  const uint4 grp = __ldg(reinterpret_cast<const uint4*>(p.codes) + (size_t)blk * 8 + (v >> 6));
+  float tx, ty, tz;
+  apply_xf(x, m, tx, ty, tz);
+  const int g8 = v >> 6, wi = (v >> 4) & 3;
+  const uint32_t gw = g8 < 2 ? gp.x : g8 < 4 ? gp.y : g8 < 6 ? gp.z : gp.w;
+  uint32_t r = (gw >> ((g8 & 1) * 16)) & 0xffffu;
+  const uint32_t A = 0xAAAAAAAAu;
+  r += (wi > 0 ? __popc(grp.x & A) : 0) + (wi > 1 ? __popc(grp.y & A) : 0) + (wi > 2 ? __popc(grp.z & A) : 0);
+  const uint32_t word = wi == 0 ? grp.x : wi == 1 ? grp.y : wi == 2 ? grp.z : grp.w;
+  r += __popc(word & A & ((1u << ((v & 15) * 2)) - 1u));
+  const uint32_t* reg = p.lists + h1.x;
+  const uint32_t s0 = __ldg(reg + r), s1 = __ldg(reg + r + 1);
+  const float r2 = p.g.r2;
+  for (uint32_t j = s0; j < s1; ++j) {
+    const float4 sp = __ldg(p.pts + __ldg(reg + j));
+    if (sqdist3(tx, ty, tz, sp.x, sp.y, sp.z) <= r2) return 1;
+  }
+  return 0;
+}
+
+// one hypothesis, all model points of the staged tile (tn_pad = tile size rounded up to 64; the pad
+// slots hold NaN points, which convert to voxel 0 and fail the range test).
+// FAST: voxel coordinates from the pre-scaled FMA transform a[]; otherwise the reference's
+// rounding sequence followed by the grid's own cell_coord (huge / non-finite matrices).
+template <bool SMEM_TABLE, bool FAST>
+__device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCtx& f, const float* __restrict__ T, long long h, int tn_pad) {
+  const Xf x = load_xf(T, h);
+  float a[12];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    a[4 * r + 0] = x.m[4 * r + 0] * p.g.inv_hf;
+    a[4 * r + 1] = x.m[4 * r + 1] * p.g.inv_hf;
+    a[4 * r + 2] = x.m[4 * r + 2] * p.g.inv_hf;
+    a[4 * r + 3] = (x.m[4 * r + 3] - p.g.lo[r]) * p.g.inv_hf;
+  }
+  auto voxel_of = [&](const float4 m, int& ix, int& iy, int& iz) {
+    float ux, uy, uz;
+    if (FAST) {
+      ux = __fmaf_rn(a[0], m.x, __fmaf_rn(a[1], m.y, __fmaf_rn(a[2], m.z, a[3])));
+      uy = __fmaf_rn(a[4], m.x, __fmaf_rn(a[5], m.y, __fmaf_rn(a[6], m.z, a[7])));
+      uz = __fmaf_rn(a[8], m.x, __fmaf_rn(a[9], m.y, __fmaf_rn(a[10], m.z, a[11])));
+    } else {
+      float tx, ty, tz;
+      apply_xf(x, m, tx, ty, tz);
+      ux = cell_coord(tx, p.g.lo[0], p.g.inv_hf); uy = cell_coord(ty, p.g.lo[1], p.g.inv_hf); uz = cell_coord(tz, p.g.lo[2], p.g.inv_hf);
+    }
+    ix = __float2int_rz(ux); iy = __float2int_rz(uy); iz = __float2int_rz(uz);   // saturating, NaN -> 0
+  };
+  int good = 0, qn = 0;
+  auto drain = [&](int take) {
+    if (f.lane < take) {
+      const int i = f.q[qn - take + f.lane];
+      const float4 m = f.s_model[i];
+      int ix, iy, iz;
+      voxel_of(m, ix, iy, iz);                      // same arithmetic as phase 1 -> same voxel
+      const Xf xe = FAST ? load_xf(T, h) : x;       // FAST keeps only a[] live across the loop; the exact matrix is re-read (L1)
+      good += resolve_ambiguous<SMEM_TABLE>(p, f, xe, m, ix, iy, iz);
+    }
+    qn -= take;
+  };
+  for (int base = 0; base < tn_pad; base += 64) {
+    const int i0 = base + f.lane, i1 = i0 + 32;
+    const float4 m0 = f.s_model[i0], m1 = f.s_model[i1];
+    int ix0, iy0, iz0, ix1, iy1, iz1;
+    voxel_of(m0, ix0, iy0, iz0);
+    voxel_of(m1, ix1, iy1, iz1);
+    const uint32_t c0 = voxel_label<SMEM_TABLE>(p, f, ix0, iy0, iz0);
+    const uint32_t c1 = voxel_label<SMEM_TABLE>(p, f, ix1, iy1, iz1);
+    good += (c0 == 1u) + (c1 == 1u);
+    const unsigned b0 = __ballot_sync(0xffffffffu, c0 == 2u), b1 = __ballot_sync(0xffffffffu, c1 == 2u);
+    if (b0 | b1) {
+      if (c0 == 2u) f.q[qn + __popc(b0 & f.lt_mask)] = (uint16_t)i0;
+      qn += __popc(b0);
+      if (c1 == 2u) f.q[qn + __popc(b1 & f.lt_mask)] = (uint16_t)i1;
+      qn += __popc(b1);
+      __syncwarp();
+      while (qn >= 32) { drain(32); __syncwarp(); }
+    }
+  }
+  if (qn > 0) { drain(qn); __syncwarp(); }
+  return __reduce_add_sync(0xffffffffu, good);
+}
+
+template <bool SMEM_TABLE>
 __global__ void __launch_bounds__(FTHREADS, 1) k3_count_fine_kernel(const __grid_constant__ LcpParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t mbar;
@@ -299,11 +426,13 @@ __global__ void __launch_bounds__(FTHREADS, 1) k3_count_fine_kernel(const __grid
   uint2* s_bmrank = reinterpret_cast<uint2*>(smem + (size_t)p.tile_cap * 16);
   uint16_t* s_queue = reinterpret_cast<uint16_t*>(s_bmrank + p.bmrank_words);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint16_t* q = s_queue + warp * QCAP;
-  const uint2* bmrank = p.bmrank_words ? s_bmrank : p.bmrank;
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const int dimx = p.g.dim[0], dimy = p.g.dim[1];
-  const unsigned rx = (unsigned)(p.g.dim[0] - 2) * 8u, ry = (unsigned)(p.g.dim[1] - 2) * 8u, rz = (unsigned)(p.g.dim[2] - 2) * 8u;
+  FineCtx f;
+  f.s_model = s_model;
+  f.table = SMEM_TABLE ? s_bmrank : p.bmrank;
+  f.q = s_queue + warp * FQCAP;
+  f.dimx = p.g.dim[0]; f.dimy = p.g.dim[1];
+  f.rx = (unsigned)(p.g.dim[0] - 2) * 8u; f.ry = (unsigned)(p.g.dim[1] - 2) * 8u; f.rz = (unsigned)(p.g.dim[2] - 2) * 8u;
+  f.lane = lane; f.lt_mask = (1u << lane) - 1u;
 
   if (threadIdx.x == 0) mbar_init(&mbar, 1);
   __syncthreads();
@@ -311,118 +440,34 @@ __global__ void __launch_bounds__(FTHREADS, 1) k3_count_fine_kernel(const __grid
   for (int tile = 0; tile < p.n_tiles; ++tile) {
     const int t0 = tile * p.tile_cap;
     const int tn = min(p.tile_cap, p.nv - t0);
+    const int tn_pad = (tn + 63) & ~63;
     if (threadIdx.x == 0) {
       uint32_t bytes = (uint32_t)tn * 16u;
-      uint32_t bm = tile == 0 ? (uint32_t)p.bmrank_words * 8u : 0u;
+      uint32_t bm = (SMEM_TABLE && tile == 0) ? (uint32_t)p.bmrank_words * 8u : 0u;
       mbar_expect_tx(&mbar, bytes + bm);
       tma_bulk_g2s(s_model, p.model + t0, bytes, &mbar);
-      // one bulk copy moves at most 2^20 - 16 bytes; the table is far below that
       if (bm) tma_bulk_g2s(s_bmrank, p.bmrank, bm, &mbar);
     }
+    // pad slots: NaN points (their voxel converts to 0 and fails the range test); disjoint from the bulk copy's bytes
+    for (int i = tn + (int)threadIdx.x; i < tn_pad; i += FTHREADS) s_model[i] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
     mbar_wait(&mbar, tile & 1);
+    __syncthreads();
 
     for (;;) {
       long long h = 0;
       if (lane == 0) h = (long long)atomicAdd(p.work + tile, 1ull);
       h = __shfl_sync(0xffffffffu, h, 0);
       if (h >= p.n) break;
-      const Xf x = load_xf(p.T, h);
-      // voxel-unit transform: u = (T q - lo) / hf, folded into the matrix
-      float a[12];
+      // bound on the transform's intermediates: decides whether the FMA fast path's error budget holds
       float bound = 0.f;
+      {
+        const Xf x = load_xf(p.T, h);
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        a[4 * r + 0] = x.m[4 * r + 0] * p.g.inv_hf;
-        a[4 * r + 1] = x.m[4 * r + 1] * p.g.inv_hf;
-        a[4 * r + 2] = x.m[4 * r + 2] * p.g.inv_hf;
-        a[4 * r + 3] = (x.m[4 * r + 3] - p.g.lo[r]) * p.g.inv_hf;
-        bound = fmaxf(bound, (fabsf(x.m[4 * r]) + fabsf(x.m[4 * r + 1]) + fabsf(x.m[4 * r + 2])) * p.model_rinf + fabsf(x.m[4 * r + 3]));
+        for (int r = 0; r < 3; ++r)
+          bound = fmaxf(bound, (fabsf(x.m[4 * r]) + fabsf(x.m[4 * r + 1]) + fabsf(x.m[4 * r + 2])) * p.model_rinf + fabsf(x.m[4 * r + 3]));
       }
       const bool fast = bound <= p.g.pos_bound;     // false for NaN / huge matrices: those take the reference's arithmetic
-      int good = 0;
-      int qn = 0;
-
-      // voxel of model point m under this hypothesis -- the SAME arithmetic in phase 1 and phase 2
-      auto voxel_of = [&](const float4 m, int& ix, int& iy, int& iz) {
-        float ux, uy, uz;
-        if (fast) {
-          ux = __fmaf_rn(a[0], m.x, __fmaf_rn(a[1], m.y, __fmaf_rn(a[2], m.z, a[3])));
-          uy = __fmaf_rn(a[4], m.x, __fmaf_rn(a[5], m.y, __fmaf_rn(a[6], m.z, a[7])));
-          uz = __fmaf_rn(a[8], m.x, __fmaf_rn(a[9], m.y, __fmaf_rn(a[10], m.z, a[11])));
-        } else {
-          float tx, ty, tz;
-          apply_xf(x, m, tx, ty, tz);
-          ux = cell_coord(tx, p.g.lo[0], p.g.inv_hf); uy = cell_coord(ty, p.g.lo[1], p.g.inv_hf); uz = cell_coord(tz, p.g.lo[2], p.g.inv_hf);
-        }
-        ix = __float2int_rz(ux); iy = __float2int_rz(uy); iz = __float2int_rz(uz);   // saturating, NaN -> 0
-      };
-
-      // phase 2: the reference's exact test, restricted to the candidate list of the query's AMBIG voxel
-      auto drain = [&](int take) {
-        if (lane < take) {
-          const int i = q[qn - take + lane];
-          const float4 m = s_model[i];
-          int ix, iy, iz;
-          voxel_of(m, ix, iy, iz);
-          const int c = ((iz >> 3) * dimy + (iy >> 3)) * dimx + (ix >> 3);
-          const uint2 wr = bmrank[c >> 5];
-          const unsigned blk = wr.y + __popc(wr.x & ((1u << (c & 31)) - 1u));
-          const int v = ((iz & 7) << 6) | ((iy & 7) << 3) | (ix & 7);
-          const uint4 gp = __ldg(p.hdr + (size_t)blk * 2);
-          const uint4 h1 = __ldg(p.hdr + (size_t)blk * 2 + 1);
-          const uint4 grp = __ldg(reinterpret_cast<const uint4*>(p.codes) + (size_t)blk * 8 + (v >> 6));
-          float tx, ty, tz;
-          apply_xf(x, m, tx, ty, tz);
-          const int g8 = v >> 6, wi = (v >> 4) & 3;
-          const uint32_t gw = g8 < 2 ? gp.x : g8 < 4 ? gp.y : g8 < 6 ? gp.z : gp.w;
-          uint32_t r = (gw >> ((g8 & 1) * 16)) & 0xffffu;
-          const uint32_t A = 0xAAAAAAAAu;
-          r += (wi > 0 ? __popc(grp.x & A) : 0) + (wi > 1 ? __popc(grp.y & A) : 0) + (wi > 2 ? __popc(grp.z & A) : 0);
-          const uint32_t word = wi == 0 ? grp.x : wi == 1 ? grp.y : wi == 2 ? grp.z : grp.w;
-          r += __popc(word & A & ((1u << ((v & 15) * 2)) - 1u));
-          const uint32_t* reg = p.lists + h1.x;
-          const uint32_t s0 = __ldg(reg + r), s1 = __ldg(reg + r + 1);
-          const float r2 = p.g.r2;
-          bool hit = false;
-          for (uint32_t j = s0; j < s1; ++j) {
-            const float4 sp = __ldg(p.pts + __ldg(reg + j));
-            if (sqdist3(tx, ty, tz, sp.x, sp.y, sp.z) <= r2) { hit = true; break; }
-          }
-          good += hit ? 1 : 0;
-        }
-        qn -= take;
-      };
-
-      for (int base = 0; base < tn; base += 32) {
-        const int i = base + lane;
-        bool amb = false;
-        if (i < tn) {
-          int ix, iy, iz;
-          voxel_of(s_model[i], ix, iy, iz);
-          if ((unsigned)(ix - 8) < rx && (unsigned)(iy - 8) < ry && (unsigned)(iz - 8) < rz) {   // cells 1 .. dim-2
-            const int c = ((iz >> 3) * dimy + (iy >> 3)) * dimx + (ix >> 3);
-            const uint2 wr = bmrank[c >> 5];
-            const unsigned bit = 1u << (c & 31);
-            if (wr.x & bit) {
-              const unsigned blk = wr.y + __popc(wr.x & (bit - 1u));
-              const int v = ((iz & 7) << 6) | ((iy & 7) << 3) | (ix & 7);
-              const uint32_t code = (__ldg(p.codes + (size_t)blk * 32 + (v >> 4)) >> ((v & 15) * 2)) & 3u;
-              good += (code == 1u);
-              amb = (code == 2u);
-            }
-          }
-        }
-        const unsigned b = __ballot_sync(0xffffffffu, amb);
-        if (b) {
-          if (amb) q[qn + __popc(b & lt_mask)] = (uint16_t)i;
-          qn += __popc(b);
-          __syncwarp();
-          if (qn >= 32) { drain(32); __syncwarp(); }
-        }
-      }
-      if (qn > 0) { drain(qn); __syncwarp(); }
-
-      const int tot = __reduce_add_sync(0xffffffffu, good);
+      const int tot = fast ? score_hypothesis<SMEM_TABLE, true>(p, f, p.T, h, tn_pad) : score_hypothesis<SMEM_TABLE, false>(p, f, p.T, h, tn_pad);
       if (lane == 0) {
         if (p.n_tiles == 1) {
           p.counts[h] = (uint32_t)tot;
@@ -525,11 +570,11 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
   p.work = reinterpret_cast<unsigned long long*>(ctx->work.as<char>() + 1024);
 
   if (mode == PGP_LCP_COUNT && s.g.fine == 8 && !ctx->force_coarse) {
-    const size_t smem_max = 200 * 1024, qb = (size_t)FWARPS * QCAP * 2;
+    const size_t smem_max = 200 * 1024, qb = (size_t)FWARPS * FQCAP * 2;
     size_t bm = (size_t)s.bitmap_words * 8;
-    int tile_cap = std::min((m.nv + 3) & ~3, 8192);
+    int tile_cap = std::min((m.nv + 63) & ~63, 8192);
     if (bm + qb + (size_t)std::min(tile_cap, 2048) * 16 > smem_max) bm = 0;          // table too big for smem: read it through L1
-    if ((size_t)tile_cap * 16 + bm + qb > smem_max) tile_cap = (int)((smem_max - bm - qb) / 16) & ~3;
+    if ((size_t)tile_cap * 16 + bm + qb > smem_max) tile_cap = (int)((smem_max - bm - qb) / 16) & ~63;
     p.tile_cap = tile_cap;
     p.n_tiles = (m.nv + tile_cap - 1) / tile_cap;
     if (p.n_tiles > 256) return pgp_fail(ctx, PGP_E_INVALID, "validation model too large (%d points)", m.nv);
@@ -541,8 +586,13 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     PGP_CUDA(ctx, cudaMemsetAsync(p.work, 0, 8 * (size_t)p.n_tiles, st));
     if (p.n_tiles > 1) PGP_CUDA(ctx, cudaMemsetAsync(counts_dev, 0, (size_t)n * 4, st));
     int grid = (int)std::min<long long>((n + FWARPS - 1) / FWARPS, ctx->sm_count);
-    PGP_CUDA(ctx, cudaFuncSetAttribute(k3_count_fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k3_count_fine_kernel<<<grid, FTHREADS, smem, st>>>(p);
+    if (bm) {
+      PGP_CUDA(ctx, cudaFuncSetAttribute(k3_count_fine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k3_count_fine_kernel<true><<<grid, FTHREADS, smem, st>>>(p);
+    } else {
+      PGP_CUDA(ctx, cudaFuncSetAttribute(k3_count_fine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k3_count_fine_kernel<false><<<grid, FTHREADS, smem, st>>>(p);
+    }
     ctx->launches++;
     if (p.n_tiles > 1 && scores_dev) {
       k3_finalise<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(counts_dev, scores_dev, n, m.nv, mode);

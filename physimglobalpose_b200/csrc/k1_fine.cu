@@ -229,9 +229,10 @@ int k1_build_fine(pgp_ctx* ctx) {
   uint32_t nb = 0;
   PGP_CUDA(ctx, cudaMemcpyAsync(&nb, pre + nw, 4, cudaMemcpyDeviceToHost, st));
   PGP_CUDA(ctx, cudaStreamSynchronize(st));
-  if ((size_t)nb * 128 > ((size_t)24 << 30)) return PGP_OK;     // absurdly large: stay on the 27-cell path
+  if ((size_t)nb * 128 > ((size_t)8 << 30)) return PGP_OK;      // absurdly large (and label offsets are 32-bit): stay on the 27-cell path
   PGP_CUDA(ctx, s.block_cell.reserve((size_t)nb * 4 + 16));
-  PGP_CUDA(ctx, s.codes.reserve((size_t)nb * 128 + 16));
+  PGP_CUDA(ctx, s.codes.reserve((size_t)nb * 128 + 256));
+  PGP_CUDA(ctx, cudaMemsetAsync(s.codes.as<char>() + (size_t)nb * 128, 0, 128, st));   // zero dummy block behind the last one
   k1f_bmrank<<<(unsigned)((nw * 32 + 255) / 256), 256, 0, st>>>(s.bitmap.as<uint32_t>(), pre, nw, g.n_cells, s.bmrank.as<uint2>(),
                                                               s.block_cell.as<uint32_t>());
   ctx->launches++;

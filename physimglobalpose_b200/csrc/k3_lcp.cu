@@ -291,7 +291,8 @@ __global__ void __launch_bounds__(THREADS, 2) k3_lcp_kernel(const __grid_constan
 // rounding sequence (GridParams::inflate), so counts stay bit-exact.
 constexpr int FWARPS = 32;
 constexpr int FTHREADS = FWARPS * 32;
-constexpr int FQCAP = 96;            // queue slots per warp: < 32 left over + 64 new per step
+constexpr int FUNROLL = 4;           // model points per lane per step (their label gathers are issued together)
+constexpr int FQCAP = 32 + 32 * FUNROLL;   // queue slots per warp: < 32 left over + the new ones of one step
 
 struct FineCtx {
   const float4* s_model;
@@ -301,6 +302,7 @@ struct FineCtx {
   unsigned rx, ry, rz;
   int lane;
   unsigned lt_mask;
+  uint32_t dummy_word;       // offset of a zero word in `codes`
 };
 
 template <bool SMEM_TABLE>
@@ -309,21 +311,19 @@ __device__ __forceinline__ uint2 table_word(const FineCtx& f, int w) {
   return __ldg(f.table + w);
 }
 
-// label of the voxel (ix,iy,iz): 0 OUT (or outside the grid / empty neighbourhood), 1 IN, 2 AMBIG
+// Branch-free label fetch, split in two so that several queries' gathers can be in flight at once:
+// label_slot() gives the word offset into `codes` (a zero dummy word behind the last block for
+// queries outside the grid or in cells with an empty neighbourhood) and the bit shift.
 template <bool SMEM_TABLE>
-__device__ __forceinline__ uint32_t voxel_label(const LcpParams& p, const FineCtx& f, int ix, int iy, int iz) {
-  uint32_t code = 0;
-  if ((unsigned)(ix - 8) < f.rx && (unsigned)(iy - 8) < f.ry && (unsigned)(iz - 8) < f.rz) {   // cells 1 .. dim-2
-    const int c = ((iz >> 3) * f.dimy + (iy >> 3)) * f.dimx + (ix >> 3);
-    const uint2 wr = table_word<SMEM_TABLE>(f, c >> 5);
-    const unsigned bit = 1u << (c & 31);
-    if (wr.x & bit) {
-      const unsigned blk = wr.y + __popc(wr.x & (bit - 1u));
-      const int v = ((iz & 7) << 6) | ((iy & 7) << 3) | (ix & 7);
-      code = (__ldg(p.codes + ((size_t)blk * 32 + (v >> 4))) >> ((v & 15) * 2)) & 3u;
-    }
-  }
-  return code;
+__device__ __forceinline__ uint32_t label_slot(const LcpParams& p, const FineCtx& f, int ix, int iy, int iz, uint32_t& shift) {
+  const bool inr = (unsigned)(ix - 8) < f.rx && (unsigned)(iy - 8) < f.ry && (unsigned)(iz - 8) < f.rz;   // cells 1 .. dim-2
+  const int c = inr ? ((iz >> 3) * f.dimy + (iy >> 3)) * f.dimx + (ix >> 3) : 0;                        // cell 0 is apron: bit clear
+  const uint2 wr = table_word<SMEM_TABLE>(f, c >> 5);
+  const unsigned bit = 1u << (c & 31);
+  const unsigned blk = wr.y + __popc(wr.x & (bit - 1u));
+  const int v = ((iz & 7) << 6) | ((iy & 7) << 3) | (ix & 7);
+  shift = (uint32_t)(v & 15) * 2u;
+  return (wr.x & bit) ? blk * 32u + (uint32_t)(v >> 4) : f.dummy_word;
 }
 
 // phase 2 for one queued query: the reference's exact test against the voxel's candidate list
@@ -395,21 +395,31 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
     }
     qn -= take;
   };
-  for (int base = 0; base < tn_pad; base += 64) {
-    const int i0 = base + f.lane, i1 = i0 + 32;
-    const float4 m0 = f.s_model[i0], m1 = f.s_model[i1];
-    int ix0, iy0, iz0, ix1, iy1, iz1;
-    voxel_of(m0, ix0, iy0, iz0);
-    voxel_of(m1, ix1, iy1, iz1);
-    const uint32_t c0 = voxel_label<SMEM_TABLE>(p, f, ix0, iy0, iz0);
-    const uint32_t c1 = voxel_label<SMEM_TABLE>(p, f, ix1, iy1, iz1);
-    good += (c0 == 1u) + (c1 == 1u);
-    const unsigned b0 = __ballot_sync(0xffffffffu, c0 == 2u), b1 = __ballot_sync(0xffffffffu, c1 == 2u);
-    if (b0 | b1) {
-      if (c0 == 2u) f.q[qn + __popc(b0 & f.lt_mask)] = (uint16_t)i0;
-      qn += __popc(b0);
-      if (c1 == 2u) f.q[qn + __popc(b1 & f.lt_mask)] = (uint16_t)i1;
-      qn += __popc(b1);
+  const float4* mp = f.s_model + f.lane;
+  for (int base = 0; base < tn_pad; base += 32 * FUNROLL) {
+    uint32_t off[FUNROLL], sh[FUNROLL], code[FUNROLL];
+#pragma unroll
+    for (int u = 0; u < FUNROLL; ++u) {
+      int ix, iy, iz;
+      voxel_of(mp[base + 32 * u], ix, iy, iz);
+      off[u] = label_slot<SMEM_TABLE>(p, f, ix, iy, iz, sh[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < FUNROLL; ++u) code[u] = __ldg(p.codes + off[u]);
+    unsigned any = 0;
+#pragma unroll
+    for (int u = 0; u < FUNROLL; ++u) {
+      code[u] = (code[u] >> sh[u]) & 3u;
+      good += (code[u] == 1u);
+      any |= (code[u] == 2u);
+    }
+    if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+      for (int u = 0; u < FUNROLL; ++u) {
+        const unsigned bb = __ballot_sync(0xffffffffu, code[u] == 2u);
+        if (code[u] == 2u) f.q[qn + __popc(bb & f.lt_mask)] = (uint16_t)(base + 32 * u + f.lane);
+        qn += __popc(bb);
+      }
       __syncwarp();
       while (qn >= 32) { drain(32); __syncwarp(); }
     }
@@ -433,6 +443,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) k3_count_fine_kernel(const __grid
   f.dimx = p.g.dim[0]; f.dimy = p.g.dim[1];
   f.rx = (unsigned)(p.g.dim[0] - 2) * 8u; f.ry = (unsigned)(p.g.dim[1] - 2) * 8u; f.rz = (unsigned)(p.g.dim[2] - 2) * 8u;
   f.lane = lane; f.lt_mask = (1u << lane) - 1u;
+  f.dummy_word = (uint32_t)p.g.n_blocks * 32u;
 
   if (threadIdx.x == 0) mbar_init(&mbar, 1);
   __syncthreads();
@@ -440,7 +451,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) k3_count_fine_kernel(const __grid
   for (int tile = 0; tile < p.n_tiles; ++tile) {
     const int t0 = tile * p.tile_cap;
     const int tn = min(p.tile_cap, p.nv - t0);
-    const int tn_pad = (tn + 63) & ~63;
+    const int tn_pad = (tn + 32 * FUNROLL - 1) / (32 * FUNROLL) * (32 * FUNROLL);
     if (threadIdx.x == 0) {
       uint32_t bytes = (uint32_t)tn * 16u;
       uint32_t bm = (SMEM_TABLE && tile == 0) ? (uint32_t)p.bmrank_words * 8u : 0u;
@@ -572,9 +583,9 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
   if (mode == PGP_LCP_COUNT && s.g.fine == 8 && !ctx->force_coarse) {
     const size_t smem_max = 200 * 1024, qb = (size_t)FWARPS * FQCAP * 2;
     size_t bm = (size_t)s.bitmap_words * 8;
-    int tile_cap = std::min((m.nv + 63) & ~63, 8192);
+    int tile_cap = std::min((m.nv + 127) & ~127, 8192);
     if (bm + qb + (size_t)std::min(tile_cap, 2048) * 16 > smem_max) bm = 0;          // table too big for smem: read it through L1
-    if ((size_t)tile_cap * 16 + bm + qb > smem_max) tile_cap = (int)((smem_max - bm - qb) / 16) & ~63;
+    if ((size_t)tile_cap * 16 + bm + qb > smem_max) tile_cap = (int)((smem_max - bm - qb) / 16) & ~127;
     p.tile_cap = tile_cap;
     p.n_tiles = (m.nv + tile_cap - 1) / tile_cap;
     if (p.n_tiles > 256) return pgp_fail(ctx, PGP_E_INVALID, "validation model too large (%d points)", m.nv);

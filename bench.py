@@ -83,6 +83,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE K3 launch, from the committed ncu --set full capture
+    (profiles/k3_traffic.json; ncu cannot run inside the timed bench)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "k3_traffic.json")) as f:
+            t = json.load(f)
+        return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def make_inputs(rank: int):
     from physimglobalpose_b200 import synth
     prob = synth.make_problem(N_MODEL, N_SCENE, DELTA, seed=1234)
@@ -253,7 +264,7 @@ def run_ours(args, rank, local_rank, world):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                         "traffic": None, "peak_kind": peak_kind, "kernel": "k3_count_fine_kernel", "kernel_ms": kernel_ms,
+                         "traffic": ncu_traffic(), "peak_kind": peak_kind, "kernel": "k3_count_fine_kernel", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_hyp": b_hyp, "kbar_27": kbar, "nonempty_query_fraction": nonempty,
                          "note": "algorithmic bytes of the canonical 27-cell probe (SURVEY.md 8d); the working set is L2-resident and "
                                  "the bitmap cull skips empty queries, so this fraction is not capped at 1"},

@@ -264,7 +264,7 @@ def run_ours(args, rank, local_rank, world):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                         "traffic": ncu_traffic(), "peak_kind": peak_kind, "kernel": "k3_count_fine_kernel", "kernel_ms": kernel_ms,
+                         "traffic": ncu_traffic(), "peak_kind": peak_kind, "kernel": "k3_fine_kernel<smem table, count>", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_hyp": b_hyp, "kbar_27": kbar, "nonempty_query_fraction": nonempty,
                          "note": "algorithmic bytes of the canonical 27-cell probe (SURVEY.md 8d); the working set is L2-resident and "
                                  "the bitmap cull skips empty queries, so this fraction is not capped at 1"},

@@ -43,7 +43,6 @@ __global__ void __launch_bounds__(CLS_THREADS) k1f_classify(const uint32_t* __re
                                                             uint32_t* __restrict__ region_words, int* __restrict__ overflow) {
   __shared__ float4 s_p[CLS_CHUNK];
   __shared__ unsigned char s_code[F * F * F];
-  __shared__ uint32_t s_words[32];
   __shared__ uint32_t s_tot;
   const int b = blockIdx.x;
   const uint32_t c = block_cell[b];
@@ -103,8 +102,6 @@ __global__ void __launch_bounds__(CLS_THREADS) k1f_classify(const uint32_t* __re
 #pragma unroll
     for (int k = 0; k < 16; ++k) w |= (uint32_t)s_code[threadIdx.x * 16 + k] << (2 * k);
     codes[(size_t)b * 32 + threadIdx.x] = w;
-    s_words[threadIdx.x] = w;
-    __syncwarp();
     // header: ambig-rank prefix per group of 64 voxels (4 words), number of ambig voxels, list words
     const uint32_t amb = __popc(w & 0xAAAAAAAAu);
     uint32_t incl = amb;
@@ -136,7 +133,6 @@ __global__ void __launch_bounds__(CLS_THREADS) k1f_fill_lists(const uint32_t* __
   __shared__ float4 s_p[CLS_CHUNK];
   __shared__ uint16_t s_av[F * F * F];       // AMBIG voxels in rank order
   __shared__ uint32_t s_off[F * F * F + 1];  // their list offsets
-  __shared__ uint32_t s_wpre[33];
   const int b = blockIdx.x;
   const uint32_t n_amb = hdr[(size_t)b * 8 + 5];
   if (threadIdx.x == 0) hdr[(size_t)b * 8 + 4] = region_base[b];
@@ -208,6 +204,188 @@ __global__ void __launch_bounds__(CLS_THREADS) k1f_fill_lists(const uint32_t* __
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K1c -- nearest-candidate lists of every non-OUT voxel, for WeightedVerify
+// (S4/algorithms/match4pcsBase.cc:1733-1766), which needs the IDENTITY of the nearest in-range
+// scene point (KdTree::doQueryRestrictedClosestIndex, S4/accelerators/kdtree.h:394-459), not just
+// its existence.  For a voxel V (inflated box) and a scene point p let lo(p) / hi(p) be the
+// smallest / largest distance from p to a point of V.  Whatever query q lands in V, its nearest
+// scene point p* satisfies d(q,p*) <= d(q,p') <= hi(p') for every p', and d(q,p*) <= delta, hence
+//     lo(p*)^2 <= min( min_p' hi(p')^2 , delta^2 )      (+ rounding margins)
+// -- the list of all points passing that bound holds the nearest neighbour (and every point that
+// can tie with it) of every query of the voxel.  At 1/8-cell voxels that is ~5 points instead of
+// the ~60 in the 27 cells.  Layout mirrors the AMBIG lists: per block a header of non-OUT rank
+// prefixes and a region [n_nonout + 1 offsets][ids].
+__device__ __forceinline__ void box_d2(const float4 p, float vx, float vy, float vz, float hs, float& mind2, float& maxd2) {
+  const float ax = fabsf(p.x - vx), ay = fabsf(p.y - vy), az = fabsf(p.z - vz);
+  const float lx = fmaxf(ax - hs, 0.f), ly = fmaxf(ay - hs, 0.f), lz = fmaxf(az - hs, 0.f);
+  const float hx = ax + hs, hy = ay + hs, hz = az + hs;
+  mind2 = __fmaf_rn(lx, lx, __fmaf_rn(ly, ly, lz * lz));
+  maxd2 = __fmaf_rn(hx, hx, __fmaf_rn(hy, hy, hz * hz));
+}
+
+// all scene points of the 27 cells around cell (cx,cy,cz), staged through shared memory; every
+// thread of the CTA must call it (it synchronises).  fn(point, sorted position)
+template <class Fn>
+__device__ __forceinline__ void sweep27(const uint32_t* __restrict__ cell_start, const float4* __restrict__ pts, const GridParams& g, int cx, int cy,
+                                        int cz, float4* s_p, Fn&& fn) {
+  for (int row = 0; row < 9; ++row) {
+    const int oy = row % 3 - 1, oz = row / 3 - 1;
+    const int r = ((cz + oz) * g.dim[1] + (cy + oy)) * g.dim[0] + cx;
+    const uint32_t s = cell_start[r - 1], e = cell_start[r + 2];
+    for (uint32_t base = s; base < e; base += CLS_CHUNK) {
+      const int m = (int)min((uint32_t)CLS_CHUNK, e - base);
+      __syncthreads();
+      for (int t = threadIdx.x; t < m; t += CLS_THREADS) s_p[t] = pts[base + t];
+      __syncthreads();
+      for (int t = 0; t < m; ++t) fn(s_p[t], base + (uint32_t)t);
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t nonout_mask(uint32_t w) { return (w | (w >> 1)) & 0x55555555u; }
+__device__ __forceinline__ float wlist_threshold(float u2, float dhi2) { return fminf(u2 * (1.0f + 4e-5f), dhi2); }
+
+// Pass A: list length of every non-OUT voxel + block header.  4 voxels per thread (v = tid + 128 j).
+__global__ void __launch_bounds__(CLS_THREADS) k1w_count(const uint32_t* __restrict__ block_cell, const uint32_t* __restrict__ cell_start,
+                                                         const float4* __restrict__ pts, GridParams g, const uint32_t* __restrict__ codes,
+                                                         uint16_t* __restrict__ wcnt, uint32_t* __restrict__ whdr,
+                                                         uint32_t* __restrict__ region_words, unsigned long long* __restrict__ total_words,
+                                                         int* __restrict__ overflow) {
+  __shared__ float4 s_p[CLS_CHUNK];
+  __shared__ uint32_t s_tot;
+  const int b = blockIdx.x;
+  const uint32_t c = block_cell[b];
+  const int cx = (int)(c % g.dim[0]), cy = (int)((c / g.dim[0]) % g.dim[1]), cz = (int)(c / ((uint32_t)g.dim[0] * g.dim[1]));
+  const float hs = 0.5f * g.hf + g.inflate;
+  float vx[4], vy[4], vz[4], u2[4], thr[4];
+  int cnt[4] = {0, 0, 0, 0};
+  bool live[4];
+  if (threadIdx.x == 0) s_tot = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int v = threadIdx.x + CLS_THREADS * j;
+    vx[j] = __fmaf_rn((float)(cx * F + (v & 7)) + 0.5f, g.hf, g.lo[0]);
+    vy[j] = __fmaf_rn((float)(cy * F + ((v >> 3) & 7)) + 0.5f, g.hf, g.lo[1]);
+    vz[j] = __fmaf_rn((float)(cz * F + (v >> 6)) + 0.5f, g.hf, g.lo[2]);
+    u2[j] = INFINITY;
+    live[j] = ((codes[(size_t)b * 32 + (v >> 4)] >> ((v & 15) * 2)) & 3u) != 0u;
+  }
+  sweep27(cell_start, pts, g, cx, cy, cz, s_p, [&](const float4 p, uint32_t) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float lo2, hi2; box_d2(p, vx[j], vy[j], vz[j], hs, lo2, hi2); u2[j] = fminf(u2[j], hi2); }
+  });
+#pragma unroll
+  for (int j = 0; j < 4; ++j) thr[j] = wlist_threshold(u2[j], g.dhi2);
+  sweep27(cell_start, pts, g, cx, cy, cz, s_p, [&](const float4 p, uint32_t) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float lo2, hi2; box_d2(p, vx[j], vy[j], vz[j], hs, lo2, hi2); cnt[j] += (lo2 <= thr[j]) ? 1 : 0; }
+  });
+  uint32_t mine = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int v = threadIdx.x + CLS_THREADS * j;
+    const int nn = live[j] ? cnt[j] : 0;
+    if (nn > 65535) atomicOr(overflow, 1);
+    wcnt[(size_t)b * 512 + v] = (uint16_t)min(nn, 65535);
+    mine += (uint32_t)min(nn, 65535);
+  }
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_tot, mine);
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const uint32_t w = nonout_mask(codes[(size_t)b * 32 + threadIdx.x]);
+    const uint32_t k = __popc(w);
+    uint32_t incl = k;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += t; }
+    const uint32_t excl = incl - k;
+    const uint32_t n_live = __shfl_sync(0xffffffffu, incl, 31);
+    const uint32_t g_lo = __shfl_sync(0xffffffffu, excl, (threadIdx.x & 3) * 8);
+    const uint32_t g_hi = __shfl_sync(0xffffffffu, excl, (threadIdx.x & 3) * 8 + 4);
+    if (threadIdx.x < 4) whdr[(size_t)b * 8 + threadIdx.x] = g_lo | (g_hi << 16);
+    if (threadIdx.x == 0) {
+      whdr[(size_t)b * 8 + 4] = 0;
+      whdr[(size_t)b * 8 + 5] = n_live;
+      whdr[(size_t)b * 8 + 6] = s_tot;
+      whdr[(size_t)b * 8 + 7] = 0;
+      const uint32_t words = n_live ? n_live + 1 + s_tot : 0;
+      region_words[b] = words;
+      if (words) atomicAdd(total_words, (unsigned long long)words);
+    }
+  }
+}
+
+// Pass B: fill.  Thread t owns the non-OUT voxels of rank t, t+128, ... of its block.
+__global__ void __launch_bounds__(CLS_THREADS) k1w_fill(const uint32_t* __restrict__ block_cell, const uint32_t* __restrict__ cell_start,
+                                                        const float4* __restrict__ pts, GridParams g, const uint32_t* __restrict__ codes,
+                                                        const uint16_t* __restrict__ wcnt, uint32_t* __restrict__ whdr,
+                                                        const uint32_t* __restrict__ region_base, uint32_t* __restrict__ wlists) {
+  __shared__ float4 s_p[CLS_CHUNK];
+  __shared__ uint16_t s_av[F * F * F];
+  __shared__ uint32_t s_off[F * F * F + 1];
+  const int b = blockIdx.x;
+  const uint32_t n_live = whdr[(size_t)b * 8 + 5];
+  if (threadIdx.x == 0) whdr[(size_t)b * 8 + 4] = region_base[b];
+  if (n_live == 0) return;
+  const uint32_t base_w = region_base[b];
+  const uint32_t c = block_cell[b];
+  const int cx = (int)(c % g.dim[0]), cy = (int)((c / g.dim[0]) % g.dim[1]), cz = (int)(c / ((uint32_t)g.dim[0] * g.dim[1]));
+  const float hs = 0.5f * g.hf + g.inflate;
+  if (threadIdx.x < 32) {
+    const uint32_t w = nonout_mask(codes[(size_t)b * 32 + threadIdx.x]);
+    uint32_t k = __popc(w), incl = k;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += t; }
+    uint32_t r = incl - k, ww = w;
+    while (ww) { int bit = __ffs(ww) - 1; ww &= ww - 1; s_av[r++] = (uint16_t)(threadIdx.x * 16 + (bit >> 1)); }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t run = n_live + 1;
+    for (uint32_t r0 = 0; r0 < n_live; r0 += 32) {
+      const uint32_t r = r0 + threadIdx.x;
+      uint32_t k = r < n_live ? wcnt[(size_t)b * 512 + s_av[r]] : 0u, incl = k;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += t; }
+      if (r < n_live) s_off[r] = run + incl - k;
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (threadIdx.x == 0) s_off[n_live] = run;
+  }
+  __syncthreads();
+  for (uint32_t r = threadIdx.x; r <= n_live; r += CLS_THREADS) wlists[base_w + r] = s_off[r];
+  float vx[4], vy[4], vz[4], u2[4], thr[4];
+  uint32_t wr[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t r = threadIdx.x + CLS_THREADS * j;
+    const int v = r < n_live ? s_av[r] : 0;
+    vx[j] = __fmaf_rn((float)(cx * F + (v & 7)) + 0.5f, g.hf, g.lo[0]);
+    vy[j] = __fmaf_rn((float)(cy * F + ((v >> 3) & 7)) + 0.5f, g.hf, g.lo[1]);
+    vz[j] = __fmaf_rn((float)(cz * F + (v >> 6)) + 0.5f, g.hf, g.lo[2]);
+    u2[j] = INFINITY;
+    wr[j] = r < n_live ? base_w + s_off[r] : 0xffffffffu;
+  }
+  sweep27(cell_start, pts, g, cx, cy, cz, s_p, [&](const float4 p, uint32_t) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { float lo2, hi2; box_d2(p, vx[j], vy[j], vz[j], hs, lo2, hi2); u2[j] = fminf(u2[j], hi2); }
+  });
+#pragma unroll
+  for (int j = 0; j < 4; ++j) thr[j] = wlist_threshold(u2[j], g.dhi2);
+  sweep27(cell_start, pts, g, cx, cy, cz, s_p, [&](const float4 p, uint32_t pos) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (wr[j] != 0xffffffffu) {
+        float lo2, hi2;
+        box_d2(p, vx[j], vy[j], vz[j], hs, lo2, hi2);
+        if (lo2 <= thr[j]) wlists[wr[j]++] = pos;
+      }
+    }
+  });
+}
+
 }  // namespace
 
 int k1_build_fine(pgp_ctx* ctx) {
@@ -216,6 +394,7 @@ int k1_build_fine(pgp_ctx* ctx) {
   cudaStream_t st = ctx->stream;
   const int64_t nw = s.bitmap_words;
   g.fine = 0; g.n_blocks = 0;
+  s.wlists_ready = false; s.wlists_tried = false;
   // rank structure over the dilated-occupancy bitmap
   PGP_CUDA(ctx, s.bmrank.reserve((size_t)nw * 8 + 16));
   PGP_CUDA(ctx, s.cursor.reserve((size_t)(nw + 1) * 4));
@@ -284,5 +463,49 @@ int k1_build_fine(pgp_ctx* ctx) {
   PGP_CUDA(ctx, cudaGetLastError());
   g.n_blocks = (int)nb;
   g.fine = F;
+  return PGP_OK;
+}
+
+// K1c driver: built lazily by the first WEIGHTED scoring call on a scene (k3_score).
+// Leaves scene.wlists_ready false (scoring keeps the 27-cell search) when the lists would not fit.
+int k1_build_wlists(pgp_ctx* ctx) {
+  Scene& s = ctx->scene;
+  const GridParams& g = s.g;
+  s.wlists_ready = false;
+  s.wlists_tried = true;
+  if (g.fine != F || g.n_blocks <= 0) return PGP_OK;
+  cudaStream_t st = ctx->stream;
+  const uint32_t nb = (uint32_t)g.n_blocks;
+  PGP_CUDA(ctx, s.near_cnt.reserve((size_t)nb * 512 * 2));
+  PGP_CUDA(ctx, s.whdr.reserve((size_t)nb * 32));
+  PGP_CUDA(ctx, s.region.reserve((size_t)(nb + 1) * 4));
+  PGP_CUDA(ctx, s.scratch.reserve((size_t)((nb + 1) / 2048 + 4096) * 4));
+  uint32_t* region = s.region.as<uint32_t>();
+  unsigned long long* d_total = reinterpret_cast<unsigned long long*>(ctx->work.as<char>() + 192);
+  int* d_over = ctx->work.as<int>() + 40;
+  PGP_CUDA(ctx, cudaMemsetAsync(region, 0, (size_t)(nb + 1) * 4, st));
+  PGP_CUDA(ctx, cudaMemsetAsync(d_total, 0, 8, st));
+  PGP_CUDA(ctx, cudaMemsetAsync(d_over, 0, 4, st));
+  k1w_count<<<nb, CLS_THREADS, 0, st>>>(s.block_cell.as<uint32_t>(), s.cell_start.as<uint32_t>(), s.pts.as<float4>(), g, s.codes.as<uint32_t>(),
+                                        s.near_cnt.as<uint16_t>(), s.whdr.as<uint32_t>(), region, d_total, d_over);
+  ctx->launches++;
+  unsigned long long total = 0;
+  int overflow = 0;
+  PGP_CUDA(ctx, cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
+  PGP_CUDA(ctx, cudaMemcpyAsync(&overflow, d_over, 4, cudaMemcpyDeviceToHost, st));
+  PGP_CUDA(ctx, cudaStreamSynchronize(st));
+  if (overflow || total >= (1ull << 32) - 64) return PGP_OK;      // 32-bit word offsets
+  size_t free_b = 0, total_b = 0;
+  PGP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+  if ((size_t)total * 4 + (64u << 20) > free_b + s.wlists.cap) return PGP_OK;
+  int rc = pgp_scan_exclusive_u32(ctx, region, (int64_t)nb + 1, s.scratch.as<uint32_t>());
+  if (rc) return rc;
+  PGP_CUDA(ctx, s.wlists.reserve((size_t)total * 4 + 16));
+  k1w_fill<<<nb, CLS_THREADS, 0, st>>>(s.block_cell.as<uint32_t>(), s.cell_start.as<uint32_t>(), s.pts.as<float4>(), g, s.codes.as<uint32_t>(),
+                                       s.near_cnt.as<uint16_t>(), s.whdr.as<uint32_t>(), region, s.wlists.as<uint32_t>());
+  ctx->launches++;
+  PGP_CUDA(ctx, cudaGetLastError());
+  s.n_wlist_words = (int64_t)total;
+  s.wlists_ready = true;
   return PGP_OK;
 }

@@ -50,6 +50,8 @@ struct LcpParams {
   const uint4* hdr;          // n_blocks x 2 uint4: {u16 ambig-rank prefix per 64-voxel group x 8}, {list region base, #ambig, #ids, 0}
   const uint32_t* lists;     // candidate ids of the AMBIG voxels (K1b pass B)
   float model_rinf;          // max |coordinate| of the validation model (bounds the transform's intermediates)
+  const uint4* whdr;         // K1c: like hdr, ranking the non-OUT voxels
+  const uint32_t* wlists;    // K1c: nearest-neighbour candidate ids of every non-OUT voxel
 };
 
 // ---- mbarrier + TMA bulk copy (global -> shared), sm_90+/sm_100a PTX ---------------------------
@@ -296,6 +298,7 @@ constexpr int FQCAP = 32 + 32 * FUNROLL;   // queue slots per warp: < 32 left ov
 
 struct FineCtx {
   const float4* s_model;
+  const float4* s_nrm;       // weighted mode only
   const uint2* table;        // bmrank: shared (SMEM_TABLE) or global
   uint16_t* q;
   int dimx, dimy;
@@ -326,27 +329,42 @@ __device__ __forceinline__ uint32_t label_slot(const LcpParams& p, const FineCtx
   return (wr.x & bit) ? blk * 32u + (uint32_t)(v >> 4) : f.dummy_word;
 }
 
-// phase 2 for one queued query: the reference's exact test against the voxel's candidate list
-template <bool SMEM_TABLE>
-__device__ __forceinline__ int resolve_ambiguous(const LcpParams& p, const FineCtx& f, const Xf& x, const float4 m, int ix, int iy, int iz) {
+// Candidate list of the voxel a queued query fell into: [s0, s1) word offsets into the block's region `reg`.
+// NONOUT = false: AMBIG lists of K1b (hdr / lists);  true: nearest-candidate lists of K1c (whdr / wlists).
+template <bool SMEM_TABLE, bool NONOUT>
+__device__ __forceinline__ const uint32_t* list_range(const LcpParams& p, const FineCtx& f, int ix, int iy, int iz, uint32_t& s0, uint32_t& s1) {
   const int c = ((iz >> 3) * f.dimy + (iy >> 3)) * f.dimx + (ix >> 3);
   const uint2 wr = table_word<SMEM_TABLE>(f, c >> 5);
   const unsigned blk = wr.y + __popc(wr.x & ((1u << (c & 31)) - 1u));
   const int v = ((iz & 7) << 6) | ((iy & 7) << 3) | (ix & 7);
-  const uint4 gp = __ldg(p.hdr + (size_t)blk * 2);
-  const uint4 h1 = __ldg(p.hdr + (size_t)blk * 2 + 1);
-  const uint4 grp = __ldg(reinterpret_cast<const uint4*>(p.codes) + (size_t)blk * 8 + (v >> 6));
-  float tx, ty, tz;
-  apply_xf(x, m, tx, ty, tz);
+  const uint4* hdr = NONOUT ? p.whdr : p.hdr;
+  const uint4 gp = __ldg(hdr + (size_t)blk * 2);
+  const uint4 h1 = __ldg(hdr + (size_t)blk * 2 + 1);
+  uint4 grp = __ldg(reinterpret_cast<const uint4*>(p.codes) + (size_t)blk * 8 + (v >> 6));
+  if (NONOUT) {
+    grp.x = (grp.x | (grp.x >> 1)) & 0x55555555u; grp.y = (grp.y | (grp.y >> 1)) & 0x55555555u;
+    grp.z = (grp.z | (grp.z >> 1)) & 0x55555555u; grp.w = (grp.w | (grp.w >> 1)) & 0x55555555u;
+  } else {
+    grp.x &= 0xAAAAAAAAu; grp.y &= 0xAAAAAAAAu; grp.z &= 0xAAAAAAAAu; grp.w &= 0xAAAAAAAAu;
+  }
   const int g8 = v >> 6, wi = (v >> 4) & 3;
   const uint32_t gw = g8 < 2 ? gp.x : g8 < 4 ? gp.y : g8 < 6 ? gp.z : gp.w;
   uint32_t r = (gw >> ((g8 & 1) * 16)) & 0xffffu;
-  const uint32_t A = 0xAAAAAAAAu;
-  r += (wi > 0 ? __popc(grp.x & A) : 0) + (wi > 1 ? __popc(grp.y & A) : 0) + (wi > 2 ? __popc(grp.z & A) : 0);
+  r += (wi > 0 ? __popc(grp.x) : 0) + (wi > 1 ? __popc(grp.y) : 0) + (wi > 2 ? __popc(grp.z) : 0);
   const uint32_t word = wi == 0 ? grp.x : wi == 1 ? grp.y : wi == 2 ? grp.z : grp.w;
-  r += __popc(word & A & ((1u << ((v & 15) * 2)) - 1u));
-  const uint32_t* reg = p.lists + h1.x;
-  const uint32_t s0 = __ldg(reg + r), s1 = __ldg(reg + r + 1);
+  r += __popc(word & ((1u << ((v & 15) * 2)) - 1u));
+  const uint32_t* reg = (NONOUT ? p.wlists : p.lists) + h1.x;
+  s0 = __ldg(reg + r); s1 = __ldg(reg + r + 1);
+  return reg;
+}
+
+// phase 2 for one queued query: the reference's exact test against the voxel's candidate list
+template <bool SMEM_TABLE>
+__device__ __forceinline__ int resolve_ambiguous(const LcpParams& p, const FineCtx& f, const Xf& x, const float4 m, int ix, int iy, int iz) {
+  uint32_t s0, s1;
+  const uint32_t* reg = list_range<SMEM_TABLE, false>(p, f, ix, iy, iz, s0, s1);
+  float tx, ty, tz;
+  apply_xf(x, m, tx, ty, tz);
   const float r2 = p.g.r2;
   for (uint32_t j = s0; j < s1; ++j) {
     const float4 sp = __ldg(p.pts + __ldg(reg + j));
@@ -355,11 +373,41 @@ __device__ __forceinline__ int resolve_ambiguous(const LcpParams& p, const FineC
   return 0;
 }
 
+// nearest in-range scene point among the voxel's K1c candidates (same acceptance / tie rule as
+// nearest_within): sorted position or -1
+__device__ __forceinline__ int nearest_in_list(const LcpParams& p, const uint32_t* __restrict__ reg, uint32_t s0, uint32_t s1, float tx, float ty,
+                                               float tz) {
+  float best = p.g.r2;
+  int best_pos = -1, best_orig = 0x7fffffff;
+  for (uint32_t j = s0; j < s1; ++j) {
+    const uint32_t pos = __ldg(reg + j);
+    const float4 sp = __ldg(p.pts + pos);
+    const float d2 = sqdist3(tx, ty, tz, sp.x, sp.y, sp.z);
+    const int orig = __float_as_int(sp.w);
+    if (d2 < best || (d2 == best && (best_pos < 0 || orig < best_orig))) { best = d2; best_pos = (int)pos; best_orig = orig; }
+  }
+  return best_pos;
+}
+
+// phase 2 of the weighted mode: nearest in-range point, then the normal gate.  0x10001: gated and prior == 1, 0x1: gated
+template <bool SMEM_TABLE>
+__device__ __forceinline__ int resolve_nearest(const LcpParams& p, const FineCtx& f, const Xf& x, const float4 m, const float4 nm, int ix, int iy, int iz) {
+  uint32_t s0, s1;
+  const uint32_t* reg = list_range<SMEM_TABLE, true>(p, f, ix, iy, iz, s0, s1);
+  float tx, ty, tz;
+  apply_xf(x, m, tx, ty, tz);
+  const int pos = nearest_in_list(p, reg, s0, s1, tx, ty, tz);
+  if (pos < 0) return 0;
+  const float4 ns = __ldg(p.aux + pos);
+  if (!normal_gate(x, nm, ns)) return 0;
+  return (ns.w != 0.f) ? 0x10001 : 0x1;
+}
+
 // one hypothesis, all model points of the staged tile (tn_pad = tile size rounded up to 64; the pad
 // slots hold NaN points, which convert to voxel 0 and fail the range test).
 // FAST: voxel coordinates from the pre-scaled FMA transform a[]; otherwise the reference's
 // rounding sequence followed by the grid's own cell_coord (huge / non-finite matrices).
-template <bool SMEM_TABLE, bool FAST>
+template <bool SMEM_TABLE, bool FAST, int MODE>
 __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCtx& f, const float* __restrict__ T, long long h, int tn_pad) {
   const Xf x = load_xf(T, h);
   float a[12];
@@ -391,7 +439,8 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
       int ix, iy, iz;
       voxel_of(m, ix, iy, iz);                      // same arithmetic as phase 1 -> same voxel
       const Xf xe = FAST ? load_xf(T, h) : x;       // FAST keeps only a[] live across the loop; the exact matrix is re-read (L1)
-      good += resolve_ambiguous<SMEM_TABLE>(p, f, xe, m, ix, iy, iz);
+      if (MODE == 0) good += resolve_ambiguous<SMEM_TABLE>(p, f, xe, m, ix, iy, iz);
+      else good += resolve_nearest<SMEM_TABLE>(p, f, xe, m, f.s_nrm[i], ix, iy, iz);
     }
     qn -= take;
   };
@@ -410,7 +459,11 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
 #pragma unroll
     for (int u = 0; u < FUNROLL; ++u) {
       code[u] = (code[u] >> sh[u]) & 3u;
-      good += (code[u] == 1u);
+      if (MODE == 0) {
+        good += (code[u] == 1u);
+      } else {
+        code[u] = code[u] ? 2u : 0u;       // weighted: IN voxels need the nearest point's identity too
+      }
       any |= (code[u] == 2u);
     }
     if (__any_sync(0xffffffffu, any)) {
@@ -428,16 +481,18 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
   return __reduce_add_sync(0xffffffffu, good);
 }
 
-template <bool SMEM_TABLE>
-__global__ void __launch_bounds__(FTHREADS, 1) k3_count_fine_kernel(const __grid_constant__ LcpParams p) {
+template <bool SMEM_TABLE, int MODE>   // MODE 0 = count (Verify), 1 = weighted with binary priors (WeightedVerify)
+__global__ void __launch_bounds__(FTHREADS, 1) k3_fine_kernel(const __grid_constant__ LcpParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t mbar;
   float4* s_model = reinterpret_cast<float4*>(smem);
-  uint2* s_bmrank = reinterpret_cast<uint2*>(smem + (size_t)p.tile_cap * 16);
+  float4* s_nrm = s_model + p.tile_cap;                                   // only MODE 1
+  uint2* s_bmrank = reinterpret_cast<uint2*>(smem + (size_t)p.tile_cap * 16 * (MODE == 1 ? 2 : 1));
   uint16_t* s_queue = reinterpret_cast<uint16_t*>(s_bmrank + p.bmrank_words);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   FineCtx f;
   f.s_model = s_model;
+  f.s_nrm = s_nrm;
   f.table = SMEM_TABLE ? s_bmrank : p.bmrank;
   f.q = s_queue + warp * FQCAP;
   f.dimx = p.g.dim[0]; f.dimy = p.g.dim[1];
@@ -455,8 +510,9 @@ __global__ void __launch_bounds__(FTHREADS, 1) k3_count_fine_kernel(const __grid
     if (threadIdx.x == 0) {
       uint32_t bytes = (uint32_t)tn * 16u;
       uint32_t bm = (SMEM_TABLE && tile == 0) ? (uint32_t)p.bmrank_words * 8u : 0u;
-      mbar_expect_tx(&mbar, bytes + bm);
+      mbar_expect_tx(&mbar, bytes * (MODE == 1 ? 2u : 1u) + bm);
       tma_bulk_g2s(s_model, p.model + t0, bytes, &mbar);
+      if (MODE == 1) tma_bulk_g2s(s_nrm, p.model_nrm + t0, bytes, &mbar);
       if (bm) tma_bulk_g2s(s_bmrank, p.bmrank, bm, &mbar);
     }
     // pad slots: NaN points (their voxel converts to 0 and fails the range test); disjoint from the bulk copy's bytes
@@ -478,13 +534,24 @@ __global__ void __launch_bounds__(FTHREADS, 1) k3_count_fine_kernel(const __grid
           bound = fmaxf(bound, (fabsf(x.m[4 * r]) + fabsf(x.m[4 * r + 1]) + fabsf(x.m[4 * r + 2])) * p.model_rinf + fabsf(x.m[4 * r + 3]));
       }
       const bool fast = bound <= p.g.pos_bound;     // false for NaN / huge matrices: those take the reference's arithmetic
-      const int tot = fast ? score_hypothesis<SMEM_TABLE, true>(p, f, p.T, h, tn_pad) : score_hypothesis<SMEM_TABLE, false>(p, f, p.T, h, tn_pad);
+      const int tot = fast ? score_hypothesis<SMEM_TABLE, true, MODE>(p, f, p.T, h, tn_pad) : score_hypothesis<SMEM_TABLE, false, MODE>(p, f, p.T, h, tn_pad);
       if (lane == 0) {
-        if (p.n_tiles == 1) {
-          p.counts[h] = (uint32_t)tot;
-          if (p.scores) p.scores[h] = __fdiv_rn((float)tot, (float)p.nv);
-        } else if (tot) {
-          atomicAdd(p.counts + h, (uint32_t)tot);
+        if (MODE == 0) {
+          if (p.n_tiles == 1) {
+            p.counts[h] = (uint32_t)tot;
+            if (p.scores) p.scores[h] = __fdiv_rn((float)tot, (float)p.nv);
+          } else if (tot) {
+            atomicAdd(p.counts + h, (uint32_t)tot);
+          }
+        } else {
+          const uint32_t gated = (uint32_t)tot & 0xffffu, w = (uint32_t)tot >> 16;   // tile <= 8192 points keeps the halves apart
+          if (p.n_tiles == 1) {
+            p.counts[h] = gated;
+            if (p.scores) p.scores[h] = __fdiv_rn((float)w, (float)p.nv);           // weighted_match / Scalar(n) :1765
+          } else {
+            if (gated) atomicAdd(p.counts + h, gated);
+            if (w && p.scores) atomicAdd(reinterpret_cast<uint32_t*>(p.scores) + h, w);   // integer until k3_finalise
+          }
         }
       }
     }
@@ -505,11 +572,17 @@ __global__ void k3_finalise(const uint32_t* __restrict__ counts, float* __restri
 // formed in exactly that order: per 32-point step the lanes' contributions are folded in lane order.
 // One warp per hypothesis, model read from global in ORIGINAL order.  Also the kernel behind
 // pgp_registered_points / pgp_nearest_in_range (idx_out != nullptr, one hypothesis).
+template <bool LISTS>   // LISTS: OUT label cull + K1c candidate lists instead of the 27-cell search
 __global__ void __launch_bounds__(256) k3_weighted_ordered(const LcpParams p, int32_t* __restrict__ idx_out, int gate) {
   const int lane = threadIdx.x & 31;
   const long long h = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (h >= p.n) return;
   const Xf x = load_xf(p.T, h);
+  FineCtx f;
+  f.table = p.bmrank;
+  f.dimx = p.g.dim[0]; f.dimy = p.g.dim[1];
+  f.rx = (unsigned)(p.g.dim[0] - 2) * 8u; f.ry = (unsigned)(p.g.dim[1] - 2) * 8u; f.rz = (unsigned)(p.g.dim[2] - 2) * 8u;
+  f.dummy_word = (uint32_t)p.g.n_blocks * 32u;
   float acc = 0.f;
   int gated = 0;
   for (int base = 0; base < p.nv; base += 32) {
@@ -521,7 +594,24 @@ __global__ void __launch_bounds__(256) k3_weighted_ordered(const LcpParams p, in
       float tx, ty, tz;
       int cx, cy, cz;
       apply_xf(x, __ldg(p.model + i), tx, ty, tz);
-      if (query_cell(p.g, tx, ty, tz, cx, cy, cz)) {
+      if (LISTS) {
+        // the reference's own rounding sequence, then the grid's cell_coord: exactly the non-FAST voxel of the fine kernel
+        const int ix = __float2int_rz(cell_coord(tx, p.g.lo[0], p.g.inv_hf)), iy = __float2int_rz(cell_coord(ty, p.g.lo[1], p.g.inv_hf)),
+                  iz = __float2int_rz(cell_coord(tz, p.g.lo[2], p.g.inv_hf));
+        uint32_t sh;
+        const uint32_t off = label_slot<false>(p, f, ix, iy, iz, sh);
+        if ((__ldg(p.codes + off) >> sh) & 3u) {
+          uint32_t s0, s1;
+          const uint32_t* reg = list_range<false, true>(p, f, ix, iy, iz, s0, s1);
+          const int pos = nearest_in_list(p, reg, s0, s1, tx, ty, tz);
+          if (pos >= 0) {
+            float4 ns = __ldg(p.aux + pos);
+            if (!gate || normal_gate(x, __ldg(p.model_nrm + i), ns)) {
+              hit = true; w = ns.w; orig = __float_as_int(__ldg(p.pts + pos).w);
+            }
+          }
+        }
+      } else if (query_cell(p.g, tx, ty, tz, cx, cy, cz)) {
         int pos = nearest_within(p, tx, ty, tz, cx, cy, cz);
         if (pos >= 0) {
           float4 ns = __ldg(p.aux + pos);
@@ -562,7 +652,7 @@ static LcpParams make_params(pgp_ctx* ctx, const Model& m, const float* T, int64
 
 int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mode, uint32_t* counts_dev, float* scores_dev) {
   if (n == 0) return PGP_OK;
-  const Scene& s = ctx->scene;
+  Scene& s = ctx->scene;
   LcpParams p = make_params(ctx, m, T_dev, n, counts_dev, scores_dev);
   cudaStream_t st = ctx->stream;
 
@@ -570,7 +660,14 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     p.model = m.val_orig.as<float4>(); p.model_nrm = m.val_nrm_orig.as<float4>();
     const int T = 256;
     long long blocks = (n * 32 + T - 1) / T;
-    k3_weighted_ordered<<<(unsigned)blocks, T, 0, st>>>(p, nullptr, 1);
+    if (s.g.fine == 8 && !ctx->force_coarse && !s.wlists_tried) { int rc = k1_build_wlists(ctx); if (rc) return rc; }
+    if (s.g.fine == 8 && !ctx->force_coarse && s.wlists_ready) {
+      p.bmrank = s.bmrank.as<uint2>(); p.codes = s.codes.as<uint32_t>();
+      p.whdr = s.whdr.as<uint4>(); p.wlists = s.wlists.as<uint32_t>();
+      k3_weighted_ordered<true><<<(unsigned)blocks, T, 0, st>>>(p, nullptr, 1);
+    } else {
+      k3_weighted_ordered<false><<<(unsigned)blocks, T, 0, st>>>(p, nullptr, 1);
+    }
     ctx->launches++;
     PGP_CUDA(ctx, cudaGetLastError());
     return PGP_OK;
@@ -580,30 +677,42 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
   PGP_CUDA(ctx, ctx->work.reserve(4096));
   p.work = reinterpret_cast<unsigned long long*>(ctx->work.as<char>() + 1024);
 
-  if (mode == PGP_LCP_COUNT && s.g.fine == 8 && !ctx->force_coarse) {
+  if (mode == PGP_LCP_WEIGHTED && s.g.fine == 8 && !ctx->force_coarse && !s.wlists_tried) {
+    int rc = k1_build_wlists(ctx);      // K1c, once per scene, on the first weighted call
+    if (rc) return rc;
+  }
+  const bool fine_ok = s.g.fine == 8 && !ctx->force_coarse && (mode == PGP_LCP_COUNT || s.wlists_ready);
+  if (fine_ok) {
+    const int per_pt = mode == PGP_LCP_WEIGHTED ? 32 : 16;
     const size_t smem_max = 200 * 1024, qb = (size_t)FWARPS * FQCAP * 2;
     size_t bm = (size_t)s.bitmap_words * 8;
     int tile_cap = std::min((m.nv + 127) & ~127, 8192);
-    if (bm + qb + (size_t)std::min(tile_cap, 2048) * 16 > smem_max) bm = 0;          // table too big for smem: read it through L1
-    if ((size_t)tile_cap * 16 + bm + qb > smem_max) tile_cap = (int)((smem_max - bm - qb) / 16) & ~127;
+    if (bm + qb + (size_t)std::min(tile_cap, 2048) * per_pt > smem_max) bm = 0;          // table too big for smem: read it through L1
+    if ((size_t)tile_cap * per_pt + bm + qb > smem_max) tile_cap = (int)((smem_max - bm - qb) / per_pt) & ~127;
     p.tile_cap = tile_cap;
     p.n_tiles = (m.nv + tile_cap - 1) / tile_cap;
     if (p.n_tiles > 256) return pgp_fail(ctx, PGP_E_INVALID, "validation model too large (%d points)", m.nv);
     p.bmrank = s.bmrank.as<uint2>(); p.codes = s.codes.as<uint32_t>();
     p.hdr = s.hdr.as<uint4>(); p.lists = s.lists.as<uint32_t>();
+    p.whdr = s.whdr.as<uint4>(); p.wlists = s.wlists.as<uint32_t>();
     p.bmrank_words = (int)(bm / 8);
     p.model_rinf = m.val_rinf;
-    const size_t smem = (size_t)tile_cap * 16 + bm + qb;
+    const size_t smem = (size_t)tile_cap * per_pt + bm + qb;
     PGP_CUDA(ctx, cudaMemsetAsync(p.work, 0, 8 * (size_t)p.n_tiles, st));
-    if (p.n_tiles > 1) PGP_CUDA(ctx, cudaMemsetAsync(counts_dev, 0, (size_t)n * 4, st));
-    int grid = (int)std::min<long long>((n + FWARPS - 1) / FWARPS, ctx->sm_count);
-    if (bm) {
-      PGP_CUDA(ctx, cudaFuncSetAttribute(k3_count_fine_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k3_count_fine_kernel<true><<<grid, FTHREADS, smem, st>>>(p);
-    } else {
-      PGP_CUDA(ctx, cudaFuncSetAttribute(k3_count_fine_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      k3_count_fine_kernel<false><<<grid, FTHREADS, smem, st>>>(p);
+    if (p.n_tiles > 1) {
+      PGP_CUDA(ctx, cudaMemsetAsync(counts_dev, 0, (size_t)n * 4, st));
+      if (mode == PGP_LCP_WEIGHTED && scores_dev) PGP_CUDA(ctx, cudaMemsetAsync(scores_dev, 0, (size_t)n * 4, st));
     }
+    int grid = (int)std::min<long long>((n + FWARPS - 1) / FWARPS, ctx->sm_count);
+    auto launch = [&](auto kern) -> int {
+      PGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, FTHREADS, smem, st>>>(p);
+      return PGP_OK;
+    };
+    int rc;
+    if (mode == PGP_LCP_COUNT) rc = bm ? launch(k3_fine_kernel<true, 0>) : launch(k3_fine_kernel<false, 0>);
+    else rc = bm ? launch(k3_fine_kernel<true, 1>) : launch(k3_fine_kernel<false, 1>);
+    if (rc) return rc;
     ctx->launches++;
     if (p.n_tiles > 1 && scores_dev) {
       k3_finalise<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(counts_dev, scores_dev, n, m.nv, mode);
@@ -662,7 +771,7 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
 int k3_nearest(pgp_ctx* ctx, const Model& m, const float* T_dev, int32_t* idx_dev, int gate) {
   LcpParams p = make_params(ctx, m, T_dev, 1, nullptr, nullptr);
   p.model = m.val_orig.as<float4>(); p.model_nrm = m.val_nrm_orig.as<float4>();
-  k3_weighted_ordered<<<1, 32, 0, ctx->stream>>>(p, idx_dev, gate);
+  k3_weighted_ordered<false><<<1, 32, 0, ctx->stream>>>(p, idx_dev, gate);
   ctx->launches++;
   PGP_CUDA(ctx, cudaGetLastError());
   return PGP_OK;

@@ -74,6 +74,10 @@ struct Scene {
   DevBuf region;       // build scratch: region sizes / bases
   DevBuf lists;        // per-block regions: offsets + candidate ids of the AMBIG voxels
   int64_t n_list_words = 0;
+  DevBuf whdr;         // K1c: n_blocks x 8 u32, like hdr but ranking the non-OUT voxels
+  DevBuf wlists;       // K1c: per-block regions [offsets][ids]: nearest-neighbour candidates of every non-OUT voxel
+  int64_t n_wlist_words = 0;
+  bool wlists_ready = false, wlists_tried = false;
   DevBuf prior;        // n x f32 in ORIGINAL order
   DevBuf scratch;      // scan scratch etc.
   int64_t n_occupied = 0;
@@ -150,6 +154,7 @@ int k1_project_priors(pgp_ctx* ctx, const uint16_t* img_dev, int rows, int cols,
 int k1_refresh_sorted_priors(pgp_ctx* ctx);
 int k1_fill_priors(pgp_ctx* ctx, float v);
 int k1_build_fine(pgp_ctx* ctx);
+int k1_build_wlists(pgp_ctx* ctx);
 int pgp_scan_exclusive_u32(pgp_ctx* ctx, uint32_t* data, int64_t n, uint32_t* scratch);
 // k3_lcp.cu
 int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mode, uint32_t* counts_dev, float* scores_dev);

@@ -106,3 +106,52 @@ def test_fine_grid_equals_coarse_path_and_oracle(engine, port_lib):
         engine.set_option("force_coarse", 0)
     assert np.array_equal(coarse, want)
     assert np.array_equal(fine, want)
+
+
+def test_weighted_lists_equal_coarse_path_and_oracle(engine, port_lib):
+    """WeightedVerify on the K1c nearest-candidate lists (OUT cull + per-voxel lists) must pick the same nearest
+    scene point as the 27-cell search and as the oracle's kd-tree: same gated counts, same scores -- with binary
+    priors (integer sums, fast kernel) and with general priors (ordered fp32 sums)."""
+    prob = synth.make_problem(800, 30000, 0.01, seed=31)
+    T = synth.make_hypotheses(prob, 2000, seed=32).copy()
+    rng = np.random.default_rng(1)
+    T[5] = 0.0
+    T[6] = T[1] * 1e4
+    T[7, 0, 0] = np.nan
+    T[8, :, 3] = np.inf
+    T[9] = rng.normal(size=(3, 4)).astype(np.float32)
+    T[10, :, :3] *= 1.5
+    _setup(engine, prob)
+    o = _oracle(port_lib, prob)
+    ws, wn = o.weighted_verify(T)
+    counts, scores = engine.score_lcp(0, T, "weighted")
+    engine.set_option("force_coarse", 1)
+    try:
+        c2, s2 = engine.score_lcp(0, T, "weighted")
+    finally:
+        engine.set_option("force_coarse", 0)
+    assert np.array_equal(c2, wn.astype(np.uint32)) and np.array_equal(s2, ws)
+    assert np.array_equal(counts, wn.astype(np.uint32)) and np.array_equal(scores, ws)
+    # general priors: the ordered kernel on the lists
+    img = rng.integers(0, 10001, size=(480, 640)).astype(np.uint16)
+    K = np.array([[600.0, 0, 320], [0, 600.0, 240], [0, 0, 1]], np.float32)
+    o2 = _oracle(port_lib, prob, K=K, prior_img=img)
+    engine.set_scene_prior_image(img, K)
+    ws, wn = o2.weighted_verify(T[:300])
+    counts, scores = engine.score_lcp(0, T[:300], "weighted")
+    assert np.array_equal(counts, wn.astype(np.uint32)) and np.array_equal(scores, ws)
+
+
+def test_multi_tile_model(engine, port_lib):
+    """A validation model larger than one shared-memory tile (8192 points): partial sums are combined with atomics."""
+    prob = synth.make_problem(9000, 20000, 0.01, seed=41)
+    T = synth.make_hypotheses(prob, 96, seed=42)
+    _setup(engine, prob)
+    o = _oracle(port_lib, prob)
+    want = o.verify(T)
+    counts, scores = engine.score_lcp(0, T, "count")
+    assert np.array_equal(counts, want)
+    assert np.array_equal(scores, want.astype(np.float32) / np.float32(9000))
+    ws, wn = o.weighted_verify(T)
+    counts, scores = engine.score_lcp(0, T, "weighted")
+    assert np.array_equal(counts, wn.astype(np.uint32)) and np.array_equal(scores, ws)

@@ -17,7 +17,7 @@ want = o.verify(T[:nchk])
 c, s = e.score_lcp(0, T, 'count')
 print('mismatch', int((c[:nchk] != want).sum()), c[:8], want[:8])
 Td = torch.from_numpy(T.reshape(-1,12)).cuda(); cd = torch.zeros(len(T), dtype=torch.int32, device='cuda'); sd = torch.zeros(len(T), device='cuda')
-for mode, fc in (('count',0),('count',1),('weighted',0)):
+for mode, fc in (('count',0),('count',1),('weighted',0),('weighted',1)):
     e.set_option('force_coarse', fc)
     for it in range(3):
         a=torch.cuda.Event(enable_timing=True); b=torch.cuda.Event(enable_timing=True)

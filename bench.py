@@ -150,6 +150,51 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------ GPU
+def secondary_metrics(eng, prob, T_dev, counts_dev, scores_dev, flush, stream) -> dict:
+    """SURVEY.md 8(d) secondary figures, measured after the headline (N = 1 only, outside its timed region):
+    WeightedVerify throughput on the same workload, scene-grid build time, PCS hypotheses generated/s and
+    TrICP poses refined/s on a test-scene-sized object request.  Device-timed with CUDA events."""
+    import torch
+    from physimglobalpose_b200 import synth
+
+    def timed(fn, reps=5, pre=None):
+        out = []
+        for _ in range(reps):
+            if pre:
+                pre()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); fn(); b.record(stream)
+            torch.cuda.synchronize()
+            out.append(a.elapsed_time(b))
+        return statistics.median(out)
+
+    sec = {}
+    eng.score_lcp_device(0, T_dev, counts_dev, scores_dev, "weighted")     # builds the K1c lists once
+    ms = timed(lambda: eng.score_lcp_device(0, T_dev, counts_dev, scores_dev, "weighted"), pre=flush.zero_)
+    sec["weighted_lcp"] = {"value": N_HYP / ms * 1e3, "unit": UNIT, "kernel_ms": ms, "mode": "WeightedVerify, binary priors, same workload"}
+    ms = timed(lambda: eng.set_scene(prob.scene_xyz, prob.scene_nrm, prob.delta), reps=3)
+    sec["scene_grid_build_ms"] = {"value": ms, "unit": "ms", "what": "pgp_set_scene: H2D of 100k points + K1 grid + K1b labels/lists"}
+    seg = synth.make_segment_problem(2000, 2000, 0.005, seed=5)
+    eng.set_scene(seg.scene_xyz, seg.scene_nrm, seg.delta)
+    eng.set_model(1, seg.model_xyz, seg.model_nrm)
+    n_gen = [0]
+    def gen():
+        n_gen[0] = eng.generate_pcs(1, seed=3, max_hyp=20000)
+    ms = timed(gen, reps=3)
+    sec["pcs_generation"] = {"value": n_gen[0] / ms * 1e3, "unit": "hyp generated/s", "ms": ms, "hypotheses": n_gen[0],
+                             "what": "100 bases x <=100 congruent quads, 2k-pt model, 2k-pt segment (pgp_generate_pcs)"}
+    eng.score_generated(1, "weighted")
+    top = eng.topk(1, 64)
+    poses = eng.centred_to_pose(1, top["T"])
+    t0 = time.perf_counter()
+    _, iters, _ = eng.tricp(1, seg.scene_xyz, poses, trim=0.5, ratio=0.99, max_iter=100)
+    dt = time.perf_counter() - t0
+    sec["tricp"] = {"value": len(poses) / dt, "unit": "poses refined/s", "ms": dt * 1e3, "poses": int(len(poses)), "mean_iterations": float(iters.mean()),
+                    "what": "top-64 of the generated set, trim 0.5, 2k-pt segment vs 2k-pt model (pgp_tricp, host call incl. copies)"}
+    eng.set_scene(prob.scene_xyz, prob.scene_nrm, prob.delta)
+    return sec
+
+
 def run_ours(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
@@ -271,6 +316,7 @@ def run_ours(args, rank, local_rank, world):
             "best": {"index": int(top["index"][0]), "count": int(top["count"][0])},
         }
         if world == 1:
+            line["secondary"] = secondary_metrics(eng, prob, T_dev, counts_dev, scores_dev, flush, stream)
             base, _, cpu_counts, sample = cpu_reference_run(prob, T, seconds_per_step=12.0, steps=1, warmup=0)
             line["cpu_baseline"] = base
             got = counts_host.numpy()[:sample].astype(np.uint32)

@@ -48,6 +48,7 @@ _SIGNATURES = {
     "pgp_pose_to_centred": (_i, [_vp, _i, _vp, _vp]),
     "pgp_centred_to_pose": (_i, [_vp, _i, _vp, _vp]),
     "pgp_grid_info": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "pgp_label_stats": (_i, [_vp, _vp]),
     "pgp_score_lcp": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp]),
     "pgp_score_lcp_dev": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp]),
     "pgp_registered_points": (_i, [_vp, _i, _vp, _vp, _i]),

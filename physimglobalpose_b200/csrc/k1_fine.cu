@@ -215,8 +215,9 @@ __global__ void __launch_bounds__(CLS_THREADS) k1f_fill_lists(const uint32_t* __
 //     lo(p*)^2 <= min( min_p' hi(p')^2 , delta^2 )      (+ rounding margins)
 // -- the list of all points passing that bound holds the nearest neighbour (and every point that
 // can tie with it) of every query of the voxel.  At 1/8-cell voxels that is ~5 points instead of
-// the ~60 in the 27 cells.  Layout mirrors the AMBIG lists: per block a header of non-OUT rank
-// prefixes and a region [n_nonout + 1 offsets][ids].
+// the ~60 in the 27 cells.  Layout: wvox[block * 512 + voxel] = (offset within the block's region << 10) | count,
+// wbase[block] = first entry of the region, wlists = float4 COPIES of the candidate points {x, y, z, original
+// index}: scoring reaches the candidates with one indexed load and no rank arithmetic.
 __device__ __forceinline__ void box_d2(const float4 p, float vx, float vy, float vz, float hs, float& mind2, float& maxd2) {
   const float ax = fabsf(p.x - vx), ay = fabsf(p.y - vy), az = fabsf(p.z - vz);
   const float lx = fmaxf(ax - hs, 0.f), ly = fmaxf(ay - hs, 0.f), lz = fmaxf(az - hs, 0.f);
@@ -244,15 +245,16 @@ __device__ __forceinline__ void sweep27(const uint32_t* __restrict__ cell_start,
   }
 }
 
-__device__ __forceinline__ uint32_t nonout_mask(uint32_t w) { return (w | (w >> 1)) & 0x55555555u; }
 __device__ __forceinline__ float wlist_threshold(float u2, float dhi2) { return fminf(u2 * (1.0f + 4e-5f), dhi2); }
 
-// Pass A: list length of every non-OUT voxel + block header.  4 voxels per thread (v = tid + 128 j).
+constexpr uint32_t WV_CNT_BITS = 10, WV_CNT_MAX = (1u << WV_CNT_BITS) - 1u, WV_REL_MAX = (1u << (32 - WV_CNT_BITS)) - 1u;
+
+// Pass A: list length of every voxel of the block (0 for OUT voxels) -> wvox (count only), block total -> region.
+// 4 voxels per thread (v = tid + 128 j).
 __global__ void __launch_bounds__(CLS_THREADS) k1w_count(const uint32_t* __restrict__ block_cell, const uint32_t* __restrict__ cell_start,
                                                          const float4* __restrict__ pts, GridParams g, const uint32_t* __restrict__ codes,
-                                                         uint16_t* __restrict__ wcnt, uint32_t* __restrict__ whdr,
-                                                         uint32_t* __restrict__ region_words, unsigned long long* __restrict__ total_words,
-                                                         int* __restrict__ overflow) {
+                                                         uint32_t* __restrict__ wvox, uint32_t* __restrict__ region_entries,
+                                                         unsigned long long* __restrict__ total_entries, int* __restrict__ overflow) {
   __shared__ float4 s_p[CLS_CHUNK];
   __shared__ uint32_t s_tot;
   const int b = blockIdx.x;
@@ -286,87 +288,62 @@ __global__ void __launch_bounds__(CLS_THREADS) k1w_count(const uint32_t* __restr
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int v = threadIdx.x + CLS_THREADS * j;
-    const int nn = live[j] ? cnt[j] : 0;
-    if (nn > 65535) atomicOr(overflow, 1);
-    wcnt[(size_t)b * 512 + v] = (uint16_t)min(nn, 65535);
-    mine += (uint32_t)min(nn, 65535);
+    const uint32_t nn = live[j] ? (uint32_t)cnt[j] : 0u;
+    if (nn > WV_CNT_MAX) atomicOr(overflow, 1);
+    wvox[(size_t)b * 512 + v] = min(nn, WV_CNT_MAX);
+    mine += min(nn, WV_CNT_MAX);
   }
   mine = __reduce_add_sync(0xffffffffu, mine);
   if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_tot, mine);
   __syncthreads();
-  if (threadIdx.x < 32) {
-    const uint32_t w = nonout_mask(codes[(size_t)b * 32 + threadIdx.x]);
-    const uint32_t k = __popc(w);
-    uint32_t incl = k;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += t; }
-    const uint32_t excl = incl - k;
-    const uint32_t n_live = __shfl_sync(0xffffffffu, incl, 31);
-    const uint32_t g_lo = __shfl_sync(0xffffffffu, excl, (threadIdx.x & 3) * 8);
-    const uint32_t g_hi = __shfl_sync(0xffffffffu, excl, (threadIdx.x & 3) * 8 + 4);
-    if (threadIdx.x < 4) whdr[(size_t)b * 8 + threadIdx.x] = g_lo | (g_hi << 16);
-    if (threadIdx.x == 0) {
-      whdr[(size_t)b * 8 + 4] = 0;
-      whdr[(size_t)b * 8 + 5] = n_live;
-      whdr[(size_t)b * 8 + 6] = s_tot;
-      whdr[(size_t)b * 8 + 7] = 0;
-      const uint32_t words = n_live ? n_live + 1 + s_tot : 0;
-      region_words[b] = words;
-      if (words) atomicAdd(total_words, (unsigned long long)words);
-    }
+  if (threadIdx.x == 0) {
+    if (s_tot > WV_REL_MAX) atomicOr(overflow, 1);
+    region_entries[b] = s_tot;
+    if (s_tot) atomicAdd(total_entries, (unsigned long long)s_tot);
   }
 }
 
-// Pass B: fill.  Thread t owns the non-OUT voxels of rank t, t+128, ... of its block.
+// Pass B: per-block exclusive scan of the counts -> wvox = rel << 10 | count, then the fill (copies of the
+// candidates' float4 records {x, y, z, original index}, so that scoring needs no second indirection).
 __global__ void __launch_bounds__(CLS_THREADS) k1w_fill(const uint32_t* __restrict__ block_cell, const uint32_t* __restrict__ cell_start,
-                                                        const float4* __restrict__ pts, GridParams g, const uint32_t* __restrict__ codes,
-                                                        const uint16_t* __restrict__ wcnt, uint32_t* __restrict__ whdr,
-                                                        const uint32_t* __restrict__ region_base, uint32_t* __restrict__ wlists) {
+                                                        const float4* __restrict__ pts, GridParams g, uint32_t* __restrict__ wvox,
+                                                        const uint32_t* __restrict__ region_base, float4* __restrict__ wlists) {
   __shared__ float4 s_p[CLS_CHUNK];
-  __shared__ uint16_t s_av[F * F * F];
-  __shared__ uint32_t s_off[F * F * F + 1];
+  __shared__ uint32_t s_warp[CLS_THREADS / 32];
   const int b = blockIdx.x;
-  const uint32_t n_live = whdr[(size_t)b * 8 + 5];
-  if (threadIdx.x == 0) whdr[(size_t)b * 8 + 4] = region_base[b];
-  if (n_live == 0) return;
-  const uint32_t base_w = region_base[b];
+  const uint32_t base = region_base[b];
   const uint32_t c = block_cell[b];
   const int cx = (int)(c % g.dim[0]), cy = (int)((c / g.dim[0]) % g.dim[1]), cz = (int)(c / ((uint32_t)g.dim[0] * g.dim[1]));
   const float hs = 0.5f * g.hf + g.inflate;
-  if (threadIdx.x < 32) {
-    const uint32_t w = nonout_mask(codes[(size_t)b * 32 + threadIdx.x]);
-    uint32_t k = __popc(w), incl = k;
+  // thread t owns voxels 4t .. 4t+3 here (contiguous, so the scan is one pass)
+  uint32_t cnt[4], rel[4];
+  uint32_t mine = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += t; }
-    uint32_t r = incl - k, ww = w;
-    while (ww) { int bit = __ffs(ww) - 1; ww &= ww - 1; s_av[r++] = (uint16_t)(threadIdx.x * 16 + (bit >> 1)); }
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    uint32_t run = n_live + 1;
-    for (uint32_t r0 = 0; r0 < n_live; r0 += 32) {
-      const uint32_t r = r0 + threadIdx.x;
-      uint32_t k = r < n_live ? wcnt[(size_t)b * 512 + s_av[r]] : 0u, incl = k;
+  for (int j = 0; j < 4; ++j) { cnt[j] = wvox[(size_t)b * 512 + threadIdx.x * 4 + j] & WV_CNT_MAX; mine += cnt[j]; }
+  uint32_t incl = mine;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += t; }
-      if (r < n_live) s_off[r] = run + incl - k;
-      run += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (threadIdx.x == 0) s_off[n_live] = run;
-  }
+  for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)(threadIdx.x & 31) >= o) incl += t; }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
   __syncthreads();
-  for (uint32_t r = threadIdx.x; r <= n_live; r += CLS_THREADS) wlists[base_w + r] = s_off[r];
+  uint32_t run = incl - mine;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) run += s_warp[w];
+  const uint32_t total = s_warp[0] + s_warp[1] + s_warp[2] + s_warp[3];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    rel[j] = run; run += cnt[j];
+    wvox[(size_t)b * 512 + threadIdx.x * 4 + j] = (rel[j] << WV_CNT_BITS) | cnt[j];
+  }
+  if (total == 0) return;      // uniform over the CTA
   float vx[4], vy[4], vz[4], u2[4], thr[4];
   uint32_t wr[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const uint32_t r = threadIdx.x + CLS_THREADS * j;
-    const int v = r < n_live ? s_av[r] : 0;
+    const int v = threadIdx.x * 4 + j;
     vx[j] = __fmaf_rn((float)(cx * F + (v & 7)) + 0.5f, g.hf, g.lo[0]);
     vy[j] = __fmaf_rn((float)(cy * F + ((v >> 3) & 7)) + 0.5f, g.hf, g.lo[1]);
     vz[j] = __fmaf_rn((float)(cz * F + (v >> 6)) + 0.5f, g.hf, g.lo[2]);
     u2[j] = INFINITY;
-    wr[j] = r < n_live ? base_w + s_off[r] : 0xffffffffu;
+    wr[j] = cnt[j] ? base + rel[j] : 0xffffffffu;
   }
   sweep27(cell_start, pts, g, cx, cy, cz, s_p, [&](const float4 p, uint32_t) {
 #pragma unroll
@@ -374,16 +351,32 @@ __global__ void __launch_bounds__(CLS_THREADS) k1w_fill(const uint32_t* __restri
   });
 #pragma unroll
   for (int j = 0; j < 4; ++j) thr[j] = wlist_threshold(u2[j], g.dhi2);
-  sweep27(cell_start, pts, g, cx, cy, cz, s_p, [&](const float4 p, uint32_t pos) {
+  sweep27(cell_start, pts, g, cx, cy, cz, s_p, [&](const float4 p, uint32_t) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (wr[j] != 0xffffffffu) {
         float lo2, hi2;
         box_d2(p, vx[j], vy[j], vz[j], hs, lo2, hi2);
-        if (lo2 <= thr[j]) wlists[wr[j]++] = pos;
+        if (lo2 <= thr[j]) wlists[wr[j]++] = p;
       }
     }
   });
+}
+
+
+// statistics of the label structure (reports / tuning): out[0..5] = blocks all-OUT, all-IN, mixed; voxels OUT, IN, AMBIG
+__global__ void k1f_stats(const uint32_t* __restrict__ codes, int n_blocks, unsigned long long* __restrict__ out) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= n_blocks) return;
+  const uint32_t w = codes[(size_t)b * 32 + (threadIdx.x & 31)];
+  const int n_in = __popc(w & 0x55555555u), n_amb = __popc(w & 0xAAAAAAAAu);
+  const int tin = __reduce_add_sync(0xffffffffu, n_in), tam = __reduce_add_sync(0xffffffffu, n_amb);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out + (tin == 512 ? 1 : (tin + tam == 0 ? 0 : 2)), 1ull);
+    atomicAdd(out + 3, (unsigned long long)(512 - tin - tam));
+    atomicAdd(out + 4, (unsigned long long)tin);
+    atomicAdd(out + 5, (unsigned long long)tam);
+  }
 }
 
 }  // namespace
@@ -476,36 +469,54 @@ int k1_build_wlists(pgp_ctx* ctx) {
   if (g.fine != F || g.n_blocks <= 0) return PGP_OK;
   cudaStream_t st = ctx->stream;
   const uint32_t nb = (uint32_t)g.n_blocks;
-  PGP_CUDA(ctx, s.near_cnt.reserve((size_t)nb * 512 * 2));
-  PGP_CUDA(ctx, s.whdr.reserve((size_t)nb * 32));
-  PGP_CUDA(ctx, s.region.reserve((size_t)(nb + 1) * 4));
+  size_t free_b = 0, total_b = 0;
+  PGP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+  if ((size_t)nb * 2048 + (64u << 20) > free_b + s.wvox.cap) return PGP_OK;
+  PGP_CUDA(ctx, s.wvox.reserve((size_t)nb * 512 * 4));
+  PGP_CUDA(ctx, s.wbase.reserve((size_t)(nb + 1) * 4));
   PGP_CUDA(ctx, s.scratch.reserve((size_t)((nb + 1) / 2048 + 4096) * 4));
-  uint32_t* region = s.region.as<uint32_t>();
+  uint32_t* region = s.wbase.as<uint32_t>();
   unsigned long long* d_total = reinterpret_cast<unsigned long long*>(ctx->work.as<char>() + 192);
   int* d_over = ctx->work.as<int>() + 40;
   PGP_CUDA(ctx, cudaMemsetAsync(region, 0, (size_t)(nb + 1) * 4, st));
   PGP_CUDA(ctx, cudaMemsetAsync(d_total, 0, 8, st));
   PGP_CUDA(ctx, cudaMemsetAsync(d_over, 0, 4, st));
   k1w_count<<<nb, CLS_THREADS, 0, st>>>(s.block_cell.as<uint32_t>(), s.cell_start.as<uint32_t>(), s.pts.as<float4>(), g, s.codes.as<uint32_t>(),
-                                        s.near_cnt.as<uint16_t>(), s.whdr.as<uint32_t>(), region, d_total, d_over);
+                                        s.wvox.as<uint32_t>(), region, d_total, d_over);
   ctx->launches++;
   unsigned long long total = 0;
   int overflow = 0;
   PGP_CUDA(ctx, cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
   PGP_CUDA(ctx, cudaMemcpyAsync(&overflow, d_over, 4, cudaMemcpyDeviceToHost, st));
   PGP_CUDA(ctx, cudaStreamSynchronize(st));
-  if (overflow || total >= (1ull << 32) - 64) return PGP_OK;      // 32-bit word offsets
-  size_t free_b = 0, total_b = 0;
+  if (overflow || total >= (1ull << 32) - 64) return PGP_OK;      // 32-bit entry offsets
   PGP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-  if ((size_t)total * 4 + (64u << 20) > free_b + s.wlists.cap) return PGP_OK;
+  if ((size_t)total * 16 + (64u << 20) > free_b + s.wlists.cap) return PGP_OK;
   int rc = pgp_scan_exclusive_u32(ctx, region, (int64_t)nb + 1, s.scratch.as<uint32_t>());
   if (rc) return rc;
-  PGP_CUDA(ctx, s.wlists.reserve((size_t)total * 4 + 16));
-  k1w_fill<<<nb, CLS_THREADS, 0, st>>>(s.block_cell.as<uint32_t>(), s.cell_start.as<uint32_t>(), s.pts.as<float4>(), g, s.codes.as<uint32_t>(),
-                                       s.near_cnt.as<uint16_t>(), s.whdr.as<uint32_t>(), region, s.wlists.as<uint32_t>());
+  PGP_CUDA(ctx, s.wlists.reserve((size_t)total * 16 + 16));
+  k1w_fill<<<nb, CLS_THREADS, 0, st>>>(s.block_cell.as<uint32_t>(), s.cell_start.as<uint32_t>(), s.pts.as<float4>(), g, s.wvox.as<uint32_t>(), region,
+                                       s.wlists.as<float4>());
   ctx->launches++;
   PGP_CUDA(ctx, cudaGetLastError());
-  s.n_wlist_words = (int64_t)total;
+  s.n_wlist_entries = (int64_t)total;
   s.wlists_ready = true;
+  return PGP_OK;
+}
+
+int k1_fine_stats(pgp_ctx* ctx, int64_t* out8) {
+  Scene& s = ctx->scene;
+  for (int i = 0; i < 8; ++i) out8[i] = 0;
+  if (s.g.fine != F || s.g.n_blocks <= 0) return PGP_OK;
+  unsigned long long* d = reinterpret_cast<unsigned long long*>(ctx->work.as<char>() + 256);
+  PGP_CUDA(ctx, cudaMemsetAsync(d, 0, 64, ctx->stream));
+  k1f_stats<<<(s.g.n_blocks + 7) / 8, 256, 0, ctx->stream>>>(s.codes.as<uint32_t>(), s.g.n_blocks, d);
+  ctx->launches++;
+  unsigned long long h[8];
+  PGP_CUDA(ctx, cudaMemcpyAsync(h, d, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < 6; ++i) out8[i] = (int64_t)h[i];
+  out8[6] = s.n_list_words;
+  out8[7] = s.wlists_ready ? s.n_wlist_entries : 0;
   return PGP_OK;
 }

@@ -164,7 +164,7 @@ __global__ void k1_dilate(const uint32_t* __restrict__ cell_start, GridParams g,
 // Point3D::set_normal (S4/shared4pcs.h:85-87: n / sqrt(n.n)) with tiny normals zeroed
 // (S4/utils/geometry.h:56-82).
 __global__ void k1_build_aux(const float4* __restrict__ pts, int n, const float* __restrict__ nrm_raw,
-                             const float* __restrict__ prior, float4* __restrict__ aux) {
+                             const float* __restrict__ prior, float4* __restrict__ aux, float4* __restrict__ aux_orig) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int o = __float_as_int(pts[i].w);
@@ -177,7 +177,9 @@ __global__ void k1_build_aux(const float4* __restrict__ pts, int n, const float*
       nx = __fdiv_rn(x, len); ny = __fdiv_rn(y, len); nz = __fdiv_rn(z, len);
     }
   }
-  aux[i] = make_float4(nx, ny, nz, prior[o]);
+  const float4 a = make_float4(nx, ny, nz, prior[o]);
+  aux[i] = a;
+  aux_orig[o] = a;
 }
 
 // prior of scene point i = img[row][col]/10000 at the pin-hole projection of the UN-centred point
@@ -228,6 +230,7 @@ int k1_build_grid(pgp_ctx* ctx) {
 
   PGP_CUDA(ctx, s.pts.reserve((size_t)n * 16));
   PGP_CUDA(ctx, s.aux.reserve((size_t)n * 16));
+  PGP_CUDA(ctx, s.aux_orig.reserve((size_t)n * 16));
   PGP_CUDA(ctx, s.unsorted.reserve((size_t)n * 16));
   PGP_CUDA(ctx, s.cell_of.reserve((size_t)n * 4));
   PGP_CUDA(ctx, ctx->work.reserve(4096));
@@ -292,7 +295,7 @@ int k1_build_grid(pgp_ctx* ctx) {
   ctx->launches++;
   s.bitmap_words = n_words;
   // 5. normals + priors in sorted order
-  k1_build_aux<<<B, T, 0, st>>>(s.pts.as<float4>(), n, s.has_nrm ? s.nrm_raw.as<float>() : nullptr, s.prior.as<float>(), s.aux.as<float4>());
+  k1_build_aux<<<B, T, 0, st>>>(s.pts.as<float4>(), n, s.has_nrm ? s.nrm_raw.as<float>() : nullptr, s.prior.as<float>(), s.aux.as<float4>(), s.aux_orig.as<float4>());
   ctx->launches++;
   unsigned long long occ = 0;
   PGP_CUDA(ctx, cudaMemcpyAsync(&occ, d_occ, 8, cudaMemcpyDeviceToHost, st));
@@ -321,7 +324,7 @@ int k1_refresh_sorted_priors(pgp_ctx* ctx) {
   PGP_CUDA(ctx, cudaMemsetAsync(flag, 0, 4, ctx->stream));
   k1_check_binary<<<(s.n + 255) / 256, 256, 0, ctx->stream>>>(s.prior.as<float>(), s.n, flag);
   k1_build_aux<<<(s.n + 255) / 256, 256, 0, ctx->stream>>>(s.pts.as<float4>(), s.n, s.has_nrm ? s.nrm_raw.as<float>() : nullptr,
-                                                          s.prior.as<float>(), s.aux.as<float4>());
+                                                          s.prior.as<float>(), s.aux.as<float4>(), s.aux_orig.as<float4>());
   ctx->launches += 2;
   int h = 0;
   PGP_CUDA(ctx, cudaMemcpyAsync(&h, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -50,8 +50,10 @@ struct LcpParams {
   const uint4* hdr;          // n_blocks x 2 uint4: {u16 ambig-rank prefix per 64-voxel group x 8}, {list region base, #ambig, #ids, 0}
   const uint32_t* lists;     // candidate ids of the AMBIG voxels (K1b pass B)
   float model_rinf;          // max |coordinate| of the validation model (bounds the transform's intermediates)
-  const uint4* whdr;         // K1c: like hdr, ranking the non-OUT voxels
-  const uint32_t* wlists;    // K1c: nearest-neighbour candidate ids of every non-OUT voxel
+  const uint32_t* wvox;      // K1c: per voxel (offset in the block's region << 10) | candidate count
+  const uint32_t* wbase;     // K1c: per block first entry of its region
+  const float4* wlists;      // K1c: candidate records {x, y, z, original index}
+  const float4* aux_orig;    // unit normal + prior by ORIGINAL scene index
 };
 
 // ---- mbarrier + TMA bulk copy (global -> shared), sm_90+/sm_100a PTX ---------------------------
@@ -329,40 +331,46 @@ __device__ __forceinline__ uint32_t label_slot(const LcpParams& p, const FineCtx
   return (wr.x & bit) ? blk * 32u + (uint32_t)(v >> 4) : f.dummy_word;
 }
 
-// Candidate list of the voxel a queued query fell into: [s0, s1) word offsets into the block's region `reg`.
-// NONOUT = false: AMBIG lists of K1b (hdr / lists);  true: nearest-candidate lists of K1c (whdr / wlists).
-template <bool SMEM_TABLE, bool NONOUT>
+// AMBIG candidate list (K1b) of the voxel a queued query fell into: [s0, s1) word offsets into the block's region `reg`.
+template <bool SMEM_TABLE>
 __device__ __forceinline__ const uint32_t* list_range(const LcpParams& p, const FineCtx& f, int ix, int iy, int iz, uint32_t& s0, uint32_t& s1) {
   const int c = ((iz >> 3) * f.dimy + (iy >> 3)) * f.dimx + (ix >> 3);
   const uint2 wr = table_word<SMEM_TABLE>(f, c >> 5);
   const unsigned blk = wr.y + __popc(wr.x & ((1u << (c & 31)) - 1u));
   const int v = ((iz & 7) << 6) | ((iy & 7) << 3) | (ix & 7);
-  const uint4* hdr = NONOUT ? p.whdr : p.hdr;
-  const uint4 gp = __ldg(hdr + (size_t)blk * 2);
-  const uint4 h1 = __ldg(hdr + (size_t)blk * 2 + 1);
-  uint4 grp = __ldg(reinterpret_cast<const uint4*>(p.codes) + (size_t)blk * 8 + (v >> 6));
-  if (NONOUT) {
-    grp.x = (grp.x | (grp.x >> 1)) & 0x55555555u; grp.y = (grp.y | (grp.y >> 1)) & 0x55555555u;
-    grp.z = (grp.z | (grp.z >> 1)) & 0x55555555u; grp.w = (grp.w | (grp.w >> 1)) & 0x55555555u;
-  } else {
-    grp.x &= 0xAAAAAAAAu; grp.y &= 0xAAAAAAAAu; grp.z &= 0xAAAAAAAAu; grp.w &= 0xAAAAAAAAu;
-  }
+  const uint4 gp = __ldg(p.hdr + (size_t)blk * 2);
+  const uint4 h1 = __ldg(p.hdr + (size_t)blk * 2 + 1);
+  const uint4 grp = __ldg(reinterpret_cast<const uint4*>(p.codes) + (size_t)blk * 8 + (v >> 6));
   const int g8 = v >> 6, wi = (v >> 4) & 3;
   const uint32_t gw = g8 < 2 ? gp.x : g8 < 4 ? gp.y : g8 < 6 ? gp.z : gp.w;
   uint32_t r = (gw >> ((g8 & 1) * 16)) & 0xffffu;
-  r += (wi > 0 ? __popc(grp.x) : 0) + (wi > 1 ? __popc(grp.y) : 0) + (wi > 2 ? __popc(grp.z) : 0);
+  const uint32_t A = 0xAAAAAAAAu;
+  r += (wi > 0 ? __popc(grp.x & A) : 0) + (wi > 1 ? __popc(grp.y & A) : 0) + (wi > 2 ? __popc(grp.z & A) : 0);
   const uint32_t word = wi == 0 ? grp.x : wi == 1 ? grp.y : wi == 2 ? grp.z : grp.w;
-  r += __popc(word & ((1u << ((v & 15) * 2)) - 1u));
-  const uint32_t* reg = (NONOUT ? p.wlists : p.lists) + h1.x;
+  r += __popc(word & A & ((1u << ((v & 15) * 2)) - 1u));
+  const uint32_t* reg = p.lists + h1.x;
   s0 = __ldg(reg + r); s1 = __ldg(reg + r + 1);
   return reg;
+}
+
+// K1c nearest-candidate records of the voxel: one indexed load, no rank arithmetic
+template <bool SMEM_TABLE>
+__device__ __forceinline__ const float4* wlist_of(const LcpParams& p, const FineCtx& f, int ix, int iy, int iz, uint32_t& cnt) {
+  const int c = ((iz >> 3) * f.dimy + (iy >> 3)) * f.dimx + (ix >> 3);
+  const uint2 wr = table_word<SMEM_TABLE>(f, c >> 5);
+  const unsigned blk = wr.y + __popc(wr.x & ((1u << (c & 31)) - 1u));
+  const int v = ((iz & 7) << 6) | ((iy & 7) << 3) | (ix & 7);
+  const uint32_t e = __ldg(p.wvox + (size_t)blk * 512 + v);
+  const uint32_t base = __ldg(p.wbase + blk);
+  cnt = e & 1023u;
+  return p.wlists + base + (e >> 10);
 }
 
 // phase 2 for one queued query: the reference's exact test against the voxel's candidate list
 template <bool SMEM_TABLE>
 __device__ __forceinline__ int resolve_ambiguous(const LcpParams& p, const FineCtx& f, const Xf& x, const float4 m, int ix, int iy, int iz) {
   uint32_t s0, s1;
-  const uint32_t* reg = list_range<SMEM_TABLE, false>(p, f, ix, iy, iz, s0, s1);
+  const uint32_t* reg = list_range<SMEM_TABLE>(p, f, ix, iy, iz, s0, s1);
   float tx, ty, tz;
   apply_xf(x, m, tx, ty, tz);
   const float r2 = p.g.r2;
@@ -374,31 +382,29 @@ __device__ __forceinline__ int resolve_ambiguous(const LcpParams& p, const FineC
 }
 
 // nearest in-range scene point among the voxel's K1c candidates (same acceptance / tie rule as
-// nearest_within): sorted position or -1
-__device__ __forceinline__ int nearest_in_list(const LcpParams& p, const uint32_t* __restrict__ reg, uint32_t s0, uint32_t s1, float tx, float ty,
-                                               float tz) {
+// nearest_within: d2 <= delta^2, exact ties to the smaller original index): original index or -1
+__device__ __forceinline__ int nearest_in_list(const LcpParams& p, const float4* __restrict__ l, uint32_t cnt, float tx, float ty, float tz) {
   float best = p.g.r2;
-  int best_pos = -1, best_orig = 0x7fffffff;
-  for (uint32_t j = s0; j < s1; ++j) {
-    const uint32_t pos = __ldg(reg + j);
-    const float4 sp = __ldg(p.pts + pos);
+  int best_orig = 0x7fffffff;
+  for (uint32_t j = 0; j < cnt; ++j) {
+    const float4 sp = __ldg(l + j);
     const float d2 = sqdist3(tx, ty, tz, sp.x, sp.y, sp.z);
     const int orig = __float_as_int(sp.w);
-    if (d2 < best || (d2 == best && (best_pos < 0 || orig < best_orig))) { best = d2; best_pos = (int)pos; best_orig = orig; }
+    if (d2 < best || (d2 == best && orig < best_orig)) { best = d2; best_orig = orig; }
   }
-  return best_pos;
+  return best_orig == 0x7fffffff ? -1 : best_orig;
 }
 
 // phase 2 of the weighted mode: nearest in-range point, then the normal gate.  0x10001: gated and prior == 1, 0x1: gated
 template <bool SMEM_TABLE>
 __device__ __forceinline__ int resolve_nearest(const LcpParams& p, const FineCtx& f, const Xf& x, const float4 m, const float4 nm, int ix, int iy, int iz) {
-  uint32_t s0, s1;
-  const uint32_t* reg = list_range<SMEM_TABLE, true>(p, f, ix, iy, iz, s0, s1);
+  uint32_t cnt;
+  const float4* l = wlist_of<SMEM_TABLE>(p, f, ix, iy, iz, cnt);
   float tx, ty, tz;
   apply_xf(x, m, tx, ty, tz);
-  const int pos = nearest_in_list(p, reg, s0, s1, tx, ty, tz);
-  if (pos < 0) return 0;
-  const float4 ns = __ldg(p.aux + pos);
+  const int orig = nearest_in_list(p, l, cnt, tx, ty, tz);
+  if (orig < 0) return 0;
+  const float4 ns = __ldg(p.aux_orig + orig);
   if (!normal_gate(x, nm, ns)) return 0;
   return (ns.w != 0.f) ? 0x10001 : 0x1;
 }
@@ -601,13 +607,13 @@ __global__ void __launch_bounds__(256) k3_weighted_ordered(const LcpParams p, in
         uint32_t sh;
         const uint32_t off = label_slot<false>(p, f, ix, iy, iz, sh);
         if ((__ldg(p.codes + off) >> sh) & 3u) {
-          uint32_t s0, s1;
-          const uint32_t* reg = list_range<false, true>(p, f, ix, iy, iz, s0, s1);
-          const int pos = nearest_in_list(p, reg, s0, s1, tx, ty, tz);
-          if (pos >= 0) {
-            float4 ns = __ldg(p.aux + pos);
+          uint32_t cnt;
+          const float4* l = wlist_of<false>(p, f, ix, iy, iz, cnt);
+          const int o = nearest_in_list(p, l, cnt, tx, ty, tz);
+          if (o >= 0) {
+            float4 ns = __ldg(p.aux_orig + o);
             if (!gate || normal_gate(x, __ldg(p.model_nrm + i), ns)) {
-              hit = true; w = ns.w; orig = __float_as_int(__ldg(p.pts + pos).w);
+              hit = true; w = ns.w; orig = o;
             }
           }
         }
@@ -663,7 +669,7 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     if (s.g.fine == 8 && !ctx->force_coarse && !s.wlists_tried) { int rc = k1_build_wlists(ctx); if (rc) return rc; }
     if (s.g.fine == 8 && !ctx->force_coarse && s.wlists_ready) {
       p.bmrank = s.bmrank.as<uint2>(); p.codes = s.codes.as<uint32_t>();
-      p.whdr = s.whdr.as<uint4>(); p.wlists = s.wlists.as<uint32_t>();
+      p.wvox = s.wvox.as<uint32_t>(); p.wbase = s.wbase.as<uint32_t>(); p.wlists = s.wlists.as<float4>(); p.aux_orig = s.aux_orig.as<float4>();
       k3_weighted_ordered<true><<<(unsigned)blocks, T, 0, st>>>(p, nullptr, 1);
     } else {
       k3_weighted_ordered<false><<<(unsigned)blocks, T, 0, st>>>(p, nullptr, 1);
@@ -694,7 +700,7 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     if (p.n_tiles > 256) return pgp_fail(ctx, PGP_E_INVALID, "validation model too large (%d points)", m.nv);
     p.bmrank = s.bmrank.as<uint2>(); p.codes = s.codes.as<uint32_t>();
     p.hdr = s.hdr.as<uint4>(); p.lists = s.lists.as<uint32_t>();
-    p.whdr = s.whdr.as<uint4>(); p.wlists = s.wlists.as<uint32_t>();
+    p.wvox = s.wvox.as<uint32_t>(); p.wbase = s.wbase.as<uint32_t>(); p.wlists = s.wlists.as<float4>(); p.aux_orig = s.aux_orig.as<float4>();
     p.bmrank_words = (int)(bm / 8);
     p.model_rinf = m.val_rinf;
     const size_t smem = (size_t)tile_cap * per_pt + bm + qb;

@@ -106,7 +106,7 @@ void pgp_destroy(pgp_ctx* ctx) {
   cudaDeviceSynchronize();
   Scene& s = ctx->scene;
   for (DevBuf* b : {&s.xyz_raw, &s.nrm_raw, &s.unsorted, &s.cursor, &s.pts, &s.aux, &s.cell_start, &s.cell_of, &s.bitmap, &s.bmrank,
-                    &s.block_cell, &s.codes, &s.near_cnt, &s.hdr, &s.region, &s.lists, &s.whdr, &s.wlists, &s.prior, &s.scratch, &ctx->batch_T, &ctx->batch_counts, &ctx->batch_scores, &ctx->work, &ctx->topk_out})
+                    &s.block_cell, &s.codes, &s.near_cnt, &s.hdr, &s.region, &s.lists, &s.wvox, &s.wbase, &s.wlists, &s.aux_orig, &s.prior, &s.scratch, &ctx->batch_T, &ctx->batch_counts, &ctx->batch_scores, &ctx->work, &ctx->topk_out})
     b->release();
   for (Model& m : ctx->models)
     for (DevBuf* b : {&m.search, &m.search_nrm, &m.search_unit, &m.val, &m.val_nrm, &m.val_orig, &m.val_nrm_orig, &m.gen_T, &m.gen_counts, &m.gen_scores,
@@ -339,8 +339,19 @@ int pgp_grid_info(pgp_ctx* ctx, int* dims3, int64_t* n_cells, int64_t* n_occupie
   if (n_cells) *n_cells = s.g.n_cells;
   if (n_occupied) *n_occupied = s.n_occupied;
   if (cell) *cell = s.g.h;
-  if (bytes) *bytes = (int64_t)s.n * 32 + (s.g.n_cells + 1) * 4 + s.bitmap_words * 4;
+  if (bytes) {
+    *bytes = (int64_t)s.n * 32 + (s.g.n_cells + 1) * 4 + s.bitmap_words * 4;
+    if (s.g.fine) *bytes += s.bitmap_words * 8 + (int64_t)s.g.n_blocks * (128 + 32) + s.n_list_words * 4;                 // K1b: bmrank, codes, hdr, lists
+    if (s.wlists_ready) *bytes += (int64_t)s.g.n_blocks * 2052 + s.n_wlist_entries * 16 + (int64_t)s.n * 16;               // K1c: wvox, wbase, wlists, aux_orig
+  }
   return PGP_OK;
+}
+
+int pgp_label_stats(pgp_ctx* ctx, int64_t* out8) {
+  CHECK_CTX(ctx);
+  if (!ctx->scene.ready) return pgp_fail(ctx, PGP_E_NO_SCENE, "pgp_set_scene first");
+  if (!out8) return pgp_fail(ctx, PGP_E_INVALID, "null output");
+  return k1_fine_stats(ctx, out8);
 }
 
 static int check_score_args(pgp_ctx* ctx, int obj, int64_t n, int mode, Model** m) {

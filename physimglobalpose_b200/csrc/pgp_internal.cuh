@@ -74,9 +74,11 @@ struct Scene {
   DevBuf region;       // build scratch: region sizes / bases
   DevBuf lists;        // per-block regions: offsets + candidate ids of the AMBIG voxels
   int64_t n_list_words = 0;
-  DevBuf whdr;         // K1c: n_blocks x 8 u32, like hdr but ranking the non-OUT voxels
-  DevBuf wlists;       // K1c: per-block regions [offsets][ids]: nearest-neighbour candidates of every non-OUT voxel
-  int64_t n_wlist_words = 0;
+  DevBuf wvox;         // K1c: n_blocks x 512 u32: (offset in the block's region << 10) | candidate count, 0 for OUT voxels
+  DevBuf wbase;        // K1c: n_blocks u32: first wlists entry of the block's region
+  DevBuf wlists;       // K1c: float4 copies {x,y,z,original index} of the nearest-neighbour candidates of every non-OUT voxel
+  int64_t n_wlist_entries = 0;
+  DevBuf aux_orig;     // n x float4 in ORIGINAL order: unit normal, prior (the K1c records carry original indices)
   bool wlists_ready = false, wlists_tried = false;
   DevBuf prior;        // n x f32 in ORIGINAL order
   DevBuf scratch;      // scan scratch etc.
@@ -155,6 +157,7 @@ int k1_refresh_sorted_priors(pgp_ctx* ctx);
 int k1_fill_priors(pgp_ctx* ctx, float v);
 int k1_build_fine(pgp_ctx* ctx);
 int k1_build_wlists(pgp_ctx* ctx);
+int k1_fine_stats(pgp_ctx* ctx, int64_t* out8);
 int pgp_scan_exclusive_u32(pgp_ctx* ctx, uint32_t* data, int64_t n, uint32_t* scratch);
 // k3_lcp.cu
 int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mode, uint32_t* counts_dev, float* scores_dev);

@@ -141,6 +141,13 @@ class PoseEngine:
         self._check(self._lib.pgp_grid_info(self._ctx, dims, C.byref(nc), C.byref(no), C.byref(cell), C.byref(b)))
         return dict(dims=tuple(dims), n_cells=nc.value, n_occupied=no.value, cell=cell.value, bytes=b.value)
 
+    def label_stats(self) -> dict:
+        """Tri-state label structure of the current scene (pgp_label_stats)."""
+        out = np.zeros(8, np.int64)
+        self._check(self._lib.pgp_label_stats(self._ctx, _ptr(out)))
+        keys = ("cells_all_out", "cells_all_in", "cells_mixed", "voxels_out", "voxels_in", "voxels_ambig", "ambig_list_words", "nearest_list_entries")
+        return dict(zip(keys, (int(v) for v in out)))
+
     # ------------------------------------------------------------------ K3
     def score_lcp(self, obj: int, T, mode="count"):
         """Host buffers in, host buffers out (counts u32, scores f32); copies are inside the call."""

@@ -204,6 +204,7 @@ def run_ours(args, rank, local_rank, world):
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the ONE JSON line (NCCL_DEBUG=VERSION prints a banner)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     prob, T = make_inputs(rank)
     peaks, peak_kind = measured_peaks()

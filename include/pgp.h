@@ -191,6 +191,11 @@ PGP_API int pgp_score_generated(pgp_ctx* ctx, int obj, int mode);
 /* Copies generated transforms / their scores to the host (n x 12, n). */
 PGP_API int pgp_get_generated(pgp_ctx* ctx, int obj, float* T_host, uint32_t* counts_host, float* scores_host, int64_t cap);
 
+/* The bases the last pgp_generate_pcs call drew from the scene (baseSet of Perform_N_steps, match4pcsBase.cc:1838-1853):
+ * ids cap x 4 scene indices in the pairing TryQuadrilateral chose (:415-464), inv cap x 2 invariants, ok cap flags
+ * (0 = no admissible base was found for that draw).  Returns the number of bases written. */
+PGP_API int pgp_get_bases(pgp_ctx* ctx, int obj, int32_t* ids, float* inv, uint8_t* ok, int cap);
+
 /* ---------------------------------------------------------------- K5: trimmed ICP ---------- */
 
 /* Trimmed ICP of k poses of object `obj` against the segment (source) with the model's

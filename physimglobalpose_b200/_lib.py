@@ -66,6 +66,7 @@ _SIGNATURES = {
     "pgp_generate_pcs": (_i, [_vp, _i, _vp, C.c_uint64, _i64, _vp]),
     "pgp_score_generated": (_i, [_vp, _i, _i]),
     "pgp_get_generated": (_i, [_vp, _i, _vp, _vp, _vp, _i64]),
+    "pgp_get_bases": (_i, [_vp, _i, _vp, _vp, _vp, _i]),
     "pgp_tricp": (_i, [_vp, _i, _vp, _i, _vp, _i, _f, _f, _i, _vp, _vp]),
 }
 

@@ -61,6 +61,51 @@ __global__ void __launch_bounds__(256) k2_pairs(const float4* __restrict__ Q, in
   if (!FILL && i < nq) cnt[i] = n;
 }
 
+struct BaseOut { int id[4]; float inv1, inv2; int ok; float d1, d2, cos_alpha; };
+
+// largest c with off[c] <= k   (off ascending, off[0] = 0, k < off[n])
+__device__ __forceinline__ int segment_of(const uint32_t* __restrict__ off, int n, uint32_t k) {
+  int lo = 0, hi = n;
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (__ldg(off + mid) <= k) lo = mid; else hi = mid; }
+  return lo;
+}
+
+// batched pair extraction: combo c = 2 base + edge; blockIdx.y = combo
+template <bool FILL>
+__global__ void __launch_bounds__(256) k2b_pairs(const float4* __restrict__ Q, int nq, const BaseOut* __restrict__ bases, float eps,
+                                                 uint32_t* __restrict__ cnt, int2* __restrict__ out) {
+  __shared__ float4 tile[256];
+  const int c = blockIdx.y;
+  const BaseOut bo = bases[c >> 1];
+  if (!bo.ok) return;                                   // uniform over the CTA
+  const float dist = (c & 1) ? bo.d2 : bo.d1;
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  const float4 qi = i < nq ? Q[i] : make_float4(0, 0, 0, 0);
+  const double d = (double)dist, e = (double)eps;
+  uint32_t n = 0;
+  long long w = FILL && i < nq ? 2ll * cnt[(size_t)c * nq + i] : 0;
+  const int jmax = min(nq, (int)(blockIdx.x + 1) * 256);
+  for (int j0 = 0; j0 < jmax; j0 += 256) {
+    __syncthreads();
+    if (j0 + (int)threadIdx.x < nq) tile[threadIdx.x] = Q[j0 + threadIdx.x];
+    __syncthreads();
+    const int m = i < nq ? min(256, i - j0) : 0;
+    for (int t = 0; t < m; ++t) {
+      const float4 p = tile[t];
+      const float dx = __fsub_rn(qi.x, p.x), dy = __fsub_rn(qi.y, p.y), dz = __fsub_rn(qi.z, p.z);
+      const float dd = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz))));
+      if (fabs((double)dd - d) > e) continue;
+      if (FILL) { out[w] = make_int2(j0 + t, i); out[w + 1] = make_int2(i, j0 + t); w += 2; }
+      ++n;
+    }
+  }
+  if (!FILL && i < nq) cnt[(size_t)c * nq + i] = n;
+}
+__global__ void k2b_combo_offsets(const uint32_t* __restrict__ scan, int nq, int ncombo, uint32_t* __restrict__ coff) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c <= ncombo) coff[c] = 2u * scan[(size_t)c * nq];
+}
+
 // ------------------------------------------------------------------------------- quad join
 struct JoinParams {
   const float4* Qn;      // model points in the unit cube (worldToUnit, pairCreationFunctor.h:76-80)
@@ -70,8 +115,21 @@ struct JoinParams {
   float inv1, inv2, cos_alpha, thr2;
   float cell;            // 1 / egSize
   int eg;                // position grid cells per axis (power of two)
-  uint32_t n_buckets;    // power of two
+  uint32_t n_buckets;    // power of two (per base)
+  // batched mode (bases != nullptr): A == B == all pair lists of the chunk back to back, combo c = 2 base + edge
+  // owns [coff[c], coff[c+1]); even combos are the A side, odd ones the B side; base b's buckets start at b * n_buckets
+  const BaseOut* bases; const uint32_t* coff; int ncombo;
 };
+
+// per-pair join context; false when pair k is not on the wanted side
+__device__ __forceinline__ bool join_ctx(const JoinParams& p, long long k, int side, float& inv1, float& inv2, float& cos_alpha, uint32_t& bkt_base) {
+  if (!p.bases) { inv1 = p.inv1; inv2 = p.inv2; cos_alpha = p.cos_alpha; bkt_base = 0; return true; }
+  const int c = segment_of(p.coff, p.ncombo, (uint32_t)k);
+  if ((c & 1) != side) return false;
+  const BaseOut& bo = p.bases[c >> 1];
+  inv1 = bo.inv1; inv2 = bo.inv2; cos_alpha = bo.cos_alpha; bkt_base = (uint32_t)(c >> 1) * p.n_buckets;
+  return true;
+}
 
 __device__ __forceinline__ int pos_cell(const JoinParams& p, float x, float y, float z) {
   // coordinatesPos = p / _epsilon ; index = int(x) + int(y) g + int(z) g^2   (accelerators/utils.h:141-148)
@@ -96,14 +154,16 @@ __device__ __forceinline__ void normalize3(float& x, float& y, float& z) {
 __global__ void k2_join_keys(JoinParams p, uint32_t* __restrict__ bucket_of, uint32_t* __restrict__ key_of, uint32_t* __restrict__ counts) {
   const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= p.n1) return;
+  float inv1, inv2, cos_alpha; uint32_t bkt_base;
+  if (!join_ctx(p, k, 0, inv1, inv2, cos_alpha, bkt_base)) { bucket_of[k] = 0xffffffffu; return; }
   const int2 pr = p.A[k];
   const float4 a = p.Qn[pr.x], b = p.Qn[pr.y];
   float dx = __fsub_rn(b.x, a.x), dy = __fsub_rn(b.y, a.y), dz = __fsub_rn(b.z, a.z);
-  const float ex = __fadd_rn(a.x, __fmul_rn(p.inv1, dx)), ey = __fadd_rn(a.y, __fmul_rn(p.inv1, dy)), ez = __fadd_rn(a.z, __fmul_rn(p.inv1, dz));
+  const float ex = __fadd_rn(a.x, __fmul_rn(inv1, dx)), ey = __fadd_rn(a.y, __fmul_rn(inv1, dy)), ez = __fadd_rn(a.z, __fmul_rn(inv1, dz));
   normalize3(dx, dy, dz);
   const int pc = pos_cell(p, ex, ey, ez), dc = dir_cell(dx, dy, dz);
   const bool ok = pc >= 0 && dc >= 0 && dc < NG * NG * NG && ex >= 0.f && ey >= 0.f && ez >= 0.f && ex < 1.f && ey < 1.f && ez < 1.f;
-  const uint32_t bkt = ok ? ((uint32_t)pc & (p.n_buckets - 1)) : 0xffffffffu;
+  const uint32_t bkt = ok ? bkt_base + ((uint32_t)pc & (p.n_buckets - 1)) : 0xffffffffu;
   bucket_of[k] = bkt;
   key_of[k] = ((uint32_t)pc << 9) | (uint32_t)(dc & 511);     // eg <= 128 -> pc < 2^21
   if (ok) atomicAdd(counts + bkt, 1u);
@@ -122,28 +182,30 @@ __global__ void __launch_bounds__(128) k2_join_query(JoinParams p, const uint32_
                                                      const uint32_t* __restrict__ key_of, uint32_t* __restrict__ cnt, int4* __restrict__ out, long long cap) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n2) return;
+  float inv1, inv2, cos_alpha; uint32_t bkt_base;
+  if (!join_ctx(p, i, 1, inv1, inv2, cos_alpha, bkt_base)) { if (!FILL) cnt[i] = 0; return; }
   const int2 pr = p.B[i];
   const float4 a = p.Qn[pr.x], b = p.Qn[pr.y];
   float dx = __fsub_rn(b.x, a.x), dy = __fsub_rn(b.y, a.y), dz = __fsub_rn(b.z, a.z);
-  const float fx = __fadd_rn(a.x, __fmul_rn(p.inv2, dx)), fy = __fadd_rn(a.y, __fmul_rn(p.inv2, dy)), fz = __fadd_rn(a.z, __fmul_rn(p.inv2, dz));
+  const float fx = __fadd_rn(a.x, __fmul_rn(inv2, dx)), fy = __fadd_rn(a.y, __fmul_rn(inv2, dy)), fz = __fadd_rn(a.z, __fmul_rn(inv2, dz));
   uint32_t n = 0;
   long long w = FILL ? (long long)cnt[i] : 0;
   if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < 1.f && fy < 1.f && fz < 1.f) {
     const int pc = pos_cell(p, fx, fy, fz);
-    const uint32_t bkt = (uint32_t)pc & (p.n_buckets - 1);
+    const uint32_t bkt = bkt_base + ((uint32_t)pc & (p.n_buckets - 1));
     const uint32_t s = bucket_start[bkt], e = bucket_start[bkt + 1];
     if (e > s) {
       normalize3(dx, dy, dz);                      // queryn
       // world-space query point for the final check (super4pcs.cc:135-139,160-170)
       const float4 wa = p.Q[pr.x], wb = p.Q[pr.y];
-      const float qx = __fadd_rn(wa.x, __fmul_rn(p.inv2, __fsub_rn(wb.x, wa.x)));
-      const float qy = __fadd_rn(wa.y, __fmul_rn(p.inv2, __fsub_rn(wb.y, wa.y)));
-      const float qz = __fadd_rn(wa.z, __fmul_rn(p.inv2, __fsub_rn(wb.z, wa.z)));
+      const float qx = __fadd_rn(wa.x, __fmul_rn(inv2, __fsub_rn(wb.x, wa.x)));
+      const float qy = __fadd_rn(wa.y, __fmul_rn(inv2, __fsub_rn(wb.y, wa.y)));
+      const float qz = __fadd_rn(wa.z, __fmul_rn(inv2, __fsub_rn(wb.z, wa.z)));
       // coloured direction cells: 343 bits
       uint32_t col[11];
 #pragma unroll
       for (int t = 0; t < 11; ++t) col[t] = 0;
-      const float alpha = acosf(p.cos_alpha);
+      const float alpha = acosf(cos_alpha);
       const float perimeter = 2.0f * 3.14159265358979323846f * atanf(alpha);
       const unsigned nb = 2u * (unsigned)ceilf(perimeter * (float)NG / 2.0f);
       const float step = 2.0f * 3.14159265358979323846f / (float)nb;
@@ -158,7 +220,7 @@ __global__ void __launch_bounds__(128) k2_join_query(JoinParams p, const uint32_
       }
       for (unsigned t = 0; t < nb; ++t) {
         const float th = (float)t * step;
-        const float sx = sa * cosf(th), sy = sa * sinf(th), sz = p.cos_alpha;
+        const float sx = sa * cosf(th), sy = sa * sinf(th), sz = cos_alpha;
         // q * v = v + w * uv + vec x uv, uv = 2 vec x v
         const float ux = 2.0f * (vy * sz - vz * sy), uy = 2.0f * (vz * sx - vx * sz), uz = 2.0f * (vx * sy - vy * sx);
         float rx = sx + qw * ux + (vy * uz - vz * uy);
@@ -177,9 +239,9 @@ __global__ void __launch_bounds__(128) k2_join_query(JoinParams p, const uint32_
         const int2 ap = p.A[k];
         const float4 pa = p.Q[ap.x], pb = p.Q[ap.y];
         // invPoint = pp1 + (pp2 - pp1) * invariant1 ; squaredNorm <= distance_threshold2 (sic: un-squared threshold)
-        const float ix = __fadd_rn(pa.x, __fmul_rn(__fsub_rn(pb.x, pa.x), p.inv1));
-        const float iy = __fadd_rn(pa.y, __fmul_rn(__fsub_rn(pb.y, pa.y), p.inv1));
-        const float iz = __fadd_rn(pa.z, __fmul_rn(__fsub_rn(pb.z, pa.z), p.inv1));
+        const float ix = __fadd_rn(pa.x, __fmul_rn(__fsub_rn(pb.x, pa.x), inv1));
+        const float iy = __fadd_rn(pa.y, __fmul_rn(__fsub_rn(pb.y, pa.y), inv1));
+        const float iz = __fadd_rn(pa.z, __fmul_rn(__fsub_rn(pb.z, pa.z), inv1));
         const float ddx = __fsub_rn(qx, ix), ddy = __fsub_rn(qy, iy), ddz = __fsub_rn(qz, iz);
         const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
         if (!(d2 <= p.thr2)) continue;
@@ -275,7 +337,6 @@ __global__ void k2_rigid(const float4* __restrict__ P_unsorted, const float4* __
 // stay below max_base_diameter, the most coplanar fourth point that is not too close to the three,
 // then the pairing with the smallest segment-to-segment distance and its two invariants (in double,
 // as distSegmentToSegment is instantiated with Scalar = double, :428-435).
-struct BaseOut { int id[4]; float inv1, inv2; int ok; float d1, d2, cos_alpha; };
 
 __device__ double seg_seg(const double* p1, const double* p2, const double* q1, const double* q2, double& inv1, double& inv2) {
   const double kSmall = 0.0001;
@@ -303,6 +364,32 @@ __device__ double seg_seg(const double* p1, const double* p2, const double* q1, 
   double r[3];
   for (int k = 0; k < 3; ++k) r[k] = w[k] + inv1 * u[k] - inv2 * v[k];
   return sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+}
+
+// TryQuadrilateral (match4pcsBase.cc:415-464): all ordered (i,j) with the remaining two in ascending order; the pairing with the
+// smallest segment-to-segment distance wins (first minimum), its invariants are kept and the ids are re-ordered accordingly.
+__device__ void try_quadrilateral(const float4* __restrict__ P, const int ids[4], BaseOut& o) {
+  double pt[4][3];
+  for (int k = 0; k < 4; ++k) { const float4 q = P[ids[k]]; pt[k][0] = q.x; pt[k][1] = q.y; pt[k][2] = q.z; }
+  float min_d = 3.4028234663852886e38f; int bb[4] = {-1, -1, -1, -1}; float inv1 = 0.f, inv2 = 0.f;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 4; ++j) {
+      if (i == j) continue;
+      int k = 0; while (k == i || k == j) k++;
+      int l = 0; while (l == i || l == j || l == k) l++;
+      double li1, li2;
+      const float sd = (float)seg_seg(pt[i], pt[j], pt[k], pt[l], li1, li2);
+      if (sd < min_d) { min_d = sd; bb[0] = i; bb[1] = j; bb[2] = k; bb[3] = l; inv1 = (float)li1; inv2 = (float)li2; }
+    }
+  if (bb[0] >= 0) {
+    for (int k = 0; k < 4; ++k) o.id[k] = ids[bb[k]];
+    o.inv1 = inv1; o.inv2 = inv2; o.ok = 1;
+    const float4 a0 = P[o.id[0]], a1 = P[o.id[1]], a2 = P[o.id[2]], a3 = P[o.id[3]];
+    V3 e1 = {a1.x - a0.x, a1.y - a0.y, a1.z - a0.z}, e2 = {a3.x - a2.x, a3.y - a2.y, a3.z - a2.z};
+    o.d1 = sqrtf(dot(e1, e1)); o.d2 = sqrtf(dot(e2, e2));     // distance1 / distance6 (:1951-1952)
+    normalize(e1); normalize(e2);
+    o.cos_alpha = dot(e1, e2);                                // super4pcs.cc:109-111
+  }
 }
 
 __global__ void __launch_bounds__(256) k2_select_bases(const float4* __restrict__ P, int n, float max_diam, int trials, uint64_t seed, BaseOut* __restrict__ out) {
@@ -372,29 +459,8 @@ __global__ void __launch_bounds__(256) k2_select_bases(const float4* __restrict_
     __syncthreads();
     if (i4 == 0x7fffffff) continue;
     if (tid == 0) {
-      // TryQuadrilateral: all ordered (i,j) with the remaining two in ascending order (:419-446)
       const int ids[4] = {i1, i2, i3, i4};
-      double pt[4][3];
-      for (int k = 0; k < 4; ++k) { const float4 q = P[ids[k]]; pt[k][0] = q.x; pt[k][1] = q.y; pt[k][2] = q.z; }
-      float min_d = 3.4e38f; int bb[4] = {-1, -1, -1, -1}; float inv1 = 0.f, inv2 = 0.f;
-      for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) {
-          if (i == j) continue;
-          int k = 0; while (k == i || k == j) k++;
-          int l = 0; while (l == i || l == j || l == k) l++;
-          double li1, li2;
-          const float sd = (float)seg_seg(pt[i], pt[j], pt[k], pt[l], li1, li2);
-          if (sd < min_d) { min_d = sd; bb[0] = i; bb[1] = j; bb[2] = k; bb[3] = l; inv1 = (float)li1; inv2 = (float)li2; }
-        }
-      if (bb[0] >= 0) {
-        for (int k = 0; k < 4; ++k) o.id[k] = ids[bb[k]];
-        o.inv1 = inv1; o.inv2 = inv2; o.ok = 1;
-        const float4 a0 = P[o.id[0]], a1 = P[o.id[1]], a2 = P[o.id[2]], a3 = P[o.id[3]];
-        V3 e1 = {a1.x - a0.x, a1.y - a0.y, a1.z - a0.z}, e2 = {a3.x - a2.x, a3.y - a2.y, a3.z - a2.z};
-        o.d1 = sqrtf(dot(e1, e1)); o.d2 = sqrtf(dot(e2, e2));     // distance1 / distance6 (:1951-1952)
-        normalize(e1); normalize(e2);
-        o.cos_alpha = dot(e1, e2);                                // super4pcs.cc:109-111
-      }
+      try_quadrilateral(P, ids, o);
       s_tri[0] = o.ok;
     }
     __syncthreads();
@@ -403,15 +469,265 @@ __global__ void __launch_bounds__(256) k2_select_bases(const float4* __restrict_
   if (tid == 0) out[base] = o;
 }
 
-// keep[i] = 1 for the `keep_n` quads of a base with the smallest hash (a deterministic random subset;
-// the reference draws rand() % size until it has 100 distinct indices, :1866-1869)
-__global__ void k2_mark_subset(long long n, uint64_t seed, unsigned long long thr, uint8_t* __restrict__ keep) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) keep[i] = (mix64(seed ^ (uint64_t)i) >> 11) <= thr ? 1 : 0;
+// ------------------------------------------------------------------------------- StoCS (operMode 1, the shipped generator)
+// Point-pair feature of Match4PCSBase::computePPF (match4pcsBase.cc:582-598) with approximate_bin (:150-160):
+//   { |u| in mm -> nearest multiple of 5,  angle(n1,u), angle(n2,u), angle(n1,n2) in degrees -> nearest multiple of 10 },  u = p1 - p2.
+// fp32 in Eigen's evaluation order (3-element reductions are a0 + (a1 + a2)); atan2f is emulated by rounding the double result.
+// Packed key: d/5 << 15 | a1/10 << 10 | a2/10 << 5 | a3/10 (d < 10.24 m, angles in [0, 180]); PPF_NOKEY for anything else.
+constexpr uint32_t PPF_NOKEY = 0xffffffffu;
+constexpr int PPF_D5_MAX = 2048;
+__host__ __device__ inline int approximate_bin(int val, int disc) {
+  const int lower = val - (val % disc), upper = lower + disc;
+  return (val - lower < upper - val) ? lower : upper;
+}
+__device__ __forceinline__ int ppf_angle(float y, float x) {
+  const float a = (float)atan2((double)y, (double)x);           // atan2f
+  return (int)((double)__fmul_rn(a, 180.0f) / 3.14159265358979323846);
+}
+__device__ __forceinline__ void ppf_raw(const float4 p1, const float4 n1, const float4 p2, const float4 n2, int k[4]) {
+  const float ux = __fsub_rn(p1.x, p2.x), uy = __fsub_rn(p1.y, p2.y), uz = __fsub_rn(p1.z, p2.z);
+  const float un = __fsqrt_rn(dot3_tree(ux, uy, uz, ux, uy, uz));
+  auto crossn = [](float ax, float ay, float az, float bx, float by, float bz) {
+    const float cx = __fsub_rn(__fmul_rn(ay, bz), __fmul_rn(az, by)), cy = __fsub_rn(__fmul_rn(az, bx), __fmul_rn(ax, bz)),
+                cz = __fsub_rn(__fmul_rn(ax, by), __fmul_rn(ay, bx));
+    return __fsqrt_rn(dot3_tree(cx, cy, cz, cx, cy, cz));
+  };
+  k[0] = approximate_bin((int)__fmul_rn(un, 1000.0f), 5);
+  k[1] = approximate_bin(ppf_angle(crossn(n1.x, n1.y, n1.z, ux, uy, uz), dot3_tree(n1.x, n1.y, n1.z, ux, uy, uz)), 10);
+  k[2] = approximate_bin(ppf_angle(crossn(n2.x, n2.y, n2.z, ux, uy, uz), dot3_tree(n2.x, n2.y, n2.z, ux, uy, uz)), 10);
+  k[3] = approximate_bin(ppf_angle(crossn(n1.x, n1.y, n1.z, n2.x, n2.y, n2.z), dot3_tree(n1.x, n1.y, n1.z, n2.x, n2.y, n2.z)), 10);
+}
+__host__ __device__ inline uint32_t ppf_pack(const int k[4]) {
+  if (k[0] < 0 || k[0] % 5 || k[0] / 5 >= PPF_D5_MAX) return PPF_NOKEY;
+  for (int t = 1; t < 4; ++t) if (k[t] < 0 || k[t] > 180 || k[t] % 10) return PPF_NOKEY;
+  return ((uint32_t)(k[0] / 5) << 15) | ((uint32_t)(k[1] / 10) << 10) | ((uint32_t)(k[2] / 10) << 5) | (uint32_t)(k[3] / 10);
+}
+__device__ __forceinline__ uint32_t ppf_key(const float4 p1, const float4 n1, const float4 p2, const float4 n2) {
+  int k[4];
+  ppf_raw(p1, n1, p2, n2, k);
+  return ppf_pack(k);
+}
+__device__ __forceinline__ bool ppf_present(const uint32_t* __restrict__ bits, uint32_t key) {
+  return key != PPF_NOKEY && ((__ldg(bits + (key >> 5)) >> (key & 31)) & 1u);
+}
+
+// keys of arbitrary index pairs of one cloud (test hook + the map builder): pairs == nullptr -> all ordered (i, j), i != j, row-major
+__global__ void k2s_keys(const float4* __restrict__ pts, const float4* __restrict__ nrm, int n, const int2* __restrict__ pairs, long long np,
+                         int32_t* __restrict__ keys4, uint32_t* __restrict__ packed) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= np) return;
+  int i, j;
+  if (pairs) { i = pairs[t].x; j = pairs[t].y; } else { i = (int)(t / n); j = (int)(t % n); }
+  int k[4] = {-1, -1, -1, -1};
+  if (i != j || pairs) ppf_raw(pts[i], nrm[i], pts[j], nrm[j], k);
+  if (keys4) { keys4[4 * t] = k[0]; keys4[4 * t + 1] = k[1]; keys4[4 * t + 2] = k[2]; keys4[4 * t + 3] = k[3]; }
+  if (packed) packed[t] = (i != j || pairs) ? ppf_pack(k) : PPF_NOKEY;
+}
+
+// std::discrete_distribution<int>(w, w + n)(std::default_random_engine) exactly as libstdc++ evaluates it: probabilities
+// p_i = w_i / sum (double, sequential std::accumulate), cumulative sums (sequential std::partial_sum, last forced to 1.0),
+// u = generate_canonical<double, 53>(minstd_rand0) = two draws, index = lower_bound(cp, u).  One thread; sequential on purpose.
+struct MinStd {
+  uint32_t x;
+  __device__ explicit MinStd(uint32_t seed) { x = seed % 2147483647u; if (x == 0) x = 1; }
+  __device__ uint32_t next() { x = (uint32_t)(((uint64_t)x * 16807ull) % 2147483647ull); return x; }
+  __device__ double canonical() {
+    const double r = 2147483646.0;                 // max - min + 1
+    double sum = (double)(next() - 1u);
+    sum += (double)(next() - 1u) * r;
+    double ret = sum / (r * r);
+    if (ret >= 1.0) ret = 0.99999999999999988897769753748;   // nextafter(1, 0)
+    return ret;
+  }
+};
+__device__ int discrete_draw(const float* __restrict__ w, int n, MinStd& g) {
+  if (n < 2) return 0;                             // _M_prob.size() < 2: no cumulative table, operator() returns 0 without drawing
+  double sum = 0.0;
+  for (int i = 0; i < n; ++i) sum += (double)w[i];
+  const double u = g.canonical();
+  double acc = 0.0;
+  for (int i = 0; i < n - 1; ++i) {
+    acc += (double)w[i] / sum;
+    if (!(acc < u)) return i;                      // lower_bound: first cp_i >= u
+  }
+  return n - 1;                                    // cp.back() = 1.0 >= u always
+}
+
+struct StocsParams {
+  const float4* P;        // centred scene points, original order
+  const float4* aux;      // unit normal + prior, original order
+  int n;
+  const uint32_t* bits;   // presence bitset of the model's PPF map
+  float* curr;            // n_bases x n scratch (curr_probabilities_)
+  uint64_t seed;
+  int base0;
+};
+__host__ __device__ inline uint32_t stocs_base_seed(uint64_t seed, int base, int attempt) {
+  return (uint32_t)(mix64(seed ^ mix64(0x570C5ull + ((uint64_t)base << 8) + (uint64_t)attempt)) >> 32);
+}
+
+// One CTA per base: Match4PCSBase::SelectQuadrilateralStoCS (match4pcsBase.cc:600-792).  Each of the four points is drawn from
+// prior x "the PPF of the edge to the previous point exists in the model's map" (x the coplanarity / spread filters for the
+// 4th / 3rd point); the weights are evaluated by all threads, the float normalisation and the draw by thread 0, sequentially
+// and in the reference's order, so that a given engine seed reproduces the reference's draw.
+__global__ void __launch_bounds__(256) k2s_select_bases(StocsParams sp, BaseOut* __restrict__ out) {
+  __shared__ int s_pick;
+  __shared__ int s_any;
+  const int base = blockIdx.x, tid = threadIdx.x, n = sp.n;
+  float* curr = sp.curr + (size_t)base * n;
+  const float4* P = sp.P;
+  BaseOut o{};
+  for (int attempt = 0; attempt < 16; ++attempt) {      // Perform_N_steps re-draws until a base is accepted (:1831-1852)
+    MinStd gen(stocs_base_seed(sp.seed, sp.base0 + base, attempt));
+    // ---- point 1 ~ priors
+    for (int i = tid; i < n; i += 256) curr[i] = sp.aux[i].w;
+    __syncthreads();
+    if (tid == 0) s_pick = discrete_draw(curr, n, gen);
+    __syncthreads();
+    const int b1 = s_pick;
+    const float4 p1 = P[b1], a1 = sp.aux[b1];
+    // ---- point 2: prior_i * prior_b1 * edge(b1, i)
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+      float w = 0.f;
+      const float c = curr[i];
+      if (i != b1 && c != 0.f) {
+        const float4 ai = sp.aux[i];
+        const float e = ppf_present(sp.bits, ppf_key(p1, a1, P[i], ai)) ? 1.f : 0.f;
+        w = __fmul_rn(__fmul_rn(ai.w, a1.w), e);
+      }
+      curr[i] = w;
+      if (w != 0.f) s_any = 1;
+    }
+    __syncthreads();
+    if (!s_any) { __syncthreads(); continue; }
+    if (tid == 0) {
+      float sum = 0.f;
+      for (int i = 0; i < n; ++i) sum = __fadd_rn(sum, curr[i]);
+      for (int i = 0; i < n; ++i) curr[i] = __fdiv_rn(curr[i], sum);
+      s_pick = discrete_draw(curr, n, gen);
+    }
+    __syncthreads();
+    const int b2 = s_pick;
+    const float4 p2 = P[b2], a2 = sp.aux[b2];
+    // ---- point 3: curr_i * prior_b2 * edge(b2, i), minus the points whose (un-normalised!) angle test fails (:670-676)
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    const float v1x = __fsub_rn(p2.x, p1.x), v1y = __fsub_rn(p2.y, p1.y), v1z = __fsub_rn(p2.z, p1.z);
+    for (int i = tid; i < n; i += 256) {
+      float w = 0.f;
+      const float c = curr[i];
+      const float4 pi = P[i];
+      const float d = dot3_tree(v1x, v1y, v1z, __fsub_rn(pi.x, p1.x), __fsub_rn(pi.y, p1.y), __fsub_rn(pi.z, p1.z));
+      float ang = (float)((double)__fmul_rn((float)acos((double)d), 180.0f) / 3.14159265358979323846);
+      const float other = __fsub_rn(180.0f, ang);
+      ang = other < ang ? other : ang;                 // std::min(a, b) = (b < a) ? b : a   (NaN stays NaN -> not rejected)
+      if (i != b1 && i != b2 && c != 0.f && !(ang < 30.0f)) {
+        const float4 ai = sp.aux[i];
+        const float e = ppf_present(sp.bits, ppf_key(p2, a2, pi, ai)) ? 1.f : 0.f;
+        w = __fmul_rn(__fmul_rn(c, a2.w), e);
+      }
+      curr[i] = w;
+      if (w != 0.f) s_any = 1;
+    }
+    __syncthreads();
+    if (!s_any) { __syncthreads(); continue; }
+    if (tid == 0) {
+      float sum = 0.f;
+      for (int i = 0; i < n; ++i) sum = __fadd_rn(sum, curr[i]);
+      for (int i = 0; i < n; ++i) curr[i] = __fdiv_rn(curr[i], sum);
+      s_pick = discrete_draw(curr, n, gen);
+    }
+    __syncthreads();
+    const int b3 = s_pick;
+    const float4 p3 = P[b3], a3 = sp.aux[b3];
+    // ---- point 4: near the plane of the three (<= 1 cm), >= 1 cm away from each of them, edge(b3, i)  (:717-763)
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    const double x1 = p1.x, y1 = p1.y, z1 = p1.z, x2 = p2.x, y2 = p2.y, z2 = p2.z, x3 = p3.x, y3 = p3.y, z3 = p3.z;
+    const float denom = (float)(-x3 * y2 * z1 + x2 * y3 * z1 + x3 * y1 * z2 - x1 * y3 * z2 - x2 * y1 * z3 + x1 * y2 * z3);
+    float A = 0.f, B = 0.f, C = 0.f;
+    if (denom != 0.f) {
+      A = (float)((-y2 * z1 + y3 * z1 + y1 * z2 - y3 * z2 - y1 * z3 + y2 * z3) / (double)denom);
+      B = (float)((x2 * z1 - x3 * z1 - x1 * z2 + x3 * z2 + x1 * z3 - x2 * z3) / (double)denom);
+      C = (float)((-x2 * y1 + x3 * y1 + x1 * y2 - x3 * y2 - x1 * y3 + x2 * y3) / (double)denom);
+    }
+    for (int i = tid; i < n; i += 256) {
+      float w = 0.f;
+      const float c = curr[i];
+      if (i != b1 && i != b2 && i != b3 && c != 0.f) {
+        const float4 pi = P[i];
+        bool keep = true;
+        if (denom != 0.f) {
+          const float lin = __fadd_rn(__fadd_rn(__fmul_rn(A, pi.x), __fmul_rn(B, pi.y)), __fmul_rn(C, pi.z));
+          const float pd = (float)fabs((double)lin - 1.0);
+          auto nrm = [&](const float4 q) {
+            const float dx = __fsub_rn(pi.x, q.x), dy = __fsub_rn(pi.y, q.y), dz = __fsub_rn(pi.z, q.z);
+            return __fsqrt_rn(dot3_tree(dx, dy, dz, dx, dy, dz));
+          };
+          if ((double)pd > 0.01 || (double)nrm(p1) < 0.01 || (double)nrm(p2) < 0.01 || (double)nrm(p3) < 0.01) keep = false;
+        }
+        if (keep) {
+          const float4 ai = sp.aux[i];
+          const float e = ppf_present(sp.bits, ppf_key(p3, a3, pi, ai)) ? 1.f : 0.f;
+          w = __fmul_rn(__fmul_rn(c, a3.w), e);
+        }
+      }
+      curr[i] = w;
+      if (w != 0.f) s_any = 1;
+    }
+    __syncthreads();
+    if (!s_any) { __syncthreads(); continue; }
+    if (tid == 0) {
+      float sum = 0.f;
+      for (int i = 0; i < n; ++i) sum = __fadd_rn(sum, curr[i]);
+      for (int i = 0; i < n; ++i) curr[i] = __fdiv_rn(curr[i], sum);
+      const int b4 = discrete_draw(curr, n, gen);
+      const int ids[4] = {b1, b2, b3, b4};
+      try_quadrilateral(P, ids, o);
+      s_pick = o.ok;
+    }
+    __syncthreads();
+    if (s_pick) break;
+    __syncthreads();
+  }
+  if (tid == 0) out[base] = o;
+}
+
+// pair lists of the chunk's combos straight from the PPF map (ExtractCongruentSet in operMode 1, :1970-1981):
+// combo 2b = map[ppf(b0, b1)], combo 2b+1 = map[ppf(b2, b3)]
+struct PpfMapDev { const uint32_t* keys; const uint32_t* offsets; const int2* pairs; int n_keys; };
+__device__ __forceinline__ int ppf_find(const PpfMapDev& m, uint32_t key) {
+  if (key == PPF_NOKEY) return -1;
+  int lo = 0, hi = m.n_keys;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(m.keys + mid) < key) lo = mid + 1; else hi = mid; }
+  return (lo < m.n_keys && m.keys[lo] == key) ? lo : -1;
+}
+__global__ void k2s_combo_counts(PpfMapDev m, const float4* __restrict__ P, const float4* __restrict__ aux, const BaseOut* __restrict__ bases, int ncombo,
+                                 uint32_t* __restrict__ cnt, int* __restrict__ slot) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncombo) return;
+  const BaseOut& bo = bases[c >> 1];
+  int k = -1;
+  if (bo.ok) {
+    const int i = bo.id[(c & 1) * 2], j = bo.id[(c & 1) * 2 + 1];
+    k = ppf_find(m, ppf_key(P[i], aux[i], P[j], aux[j]));
+  }
+  slot[c] = k;
+  cnt[c] = k >= 0 ? m.offsets[k + 1] - m.offsets[k] : 0u;
+}
+// a base needs both of its lists (pairs1.size() == 0 || pairs6.size() == 0 -> no quads, :1984-1986): the join finds nothing otherwise
+__global__ void k2s_combo_copy(PpfMapDev m, const int* __restrict__ slot, const uint32_t* __restrict__ coff, int2* __restrict__ out) {
+  const int c = blockIdx.y;
+  const int k = slot[c];
+  if (k < 0) return;
+  const uint32_t n = m.offsets[k + 1] - m.offsets[k];
+  for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) out[coff[c] + t] = m.pairs[m.offsets[k] + t];
 }
 
 struct Scratch {
-  DevBuf cnt, pairs1, pairs2, quads, bucket_of, key_of, bucket_start, sorted, T, ok, base, qn;
+  DevBuf cnt, cnt2, off, flag, pairs1, pairs2, quads, bucket_of, key_of, bucket_start, sorted, T, ok, base, qn;
 };
 Scratch g_scratch[16];   // per device
 
@@ -569,85 +885,199 @@ int k2_rigid_from_quads(pgp_ctx* ctx, const Model& m, const int32_t* base4, cons
   return PGP_OK;
 }
 
-// order-preserving compaction of the accepted transforms of one base behind the ones already generated
-__global__ void k2_flags(const uint8_t* __restrict__ ok, const uint8_t* __restrict__ keep, long long n, uint32_t* __restrict__ flag) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) flag[i] = (ok[i] && (!keep || keep[i])) ? 1u : 0u;
+// ------------------------------------------------------------------------------- batched driver
+// All bases of a chunk go through every stage in ONE launch (pairs, join, transforms, subset,
+// compaction); the host only reads three totals per chunk to size the next buffer.
+namespace {
+
+// quads of base b = [qoff[b], qoff[b+1]): the quads found by the B-side pairs of combo 2b+1
+__global__ void k2b_quad_offsets(const uint32_t* __restrict__ qscan, const uint32_t* __restrict__ coff, int nb, uint32_t* __restrict__ qoff) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nb) qoff[b] = qscan[coff[2 * b + 1]];
+  if (b == nb) qoff[nb] = qscan[coff[2 * nb]];
 }
-__global__ void k2_append(const float* __restrict__ T, const uint8_t* __restrict__ ok, const uint8_t* __restrict__ keep, const uint32_t* __restrict__ off,
-                          long long n, float* __restrict__ dst, long long room) {
+
+// transform of every quad + the keep flag of the per-base random subset (Perform_N_steps draws max_sampled_csets
+// distinct quads per base, match4pcsBase.cc:1858-1869: here the ones with the smallest counter-based hash, oversampled
+// by 25 % and cut at exactly max_quads by the scan positions below)
+__global__ void k2b_rigid(const float4* __restrict__ P_unsorted, const float4* __restrict__ Q, const BaseOut* __restrict__ bases, int base0,
+                          const uint32_t* __restrict__ qoff, int nb, const int4* __restrict__ quads, long long n, int max_quads, uint64_t seed,
+                          float* __restrict__ T, uint32_t* __restrict__ flag) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || !ok[i] || (keep && !keep[i]) || (long long)off[i] >= room) return;
+  if (i >= n) return;
+  const int b = segment_of(qoff, nb, (uint32_t)i);
+  float t[12];
+  bool good = rigid_from_quad(P_unsorted, Q, bases[b].id, quads[i], t);
 #pragma unroll
-  for (int c = 0; c < 12; ++c) dst[12 * (long long)off[i] + c] = T[12 * i + c];
+  for (int c = 0; c < 12; ++c) T[12 * i + c] = good ? t[c] : 0.f;
+  const long long nq_b = (long long)qoff[b + 1] - (long long)qoff[b];
+  if (good && max_quads > 0 && nq_b > max_quads) {
+    const double frac = fmin(1.0, 1.25 * (double)max_quads / (double)nq_b);
+    const unsigned long long thr = (unsigned long long)(frac * 9007199254740992.0);   // 2^53
+    const uint64_t sb = mix64(seed ^ (0xABCDull + (uint64_t)(base0 + b)));
+    good = (mix64(sb ^ (uint64_t)(i - qoff[b])) >> 11) <= thr;
+  }
+  flag[i] = good ? 1u : 0u;
 }
+
+// one thread: per-base kept counts (capped) -> output offsets
+__global__ void k2b_base_out(const uint32_t* __restrict__ fscan, const uint32_t* __restrict__ qoff, int nb, int max_quads, uint32_t* __restrict__ outoff) {
+  if (blockIdx.x || threadIdx.x) return;
+  uint32_t run = 0;
+  for (int b = 0; b < nb; ++b) {
+    outoff[b] = run;
+    uint32_t k = fscan[qoff[b + 1]] - fscan[qoff[b]];
+    if (max_quads > 0 && k > (uint32_t)max_quads) k = (uint32_t)max_quads;
+    run += k;
+  }
+  outoff[nb] = run;
+}
+
+__global__ void k2b_append(const float* __restrict__ T, const uint32_t* __restrict__ fscan, const uint32_t* __restrict__ qoff, int nb, int max_quads,
+                           const uint32_t* __restrict__ outoff, long long n, float* __restrict__ dst, long long room) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || fscan[i + 1] == fscan[i]) return;
+  const int b = segment_of(qoff, nb, (uint32_t)i);
+  const uint32_t pos = fscan[i] - fscan[qoff[b]];
+  if (max_quads > 0 && pos >= (uint32_t)max_quads) return;
+  const long long o = (long long)outoff[b] + pos;
+  if (o >= room) return;
+#pragma unroll
+  for (int c = 0; c < 12; ++c) dst[12 * o + c] = T[12 * i + c];
+}
+
+}  // namespace
 
 int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, int64_t max_hyp, int64_t* n_hyp) {
   Scratch& sc = g_scratch[ctx->device & 15];
   const Scene& s = ctx->scene;
+  cudaStream_t st = ctx->stream;
   *n_hyp = 0;
   m.n_gen = 0;
-  const int nb = std::max(1, o->n_bases);
+  m.gen_scored = false;
+  const int nb_total = std::max(1, o->n_bases);
+  const int nq = m.nq;
   float max_diam = o->max_base_diameter;
-  if (!(max_diam > 0.f)) max_diam = m.search_diameter;   // P_diameter_ estimate of init() (:274-283): here the exact bbox diagonal bound
-  PGP_CUDA(ctx, sc.base.reserve((size_t)nb * sizeof(BaseOut) + 64));
-  PGP_CUDA(ctx, m.gen_T.reserve((size_t)max_hyp * 48));
-  int64_t cur = 0;
-  BaseOut* d_bases = reinterpret_cast<BaseOut*>(sc.base.as<char>() + 64);
-  k2_select_bases<<<nb, 256, 0, ctx->stream>>>(s.unsorted.as<float4>(), s.n, max_diam, std::max(1, o->base_trials), seed, d_bases);
-  ctx->launches++;
-  std::vector<BaseOut> bases(nb);
-  PGP_CUDA(ctx, cudaMemcpyAsync(bases.data(), d_bases, (size_t)nb * sizeof(BaseOut), cudaMemcpyDeviceToHost, ctx->stream));
-  PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  PGP_CUDA(ctx, cudaGetLastError());
+  if (!(max_diam > 0.f)) max_diam = m.search_diameter;   // P_diameter_ estimate of init() (:274-283)
   const float eps = s.delta;          // distance_factor * options_.delta, distance_factor = 1 (match4pcsBase.h:99)
-  for (int b = 0; b < nb; ++b) {
-    const BaseOut& bo = bases[b];
-    if (!bo.ok) continue;
-    int64_t n1 = 0, n2 = 0, nq = 0;
-    int rc = extract_pairs_dev(ctx, m, bo.d1, eps, sc.pairs1, &n1);
-    if (rc) return rc;
-    if (n1 == 0) continue;
-    rc = extract_pairs_dev(ctx, m, bo.d2, eps, sc.pairs2, &n2);
-    if (rc) return rc;
-    if (n2 == 0) continue;
-    rc = find_quads_dev(ctx, m, bo.cos_alpha, bo.inv1, bo.inv2, eps, sc.pairs1.as<int2>(), n1, sc.pairs2.as<int2>(), n2, sc.quads, &nq);
-    if (rc) return rc;
-    if (nq == 0) continue;
-    PGP_CUDA(ctx, sc.T.reserve((size_t)nq * 48));
-    PGP_CUDA(ctx, sc.ok.reserve((size_t)nq * 2));
-    PGP_CUDA(ctx, cudaMemcpyAsync(sc.base.p, bo.id, 16, cudaMemcpyHostToDevice, ctx->stream));
-    k2_rigid<<<(unsigned)((nq + 127) / 128), 128, 0, ctx->stream>>>(s.unsorted.as<float4>(), m.search.as<float4>(), sc.base.as<int>(), sc.quads.as<int4>(), nq,
-                                                                   sc.T.as<float>(), sc.ok.as<uint8_t>());
+  // join grid (IndexedNormalSet, normalset.h:117-123); buckets per base capped at 2^15 (collisions are filtered by the key)
+  const float eps_n = eps / m.unit_ratio;
+  int depth = (int)(-std::log2(eps_n));
+  if (depth < 0) depth = 0;
+  if (depth > 7) return pgp_fail(ctx, PGP_E_TOO_LARGE, "quad join: model diameter / delta too large (grid depth %d > 7)", depth);
+  const uint32_t nbk = 1u << std::min(3 * depth, 15);
+  // bases per chunk: bound the pair buffer (~ 10 % of nq^2 ordered pairs per edge) to about 1 GB
+  const int chunk = (int)std::max<double>(1.0, std::min<double>(32.0, 6.0e8 / ((double)nq * (double)nq)));
+  PGP_CUDA(ctx, sc.base.reserve((size_t)nb_total * sizeof(BaseOut) + 64));
+  PGP_CUDA(ctx, m.gen_T.reserve((size_t)std::max<int64_t>(max_hyp, 1) * 48));
+  BaseOut* d_bases_all = reinterpret_cast<BaseOut*>(sc.base.as<char>() + 64);
+  k2_select_bases<<<nb_total, 256, 0, st>>>(s.unsorted.as<float4>(), s.n, max_diam, std::max(1, o->base_trials), seed, d_bases_all);
+  ctx->launches++;
+  int64_t cur = 0;
+  for (int base0 = 0; base0 < nb_total && cur < max_hyp; base0 += chunk) {
+    const int nb = std::min(chunk, nb_total - base0), ncombo = 2 * nb;
+    const BaseOut* d_bases = d_bases_all + base0;
+    // ---- pairs of all 2 nb (base, edge) combos
+    const size_t ncnt = (size_t)ncombo * nq;
+    PGP_CUDA(ctx, sc.cnt.reserve((ncnt + 1) * 4));
+    PGP_CUDA(ctx, sc.off.reserve((size_t)(3 * nb + 8) * 4 + 64));
+    uint32_t* cnt = sc.cnt.as<uint32_t>();
+    uint32_t* coff = sc.off.as<uint32_t>();            // ncombo + 1
+    uint32_t* qoff = coff + ncombo + 2;                // nb + 1
+    uint32_t* outoff = qoff + nb + 2;                  // nb + 1
+    PGP_CUDA(ctx, cudaMemsetAsync(cnt, 0, (ncnt + 1) * 4, st));
+    const dim3 pgrid((unsigned)((nq + 255) / 256), (unsigned)ncombo);
+    k2b_pairs<false><<<pgrid, 256, 0, st>>>(m.search.as<float4>(), nq, d_bases, eps, cnt, nullptr);
     ctx->launches++;
-    uint8_t* keep = nullptr;
-    if (o->max_quads_per_base > 0 && nq > o->max_quads_per_base) {
-      keep = sc.ok.as<uint8_t>() + nq;
-      // oversample by 25 % and cut at exactly max_quads_per_base through the scan offsets below
-      const double frac = std::min(1.0, 1.25 * (double)o->max_quads_per_base / (double)nq);
-      const unsigned long long thr = (unsigned long long)(frac * 9007199254740992.0);   // 2^53
-      k2_mark_subset<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(nq, mix64(seed ^ (0xABCDull + (uint64_t)b)), thr, keep);
-      ctx->launches++;
-    }
-    PGP_CUDA(ctx, sc.cnt.reserve((size_t)(nq + 1) * 4));
-    uint32_t* flag = sc.cnt.as<uint32_t>();
-    PGP_CUDA(ctx, cudaMemsetAsync(flag + nq, 0, 4, ctx->stream));
-    k2_flags<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(sc.ok.as<uint8_t>(), keep, nq, flag);
-    ctx->launches++;
-    uint64_t added = 0;
-    rc = scan_u32(ctx, flag, nq, &added);
+    uint64_t unordered = 0;
+    int rc = scan_u32(ctx, cnt, (int64_t)ncnt, &unordered);                 // sync 1
     if (rc) return rc;
-    int64_t room = max_hyp - cur;
-    if (o->max_quads_per_base > 0) room = std::min<int64_t>(room, o->max_quads_per_base);
-    k2_append<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(sc.T.as<float>(), sc.ok.as<uint8_t>(), keep, flag, nq,
-                                                                    m.gen_T.as<float>() + 12 * cur, room);
+    const int64_t ntot = (int64_t)unordered * 2;
+    if (ntot == 0) continue;
+    if (ntot >= (1ll << 31)) return pgp_fail(ctx, PGP_E_TOO_LARGE, "pair lists of one chunk exceed 2^31 entries");
+    PGP_CUDA(ctx, sc.pairs1.reserve((size_t)ntot * 8));
+    k2b_pairs<true><<<pgrid, 256, 0, st>>>(m.search.as<float4>(), nq, d_bases, eps, cnt, sc.pairs1.as<int2>());
+    k2b_combo_offsets<<<(ncombo + 256) / 256, 256, 0, st>>>(cnt, nq, ncombo, coff);
+    ctx->launches += 2;
+    // ---- join
+    JoinParams p{};
+    p.Qn = m.search_unit.as<float4>(); p.Q = m.search.as<float4>();
+    p.A = sc.pairs1.as<int2>(); p.n1 = ntot; p.B = p.A; p.n2 = ntot;
+    p.thr2 = eps;
+    p.eg = 1 << depth; p.cell = 1.0f / (float)p.eg; p.n_buckets = nbk;
+    p.bases = d_bases; p.coff = coff; p.ncombo = ncombo;
+    const size_t nbuckets = (size_t)nb * nbk;
+    PGP_CUDA(ctx, sc.bucket_of.reserve((size_t)ntot * 4));
+    PGP_CUDA(ctx, sc.key_of.reserve((size_t)ntot * 4));
+    PGP_CUDA(ctx, sc.sorted.reserve((size_t)ntot * 4));
+    PGP_CUDA(ctx, sc.bucket_start.reserve((nbuckets + 1) * 8));
+    uint32_t* bs = sc.bucket_start.as<uint32_t>();
+    uint32_t* cursor = bs + nbuckets + 1;
+    PGP_CUDA(ctx, cudaMemsetAsync(bs, 0, (nbuckets + 1) * 4, st));
+    const unsigned gk = (unsigned)((ntot + 255) / 256);
+    k2_join_keys<<<gk, 256, 0, st>>>(p, sc.bucket_of.as<uint32_t>(), sc.key_of.as<uint32_t>(), bs);
     ctx->launches++;
+    PGP_CUDA(ctx, ctx->scene.scratch.reserve((size_t)((nbuckets + 1) / 2048 + 4096) * 4));
+    rc = pgp_scan_exclusive_u32(ctx, bs, (int64_t)nbuckets + 1, ctx->scene.scratch.as<uint32_t>());
+    if (rc) return rc;
+    PGP_CUDA(ctx, cudaMemcpyAsync(cursor, bs, nbuckets * 4, cudaMemcpyDeviceToDevice, st));
+    k2_join_scatter<<<gk, 256, 0, st>>>(ntot, sc.bucket_of.as<uint32_t>(), cursor, sc.sorted.as<uint32_t>());
+    ctx->launches++;
+    PGP_CUDA(ctx, sc.cnt2.reserve((size_t)(ntot + 1) * 4));
+    uint32_t* cnt2 = sc.cnt2.as<uint32_t>();
+    PGP_CUDA(ctx, cudaMemsetAsync(cnt2 + ntot, 0, 4, st));
+    const unsigned gq = (unsigned)((ntot + 127) / 128);
+    k2_join_query<false><<<gq, 128, 0, st>>>(p, bs, sc.sorted.as<uint32_t>(), sc.key_of.as<uint32_t>(), cnt2, nullptr, 0);
+    ctx->launches++;
+    uint64_t nquads = 0;
+    rc = scan_u32(ctx, cnt2, ntot, &nquads);                                // sync 2
+    if (rc) return rc;
+    if (nquads == 0) continue;
+    if (nquads >= (1ull << 31)) return pgp_fail(ctx, PGP_E_TOO_LARGE, "congruent quads of one chunk exceed 2^31");
+    PGP_CUDA(ctx, sc.quads.reserve((size_t)nquads * 16));
+    PGP_CUDA(ctx, sc.T.reserve((size_t)nquads * 48));
+    PGP_CUDA(ctx, sc.flag.reserve((size_t)(nquads + 1) * 4));
+    k2_join_query<true><<<gq, 128, 0, st>>>(p, bs, sc.sorted.as<uint32_t>(), sc.key_of.as<uint32_t>(), cnt2, sc.quads.as<int4>(), (long long)nquads);
+    k2b_quad_offsets<<<(nb + 256) / 256, 256, 0, st>>>(cnt2, coff, nb, qoff);
+    // ---- transforms, subset, compaction behind the hypotheses already generated
+    uint32_t* flag = sc.flag.as<uint32_t>();
+    PGP_CUDA(ctx, cudaMemsetAsync(flag + nquads, 0, 4, st));
+    const unsigned gr = (unsigned)((nquads + 127) / 128);
+    k2b_rigid<<<gr, 128, 0, st>>>(s.unsorted.as<float4>(), m.search.as<float4>(), d_bases, base0, qoff, nb, sc.quads.as<int4>(), (long long)nquads,
+                                  o->max_quads_per_base, seed, sc.T.as<float>(), flag);
+    ctx->launches += 3;
+    PGP_CUDA(ctx, ctx->scene.scratch.reserve((size_t)((nquads + 1) / 2048 + 4096) * 4));
+    rc = pgp_scan_exclusive_u32(ctx, flag, (int64_t)nquads + 1, ctx->scene.scratch.as<uint32_t>());
+    if (rc) return rc;
+    k2b_base_out<<<1, 32, 0, st>>>(flag, qoff, nb, o->max_quads_per_base, outoff);
+    const int64_t room = max_hyp - cur;
+    k2b_append<<<gr, 128, 0, st>>>(sc.T.as<float>(), flag, qoff, nb, o->max_quads_per_base, outoff, (long long)nquads, m.gen_T.as<float>() + 12 * cur, room);
+    ctx->launches += 2;
+    uint32_t added = 0;
+    PGP_CUDA(ctx, cudaMemcpyAsync(&added, outoff + nb, 4, cudaMemcpyDeviceToHost, st));
+    PGP_CUDA(ctx, cudaStreamSynchronize(st));                               // sync 3
     cur += std::min<int64_t>(room, (int64_t)added);
-    if (cur >= max_hyp) break;
   }
-  PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PGP_CUDA(ctx, cudaStreamSynchronize(st));
   PGP_CUDA(ctx, cudaGetLastError());
-  m.n_gen = std::min<int64_t>((int64_t)cur, max_hyp);
+  m.n_gen = std::min<int64_t>(cur, max_hyp);
+  m.n_gen_bases = nb_total;
   *n_hyp = m.n_gen;
+  return PGP_OK;
+}
+
+// bases of the last k2_generate call on this device (they stay in the scratch buffer): ids (n x 4 scene indices,
+// in the pairing TryQuadrilateral chose), inv (n x 2), ok flags
+int k2_get_bases(pgp_ctx* ctx, int n_bases, int32_t* ids_host, float* inv_host, uint8_t* ok_host) {
+  Scratch& sc = g_scratch[ctx->device & 15];
+  if (n_bases <= 0 || sc.base.cap < (size_t)n_bases * sizeof(BaseOut) + 64) return pgp_fail(ctx, PGP_E_INVALID, "no bases generated");
+  std::vector<BaseOut> b(n_bases);
+  PGP_CUDA(ctx, cudaMemcpyAsync(b.data(), sc.base.as<char>() + 64, (size_t)n_bases * sizeof(BaseOut), cudaMemcpyDeviceToHost, ctx->stream));
+  PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n_bases; ++i) {
+    for (int k = 0; k < 4; ++k) ids_host[4 * i + k] = b[i].id[k];
+    inv_host[2 * i] = b[i].inv1; inv_host[2 * i + 1] = b[i].inv2;
+    ok_host[i] = b[i].ok ? 1 : 0;
+  }
   return PGP_OK;
 }

@@ -527,7 +527,9 @@ int pgp_score_generated(pgp_ctx* ctx, int obj, int mode) {
   if (m->n_gen <= 0) return pgp_fail(ctx, PGP_E_NO_SCORES, "pgp_generate_pcs produced no hypotheses for object %d", obj);
   PGP_CUDA(ctx, m->gen_counts.reserve((size_t)m->n_gen * 4));
   PGP_CUDA(ctx, m->gen_scores.reserve((size_t)m->n_gen * 4));
-  return pgp_score_lcp_dev(ctx, obj, m->gen_T.as<float>(), m->n_gen, mode, m->gen_counts.as<uint32_t>(), m->gen_scores.as<float>());
+  int rc = pgp_score_lcp_dev(ctx, obj, m->gen_T.as<float>(), m->n_gen, mode, m->gen_counts.as<uint32_t>(), m->gen_scores.as<float>());
+  m->gen_scored = rc == PGP_OK;
+  return rc;
 }
 
 int pgp_get_generated(pgp_ctx* ctx, int obj, float* T, uint32_t* counts, float* scores, int64_t cap) {
@@ -537,11 +539,22 @@ int pgp_get_generated(pgp_ctx* ctx, int obj, float* T, uint32_t* counts, float* 
   int64_t n = std::min<int64_t>(cap, m->n_gen);
   if (n > 0) {
     if (T) PGP_CUDA(ctx, cudaMemcpyAsync(T, m->gen_T.p, (size_t)n * 48, cudaMemcpyDeviceToHost, ctx->stream));
-    if (counts && m->gen_counts.p) PGP_CUDA(ctx, cudaMemcpyAsync(counts, m->gen_counts.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (scores && m->gen_scores.p) PGP_CUDA(ctx, cudaMemcpyAsync(scores, m->gen_scores.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (counts && m->gen_scored) PGP_CUDA(ctx, cudaMemcpyAsync(counts, m->gen_counts.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (scores && m->gen_scored) PGP_CUDA(ctx, cudaMemcpyAsync(scores, m->gen_scores.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return (int)std::min<int64_t>(n, 0x7fffffff);
+}
+
+int pgp_get_bases(pgp_ctx* ctx, int obj, int32_t* ids, float* inv, uint8_t* ok, int cap) {
+  CHECK_CTX(ctx);
+  Model* m = get_model(ctx, obj);
+  if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", obj);
+  if (!ids || !inv || !ok) return pgp_fail(ctx, PGP_E_INVALID, "null output");
+  const int n = std::min(cap, m->n_gen_bases);
+  if (n <= 0) return 0;
+  int rc = k2_get_bases(ctx, n, ids, inv, ok);
+  return rc ? rc : n;
 }
 
 int pgp_tricp(pgp_ctx* ctx, int obj, const float* seg, int ns, double* poses, int k, float trim, float ratio, int max_iter, int* iters, float* energy) {

@@ -112,6 +112,8 @@ struct Model {
   // generated hypotheses (K2)
   DevBuf gen_T, gen_counts, gen_scores;
   int64_t n_gen = 0;
+  int n_gen_bases = 0;
+  bool gen_scored = false;
 };
 
 struct LastBatch {
@@ -172,6 +174,7 @@ int k2_find_quads(pgp_ctx* ctx, const Model& m, const int32_t* base4, float inv1
                   const int32_t* p1, int64_t n1, const int32_t* p2, int64_t n2, int32_t* quads_host, int64_t cap, int64_t* n_quads);
 int k2_rigid_from_quads(pgp_ctx* ctx, const Model& m, const int32_t* base4, const int32_t* quads_host, int64_t n, float* T_host, uint8_t* ok_host);
 int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, int64_t max_hyp, int64_t* n_hyp);
+int k2_get_bases(pgp_ctx* ctx, int n_bases, int32_t* ids_host, float* inv_host, uint8_t* ok_host);
 // k5_tricp.cu
 int k5_tricp(pgp_ctx* ctx, Model& m, const float* seg_xyz_host, int ns, double* poses16_host, int k, float trim, float ratio,
              int max_iter, int* iters_out, float* energy_out);

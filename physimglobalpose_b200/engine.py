@@ -255,6 +255,14 @@ class PoseEngine:
         self._check(self._lib.pgp_get_generated(self._ctx, obj, _ptr(T), _ptr(counts), _ptr(scores), n))
         return T.reshape(-1, 3, 4), counts, scores
 
+    def get_bases(self, obj: int, cap: int = 4096):
+        """Bases of the last generate_pcs call: (ids (n,4) scene indices, invariants (n,2), ok (n,) bool)."""
+        ids = np.zeros((cap, 4), np.int32)
+        inv = np.zeros((cap, 2), np.float32)
+        ok = np.zeros(cap, np.uint8)
+        n = self._check(self._lib.pgp_get_bases(self._ctx, obj, _ptr(ids), _ptr(inv), _ptr(ok), cap))
+        return ids[:n].copy(), inv[:n].copy(), ok[:n].astype(bool)
+
     # ------------------------------------------------------------------ K5
     def tricp(self, obj: int, segment_xyz, poses44, trim: float = 0.5, ratio: float = 0.99, max_iter: int = 100):
         seg = _f32(segment_xyz, 3)

@@ -72,3 +72,46 @@ def test_tricp_matches_oracle(engine, port_lib):
 def _oracle_tricp(port_lib, prob, T0):
     o = port_lib.PortOracle(prob.scene_xyz[:10], prob.scene_nrm[:10], prob.model_xyz, prob.model_nrm, prob.model_xyz, prob.model_nrm, prob.delta)
     return o.tricp(prob.scene_xyz, prob.model_xyz, T0, trim=0.5, ratio=0.99, max_iter=100)
+
+
+def _edge_len(a, b):
+    """(a - b).norm() in fp32 with the device's operation order: sqrt((x*x + y*y) + z*z)."""
+    e = (b - a).astype(np.float32)
+    return np.sqrt(np.float32(np.float32(e[0] * e[0]) + np.float32(e[1] * e[1])) + np.float32(e[2] * e[2]), dtype=np.float32)
+
+
+def test_batched_generator_equals_stage_composition(engine):
+    """pgp_generate_pcs (all bases of a chunk per launch) must produce exactly what the per-stage entry points
+    (pair extraction -> quad join -> rigid transforms, each pinned against the reference by the golden tests)
+    produce base by base: same transforms, same order, nothing dropped when no per-base cap applies."""
+    prob = synth.make_segment_problem(600, 900, 0.005, seed=15)
+    engine.set_scene(prob.scene_xyz, prob.scene_nrm, prob.delta)
+    engine.set_model(0, prob.model_xyz, prob.model_nrm)
+    n = engine.generate_pcs(0, seed=11, max_hyp=2_000_000, n_bases=40, max_quads_per_base=0)    # spans two chunks of 32 bases
+    T, _, _ = engine.get_generated(0)
+    ids, inv, ok = engine.get_bases(0)
+    assert len(ids) == 40 and ok.any()
+    P = prob.scene_xyz - engine.centroids(0)[0]
+    want = []
+    for b in range(40):
+        if not ok[b]:
+            continue
+        d1, d2 = _edge_len(P[ids[b, 0]], P[ids[b, 1]]), _edge_len(P[ids[b, 2]], P[ids[b, 3]])
+        p1 = engine.extract_pairs(0, float(d1), prob.delta)
+        p2 = engine.extract_pairs(0, float(d2), prob.delta)
+        if len(p1) == 0 or len(p2) == 0:
+            continue
+        quads = engine.find_quads(0, ids[b], inv[b, 0], inv[b, 1], prob.delta, p1, p2)
+        if len(quads) == 0:
+            continue
+        Tb, good = engine.rigid_from_quads(0, ids[b], quads)
+        want.append(Tb[good])
+    want = np.concatenate(want) if want else np.zeros((0, 3, 4), np.float32)
+    assert n == len(want) and n > 0
+    assert np.array_equal(T, want)
+    # with the per-base cap: at most 100 per base, a subset of the uncapped list in the same order
+    n2 = engine.generate_pcs(0, seed=11, max_hyp=2_000_000, n_bases=40, max_quads_per_base=100)
+    T2, _, _ = engine.get_generated(0)
+    assert n2 <= 40 * 100 and n2 <= n
+    rows = {r.tobytes() for r in want.reshape(len(want), -1)}
+    assert all(r.tobytes() in rows for r in T2.reshape(len(T2), -1))

@@ -66,6 +66,8 @@ typedef struct pgp_pcs_opts {
   float max_base_diameter;   /* <=0: estimate like init(), match4pcsBase.cc:274-283 */
   float overlap;             /* overlap_estimation (only scales the wide-base target), default 0.5 */
   int base_trials;           /* kNumberOfDiameterTrials = 1000 random triangles per base, :377-410 */
+  int mode;                  /* operMode (match4pcsBase.cc:300): 0 = wide random base + Super4PCS pair extraction (default here),
+                                1 = StoCS base sampling + PPF-map pair lookup (what the reference ships; needs a PPF map) */
 } pgp_pcs_opts;
 
 /* ---------------------------------------------------------------- context ------------------ */
@@ -190,6 +192,23 @@ PGP_API int pgp_generate_pcs(pgp_ctx* ctx, int obj, const pgp_pcs_opts* opts, ui
 PGP_API int pgp_score_generated(pgp_ctx* ctx, int obj, int mode);
 /* Copies generated transforms / their scores to the host (n x 12, n). */
 PGP_API int pgp_get_generated(pgp_ctx* ctx, int obj, float* T_host, uint32_t* counts_host, float* scores_host, int64_t cap);
+
+/* PPF map of object `obj`'s SEARCH cloud (the PPFMap argument of getProbableTransformsSuper4PCS, S4/super4pcs_test.cc:39-43,
+ * loaded from PPFMap.txt by Objects::readPPFMap, PPE/src/data_layer/Objects.cpp:31-49): n_keys rows, row k = key
+ * keys4[4k..4k+3] (computePPF bins, match4pcsBase.cc:582-598) -> pairs[2 offsets[k] .. 2 offsets[k+1]) of search-cloud
+ * indices.  Call after pgp_set_model. */
+PGP_API int pgp_set_ppf_map(pgp_ctx* ctx, int obj, const int32_t* keys4, const int64_t* offsets, const int32_t* pairs, int64_t n_keys);
+/* Builds that map on the device from the search cloud itself (all ordered pairs i != j) -- the offline generator the
+ * reference does not ship -- and installs it. */
+PGP_API int pgp_build_ppf_map(pgp_ctx* ctx, int obj);
+/* Copies the installed map out (any pointer may be NULL); *n_keys / *n_pairs receive the sizes.  Rows are in key order. */
+PGP_API int pgp_get_ppf_map(pgp_ctx* ctx, int obj, int32_t* keys4, int64_t cap_keys, int64_t* offsets, int32_t* pairs, int64_t cap_pairs,
+                            int64_t* n_keys, int64_t* n_pairs);
+/* computePPF (match4pcsBase.cc:582-598) of n scene index pairs: keys4 n x 4.  Parity hook. */
+PGP_API int pgp_scene_ppf_keys(pgp_ctx* ctx, const int32_t* pairs, int64_t n, int32_t* keys4);
+/* The engine seed the StoCS sampler gives std::default_random_engine for base `base`, attempt `attempt` of a generation
+ * seeded with `seed` (the reference seeds from the wall clock, match4pcsBase.cc:611). */
+PGP_API uint32_t pgp_stocs_engine_seed(uint64_t seed, int base, int attempt);
 
 /* The bases the last pgp_generate_pcs call drew from the scene (baseSet of Perform_N_steps, match4pcsBase.cc:1838-1853):
  * ids cap x 4 scene indices in the pairing TryQuadrilateral chose (:415-464), inv cap x 2 invariants, ok cap flags

@@ -260,3 +260,47 @@ class RefOracle(_Base):
         return dict(chain_pose=poses[:n].reshape(-1, 4, 4).transpose(0, 2, 1).copy(), chain_score=scores[:n].copy(),
                     transforms=T.reshape(-1, 3, 4), best_lcp=best.value, best_index=bi.value, stage_s=stage,
                     registered=reg[:nr].copy(), bases=bases[:nb].copy(), invariants=inv[:nb].copy())
+
+    # ---- operMode 1 (StoCS + PPF map)
+    def set_ppf_map(self, keys4, offsets, pairs):
+        k = np.ascontiguousarray(keys4, np.int32).reshape(-1, 4)
+        o = np.ascontiguousarray(offsets, np.int64)
+        p = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        self._fn("set_ppf_map", None, [C.c_void_p, _i32p, _i64p, _i32p, C.c_int64])(self.h, _p(k, _i32p), _p(o, _i64p), _p(p, _i32p), len(k))
+
+    def compute_ppf(self, pairs):
+        """Match4PCSBase::computePPF of scene index pairs -> (n, 4) int32."""
+        p = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        out = np.zeros((len(p), 4), np.int32)
+        self._fn("compute_ppf", None, [C.c_void_p, _i32p, C.c_int64, _i32p])(self.h, _p(p, _i32p), len(p), _p(out, _i32p))
+        return out
+
+    def select_stocs(self, engine_seed):
+        b = np.zeros(4, np.int32)
+        inv = np.zeros(2, np.float32)
+        ok = self._fn("select_stocs", C.c_int, [C.c_void_p, C.c_uint, _i32p, _f32p])(self.h, int(engine_seed), _p(b, _i32p), _p(inv, _f32p))
+        return bool(ok), b, inv
+
+    def congruent_set_mode1(self, base, inv1, inv2, cap=1 << 22):
+        b = np.ascontiguousarray(base, np.int32)
+        out = np.zeros((cap, 4), np.int32)
+        n = self._fn("congruent_set_mode1", C.c_int64, [C.c_void_p, _i32p, C.c_float, C.c_float, _i32p, C.c_int64])(
+            self.h, _p(b, _i32p), inv1, inv2, _p(out, _i32p), cap)
+        return out[: min(n, cap)].copy()
+
+
+def group_ppf_keys(keys4_all, n):
+    """All-ordered-pairs keys (n*n, 4; row t = pair (t // n, t % n)) -> map rows (keys4, offsets, pairs) in key order,
+    pairs inside a key in (i, j) order; the diagonal is skipped."""
+    k = np.asarray(keys4_all, np.int64).reshape(n * n, 4)
+    t = np.arange(n * n)
+    keep = (t // n) != (t % n)
+    k, t = k[keep], t[keep]
+    order = np.lexsort((t, k[:, 3], k[:, 2], k[:, 1], k[:, 0]))
+    k, t = k[order], t[order]
+    new = np.ones(len(k), bool)
+    new[1:] = np.any(k[1:] != k[:-1], axis=1)
+    starts = np.flatnonzero(new)
+    offsets = np.append(starts, len(k)).astype(np.int64)
+    pairs = np.stack([t // n, t % n], axis=1).astype(np.int32)
+    return k[starts].astype(np.int32), offsets, pairs

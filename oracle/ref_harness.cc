@@ -29,6 +29,9 @@
 
 #include "algorithms/super4pcs.h"
 
+extern "C" unsigned pgp_oracle_stocs_seed;
+unsigned pgp_oracle_stocs_seed = 1;
+
 using match_4pcs::Point3D;
 using match_4pcs::Quadrilateral;
 typedef std::map<std::vector<int>, std::vector<std::pair<int, int>>> PPFMapT;
@@ -69,6 +72,7 @@ struct Oracle : match_4pcs::MatchSuper4PCS {
   using Base::congruent_set_verification;
   using Base::P_diameter_;
   using Base::max_base_diameter_;
+  using Base::ExtractCongruentSet;
 
   std::vector<Point3D> P, Q, V;
   PPFMapT ppf;
@@ -346,6 +350,54 @@ int ref_get_bases(void* h, int32_t* ids, float* inv, int cap) {
     for (int k = 0; k < 4; ++k) ids[4 * i + k] = o->baseSet[i]->baseIds_[k];
     inv[2 * i] = o->baseSet[i]->invariant1_;
     inv[2 * i + 1] = o->baseSet[i]->invariant2_;
+  }
+  return n;
+}
+
+// ---- operMode 1 (StoCS + PPF map) pieces.  The map object lives in the Oracle (init() stored a pointer to it, :343).
+void ref_set_ppf_map(void* h, const int32_t* keys4, const int64_t* offsets, const int32_t* pairs, int64_t n_keys) {
+  Oracle* o = static_cast<Oracle*>(h);
+  o->ppf.clear();
+  for (int64_t k = 0; k < n_keys; ++k) {
+    std::vector<int> key(keys4 + 4 * k, keys4 + 4 * k + 4);
+    std::vector<std::pair<int, int>> v;
+    for (int64_t e = offsets[k]; e < offsets[k + 1]; ++e) v.push_back(std::make_pair(pairs[2 * e], pairs[2 * e + 1]));
+    o->ppf.insert(std::make_pair(key, v));
+  }
+}
+
+// Match4PCSBase::computePPF (:582-598) of n index pairs of the scene cloud P
+void ref_compute_ppf(void* h, const int32_t* pairs, int64_t n, int32_t* keys4) {
+  Oracle* o = static_cast<Oracle*>(h);
+  for (int64_t t = 0; t < n; ++t) {
+    int i = pairs[2 * t], j = pairs[2 * t + 1];
+    std::vector<int> k;
+    o->computePPF(i, j, k);
+    for (int c = 0; c < 4; ++c) keys4[4 * t + c] = k[c];
+  }
+}
+
+// SelectQuadrilateralStoCS (:600-792) with the engine seed pinned (oracle/Makefile, second patch)
+int ref_select_stocs(void* h, unsigned engine_seed, int* b, float* inv) {
+  Oracle* o = static_cast<Oracle*>(h);
+  pgp_oracle_stocs_seed = engine_seed;
+  float i1 = 0, i2 = 0, prob = 0;
+  bool ok = o->SelectQuadrilateralStoCS(i1, i2, b[0], b[1], b[2], b[3], prob);
+  inv[0] = i1; inv[1] = i2;
+  return ok ? 1 : 0;
+}
+
+// ExtractCongruentSet (:1929-2039) in operMode 1: pair lists from the PPF map, then FindCongruentQuadrilaterals
+int64_t ref_congruent_set_mode1(void* h, const int* b, float inv1, float inv2, int32_t* quads, int64_t cap) {
+  Oracle* o = static_cast<Oracle*>(h);
+  o->operMode = 1;
+  std::vector<int> ids(b, b + 4);
+  Super4PCS::BaseGraph g(ids, inv1, inv2, 1.0f);
+  o->ExtractCongruentSet(&g);
+  int64_t n = int64_t(g.congruent_quads.size());
+  for (int64_t i = 0; i < std::min(n, cap); ++i) {
+    quads[4 * i] = g.congruent_quads[i].vertices[0]; quads[4 * i + 1] = g.congruent_quads[i].vertices[1];
+    quads[4 * i + 2] = g.congruent_quads[i].vertices[2]; quads[4 * i + 3] = g.congruent_quads[i].vertices[3];
   }
   return n;
 }

@@ -22,7 +22,7 @@ class PgpHyp(C.Structure):
 
 class PgpPcsOpts(C.Structure):
     _fields_ = [("n_bases", C.c_int), ("max_quads_per_base", C.c_int), ("max_base_diameter", C.c_float),
-                ("overlap", C.c_float), ("base_trials", C.c_int)]
+                ("overlap", C.c_float), ("base_trials", C.c_int), ("mode", C.c_int)]
 
 
 class PgpError(RuntimeError):
@@ -66,6 +66,11 @@ _SIGNATURES = {
     "pgp_generate_pcs": (_i, [_vp, _i, _vp, C.c_uint64, _i64, _vp]),
     "pgp_score_generated": (_i, [_vp, _i, _i]),
     "pgp_get_generated": (_i, [_vp, _i, _vp, _vp, _vp, _i64]),
+    "pgp_set_ppf_map": (_i, [_vp, _i, _vp, _vp, _vp, _i64]),
+    "pgp_build_ppf_map": (_i, [_vp, _i]),
+    "pgp_get_ppf_map": (_i, [_vp, _i, _vp, _i64, _vp, _vp, _i64, _vp, _vp]),
+    "pgp_scene_ppf_keys": (_i, [_vp, _vp, _i64, _vp]),
+    "pgp_stocs_engine_seed": (C.c_uint32, [C.c_uint64, _i, _i]),
     "pgp_get_bases": (_i, [_vp, _i, _vp, _vp, _vp, _i]),
     "pgp_tricp": (_i, [_vp, _i, _vp, _i, _vp, _i, _f, _f, _i, _vp, _vp]),
 }

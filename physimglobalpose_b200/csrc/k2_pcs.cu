@@ -338,12 +338,17 @@ __global__ void k2_rigid(const float4* __restrict__ P_unsorted, const float4* __
 // then the pairing with the smallest segment-to-segment distance and its two invariants (in double,
 // as distSegmentToSegment is instantiated with Scalar = double, :428-435).
 
-__device__ double seg_seg(const double* p1, const double* p2, const double* q1, const double* q2, double& inv1, double& inv2) {
+// distSegmentToSegment<Vector3f, double> (match4pcsBase.cc:81-148): the difference vectors and their dot products are fp32
+// (Eigen's a0 b0 + (a1 b1 + a2 b2)), the case analysis runs in double (Scalar is deduced from the double invariants, :428-435),
+// and the closing distance |w + inv1 u - inv2 v| is fp32 again with the invariants narrowed to float.  The symmetric pairings
+// (i,j,k,l) / (k,l,i,j) tie in exact arithmetic, so which one TryQuadrilateral keeps depends on exactly this rounding.
+__device__ float seg_seg(const float* p1, const float* p2, const float* q1, const float* q2, double& inv1, double& inv2) {
   const double kSmall = 0.0001;
-  double u[3], v[3], w[3];
-  for (int k = 0; k < 3; ++k) { u[k] = p2[k] - p1[k]; v[k] = q2[k] - q1[k]; w[k] = p1[k] - q1[k]; }
-  const double a = u[0] * u[0] + u[1] * u[1] + u[2] * u[2], b = u[0] * v[0] + u[1] * v[1] + u[2] * v[2], c = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
-  const double d = u[0] * w[0] + u[1] * w[1] + u[2] * w[2], e = v[0] * w[0] + v[1] * w[1] + v[2] * w[2];
+  float u[3], v[3], w[3];
+  for (int k = 0; k < 3; ++k) { u[k] = __fsub_rn(p2[k], p1[k]); v[k] = __fsub_rn(q2[k], q1[k]); w[k] = __fsub_rn(p1[k], q1[k]); }
+  const double a = (double)dot3_tree(u[0], u[1], u[2], u[0], u[1], u[2]), b = (double)dot3_tree(u[0], u[1], u[2], v[0], v[1], v[2]),
+               c = (double)dot3_tree(v[0], v[1], v[2], v[0], v[1], v[2]), d = (double)dot3_tree(u[0], u[1], u[2], w[0], w[1], w[2]),
+               e = (double)dot3_tree(v[0], v[1], v[2], w[0], w[1], w[2]);
   const double f = a * c - b * b;
   double s1 = 0.0, s2 = f, t1 = 0.0, t2 = f;
   if (f < kSmall) { s1 = 0.0; s2 = 1.0; t1 = e; t2 = c; }
@@ -361,15 +366,16 @@ __device__ double seg_seg(const double* p1, const double* p2, const double* q1, 
   }
   inv1 = (fabs(s1) < kSmall ? 0.0 : s1 / s2);
   inv2 = (fabs(t1) < kSmall ? 0.0 : t1 / t2);
-  double r[3];
-  for (int k = 0; k < 3; ++k) r[k] = w[k] + inv1 * u[k] - inv2 * v[k];
-  return sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+  const float i1 = (float)inv1, i2 = (float)inv2;
+  float r[3];
+  for (int k = 0; k < 3; ++k) r[k] = __fsub_rn(__fadd_rn(w[k], __fmul_rn(i1, u[k])), __fmul_rn(i2, v[k]));
+  return __fsqrt_rn(dot3_tree(r[0], r[1], r[2], r[0], r[1], r[2]));
 }
 
 // TryQuadrilateral (match4pcsBase.cc:415-464): all ordered (i,j) with the remaining two in ascending order; the pairing with the
 // smallest segment-to-segment distance wins (first minimum), its invariants are kept and the ids are re-ordered accordingly.
 __device__ void try_quadrilateral(const float4* __restrict__ P, const int ids[4], BaseOut& o) {
-  double pt[4][3];
+  float pt[4][3];
   for (int k = 0; k < 4; ++k) { const float4 q = P[ids[k]]; pt[k][0] = q.x; pt[k][1] = q.y; pt[k][2] = q.z; }
   float min_d = 3.4028234663852886e38f; int bb[4] = {-1, -1, -1, -1}; float inv1 = 0.f, inv2 = 0.f;
   for (int i = 0; i < 4; ++i)
@@ -378,7 +384,7 @@ __device__ void try_quadrilateral(const float4* __restrict__ P, const int ids[4]
       int k = 0; while (k == i || k == j) k++;
       int l = 0; while (l == i || l == j || l == k) l++;
       double li1, li2;
-      const float sd = (float)seg_seg(pt[i], pt[j], pt[k], pt[l], li1, li2);
+      const float sd = seg_seg(pt[i], pt[j], pt[k], pt[l], li1, li2);
       if (sd < min_d) { min_d = sd; bb[0] = i; bb[1] = j; bb[2] = k; bb[3] = l; inv1 = (float)li1; inv2 = (float)li2; }
     }
   if (bb[0] >= 0) {
@@ -727,7 +733,7 @@ __global__ void k2s_combo_copy(PpfMapDev m, const int* __restrict__ slot, const 
 }
 
 struct Scratch {
-  DevBuf cnt, cnt2, off, flag, pairs1, pairs2, quads, bucket_of, key_of, bucket_start, sorted, T, ok, base, qn;
+  DevBuf cnt, cnt2, off, flag, curr, pairs1, pairs2, quads, bucket_of, key_of, bucket_start, sorted, T, ok, base, qn;
 };
 Scratch g_scratch[16];   // per device
 
@@ -971,7 +977,20 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
   PGP_CUDA(ctx, sc.base.reserve((size_t)nb_total * sizeof(BaseOut) + 64));
   PGP_CUDA(ctx, m.gen_T.reserve((size_t)std::max<int64_t>(max_hyp, 1) * 48));
   BaseOut* d_bases_all = reinterpret_cast<BaseOut*>(sc.base.as<char>() + 64);
-  k2_select_bases<<<nb_total, 256, 0, st>>>(s.unsorted.as<float4>(), s.n, max_diam, std::max(1, o->base_trials), seed, d_bases_all);
+  const bool stocs = o->mode == 1;
+  PpfMapDev pm{};
+  if (stocs) {
+    if (m.n_ppf_keys <= 0) return pgp_fail(ctx, PGP_E_INVALID, "PCS mode 1 (StoCS) needs the model's PPF map: pgp_set_ppf_map / pgp_build_ppf_map");
+    if (!s.has_nrm) return pgp_fail(ctx, PGP_E_INVALID, "PCS mode 1 (StoCS) needs scene normals");
+    pm.keys = m.ppf_keys.as<uint32_t>(); pm.offsets = m.ppf_offsets.as<uint32_t>(); pm.pairs = m.ppf_pairs.as<int2>(); pm.n_keys = m.n_ppf_keys;
+    PGP_CUDA(ctx, sc.curr.reserve((size_t)nb_total * s.n * 4));
+    StocsParams sp{};
+    sp.P = s.unsorted.as<float4>(); sp.aux = s.aux_orig.as<float4>(); sp.n = s.n; sp.bits = m.ppf_bits.as<uint32_t>();
+    sp.curr = sc.curr.as<float>(); sp.seed = seed; sp.base0 = 0;
+    k2s_select_bases<<<nb_total, 256, 0, st>>>(sp, d_bases_all);
+  } else {
+    k2_select_bases<<<nb_total, 256, 0, st>>>(s.unsorted.as<float4>(), s.n, max_diam, std::max(1, o->base_trials), seed, d_bases_all);
+  }
   ctx->launches++;
   int64_t cur = 0;
   for (int base0 = 0; base0 < nb_total && cur < max_hyp; base0 += chunk) {
@@ -985,20 +1004,39 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
     uint32_t* coff = sc.off.as<uint32_t>();            // ncombo + 1
     uint32_t* qoff = coff + ncombo + 2;                // nb + 1
     uint32_t* outoff = qoff + nb + 2;                  // nb + 1
-    PGP_CUDA(ctx, cudaMemsetAsync(cnt, 0, (ncnt + 1) * 4, st));
-    const dim3 pgrid((unsigned)((nq + 255) / 256), (unsigned)ncombo);
-    k2b_pairs<false><<<pgrid, 256, 0, st>>>(m.search.as<float4>(), nq, d_bases, eps, cnt, nullptr);
-    ctx->launches++;
-    uint64_t unordered = 0;
-    int rc = scan_u32(ctx, cnt, (int64_t)ncnt, &unordered);                 // sync 1
-    if (rc) return rc;
-    const int64_t ntot = (int64_t)unordered * 2;
-    if (ntot == 0) continue;
-    if (ntot >= (1ll << 31)) return pgp_fail(ctx, PGP_E_TOO_LARGE, "pair lists of one chunk exceed 2^31 entries");
-    PGP_CUDA(ctx, sc.pairs1.reserve((size_t)ntot * 8));
-    k2b_pairs<true><<<pgrid, 256, 0, st>>>(m.search.as<float4>(), nq, d_bases, eps, cnt, sc.pairs1.as<int2>());
-    k2b_combo_offsets<<<(ncombo + 256) / 256, 256, 0, st>>>(cnt, nq, ncombo, coff);
-    ctx->launches += 2;
+    int rc;
+    int64_t ntot = 0;
+    if (stocs) {
+      // pair lists come out of the PPF map: count per combo, scan, copy
+      int* slot = reinterpret_cast<int*>(cnt);
+      PGP_CUDA(ctx, cudaMemsetAsync(coff, 0, (size_t)(ncombo + 1) * 4, st));
+      k2s_combo_counts<<<(ncombo + 63) / 64, 64, 0, st>>>(pm, s.unsorted.as<float4>(), s.aux_orig.as<float4>(), d_bases, ncombo, coff, slot);
+      ctx->launches++;
+      uint64_t tot = 0;
+      rc = scan_u32(ctx, coff, ncombo, &tot);                               // sync 1
+      if (rc) return rc;
+      ntot = (int64_t)tot;
+      if (ntot == 0) continue;
+      if (ntot >= (1ll << 31)) return pgp_fail(ctx, PGP_E_TOO_LARGE, "pair lists of one chunk exceed 2^31 entries");
+      PGP_CUDA(ctx, sc.pairs1.reserve((size_t)ntot * 8));
+      k2s_combo_copy<<<dim3(64, (unsigned)ncombo), 256, 0, st>>>(pm, slot, coff, sc.pairs1.as<int2>());
+      ctx->launches++;
+    } else {
+      PGP_CUDA(ctx, cudaMemsetAsync(cnt, 0, (ncnt + 1) * 4, st));
+      const dim3 pgrid((unsigned)((nq + 255) / 256), (unsigned)ncombo);
+      k2b_pairs<false><<<pgrid, 256, 0, st>>>(m.search.as<float4>(), nq, d_bases, eps, cnt, nullptr);
+      ctx->launches++;
+      uint64_t unordered = 0;
+      rc = scan_u32(ctx, cnt, (int64_t)ncnt, &unordered);                   // sync 1
+      if (rc) return rc;
+      ntot = (int64_t)unordered * 2;
+      if (ntot == 0) continue;
+      if (ntot >= (1ll << 31)) return pgp_fail(ctx, PGP_E_TOO_LARGE, "pair lists of one chunk exceed 2^31 entries");
+      PGP_CUDA(ctx, sc.pairs1.reserve((size_t)ntot * 8));
+      k2b_pairs<true><<<pgrid, 256, 0, st>>>(m.search.as<float4>(), nq, d_bases, eps, cnt, sc.pairs1.as<int2>());
+      k2b_combo_offsets<<<(ncombo + 256) / 256, 256, 0, st>>>(cnt, nq, ncombo, coff);
+      ctx->launches += 2;
+    }
     // ---- join
     JoinParams p{};
     p.Qn = m.search_unit.as<float4>(); p.Q = m.search.as<float4>();
@@ -1081,3 +1119,106 @@ int k2_get_bases(pgp_ctx* ctx, int n_bases, int32_t* ids_host, float* inv_host, 
   }
   return PGP_OK;
 }
+
+// ------------------------------------------------------------------------------- PPF map (host side)
+// Installs a map given as {4-int key -> list of (i, j)} rows (what Objects::readPPFMap loads from PPFMap.txt,
+// PPE/src/data_layer/Objects.cpp:31-49).  Keys outside the packable range can never be produced by the scene side either.
+int k2_set_ppf_map(pgp_ctx* ctx, Model& m, const int32_t* keys4, const int64_t* offsets, const int32_t* pairs, int64_t n_keys) {
+  std::vector<std::pair<uint32_t, int64_t>> order;
+  order.reserve((size_t)n_keys);
+  for (int64_t k = 0; k < n_keys; ++k) {
+    const int kk[4] = {keys4[4 * k], keys4[4 * k + 1], keys4[4 * k + 2], keys4[4 * k + 3]};
+    const uint32_t pk = ppf_pack(kk);
+    if (pk != PPF_NOKEY && offsets[k + 1] > offsets[k]) order.push_back({pk, k});
+  }
+  std::stable_sort(order.begin(), order.end(), [](const std::pair<uint32_t, int64_t>& a, const std::pair<uint32_t, int64_t>& b) { return a.first < b.first; });
+  m.h_ppf_keys.clear(); m.h_ppf_offsets.clear(); m.h_ppf_pairs.clear();
+  m.h_ppf_offsets.push_back(0);
+  for (size_t t = 0; t < order.size(); ++t) {
+    const int64_t k = order[t].second;
+    if (t > 0 && order[t].first == order[t - 1].first) {       // duplicate key rows: concatenate
+      m.h_ppf_offsets.pop_back();
+    } else {
+      m.h_ppf_keys.push_back(order[t].first);
+    }
+    for (int64_t e = offsets[k]; e < offsets[k + 1]; ++e) {
+      const int32_t i = pairs[2 * e], j = pairs[2 * e + 1];
+      if (i < 0 || j < 0 || i >= m.nq || j >= m.nq) return pgp_fail(ctx, PGP_E_INVALID, "PPF map pair (%d, %d) out of range for a %d-point search cloud", i, j, m.nq);
+      m.h_ppf_pairs.push_back(i); m.h_ppf_pairs.push_back(j);
+    }
+    if (m.h_ppf_pairs.size() / 2 >= (1ull << 31)) return pgp_fail(ctx, PGP_E_TOO_LARGE, "PPF map too large");
+    m.h_ppf_offsets.push_back((uint32_t)(m.h_ppf_pairs.size() / 2));
+  }
+  m.n_ppf_keys = (int)m.h_ppf_keys.size();
+  m.n_ppf_pairs = (int64_t)m.h_ppf_pairs.size() / 2;
+  const size_t bit_words = ((size_t)PPF_D5_MAX << 15) / 32;
+  std::vector<uint32_t> bits(bit_words, 0u);
+  for (uint32_t pk : m.h_ppf_keys) bits[pk >> 5] |= 1u << (pk & 31);
+  cudaStream_t st = ctx->stream;
+  PGP_CUDA(ctx, m.ppf_keys.reserve(std::max<size_t>(m.h_ppf_keys.size(), 1) * 4));
+  PGP_CUDA(ctx, m.ppf_offsets.reserve(m.h_ppf_offsets.size() * 4));
+  PGP_CUDA(ctx, m.ppf_pairs.reserve(std::max<size_t>(m.h_ppf_pairs.size(), 2) * 4));
+  PGP_CUDA(ctx, m.ppf_bits.reserve(bit_words * 4));
+  if (m.n_ppf_keys) PGP_CUDA(ctx, cudaMemcpyAsync(m.ppf_keys.p, m.h_ppf_keys.data(), m.h_ppf_keys.size() * 4, cudaMemcpyHostToDevice, st));
+  PGP_CUDA(ctx, cudaMemcpyAsync(m.ppf_offsets.p, m.h_ppf_offsets.data(), m.h_ppf_offsets.size() * 4, cudaMemcpyHostToDevice, st));
+  if (m.n_ppf_pairs) PGP_CUDA(ctx, cudaMemcpyAsync(m.ppf_pairs.p, m.h_ppf_pairs.data(), m.h_ppf_pairs.size() * 4, cudaMemcpyHostToDevice, st));
+  PGP_CUDA(ctx, cudaMemcpyAsync(m.ppf_bits.p, bits.data(), bit_words * 4, cudaMemcpyHostToDevice, st));
+  PGP_CUDA(ctx, cudaStreamSynchronize(st));
+  return PGP_OK;
+}
+
+// The offline builder the reference does not ship (its PPFMap.txt files are a download): every ordered pair (i, j), i != j,
+// of the SEARCH cloud under the key computePPF gives it -- keys on the device (the same function that keys the scene side),
+// grouping on the host (stable: rows in (i, j) order inside a key).
+int k2_build_ppf_map(pgp_ctx* ctx, Model& m) {
+  Scratch& sc = g_scratch[ctx->device & 15];
+  const int n = m.nq;
+  if (n > 16384) return pgp_fail(ctx, PGP_E_TOO_LARGE, "PPF map builder: search cloud of %d points (limit 16384)", n);
+  const long long np = (long long)n * n;
+  PGP_CUDA(ctx, sc.cnt2.reserve((size_t)np * 4));
+  k2s_keys<<<(unsigned)((np + 255) / 256), 256, 0, ctx->stream>>>(m.search.as<float4>(), m.search_nrm.as<float4>(), n, nullptr, np, nullptr, sc.cnt2.as<uint32_t>());
+  ctx->launches++;
+  std::vector<uint32_t> packed((size_t)np);
+  PGP_CUDA(ctx, cudaMemcpyAsync(packed.data(), sc.cnt2.p, (size_t)np * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PGP_CUDA(ctx, cudaGetLastError());
+  std::vector<uint32_t> idx;
+  idx.reserve((size_t)np);
+  for (long long t = 0; t < np; ++t) if (packed[t] != PPF_NOKEY) idx.push_back((uint32_t)t);
+  std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return packed[a] < packed[b]; });
+  std::vector<int32_t> keys4, pairs;
+  std::vector<int64_t> offsets;
+  pairs.reserve(idx.size() * 2);
+  for (size_t t = 0; t < idx.size(); ++t) {
+    const uint32_t pk = packed[idx[t]];
+    if (t == 0 || pk != packed[idx[t - 1]]) {
+      offsets.push_back((int64_t)t);
+      keys4.push_back((int32_t)(pk >> 15) * 5); keys4.push_back((int32_t)((pk >> 10) & 31) * 10);
+      keys4.push_back((int32_t)((pk >> 5) & 31) * 10); keys4.push_back((int32_t)(pk & 31) * 10);
+    }
+    pairs.push_back((int32_t)(idx[t] / (uint32_t)n)); pairs.push_back((int32_t)(idx[t] % (uint32_t)n));
+  }
+  offsets.push_back((int64_t)idx.size());
+  return k2_set_ppf_map(ctx, m, keys4.data(), offsets.data(), pairs.data(), (int64_t)keys4.size() / 4);
+}
+
+// computePPF of arbitrary scene index pairs (parity hook): keys4_host n x 4
+int k2_scene_ppf_keys(pgp_ctx* ctx, const int32_t* pairs_host, int64_t n, int32_t* keys4_host) {
+  Scratch& sc = g_scratch[ctx->device & 15];
+  const Scene& s = ctx->scene;
+  if (n <= 0) return PGP_OK;
+  for (int64_t t = 0; t < 2 * n; ++t)
+    if (pairs_host[t] < 0 || pairs_host[t] >= s.n) return pgp_fail(ctx, PGP_E_INVALID, "scene index out of range");
+  PGP_CUDA(ctx, sc.pairs2.reserve((size_t)n * 8));
+  PGP_CUDA(ctx, sc.cnt2.reserve((size_t)n * 16));
+  PGP_CUDA(ctx, cudaMemcpyAsync(sc.pairs2.p, pairs_host, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  k2s_keys<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(s.unsorted.as<float4>(), s.aux_orig.as<float4>(), s.n, sc.pairs2.as<int2>(), n,
+                                                                 sc.cnt2.as<int32_t>(), nullptr);
+  ctx->launches++;
+  PGP_CUDA(ctx, cudaMemcpyAsync(keys4_host, sc.cnt2.p, (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PGP_CUDA(ctx, cudaGetLastError());
+  return PGP_OK;
+}
+
+uint32_t k2_stocs_engine_seed(uint64_t seed, int base, int attempt) { return stocs_base_seed(seed, base, attempt); }

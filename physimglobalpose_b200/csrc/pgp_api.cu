@@ -479,7 +479,7 @@ int pgp_topk_merge(const pgp_hyp* lists, int n_lists, int k_each, int k, pgp_hyp
 
 void pgp_pcs_default_opts(pgp_pcs_opts* o) {
   if (!o) return;
-  o->n_bases = 100; o->max_quads_per_base = 100; o->max_base_diameter = -1.f; o->overlap = 0.5f; o->base_trials = 1000;
+  o->n_bases = 100; o->max_quads_per_base = 100; o->max_base_diameter = -1.f; o->overlap = 0.5f; o->base_trials = 1000; o->mode = 0;
 }
 
 int pgp_extract_pairs(pgp_ctx* ctx, int obj, float dist, float eps, int32_t* pairs, int64_t cap, int64_t* n_pairs) {
@@ -545,6 +545,47 @@ int pgp_get_generated(pgp_ctx* ctx, int obj, float* T, uint32_t* counts, float* 
   }
   return (int)std::min<int64_t>(n, 0x7fffffff);
 }
+
+int pgp_set_ppf_map(pgp_ctx* ctx, int obj, const int32_t* keys4, const int64_t* offsets, const int32_t* pairs, int64_t n_keys) {
+  CHECK_CTX(ctx);
+  Model* m = get_model(ctx, obj);
+  if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", obj);
+  if (n_keys < 0 || (n_keys > 0 && (!keys4 || !offsets || !pairs))) return pgp_fail(ctx, PGP_E_INVALID, "bad PPF map");
+  return k2_set_ppf_map(ctx, *m, keys4, offsets, pairs, n_keys);
+}
+
+int pgp_build_ppf_map(pgp_ctx* ctx, int obj) {
+  CHECK_CTX(ctx);
+  Model* m = get_model(ctx, obj);
+  if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", obj);
+  return k2_build_ppf_map(ctx, *m);
+}
+
+int pgp_get_ppf_map(pgp_ctx* ctx, int obj, int32_t* keys4, int64_t cap_keys, int64_t* offsets, int32_t* pairs, int64_t cap_pairs,
+                    int64_t* n_keys, int64_t* n_pairs) {
+  CHECK_CTX(ctx);
+  Model* m = get_model(ctx, obj);
+  if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", obj);
+  if (n_keys) *n_keys = m->n_ppf_keys;
+  if (n_pairs) *n_pairs = m->n_ppf_pairs;
+  const int64_t nk = std::min<int64_t>(cap_keys, m->n_ppf_keys);
+  for (int64_t k = 0; k < nk; ++k) {
+    const uint32_t pk = m->h_ppf_keys[k];
+    if (keys4) { keys4[4 * k] = (int32_t)(pk >> 15) * 5; keys4[4 * k + 1] = (int32_t)((pk >> 10) & 31) * 10; keys4[4 * k + 2] = (int32_t)((pk >> 5) & 31) * 10; keys4[4 * k + 3] = (int32_t)(pk & 31) * 10; }
+    if (offsets) { offsets[k] = m->h_ppf_offsets[k]; offsets[k + 1] = m->h_ppf_offsets[k + 1]; }
+  }
+  if (pairs) memcpy(pairs, m->h_ppf_pairs.data(), (size_t)std::min<int64_t>(cap_pairs, m->n_ppf_pairs) * 8);
+  return PGP_OK;
+}
+
+int pgp_scene_ppf_keys(pgp_ctx* ctx, const int32_t* pairs, int64_t n, int32_t* keys4) {
+  CHECK_CTX(ctx);
+  if (!ctx->scene.ready) return pgp_fail(ctx, PGP_E_NO_SCENE, "pgp_set_scene first");
+  if (n < 0 || (n > 0 && (!pairs || !keys4))) return pgp_fail(ctx, PGP_E_INVALID, "null argument");
+  return k2_scene_ppf_keys(ctx, pairs, n, keys4);
+}
+
+uint32_t pgp_stocs_engine_seed(uint64_t seed, int base, int attempt) { return k2_stocs_engine_seed(seed, base, attempt); }
 
 int pgp_get_bases(pgp_ctx* ctx, int obj, int32_t* ids, float* inv, uint8_t* ok, int cap) {
   CHECK_CTX(ctx);

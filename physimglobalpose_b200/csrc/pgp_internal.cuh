@@ -114,6 +114,12 @@ struct Model {
   int64_t n_gen = 0;
   int n_gen_bases = 0;
   bool gen_scored = false;
+  // PPF map of the SEARCH cloud (operMode 1 / StoCS): sorted packed keys -> pair lists, + presence bitset
+  DevBuf ppf_keys, ppf_offsets, ppf_pairs, ppf_bits;
+  int n_ppf_keys = 0;
+  int64_t n_ppf_pairs = 0;
+  std::vector<uint32_t> h_ppf_keys, h_ppf_offsets;
+  std::vector<int32_t> h_ppf_pairs;
 };
 
 struct LastBatch {
@@ -174,6 +180,10 @@ int k2_find_quads(pgp_ctx* ctx, const Model& m, const int32_t* base4, float inv1
                   const int32_t* p1, int64_t n1, const int32_t* p2, int64_t n2, int32_t* quads_host, int64_t cap, int64_t* n_quads);
 int k2_rigid_from_quads(pgp_ctx* ctx, const Model& m, const int32_t* base4, const int32_t* quads_host, int64_t n, float* T_host, uint8_t* ok_host);
 int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, int64_t max_hyp, int64_t* n_hyp);
+int k2_set_ppf_map(pgp_ctx* ctx, Model& m, const int32_t* keys4, const int64_t* offsets, const int32_t* pairs, int64_t n_keys);
+int k2_build_ppf_map(pgp_ctx* ctx, Model& m);
+int k2_scene_ppf_keys(pgp_ctx* ctx, const int32_t* pairs_host, int64_t n, int32_t* keys4_host);
+uint32_t k2_stocs_engine_seed(uint64_t seed, int base, int attempt);
 int k2_get_bases(pgp_ctx* ctx, int n_bases, int32_t* ids_host, float* inv_host, uint8_t* ok_host);
 // k5_tricp.cu
 int k5_tricp(pgp_ctx* ctx, Model& m, const float* seg_xyz_host, int ns, double* poses16_host, int k, float trim, float ratio,

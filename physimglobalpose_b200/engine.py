@@ -255,6 +255,36 @@ class PoseEngine:
         self._check(self._lib.pgp_get_generated(self._ctx, obj, _ptr(T), _ptr(counts), _ptr(scores), n))
         return T.reshape(-1, 3, 4), counts, scores
 
+    def set_ppf_map(self, obj: int, keys4, offsets, pairs):
+        """Installs the model's PPF map (rows: key (4 ints) -> pairs[offsets[k]:offsets[k+1]]), the PPFMap argument of
+        getProbableTransformsSuper4PCS."""
+        k = np.ascontiguousarray(keys4, np.int32).reshape(-1, 4)
+        o = np.ascontiguousarray(offsets, np.int64)
+        p = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        assert len(o) == len(k) + 1
+        self._check(self._lib.pgp_set_ppf_map(self._ctx, obj, _ptr(k), _ptr(o), _ptr(p), len(k)))
+
+    def build_ppf_map(self, obj: int):
+        self._check(self._lib.pgp_build_ppf_map(self._ctx, obj))
+
+    def get_ppf_map(self, obj: int):
+        nk, npr = C.c_int64(0), C.c_int64(0)
+        self._check(self._lib.pgp_get_ppf_map(self._ctx, obj, None, 0, None, None, 0, C.byref(nk), C.byref(npr)))
+        keys = np.zeros((nk.value, 4), np.int32)
+        offs = np.zeros(nk.value + 1, np.int64)
+        pairs = np.zeros((npr.value, 2), np.int32)
+        self._check(self._lib.pgp_get_ppf_map(self._ctx, obj, _ptr(keys), nk.value, _ptr(offs), _ptr(pairs), npr.value, C.byref(nk), C.byref(npr)))
+        return keys, offs, pairs
+
+    def scene_ppf_keys(self, pairs) -> np.ndarray:
+        p = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        out = np.zeros((len(p), 4), np.int32)
+        self._check(self._lib.pgp_scene_ppf_keys(self._ctx, _ptr(p), len(p), _ptr(out)))
+        return out
+
+    def stocs_engine_seed(self, seed: int, base: int, attempt: int = 0) -> int:
+        return int(self._lib.pgp_stocs_engine_seed(int(seed), int(base), int(attempt)))
+
     def get_bases(self, obj: int, cap: int = 4096):
         """Bases of the last generate_pcs call: (ids (n,4) scene indices, invariants (n,2), ok (n,) bool)."""
         ids = np.zeros((cap, 4), np.int32)

@@ -88,7 +88,50 @@ def main():
     np.savez_compressed(os.path.join(HERE, "pcs_small.npz"), scene_xyz=seg.scene_xyz, scene_nrm=seg.scene_nrm, model_xyz=seg.model_xyz,
                         model_nrm=seg.model_nrm, delta=np.float64(seg.delta), cP=scP, cQ=scQ, bases=np.array(bases, np.int32), invariants=np.array(invs, np.float32),
                         **pairs_out, **quads_out, **rigid_out)
+    mint_stocs()
     print("golden vectors written:", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
+
+
+def mint_stocs():
+    """operMode 1 (the shipped generator): computePPF keys, the model's PPF map, SelectQuadrilateralStoCS draws with the
+    engine seed pinned (oracle/Makefile, second patch) and ExtractCongruentSet in mode 1 -- all from the reference itself."""
+    from oracle import pyoracle
+    from physimglobalpose_b200 import _lib
+    lib = _lib.load()                                    # only for the host-side seed derivation pgp_stocs_engine_seed
+    seg = synth.make_segment_problem(300, 400, 0.005, seed=301)
+    n = len(seg.model_xyz)
+    # the model's map: the reference's computePPF over all ordered pairs of the model cloud (an oracle whose P is the model)
+    mref = RefOracle(seg.model_xyz, seg.model_nrm, seg.model_xyz, seg.model_nrm, seg.model_xyz, seg.model_nrm, seg.delta)
+    allp = np.stack(np.meshgrid(np.arange(n), np.arange(n), indexing="ij"), -1).reshape(-1, 2).astype(np.int32)
+    keys4, offsets, pairs = pyoracle.group_ppf_keys(mref.compute_ppf(allp), n)
+    ref = RefOracle(seg.scene_xyz, seg.scene_nrm, seg.model_xyz, seg.model_nrm, seg.model_xyz, seg.model_nrm, seg.delta)
+    ref.set_ppf_map(keys4, offsets, pairs)
+    rng = np.random.default_rng(302)
+    sp = rng.integers(0, len(seg.scene_xyz), size=(4000, 2)).astype(np.int32)
+    scene_keys = ref.compute_ppf(sp)
+    user_seed, n_bases = 77, 48
+    ok_l, ids_l, inv_l, att_l = [], [], [], []
+    for b in range(n_bases):
+        ok, ids, inv, used = False, np.zeros(4, np.int32), np.zeros(2, np.float32), 16
+        for a in range(16):
+            ok, ids, inv = ref.select_stocs(int(lib.pgp_stocs_engine_seed(user_seed, b, a)))
+            if ok:
+                used = a
+                break
+        ok_l.append(ok); ids_l.append(ids.copy() if ok else np.zeros(4, np.int32)); inv_l.append(inv.copy() if ok else np.zeros(2, np.float32)); att_l.append(used)
+    quads = {}
+    kept = 0
+    for b in range(n_bases):
+        if not ok_l[b] or kept >= 6:
+            continue
+        q = ref.congruent_set_mode1(ids_l[b], float(inv_l[b][0]), float(inv_l[b][1]))
+        if 0 < len(q) <= 20000:
+            quads[f"quads_b{b}"] = q
+            kept += 1
+    np.savez_compressed(os.path.join(HERE, "stocs_small.npz"), scene_xyz=seg.scene_xyz, scene_nrm=seg.scene_nrm, model_xyz=seg.model_xyz,
+                        model_nrm=seg.model_nrm, delta=np.float64(seg.delta), map_keys=keys4, map_offsets=offsets, map_pairs=pairs,
+                        scene_pairs=sp, scene_keys=scene_keys, user_seed=np.int64(user_seed), base_ok=np.array(ok_l, bool),
+                        base_ids=np.array(ids_l, np.int32), base_inv=np.array(inv_l, np.float32), base_attempts=np.array(att_l, np.int32), **quads)
 
 
 if __name__ == "__main__":

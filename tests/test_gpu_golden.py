@@ -90,3 +90,45 @@ def test_pcs_golden(engine):
     # cone) is reproduced cell for cell; only samples that land within rounding of a cell border may differ.
     assert total_common >= 0.995 * total_ref, (total_common, total_ref, total_ours)
     assert total_ours <= 1.005 * total_ref + 2, (total_common, total_ref, total_ours)
+
+
+def test_stocs_golden(engine):
+    """operMode 1, the generator the reference ships: computePPF keys, the PPF-map builder, SelectQuadrilateralStoCS (with the
+    reference's own std::default_random_engine + std::discrete_distribution draw reproduced for a pinned engine seed) and the
+    mode-1 congruent sets, against vectors minted from the compiled reference (tests/golden/make_golden.py::mint_stocs)."""
+    g = np.load(os.path.join(G, "stocs_small.npz"))
+    delta = float(g["delta"])
+    engine.set_scene(g["scene_xyz"], g["scene_nrm"], delta)
+    engine.set_model(0, g["model_xyz"], g["model_nrm"])
+    assert np.array_equal(engine.scene_ppf_keys(g["scene_pairs"]), g["scene_keys"])          # computePPF, bit-exact bins
+    # the builder the reference lacks == the reference's computePPF over all ordered model pairs
+    engine.build_ppf_map(0)
+    keys, offs, pairs = engine.get_ppf_map(0)
+    assert np.array_equal(keys, g["map_keys"]) and np.array_equal(offs, g["map_offsets"]) and np.array_equal(pairs, g["map_pairs"])
+    # the same map handed over the way the ROS node does (PPFMap argument)
+    engine.set_ppf_map(0, g["map_keys"], g["map_offsets"], g["map_pairs"])
+    n_bases = len(g["base_ok"])
+    n = engine.generate_pcs(0, seed=int(g["user_seed"]), max_hyp=1_000_000, n_bases=n_bases, max_quads_per_base=0, mode=1)
+    ids, inv, ok = engine.get_bases(0)
+    assert np.array_equal(ok, g["base_ok"])
+    assert np.array_equal(ids, g["base_ids"])                    # same four points, same pairing
+    assert np.array_equal(inv, g["base_inv"])                    # same invariants, bit for bit
+    # congruent sets of the bases the golden file holds: pair lists = map rows of the two base edges
+    rows = {tuple(k): (int(a), int(b)) for k, a, b in zip(g["map_keys"].tolist(), g["map_offsets"][:-1], g["map_offsets"][1:])}
+    total = 0
+    for name in g.files:
+        if not name.startswith("quads_b"):
+            continue
+        b = int(name[len("quads_b"):])
+        k1 = tuple(engine.scene_ppf_keys([[ids[b, 0], ids[b, 1]]])[0].tolist())
+        k2 = tuple(engine.scene_ppf_keys([[ids[b, 2], ids[b, 3]]])[0].tolist())
+        p1 = g["map_pairs"][rows[k1][0]:rows[k1][1]]
+        p2 = g["map_pairs"][rows[k2][0]:rows[k2][1]]
+        q = engine.find_quads(0, ids[b], inv[b, 0], inv[b, 1], delta, p1, p2)
+        assert _pairset(q) == _pairset(g[name])
+        total += len(q)
+    assert total > 0 and n > 0
+    # and the generated batch scores like any other
+    engine.score_generated(0, "weighted")
+    T, counts, scores = engine.get_generated(0)
+    assert len(T) == n and scores.max() > 0

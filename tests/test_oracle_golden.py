@@ -102,3 +102,53 @@ def test_port_equals_reference_live(port_lib):
     assert np.array_equal(cm, ref.verify(T))                       # the multi-thread CPU baseline driver is consistent
     cp, _ = port.verify_mt(T, 3)
     assert np.array_equal(cp, cm)
+
+
+# ---------------------------------------------------------------- operMode 1 (StoCS + PPF map)
+def _stocs_inputs(g):
+    from physimglobalpose_b200 import synth
+    P = (g["scene_xyz"] - synth.seq_centroid_f32(g["scene_xyz"])).astype(np.float32)
+    N = g["scene_nrm"] / np.linalg.norm(g["scene_nrm"], axis=1, keepdims=True)
+    return P, N.astype(np.float32)
+
+
+def test_stocs_port_matches_reference_golden():
+    """The numpy restatement of computePPF / SelectQuadrilateralStoCS / TryQuadrilateral (oracle/stocs_port.py) reproduces the
+    vectors minted from the compiled reference: same keys, same four points, same pairing, same invariants."""
+    from oracle import stocs_port
+    from physimglobalpose_b200 import _lib
+    g = np.load(os.path.join(G, "stocs_small.npz"))
+    P, N = _stocs_inputs(g)
+    sp, sk = g["scene_pairs"][:600], g["scene_keys"][:600]
+    got = np.array([stocs_port.compute_ppf(P[i], N[i], P[j], N[j]) for i, j in sp])
+    assert np.array_equal(got, sk)
+    keyset = set(map(tuple, g["map_keys"].tolist()))
+    prior = np.ones(len(P), np.float32)
+    lib = _lib.load()
+    for b in range(8):
+        seed = int(lib.pgp_stocs_engine_seed(int(g["user_seed"]), b, int(g["base_attempts"][b])))
+        ok, ids, inv = stocs_port.select_stocs(P, N, prior, keyset, seed)
+        assert ok == bool(g["base_ok"][b])
+        assert np.array_equal(ids, g["base_ids"][b]) and np.array_equal(inv, g["base_inv"][b])
+        if g["base_attempts"][b] > 0:       # the attempt before the accepted one fails in the port too
+            seed0 = int(lib.pgp_stocs_engine_seed(int(g["user_seed"]), b, int(g["base_attempts"][b]) - 1))
+            assert not stocs_port.select_stocs(P, N, prior, keyset, seed0)[0]
+
+
+def test_stocs_port_equals_reference_live():
+    from oracle import pyoracle, stocs_port
+    if not pyoracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    g = np.load(os.path.join(G, "stocs_small.npz"))
+    ref = pyoracle.RefOracle(g["scene_xyz"], g["scene_nrm"], g["model_xyz"], g["model_nrm"], g["model_xyz"], g["model_nrm"], float(g["delta"]))
+    ref.set_ppf_map(g["map_keys"], g["map_offsets"], g["map_pairs"])
+    P, N = ref.centred(0)
+    P0, N0 = _stocs_inputs(g)
+    assert np.array_equal(P, P0) and np.allclose(N, N0, atol=1e-6)
+    keyset = set(map(tuple, g["map_keys"].tolist()))
+    for seed in (11, 12, 13, 14, 15, 16):
+        ok, ids, inv = ref.select_stocs(seed)
+        ok2, ids2, inv2 = stocs_port.select_stocs(P, N, ref.priors(), keyset, seed)
+        assert ok == ok2
+        if ok:
+            assert np.array_equal(ids, ids2) and np.array_equal(inv, inv2)

@@ -227,6 +227,20 @@ PGP_API int pgp_get_bases(pgp_ctx* ctx, int obj, int32_t* ids, float* inv, uint8
 PGP_API int pgp_tricp(pgp_ctx* ctx, int obj, const float* seg_xyz_host, int ns, double* poses16_host, int k,
                       float trim, float ratio, int max_iter, int* iters_out, float* energy_out);
 
+/* ---------------------------------------------------------------- K6: MCTS node helpers ---- */
+
+/* Explained-point removal of UCTState::performTrICP (PPE/src/hypothesis_verification/mcts/UCTState.cpp:149-174): segment
+ * points closer than `threshold` (pointRemovalThreshold, 8 mm) to object `obj`'s VALIDATION cloud placed at each of the
+ * n_placed poses (row-major 4x4 doubles; the reference transforms the current object's model by the poses of the objects
+ * already placed, :150-155) are flagged.  explained: ns flags (1 = removed).  Returns the number of points that REMAIN. */
+PGP_API int pgp_remove_explained(pgp_ctx* ctx, int obj, const float* seg_xyz_host, int ns, const double* placed_poses16, int n_placed,
+                                 float threshold, uint8_t* explained);
+/* One MCTS expansion's refinement (UCTState::performTrICP, :121-204) for k candidate poses of object `obj` at once:
+ * explained-point removal, then pgp_tricp on the unexplained segment.  n_unexplained may be NULL. */
+PGP_API int pgp_mcts_tricp(pgp_ctx* ctx, int obj, const float* seg_xyz_host, int ns, const double* placed_poses16, int n_placed,
+                           float threshold, double* poses16_host, int k, float trim, float ratio, int max_iter, int* iters_out,
+                           float* energy_out, int* n_unexplained);
+
 #define PGP_MAX_OBJECTS 64
 #define PGP_MAX_CELLS (1ll << 29)
 

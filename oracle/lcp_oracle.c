@@ -649,3 +649,37 @@ int lo_tricp(const float* src, int ns, const float* tgt, int nt, float* T, float
   lo_tree_free(&tree);
   return it;
 }
+
+/* Explained-point removal of UCTState::performTrICP (PPE/src/hypothesis_verification/mcts/UCTState.cpp:149-174):
+ * explained cloud = the model cloud transformed by every placed pose (pcl::transformPointCloud, fp32, each output
+ * coordinate ((m0 x + m1 y) + m2 z) + m3), one FLANN radius search per segment point (L2_Simple squared distance summed
+ * left to right; RadiusResultSet keeps dist < radius^2).  RESTATED, PARITY UNPINNED: PCL / FLANN are not vendored.
+ * placed: n_placed x 12 row-major fp32 (utilities::convertToMatrix narrows the Isometry3d to Matrix4f).
+ * flags[i] = 1 when segment point i is explained.  Returns the number of points that remain. */
+int lo_remove_explained(const float* seg, int ns, const float* model, int nm, const float* placed, int n_placed, float threshold,
+                        unsigned char* flags) {
+  const float r2 = threshold * threshold;
+  float* ex = (float*)malloc(sizeof(float) * 3 * (size_t)nm * (size_t)(n_placed > 0 ? n_placed : 1));
+  for (int k = 0; k < n_placed; ++k) {
+    const float* T = placed + 12 * k;
+    for (int j = 0; j < nm; ++j) {
+      const float x = model[3 * j], y = model[3 * j + 1], z = model[3 * j + 2];
+      float* o = ex + 3 * ((size_t)k * nm + j);
+      for (int r = 0; r < 3; ++r) o[r] = ((T[4 * r] * x + T[4 * r + 1] * y) + T[4 * r + 2] * z) + T[4 * r + 3];
+    }
+  }
+  int kept = 0;
+  const size_t ne = (size_t)nm * (size_t)n_placed;
+  for (int i = 0; i < ns; ++i) {
+    unsigned char hit = 0;
+    for (size_t j = 0; j < ne && !hit; ++j) {
+      const float dx = seg[3 * i] - ex[3 * j], dy = seg[3 * i + 1] - ex[3 * j + 1], dz = seg[3 * i + 2] - ex[3 * j + 2];
+      const float d2 = (dx * dx + dy * dy) + dz * dz;
+      if (d2 < r2) hit = 1;
+    }
+    flags[i] = hit;
+    kept += hit ? 0 : 1;
+  }
+  free(ex);
+  return kept;
+}

@@ -178,6 +178,20 @@ class PortOracle(_Base):
         return Tio.reshape(3, 4), it, e.value
 
 
+def port_remove_explained(seg_xyz, model_xyz, placed_poses44, threshold=0.008):
+    """lo_remove_explained: mask of the segment points explained by the model placed at the given poses."""
+    build_port()
+    lib = C.CDLL(PORT_SO)
+    seg, mod = _f32(seg_xyz).reshape(-1, 3), _f32(model_xyz).reshape(-1, 3)
+    T = np.ascontiguousarray(np.asarray(placed_poses44, np.float64).reshape(-1, 4, 4)[:, :3, :], dtype=np.float32)
+    flags = np.zeros(len(seg), np.uint8)
+    f = lib.lo_remove_explained
+    f.restype = C.c_int
+    f.argtypes = [_f32p, C.c_int, _f32p, C.c_int, _f32p, C.c_int, C.c_float, C.POINTER(C.c_ubyte)]
+    kept = f(_p(seg, _f32p), len(seg), _p(mod, _f32p), len(mod), _p(T, _f32p), len(T), threshold, flags.ctypes.data_as(C.POINTER(C.c_ubyte)))
+    return flags.astype(bool), kept
+
+
 class RefOracle(_Base):
     prefix = "ref_"
 

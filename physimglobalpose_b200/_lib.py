@@ -72,6 +72,8 @@ _SIGNATURES = {
     "pgp_scene_ppf_keys": (_i, [_vp, _vp, _i64, _vp]),
     "pgp_stocs_engine_seed": (C.c_uint32, [C.c_uint64, _i, _i]),
     "pgp_get_bases": (_i, [_vp, _i, _vp, _vp, _vp, _i]),
+    "pgp_remove_explained": (_i, [_vp, _i, _vp, _i, _vp, _i, _f, _vp]),
+    "pgp_mcts_tricp": (_i, [_vp, _i, _vp, _i, _vp, _i, _f, _vp, _i, _f, _f, _i, _vp, _vp, _vp]),
     "pgp_tricp": (_i, [_vp, _i, _vp, _i, _vp, _i, _f, _f, _i, _vp, _vp]),
 }
 

@@ -1,6 +1,8 @@
 // Test driver: calls the drop-in exactly as CongruentSetMatching::generate does
 // (PPE/src/hypothesis_generation/ObjectPoseCandidateSet.cpp:66-68) and prints the outputs as JSON.
 #include <cstdio>
+#include <cstdlib>
+#include <fstream>
 #include <map>
 #include <string>
 #include <utility>
@@ -17,7 +19,7 @@ void getProbableTransformsSuper4PCS(std::string input1, std::string input2, std:
                                     std::vector<int>& registered_points);
 
 int main(int argc, char** argv) {
-  if (argc < 4) { fprintf(stderr, "usage: %s segment.ply model_validation.ply model_search.ply [prob.png fx fy cx cy]\n", argv[0]); return 2; }
+  if (argc < 4) { fprintf(stderr, "usage: %s segment.ply model_validation.ply model_search.ply [prob.png fx fy cx cy [PPFMap.txt]]\n", argv[0]); return 2; }
   std::pair<Eigen::Isometry3d, float> best;
   std::vector<std::pair<Eigen::Isometry3d, float>> set;
   std::map<std::vector<int>, std::vector<std::pair<int, int>>> ppf;
@@ -25,6 +27,16 @@ int main(int argc, char** argv) {
   Eigen::Matrix3f K;
   std::string png = argc > 4 ? argv[4] : "";
   if (argc > 8) { K(0, 0) = atof(argv[5]); K(1, 1) = atof(argv[6]); K(0, 2) = atof(argv[7]); K(1, 2) = atof(argv[8]); K(2, 2) = 1.f; }
+  if (argc > 9) {   // PPFMap.txt, the format Objects::readPPFMap parses (PPE/src/data_layer/Objects.cpp:31-49): f1 f2 f3 f4 count, then count pairs
+    std::ifstream f(argv[9]);
+    std::vector<int> key(4);
+    int cnt;
+    while (f >> key[0] >> key[1] >> key[2] >> key[3] >> cnt) {
+      std::vector<std::pair<int, int>> v;
+      for (int i = 0; i < cnt; ++i) { int a, b; f >> a >> b; v.push_back(std::make_pair(a, b)); }
+      ppf.insert(std::make_pair(key, v));
+    }
+  }
   getProbableTransformsSuper4PCS(argv[1], argv[2], argv[3], best, set, png, ppf, 0, K, "obj", "/tmp/", reg);
   printf("{\"best_score\": %.9g, \"n_hypotheses\": %zu, \"n_registered\": %zu, \"best_pose\": [", best.second, set.size(), reg.size());
   for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) printf("%s%.17g", (r || c) ? ", " : "", best.first(r, c));

@@ -5,15 +5,17 @@
 // the B200 through the C ABI of include/pgp.h.  Host-only C++; no CUDA, no Eigen, no PCL needed.
 //
 //   in : segment / model_validation / model_search PLY paths (as PCL's savePLYFile writes them),
-//        16-bit probability PNG path, PPFMap (accepted, not used: pairs come from the device-side
-//        pair extraction), intrinsics, object name, scene path
+//        16-bit probability PNG path, PPFMap (uploaded to the device; selects the shipped operMode 1 = StoCS base
+//        sampling + PPF-map pair lookup; an EMPTY map selects operMode 0 = wide random bases + device-side pair
+//        extraction), intrinsics, object name, scene path
 //   out: bestHypothesis (pose, score), hypothesisSet = the strictly-improving chain in generation
 //        order (match4pcsBase.cc:1888-1914), registered_points (scene indices matched by the best pose)
 // Failure behaviour: never throws across the boundary; on any error the outputs are identity / 0 /
 // empty (the reference: exit(-1) on unreadable input, uninitialised outputs on exceptions).
 //
 // Environment: PGP_DEVICE (CUDA device, default 0), PGP_LCP_MODE = weighted (default, the shipped
-// WeightedVerify) | count, PGP_DELTA (default 0.005 = S4/super4pcs_test.cc:20), PGP_SEED.
+// WeightedVerify) | count, PGP_DELTA (default 0.005 = S4/super4pcs_test.cc:20), PGP_SEED, PGP_PCS_MODE = stocs | super4pcs
+// (default: stocs when the caller's PPFMap is not empty -- the reference hard-sets operMode 1, match4pcsBase.cc:300).
 #include <zlib.h>
 
 #include <cmath>
@@ -184,7 +186,7 @@ void getProbableTransformsSuper4PCS(std::string input1, std::string input2, std:
                                     std::map<std::vector<int>, std::vector<std::pair<int, int>>>& PPFMap,
                                     int max_count_ppf, Eigen::Matrix3f camIntrinsic, std::string objName, std::string scenePath,
                                     std::vector<int>& registered_points) {
-  (void)PPFMap; (void)max_count_ppf; (void)objName; (void)scenePath;
+  (void)max_count_ppf; (void)objName; (void)scenePath;
   Eigen::Isometry3d identity;
 #ifdef PGP_USE_REAL_EIGEN
   identity.setIdentity();
@@ -224,6 +226,28 @@ void getProbableTransformsSuper4PCS(std::string input1, std::string input2, std:
       return fail("set_model");
     pgp_pcs_opts opts;
     pgp_pcs_default_opts(&opts);                    // 100 bases x <= 100 congruent quads (match4pcsBase.cc:290,1858)
+    const char* pe = getenv("PGP_PCS_MODE");
+    bool stocs = !PPFMap.empty() && !seg.nrm.empty() && !search.nrm.empty();
+    if (pe && !strcmp(pe, "super4pcs")) stocs = false;
+    if (pe && !strcmp(pe, "stocs") && PPFMap.empty()) {
+      if (pgp_build_ppf_map(ctx, 0)) return fail("build_ppf_map");      // no PPFMap.txt was loaded: build the map from the search cloud
+      stocs = !seg.nrm.empty() && !search.nrm.empty();
+    } else if (stocs) {
+      // std::map<vector<int>, vector<pair<int,int>>> (Objects::readPPFMap, PPE/src/data_layer/Objects.cpp:31-49) -> flat rows
+      std::vector<int32_t> keys4, prs;
+      std::vector<int64_t> offs;
+      keys4.reserve(PPFMap.size() * 4);
+      offs.reserve(PPFMap.size() + 1);
+      for (const auto& kv : PPFMap) {
+        if (kv.first.size() != 4) continue;
+        offs.push_back((int64_t)prs.size() / 2);
+        for (int c = 0; c < 4; ++c) keys4.push_back(kv.first[c]);
+        for (const auto& pr : kv.second) { prs.push_back(pr.first); prs.push_back(pr.second); }
+      }
+      offs.push_back((int64_t)prs.size() / 2);
+      if (pgp_set_ppf_map(ctx, 0, keys4.data(), offs.data(), prs.data(), (int64_t)keys4.size() / 4)) return fail("set_ppf_map");
+    }
+    opts.mode = stocs ? 1 : 0;
     int64_t n_hyp = 0;
     if (pgp_generate_pcs(ctx, 0, &opts, seed, 10000, &n_hyp)) return fail("generate_pcs");
     if (n_hyp == 0) return;

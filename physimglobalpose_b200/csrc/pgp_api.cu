@@ -608,3 +608,36 @@ int pgp_tricp(pgp_ctx* ctx, int obj, const float* seg, int ns, double* poses, in
 }
 
 }  // extern "C"
+
+int pgp_remove_explained(pgp_ctx* ctx, int obj, const float* seg, int ns, const double* placed16, int n_placed, float threshold, uint8_t* explained) {
+  CHECK_CTX(ctx);
+  Model* m = get_model(ctx, obj);
+  if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", obj);
+  if (ns < 0 || n_placed < 0 || (ns > 0 && (!seg || !explained)) || (n_placed > 0 && !placed16) || !(threshold >= 0.f))
+    return pgp_fail(ctx, PGP_E_INVALID, "pgp_remove_explained: bad argument");
+  int kept = 0;
+  int rc = k6_remove_explained(ctx, *m, seg, ns, placed16, n_placed, threshold, explained, &kept);
+  return rc ? rc : kept;
+}
+
+int pgp_mcts_tricp(pgp_ctx* ctx, int obj, const float* seg, int ns, const double* placed16, int n_placed, float threshold, double* poses, int k,
+                   float trim, float ratio, int max_iter, int* iters, float* energy, int* n_unexplained) {
+  CHECK_CTX(ctx);
+  Model* m = get_model(ctx, obj);
+  if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", obj);
+  if (!seg || ns <= 0 || !poses || k <= 0) return pgp_fail(ctx, PGP_E_INVALID, "pgp_mcts_tricp: empty input");
+  if (!(trim > 0.f) || !(ratio > 0.f)) return pgp_fail(ctx, PGP_E_INVALID, "pgp_mcts_tricp: trim and ratio must be > 0");
+  std::vector<uint8_t> flag((size_t)ns, 0);
+  int kept = ns;
+  if (n_placed > 0) {
+    int rc = k6_remove_explained(ctx, *m, seg, ns, placed16, n_placed, threshold, flag.data(), &kept);
+    if (rc) return rc;
+  }
+  std::vector<float> un((size_t)std::max(kept, 1) * 3);
+  int w = 0;
+  for (int i = 0; i < ns; ++i)                       // extract.setNegative(true): the survivors in their original order
+    if (!flag[i]) { memcpy(&un[3 * (size_t)w], seg + 3 * (size_t)i, 12); ++w; }
+  if (n_unexplained) *n_unexplained = kept;
+  if (kept == 0) { for (int i = 0; i < k; ++i) { if (iters) iters[i] = 0; if (energy) energy[i] = 0.f; } return PGP_OK; }
+  return k5_tricp(ctx, *m, un.data(), kept, poses, k, trim, ratio, max_iter, iters, energy);
+}

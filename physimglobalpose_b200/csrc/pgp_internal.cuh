@@ -208,3 +208,6 @@ __device__ __forceinline__ float dot3_tree(float a0, float a1, float a2, float b
 // cell coordinate of a centred coordinate; the SAME function bins scene points and queries, and
 // it is monotone, which is what the 27-cell completeness argument needs.
 __device__ __forceinline__ float cell_coord(float x, float lo, float inv_h) { return __fmul_rn(__fsub_rn(x, lo), inv_h); }
+// k6_explained.cu
+int k6_remove_explained(pgp_ctx* ctx, Model& m, const float* seg_xyz_host, int ns, const double* placed16_host, int n_placed, float threshold,
+                        uint8_t* flags_host, int* n_unexplained);

@@ -303,6 +303,28 @@ class PoseEngine:
                                         _ptr(iters), _ptr(energy)))
         return P.reshape(-1, 4, 4), iters, energy
 
+    # ------------------------------------------------------------------ K6
+    def remove_explained(self, obj: int, segment_xyz, placed_poses44, threshold: float = 0.008) -> np.ndarray:
+        """Boolean mask of the segment points EXPLAINED by the placed objects (UCTState.cpp:149-174)."""
+        seg = _f32(segment_xyz, 3)
+        P = np.ascontiguousarray(placed_poses44, dtype=np.float64).reshape(-1, 16)
+        flag = np.zeros(len(seg), np.uint8)
+        self._check(self._lib.pgp_remove_explained(self._ctx, obj, _ptr(seg), len(seg), _ptr(P) if len(P) else None, len(P), float(threshold), _ptr(flag)))
+        return flag.astype(bool)
+
+    def mcts_tricp(self, obj: int, segment_xyz, placed_poses44, poses44, threshold: float = 0.008, trim: float = 0.5, ratio: float = 0.99,
+                   max_iter: int = 100):
+        """UCTState::performTrICP for a batch of candidate poses: explained-point removal + trimmed ICP."""
+        seg = _f32(segment_xyz, 3)
+        placed = np.ascontiguousarray(placed_poses44, dtype=np.float64).reshape(-1, 16)
+        P = np.ascontiguousarray(poses44, dtype=np.float64).reshape(-1, 16).copy()
+        iters = np.zeros(len(P), np.int32)
+        energy = np.zeros(len(P), np.float32)
+        nun = C.c_int(0)
+        self._check(self._lib.pgp_mcts_tricp(self._ctx, obj, _ptr(seg), len(seg), _ptr(placed) if len(placed) else None, len(placed), float(threshold),
+                                             _ptr(P), len(P), float(trim), float(ratio), int(max_iter), _ptr(iters), _ptr(energy), C.byref(nun)))
+        return P.reshape(-1, 4, 4), iters, energy, nun.value
+
 
 def topk_merge(lists: Sequence[np.ndarray], k: int) -> np.ndarray:
     """Deterministic merge of per-rank top-k record arrays (pgp_topk_merge)."""

@@ -132,3 +132,34 @@ def test_stocs_golden(engine):
     engine.score_generated(0, "weighted")
     T, counts, scores = engine.get_generated(0)
     assert len(T) == n and scores.max() > 0
+
+
+def _c1_mask(g, name):
+    edges = g[f"{name}_mask_rle"]
+    flat = np.zeros(480 * 640 + 1, np.int8)
+    np.add.at(flat, edges[0::2], 1)
+    np.add.at(flat, edges[1::2], -1)
+    return (np.cumsum(flat)[:-1] > 0).reshape(480, 640)
+
+
+def test_c1_test_scene_golden(engine):
+    """configs[0] of BASELINE.json: the reference's own test-scene (frame-000000 + mask.png), three objects.  On the prepared
+    segment clouds the CUDA path must give the reference's numbers for the reference's own hypotheses: priors from the mask
+    image, inlier counts, weighted scores, and therefore the same arg-max pose."""
+    g = np.load(os.path.join(G, "c1_test_scene.npz"))
+    for name in g["names"]:
+        engine.set_scene(g[f"{name}_seg_xyz"], g[f"{name}_seg_nrm"], float(g["delta"]))
+        engine.set_scene_prior_image(np.where(_c1_mask(g, name), 10000, 0).astype(np.uint16), g["K"])
+        assert np.array_equal(engine.scene_priors(), g[f"{name}_priors"])
+        engine.set_model(0, g[f"{name}_model_xyz"], g[f"{name}_model_nrm"])
+        T = g[f"{name}_T"]
+        counts, _ = engine.score_lcp(0, T, "count")
+        assert np.array_equal(counts, g[f"{name}_counts"])
+        wn, ws = engine.score_lcp(0, T, "weighted")
+        assert np.array_equal(ws, g[f"{name}_wscore"]) and np.array_equal(wn, g[f"{name}_wnreg"].astype(np.uint32))
+        top = engine.topk(0, 1)
+        assert top["index"][0] == int(np.lexsort((np.arange(len(ws)), -ws))[0])
+        # our own generator on the same clouds reaches a comparable best score (different RNG, same algorithm)
+        engine.generate_pcs(0, seed=7, max_hyp=20000)
+        engine.score_generated(0, "weighted")
+        assert engine.topk(0, 1)["score"][0] >= 0.6 * ws.max()

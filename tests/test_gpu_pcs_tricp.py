@@ -115,3 +115,33 @@ def test_batched_generator_equals_stage_composition(engine):
     assert n2 <= 40 * 100 and n2 <= n
     rows = {r.tobytes() for r in want.reshape(len(want), -1)}
     assert all(r.tobytes() in rows for r in T2.reshape(len(T2), -1))
+
+
+def test_explained_point_removal_and_node_tricp(engine, port_lib):
+    """K6 + K5 = one MCTS expansion's refinement (UCTState::performTrICP): segment points within 8 mm of the objects already
+    placed are dropped (bit-equal flags vs the restatement), the rest refines the candidate poses exactly as pgp_tricp does
+    on the pre-filtered segment."""
+    prob = synth.make_segment_problem(1500, 1400, 0.005, seed=19)
+    engine.set_scene(prob.scene_xyz, prob.scene_nrm, prob.delta)
+    engine.set_model(0, prob.model_xyz, prob.model_nrm)
+    rng = np.random.default_rng(2)
+    # two "placed" poses: one overlapping a third of the segment (GT shifted along x), one far away
+    placed = []
+    P = prob.gt_pose.copy(); P[0, 3] += 0.06; placed.append(P)
+    P = prob.gt_pose.copy(); P[:3, 3] += np.array([0.5, 0.4, 0.2]); placed.append(P)
+    placed = np.array(placed)
+    mask = engine.remove_explained(0, prob.scene_xyz, placed, 0.008)
+    want, kept = port_lib.port_remove_explained(prob.scene_xyz, prob.model_xyz, placed, 0.008)
+    assert np.array_equal(mask, want) and 0 < mask.sum() < len(mask)
+    assert not engine.remove_explained(0, prob.scene_xyz, np.zeros((0, 4, 4)), 0.008).any()
+    cand = []
+    for _ in range(4):
+        Pc = prob.gt_pose.copy()
+        Pc[:3, :3] = Pc[:3, :3] @ synth.rot_axis_angle(rng.normal(size=3), rng.normal(0, 0.06))
+        Pc[:3, 3] += rng.normal(0, 0.004, size=3)
+        cand.append(Pc)
+    cand = np.array(cand)
+    refined, iters, energy, n_un = engine.mcts_tricp(0, prob.scene_xyz, placed, cand, 0.008, trim=0.5, ratio=0.99)
+    assert n_un == kept == int((~mask).sum())
+    r2, it2, e2 = engine.tricp(0, prob.scene_xyz[~mask], cand, trim=0.5, ratio=0.99)
+    assert np.array_equal(refined, r2) and np.array_equal(iters, it2) and np.array_equal(energy, e2)

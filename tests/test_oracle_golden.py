@@ -152,3 +152,28 @@ def test_stocs_port_equals_reference_live():
         assert ok == ok2
         if ok:
             assert np.array_equal(ids, ids2) and np.array_equal(inv, inv2)
+
+
+# ---------------------------------------------------------------- configs[0]: the reference's test-scene
+def test_port_c1_test_scene_matches_reference_golden(port_lib):
+    """The C restatement reproduces the reference's Verify / WeightedVerify on the three test-scene objects (segments prepared from
+    frame-000000 + mask.png, hypotheses from the reference's own Perform_N_steps; tests/golden/make_c1.py)."""
+    g = np.load(os.path.join(G, "c1_test_scene.npz"))
+    for name in g["names"]:
+        mask = _c1_mask(g, name)
+        prior_img = np.where(mask, 10000, 0).astype(np.uint16)
+        o = port_lib.PortOracle(g[f"{name}_seg_xyz"], g[f"{name}_seg_nrm"], g[f"{name}_model_xyz"], g[f"{name}_model_nrm"], g[f"{name}_model_xyz"],
+                                g[f"{name}_model_nrm"], float(g["delta"]), K=g["K"], prior_img=prior_img)
+        assert np.array_equal(o.priors(), g[f"{name}_priors"])
+        T = g[f"{name}_T"]
+        assert np.array_equal(o.verify(T), g[f"{name}_counts"])
+        ws, wn = o.weighted_verify(T)
+        assert np.array_equal(ws, g[f"{name}_wscore"]) and np.array_equal(wn, g[f"{name}_wnreg"])
+
+
+def _c1_mask(g, name):
+    edges = g[f"{name}_mask_rle"]
+    flat = np.zeros(480 * 640 + 1, np.int8)
+    np.add.at(flat, edges[0::2], 1)
+    np.add.at(flat, edges[1::2], -1)
+    return (np.cumsum(flat)[:-1] > 0).reshape(480, 640)

@@ -155,3 +155,18 @@ def test_multi_tile_model(engine, port_lib):
     ws, wn = o.weighted_verify(T)
     counts, scores = engine.score_lcp(0, T, "weighted")
     assert np.array_equal(counts, wn.astype(np.uint32)) and np.array_equal(scores, ws)
+
+
+def test_c5_shape_parity(engine, port_lib):
+    """configs[4] shape (30k-point model, 300k-point scene): the model spans four shared-memory tiles and the scene's cell table
+    is larger than shared memory (read through L1); counts and weighted scores on a sample of hypotheses equal the oracle's."""
+    prob = synth.make_problem(30000, 300000, 0.01, seed=51)
+    T = synth.make_hypotheses(prob, 48, seed=52)
+    _setup(engine, prob)
+    o = _oracle(port_lib, prob)
+    want = o.verify(T)
+    counts, _ = engine.score_lcp(0, T, "count")
+    assert np.array_equal(counts, want) and counts[0] == 30000
+    ws, wn = o.weighted_verify(T[:24])
+    c2, s2 = engine.score_lcp(0, T[:24], "weighted")
+    assert np.array_equal(c2, wn.astype(np.uint32)) and np.array_equal(s2, ws)

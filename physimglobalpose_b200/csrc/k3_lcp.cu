@@ -33,6 +33,8 @@ struct LcpParams {
   int tile_cap;              // model points per shared-memory tile
   const float* T;            // n x 12
   long long n;
+  long long n_bulk;          // fine kernel: hypotheses [0, n_bulk) are one work unit each, the rest are split into `split` model chunks
+  int split;                 // (so that the last wave of the persistent grid ends on quarter-sized units, not whole hypotheses)
   const float4* pts;
   const float4* aux;
   const uint32_t* cell_start;
@@ -414,7 +416,7 @@ __device__ __forceinline__ int resolve_nearest(const LcpParams& p, const FineCtx
 // FAST: voxel coordinates from the pre-scaled FMA transform a[]; otherwise the reference's
 // rounding sequence followed by the grid's own cell_coord (huge / non-finite matrices).
 template <bool SMEM_TABLE, bool FAST, int MODE>
-__device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCtx& f, const float* __restrict__ T, long long h, int tn_pad) {
+__device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCtx& f, const float* __restrict__ T, long long h, int m_begin, int m_end) {
   const Xf x = load_xf(T, h);
   float a[12];
 #pragma unroll
@@ -451,7 +453,7 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
     qn -= take;
   };
   const float4* mp = f.s_model + f.lane;
-  for (int base = 0; base < tn_pad; base += 32 * FUNROLL) {
+  for (int base = m_begin; base < m_end; base += 32 * FUNROLL) {
     uint32_t off[FUNROLL], sh[FUNROLL], code[FUNROLL];
 #pragma unroll
     for (int u = 0; u < FUNROLL; ++u) {
@@ -526,11 +528,21 @@ __global__ void __launch_bounds__(FTHREADS, 1) k3_fine_kernel(const __grid_const
     mbar_wait(&mbar, tile & 1);
     __syncthreads();
 
+    const long long n_units = p.n_bulk + (p.n - p.n_bulk) * p.split;
+    const int chunk = ((tn_pad / (32 * FUNROLL) + p.split - 1) / p.split) * (32 * FUNROLL);
     for (;;) {
       long long h = 0;
       if (lane == 0) h = (long long)atomicAdd(p.work + tile, 1ull);
       h = __shfl_sync(0xffffffffu, h, 0);
-      if (h >= p.n) break;
+      if (h >= n_units) break;
+      int m_begin = 0, m_end = tn_pad;
+      const bool whole = h < p.n_bulk;
+      if (!whole) {
+        const long long u = h - p.n_bulk;
+        h = p.n_bulk + u / p.split;
+        m_begin = (int)(u % p.split) * chunk;
+        m_end = min(tn_pad, m_begin + chunk);
+      }
       // bound on the transform's intermediates: decides whether the FMA fast path's error budget holds
       float bound = 0.f;
       {
@@ -540,10 +552,10 @@ __global__ void __launch_bounds__(FTHREADS, 1) k3_fine_kernel(const __grid_const
           bound = fmaxf(bound, (fabsf(x.m[4 * r]) + fabsf(x.m[4 * r + 1]) + fabsf(x.m[4 * r + 2])) * p.model_rinf + fabsf(x.m[4 * r + 3]));
       }
       const bool fast = bound <= p.g.pos_bound;     // false for NaN / huge matrices: those take the reference's arithmetic
-      const int tot = fast ? score_hypothesis<SMEM_TABLE, true, MODE>(p, f, p.T, h, tn_pad) : score_hypothesis<SMEM_TABLE, false, MODE>(p, f, p.T, h, tn_pad);
+      const int tot = m_begin >= m_end ? 0 : fast ? score_hypothesis<SMEM_TABLE, true, MODE>(p, f, p.T, h, m_begin, m_end) : score_hypothesis<SMEM_TABLE, false, MODE>(p, f, p.T, h, m_begin, m_end);
       if (lane == 0) {
         if (MODE == 0) {
-          if (p.n_tiles == 1) {
+          if (p.n_tiles == 1 && whole) {
             p.counts[h] = (uint32_t)tot;
             if (p.scores) p.scores[h] = __fdiv_rn((float)tot, (float)p.nv);
           } else if (tot) {
@@ -551,7 +563,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) k3_fine_kernel(const __grid_const
           }
         } else {
           const uint32_t gated = (uint32_t)tot & 0xffffu, w = (uint32_t)tot >> 16;   // tile <= 8192 points keeps the halves apart
-          if (p.n_tiles == 1) {
+          if (p.n_tiles == 1 && whole) {
             p.counts[h] = gated;
             if (p.scores) p.scores[h] = __fdiv_rn((float)w, (float)p.nv);           // weighted_match / Scalar(n) :1765
           } else {
@@ -705,11 +717,15 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     p.model_rinf = m.val_rinf;
     const size_t smem = (size_t)tile_cap * per_pt + bm + qb;
     PGP_CUDA(ctx, cudaMemsetAsync(p.work, 0, 8 * (size_t)p.n_tiles, st));
-    if (p.n_tiles > 1) {
-      PGP_CUDA(ctx, cudaMemsetAsync(counts_dev, 0, (size_t)n * 4, st));
-      if (mode == PGP_LCP_WEIGHTED && scores_dev) PGP_CUDA(ctx, cudaMemsetAsync(scores_dev, 0, (size_t)n * 4, st));
-    }
     int grid = (int)std::min<long long>((n + FWARPS - 1) / FWARPS, ctx->sm_count);
+    // the last two hypotheses' worth of work per warp is handed out in quarter-model units (shorter tail of the persistent grid)
+    p.split = (ctx->tail_split > 1 && n > 4ll * grid * FWARPS && tile_cap >= 4 * 32 * FUNROLL) ? ctx->tail_split : 1;
+    p.n_bulk = p.split > 1 ? n - 2ll * grid * FWARPS : n;
+    const long long zero_from = p.n_tiles > 1 ? 0 : p.n_bulk;       // hypotheses whose sums are accumulated with atomics
+    if (zero_from < n) {
+      PGP_CUDA(ctx, cudaMemsetAsync(counts_dev + zero_from, 0, (size_t)(n - zero_from) * 4, st));
+      if (mode == PGP_LCP_WEIGHTED && scores_dev) PGP_CUDA(ctx, cudaMemsetAsync(scores_dev + zero_from, 0, (size_t)(n - zero_from) * 4, st));
+    }
     auto launch = [&](auto kern) -> int {
       PGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       kern<<<grid, FTHREADS, smem, st>>>(p);
@@ -720,8 +736,8 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     else rc = bm ? launch(k3_fine_kernel<true, 1>) : launch(k3_fine_kernel<false, 1>);
     if (rc) return rc;
     ctx->launches++;
-    if (p.n_tiles > 1 && scores_dev) {
-      k3_finalise<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(counts_dev, scores_dev, n, m.nv, mode);
+    if (zero_from < n && scores_dev) {
+      k3_finalise<<<(unsigned)((n - zero_from + 255) / 256), 256, 0, st>>>(counts_dev + zero_from, scores_dev + zero_from, n - zero_from, m.nv, mode);
       ctx->launches++;
     }
     PGP_CUDA(ctx, cudaGetLastError());

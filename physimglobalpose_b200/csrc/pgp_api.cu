@@ -138,6 +138,7 @@ int64_t pgp_launch_count(const pgp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int pgp_set_option(pgp_ctx* ctx, const char* name, int value) {
   CHECK_CTX(ctx);
   if (name && !strcmp(name, "force_coarse")) { ctx->force_coarse = value; return PGP_OK; }
+  if (name && !strcmp(name, "tail_split")) { ctx->tail_split = value < 1 ? 1 : (value > 16 ? 16 : value); return PGP_OK; }
   return pgp_fail(ctx, PGP_E_INVALID, "unknown option %s", name ? name : "(null)");
 }
 

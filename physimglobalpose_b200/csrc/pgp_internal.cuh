@@ -146,6 +146,7 @@ struct pgp_ctx {
   DevBuf topk_out;
   void* pinned = nullptr; size_t pinned_cap = 0;
   int64_t launches = 0;
+  int tail_split = 4;     // K3 fine kernel: model chunks per hypothesis in the last wave (1 = off)
   int force_coarse = 0;   // test hook: score on the 27-cell path even when the fine grid exists
   std::string err;
 };

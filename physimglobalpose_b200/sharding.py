@@ -47,7 +47,7 @@ class DeviceTopkGather:
     into the all-gather send buffer on the device (pgp_topk_dev), the all-gather runs on the same
     stream order, and only the gathered world*k*64 bytes come back for the final merge."""
 
-    def __init__(self, engine, k: int, group=None):
+    def __init__(self, engine, k: int, group=None, slots: int = 2):
         import torch
         import torch.distributed as dist
 
@@ -55,16 +55,32 @@ class DeviceTopkGather:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.send = torch.zeros(k * 64, dtype=torch.uint8, device="cuda")
         self.recv = torch.zeros(self.world * k * 64, dtype=torch.uint8, device="cuda")
-        self.host = torch.zeros(self.world * k * 64, dtype=torch.uint8).pin_memory()
+        self._free = [torch.zeros(self.world * k * 64, dtype=torch.uint8).pin_memory() for _ in range(max(1, slots))]
 
     def __call__(self, obj: int, index_base: int) -> np.ndarray:
+        return self.collect(self.submit(obj, index_base))
+
+    # Pipelined form: submit() only enqueues (K4 -> all-gather -> async D2H into a pinned slot + an event) and returns a
+    # ticket, so the next step's scoring kernel can start without a host round trip; collect() waits for the ticket's event
+    # and does the deterministic host merge.  All work of a step stays on the one stream, in order.
+    def submit(self, obj: int, index_base: int):
+        import torch
         import torch.distributed as dist
 
+        host = torch.empty(self.world * self.k * 64, dtype=torch.uint8).pin_memory() if self._free == [] else self._free.pop()
         self.engine.topk_device(obj, self.k, index_base, self.send)
         if self.world > 1:
             dist.all_gather_into_tensor(self.recv, self.send, group=self.group)
-            self.host.copy_(self.recv, non_blocking=False)
+            host.copy_(self.recv, non_blocking=True)
         else:
-            self.host.copy_(self.send, non_blocking=False)
-        rec = self.host.numpy().view(HYP_DTYPE).reshape(self.world, self.k)
+            host.copy_(self.send, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return host, ev
+
+    def collect(self, ticket) -> np.ndarray:
+        host, ev = ticket
+        ev.synchronize()
+        rec = host.numpy().view(HYP_DTYPE).reshape(self.world, self.k).copy()
+        self._free.append(host)
         return topk_merge([rec[r] for r in range(self.world)], self.k)

@@ -170,3 +170,24 @@ def test_c5_shape_parity(engine, port_lib):
     ws, wn = o.weighted_verify(T[:24])
     c2, s2 = engine.score_lcp(0, T[:24], "weighted")
     assert np.array_equal(c2, wn.astype(np.uint32)) and np.array_equal(s2, ws)
+
+
+def test_tail_split_units(engine, port_lib):
+    """With enough hypotheses the last wave of the persistent grid is handed out in quarter-model work units whose partial sums
+    are combined with atomics: results must not depend on the split, and must equal the oracle's."""
+    prob = synth.make_problem(600, 20000, 0.01, seed=61)
+    T = synth.make_hypotheses(prob, 24000, seed=62)
+    _setup(engine, prob)
+    o = _oracle(port_lib, prob)
+    res = {}
+    for split in (4, 1, 3):
+        engine.set_option("tail_split", split)
+        res[split] = (engine.score_lcp(0, T, "count"), engine.score_lcp(0, T, "weighted"))
+    engine.set_option("tail_split", 4)
+    for split in (1, 3):
+        for mode in (0, 1):
+            assert np.array_equal(res[4][mode][0], res[split][mode][0]) and np.array_equal(res[4][mode][1], res[split][mode][1])
+    sel = np.r_[0:300, len(T) - 1500:len(T)]
+    assert np.array_equal(res[4][0][0][sel], o.verify(T[sel]))
+    ws, wn = o.weighted_verify(T[sel])
+    assert np.array_equal(res[4][1][1][sel], ws) and np.array_equal(res[4][1][0][sel], wn.astype(np.uint32))

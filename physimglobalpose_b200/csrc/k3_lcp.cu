@@ -34,6 +34,7 @@ struct LcpParams {
   const float* T;            // n x 12
   long long n;
   long long n_bulk;          // fine kernel: hypotheses [0, n_bulk) are one work unit each, the rest are split into `split` model chunks
+  const uint32_t* ready;     // streamed upload: number of hypotheses whose transforms have arrived (nullptr: all of them)
   int split;                 // (so that the last wave of the persistent grid ends on quarter-sized units, not whole hypotheses)
   const float4* pts;
   const float4* aux;
@@ -543,6 +544,12 @@ __global__ void __launch_bounds__(FTHREADS, 1) k3_fine_kernel(const __grid_const
         m_begin = (int)(u % p.split) * chunk;
         m_end = min(tn_pad, m_begin + chunk);
       }
+      if (p.ready) {
+        // the transforms are still being uploaded chunk by chunk on another stream (pgp_score_lcp); the counter is written by
+        // the copy engine after each chunk, chunks end on 384-byte boundaries so no cache line of T spans two of them
+        const volatile uint32_t* rd = p.ready;
+        for (int spin = 0; (long long)*rd <= h && spin < (1 << 23); ++spin) __nanosleep(200);   // bounded (> 1.5 s): never hang the device
+      }
       // bound on the transform's intermediates: decides whether the FMA fast path's error budget holds
       float bound = 0.f;
       {
@@ -668,12 +675,21 @@ static LcpParams make_params(pgp_ctx* ctx, const Model& m, const float* T, int64
   return p;
 }
 
-int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mode, uint32_t* counts_dev, float* scores_dev) {
+// true when k3_score will run k3_fine_kernel for this mode (the only kernel that can consume a batch while it is still being uploaded)
+bool k3_streams_upload(pgp_ctx* ctx, int mode) {
+  const Scene& s = ctx->scene;
+  if (s.g.fine != 8 || ctx->force_coarse) return false;
+  if (mode == PGP_LCP_WEIGHTED) return s.wlists_ready && s.priors_binary;
+  return true;
+}
+
+int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mode, uint32_t* counts_dev, float* scores_dev, const uint32_t* ready_dev) {
   if (n == 0) return PGP_OK;
   Scene& s = ctx->scene;
   LcpParams p = make_params(ctx, m, T_dev, n, counts_dev, scores_dev);
   cudaStream_t st = ctx->stream;
 
+  if (ready_dev && !k3_streams_upload(ctx, mode)) return pgp_fail(ctx, PGP_E_INVALID, "streamed upload needs the fine-grid kernel");
   if (mode == PGP_LCP_WEIGHTED && !s.priors_binary) {
     p.model = m.val_orig.as<float4>(); p.model_nrm = m.val_nrm_orig.as<float4>();
     const int T = 256;
@@ -715,6 +731,7 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     p.wvox = s.wvox.as<uint32_t>(); p.wbase = s.wbase.as<uint32_t>(); p.wlists = s.wlists.as<float4>(); p.aux_orig = s.aux_orig.as<float4>();
     p.bmrank_words = (int)(bm / 8);
     p.model_rinf = m.val_rinf;
+    p.ready = ready_dev;
     const size_t smem = (size_t)tile_cap * per_pt + bm + qb;
     PGP_CUDA(ctx, cudaMemsetAsync(p.work, 0, 8 * (size_t)p.n_tiles, st));
     int grid = (int)std::min<long long>((n + FWARPS - 1) / FWARPS, ctx->sm_count);

@@ -89,7 +89,8 @@ pgp_ctx* pgp_create(int device) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->back_stream, cudaStreamNonBlocking) != cudaSuccess) {
     pgp_fail(nullptr, PGP_E_CUDA, "cudaStreamCreate failed");
     delete ctx;
     return nullptr;
@@ -116,6 +117,7 @@ void pgp_destroy(pgp_ctx* ctx) {
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(ctx->own_stream);
   cudaStreamDestroy(ctx->copy_stream);
+  cudaStreamDestroy(ctx->back_stream);
   delete ctx;
 }
 
@@ -388,12 +390,44 @@ int pgp_score_lcp(pgp_ctx* ctx, int obj, const float* T, int64_t n, int mode, ui
   PGP_CUDA(ctx, ctx->batch_T.reserve((size_t)n * 48));
   PGP_CUDA(ctx, ctx->batch_counts.reserve((size_t)n * 4));
   PGP_CUDA(ctx, ctx->batch_scores.reserve((size_t)n * 4));
-  PGP_CUDA(ctx, cudaMemcpyAsync(ctx->batch_T.p, T, (size_t)n * 48, cudaMemcpyHostToDevice, ctx->stream));
-  rc = pgp_score_lcp_dev(ctx, obj, ctx->batch_T.as<float>(), n, mode, ctx->batch_counts.as<uint32_t>(), ctx->batch_scores.as<float>());
-  if (rc) return rc;
-  if (counts) PGP_CUDA(ctx, cudaMemcpyAsync(counts, ctx->batch_counts.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  if (scores) PGP_CUDA(ctx, cudaMemcpyAsync(scores, ctx->batch_scores.p, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  // Large batches are uploaded in four chunks on the copy stream while ONE scoring launch is already consuming them: the kernel
+  // hands out hypotheses in index order and, before touching hypothesis h, checks a device counter that the copy engine bumps
+  // after every chunk (k3_fine_kernel, LcpParams::ready).  Chunk boundaries are multiples of 8 hypotheses = 384 bytes, so no
+  // 128-byte line of T spans two chunks.  Only the first chunk's upload is exposed.
+  float* dT = ctx->batch_T.as<float>();
+  uint32_t* dC = ctx->batch_counts.as<uint32_t>();
+  float* dS = ctx->batch_scores.as<float>();
+  const int chunks = 4;
+  if (n >= 32768 && n < (1ll << 31) && k3_streams_upload(ctx, mode)) {
+    if (!ctx->pinned) { PGP_CUDA(ctx, cudaMallocHost(&ctx->pinned, 256)); ctx->pinned_cap = 256; }
+    uint32_t* marks = static_cast<uint32_t*>(ctx->pinned);                      // [0] = 0, [1..4] = hypotheses uploaded after chunk c
+    uint32_t* ready = reinterpret_cast<uint32_t*>(ctx->work.as<char>() + 320);
+    marks[0] = 0;
+    for (int c = 0; c < chunks; ++c) marks[c + 1] = (uint32_t)(c + 1 == chunks ? n : ((n * (c + 1) / chunks) & ~7ll));
+    PGP_CUDA(ctx, cudaEventRecord(ctx->ev[8], ctx->stream));                    // everything queued on the caller's stream so far
+    PGP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[8], 0));
+    PGP_CUDA(ctx, cudaMemcpyAsync(ready, marks, 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    for (int c = 0; c < chunks; ++c) {
+      const int64_t lo = marks[c], hi = marks[c + 1];
+      PGP_CUDA(ctx, cudaMemcpyAsync(dT + 12 * lo, T + 12 * lo, (size_t)(hi - lo) * 48, cudaMemcpyHostToDevice, ctx->copy_stream));
+      PGP_CUDA(ctx, cudaMemcpyAsync(ready, marks + c + 1, 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+      if (c == 0) {
+        PGP_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->copy_stream));
+        PGP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[0], 0));
+        rc = k3_score(ctx, *m, dT, n, mode, dC, dS, ready);
+        if (rc) return rc;
+      }
+    }
+    ctx->last.T = dT; ctx->last.counts = dC; ctx->last.scores = dS; ctx->last.n = n; ctx->last.mode = mode; ctx->last.obj = obj;
+  } else {
+    PGP_CUDA(ctx, cudaMemcpyAsync(dT, T, (size_t)n * 48, cudaMemcpyHostToDevice, ctx->stream));
+    rc = pgp_score_lcp_dev(ctx, obj, dT, n, mode, dC, dS);
+    if (rc) return rc;
+  }
+  if (counts) PGP_CUDA(ctx, cudaMemcpyAsync(counts, dC, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (scores) PGP_CUDA(ctx, cudaMemcpyAsync(scores, dS, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  PGP_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
   return PGP_OK;
 }
 

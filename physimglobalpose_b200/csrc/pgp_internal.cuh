@@ -136,8 +136,9 @@ struct pgp_ctx {
   int sm_count = 148;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
-  cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t copy_stream = nullptr;      // host -> device of the host-buffer API
+  cudaStream_t back_stream = nullptr;      // device -> host of the host-buffer API (PCIe is full duplex: its own stream)
+  cudaEvent_t ev[12] = {};                 // [0..3] chunk uploaded, [4..7] chunk scored, [8] batch start
   Scene scene;
   std::vector<Model> models;
   LastBatch last;
@@ -169,7 +170,8 @@ int k1_build_wlists(pgp_ctx* ctx);
 int k1_fine_stats(pgp_ctx* ctx, int64_t* out8);
 int pgp_scan_exclusive_u32(pgp_ctx* ctx, uint32_t* data, int64_t n, uint32_t* scratch);
 // k3_lcp.cu
-int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mode, uint32_t* counts_dev, float* scores_dev);
+int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mode, uint32_t* counts_dev, float* scores_dev, const uint32_t* ready_dev = nullptr);
+bool k3_streams_upload(pgp_ctx* ctx, int mode);
 int k3_nearest(pgp_ctx* ctx, const Model& m, const float* T_dev, int32_t* idx_dev, int gate);
 // k4_select.cu
 int k4_topk(pgp_ctx* ctx, const LastBatch& b, int k, int64_t index_base, pgp_hyp* out_host, int* n_out);

@@ -176,7 +176,7 @@ def test_tail_split_units(engine, port_lib):
     """With enough hypotheses the last wave of the persistent grid is handed out in quarter-model work units whose partial sums
     are combined with atomics: results must not depend on the split, and must equal the oracle's."""
     prob = synth.make_problem(600, 20000, 0.01, seed=61)
-    T = synth.make_hypotheses(prob, 24000, seed=62)
+    T = synth.make_hypotheses(prob, 52000, seed=62)      # > 2 x 24000: the host-buffer call is also cut into two overlapped chunks
     _setup(engine, prob)
     o = _oracle(port_lib, prob)
     res = {}

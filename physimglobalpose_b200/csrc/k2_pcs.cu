@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(128) k2_join_query(JoinParams p, const uint32_
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.n2) return;
   float inv1, inv2, cos_alpha; uint32_t bkt_base;
+  if (FILL && cnt[i + 1] == cnt[i]) return;                // the count pass found nothing for this pair: skip the cone rasterisation
   if (!join_ctx(p, i, 1, inv1, inv2, cos_alpha, bkt_base)) { if (!FILL) cnt[i] = 0; return; }
   const int2 pr = p.B[i];
   const float4 a = p.Qn[pr.x], b = p.Qn[pr.y];
@@ -992,6 +993,7 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
     k2_select_bases<<<nb_total, 256, 0, st>>>(s.unsorted.as<float4>(), s.n, max_diam, std::max(1, o->base_trials), seed, d_bases_all);
   }
   ctx->launches++;
+  PGP_CUDA(ctx, cudaGetLastError());
   int64_t cur = 0;
   for (int base0 = 0; base0 < nb_total && cur < max_hyp; base0 += chunk) {
     const int nb = std::min(chunk, nb_total - base0), ncombo = 2 * nb;
@@ -999,7 +1001,7 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
     // ---- pairs of all 2 nb (base, edge) combos
     const size_t ncnt = (size_t)ncombo * nq;
     PGP_CUDA(ctx, sc.cnt.reserve((ncnt + 1) * 4));
-    PGP_CUDA(ctx, sc.off.reserve((size_t)(3 * nb + 8) * 4 + 64));
+    PGP_CUDA(ctx, sc.off.reserve((size_t)(4 * nb + 16) * 4 + 64));
     uint32_t* cnt = sc.cnt.as<uint32_t>();
     uint32_t* coff = sc.off.as<uint32_t>();            // ncombo + 1
     uint32_t* qoff = coff + ncombo + 2;                // nb + 1
@@ -1012,6 +1014,7 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
       PGP_CUDA(ctx, cudaMemsetAsync(coff, 0, (size_t)(ncombo + 1) * 4, st));
       k2s_combo_counts<<<(ncombo + 63) / 64, 64, 0, st>>>(pm, s.unsorted.as<float4>(), s.aux_orig.as<float4>(), d_bases, ncombo, coff, slot);
       ctx->launches++;
+      PGP_CUDA(ctx, cudaGetLastError());
       uint64_t tot = 0;
       rc = scan_u32(ctx, coff, ncombo, &tot);                               // sync 1
       if (rc) return rc;
@@ -1021,11 +1024,13 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
       PGP_CUDA(ctx, sc.pairs1.reserve((size_t)ntot * 8));
       k2s_combo_copy<<<dim3(64, (unsigned)ncombo), 256, 0, st>>>(pm, slot, coff, sc.pairs1.as<int2>());
       ctx->launches++;
+      PGP_CUDA(ctx, cudaGetLastError());
     } else {
       PGP_CUDA(ctx, cudaMemsetAsync(cnt, 0, (ncnt + 1) * 4, st));
       const dim3 pgrid((unsigned)((nq + 255) / 256), (unsigned)ncombo);
       k2b_pairs<false><<<pgrid, 256, 0, st>>>(m.search.as<float4>(), nq, d_bases, eps, cnt, nullptr);
       ctx->launches++;
+      PGP_CUDA(ctx, cudaGetLastError());
       uint64_t unordered = 0;
       rc = scan_u32(ctx, cnt, (int64_t)ncnt, &unordered);                   // sync 1
       if (rc) return rc;
@@ -1036,6 +1041,7 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
       k2b_pairs<true><<<pgrid, 256, 0, st>>>(m.search.as<float4>(), nq, d_bases, eps, cnt, sc.pairs1.as<int2>());
       k2b_combo_offsets<<<(ncombo + 256) / 256, 256, 0, st>>>(cnt, nq, ncombo, coff);
       ctx->launches += 2;
+      PGP_CUDA(ctx, cudaGetLastError());
     }
     // ---- join
     JoinParams p{};
@@ -1055,18 +1061,21 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
     const unsigned gk = (unsigned)((ntot + 255) / 256);
     k2_join_keys<<<gk, 256, 0, st>>>(p, sc.bucket_of.as<uint32_t>(), sc.key_of.as<uint32_t>(), bs);
     ctx->launches++;
+    PGP_CUDA(ctx, cudaGetLastError());
     PGP_CUDA(ctx, ctx->scene.scratch.reserve((size_t)((nbuckets + 1) / 2048 + 4096) * 4));
     rc = pgp_scan_exclusive_u32(ctx, bs, (int64_t)nbuckets + 1, ctx->scene.scratch.as<uint32_t>());
     if (rc) return rc;
     PGP_CUDA(ctx, cudaMemcpyAsync(cursor, bs, nbuckets * 4, cudaMemcpyDeviceToDevice, st));
     k2_join_scatter<<<gk, 256, 0, st>>>(ntot, sc.bucket_of.as<uint32_t>(), cursor, sc.sorted.as<uint32_t>());
     ctx->launches++;
+    PGP_CUDA(ctx, cudaGetLastError());
     PGP_CUDA(ctx, sc.cnt2.reserve((size_t)(ntot + 1) * 4));
     uint32_t* cnt2 = sc.cnt2.as<uint32_t>();
     PGP_CUDA(ctx, cudaMemsetAsync(cnt2 + ntot, 0, 4, st));
     const unsigned gq = (unsigned)((ntot + 127) / 128);
     k2_join_query<false><<<gq, 128, 0, st>>>(p, bs, sc.sorted.as<uint32_t>(), sc.key_of.as<uint32_t>(), cnt2, nullptr, 0);
     ctx->launches++;
+    PGP_CUDA(ctx, cudaGetLastError());
     uint64_t nquads = 0;
     rc = scan_u32(ctx, cnt2, ntot, &nquads);                                // sync 2
     if (rc) return rc;
@@ -1084,6 +1093,7 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
     k2b_rigid<<<gr, 128, 0, st>>>(s.unsorted.as<float4>(), m.search.as<float4>(), d_bases, base0, qoff, nb, sc.quads.as<int4>(), (long long)nquads,
                                   o->max_quads_per_base, seed, sc.T.as<float>(), flag);
     ctx->launches += 3;
+    PGP_CUDA(ctx, cudaGetLastError());
     PGP_CUDA(ctx, ctx->scene.scratch.reserve((size_t)((nquads + 1) / 2048 + 4096) * 4));
     rc = pgp_scan_exclusive_u32(ctx, flag, (int64_t)nquads + 1, ctx->scene.scratch.as<uint32_t>());
     if (rc) return rc;
@@ -1091,6 +1101,7 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
     const int64_t room = max_hyp - cur;
     k2b_append<<<gr, 128, 0, st>>>(sc.T.as<float>(), flag, qoff, nb, o->max_quads_per_base, outoff, (long long)nquads, m.gen_T.as<float>() + 12 * cur, room);
     ctx->launches += 2;
+    PGP_CUDA(ctx, cudaGetLastError());
     uint32_t added = 0;
     PGP_CUDA(ctx, cudaMemcpyAsync(&added, outoff + nb, 4, cudaMemcpyDeviceToHost, st));
     PGP_CUDA(ctx, cudaStreamSynchronize(st));                               // sync 3

@@ -213,6 +213,8 @@ def run_ours(args, rank, local_rank, world):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
+    if os.environ.get("PGP_STREAM_UPLOAD", "1") == "0":       # for captures under ncu, which serialises streams: upload first, then score
+        eng.set_option("stream_upload", 0)
     eng.set_scene(prob.scene_xyz, prob.scene_nrm, prob.delta)
     eng.set_model(0, prob.model_xyz, prob.model_nrm)
     grid = eng.grid_info()

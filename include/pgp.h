@@ -241,6 +241,21 @@ PGP_API int pgp_mcts_tricp(pgp_ctx* ctx, int obj, const float* seg_xyz_host, int
                            float threshold, double* poses16_host, int k, float trim, float ratio, int max_iter, int* iters_out,
                            float* energy_out, int* n_unexplained);
 
+/* ---------------------------------------------------------------- K7: segment preparation -- */
+
+/* The step in front of the path, for one object of one RGB-D frame: depth decode (utilities::readDepthImage,
+ * PPE/src/misc/utilities.cpp:47-61: ((d << 13) | (d >> 3)) / 10000), class mask (GTSegmentation::compute2dSegment,
+ * PPE/src/segmentation/Segmentation.cpp:187-207), back-projection of the pixels with 0.1 < depth < 2.0
+ * (utilities::convert3dUnOrganizedRGB, utilities.cpp:210-228), then -- restated, PCL being un-vendored -- `leaf` voxel
+ * centroids (pcl::VoxelGrid, Segmentation.cpp:226-229), normals from the neighbours within normal_radius oriented to the
+ * camera (in place of pcl::MovingLeastSquares, :231-238) and removal of points with fewer than min_neighbors within
+ * outlier_radius (pcl::RadiusOutlierRemoval, PPE/src/hypothesis_generation/ObjectPoseCandidateSet.cpp:28-51).
+ * depth_raw: rows x cols uint16 as stored in frame-*.depth.png; class_mask: rows x cols uint8; K9 row-major intrinsics.
+ * xyz_out / nrm_out: cap x 3 camera-frame points / unit normals, ready for pgp_set_scene.  Returns the number of points. */
+PGP_API int pgp_prepare_segment(pgp_ctx* ctx, const uint16_t* depth_raw, const uint8_t* class_mask, int rows, int cols, int class_id,
+                                const float* K9, float leaf, float normal_radius, float outlier_radius, int min_neighbors,
+                                float* xyz_out, float* nrm_out, int cap, int* n_valid_pixels);
+
 #define PGP_MAX_OBJECTS 64
 #define PGP_MAX_CELLS (1ll << 29)
 

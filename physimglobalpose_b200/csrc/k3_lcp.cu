@@ -34,7 +34,7 @@ struct LcpParams {
   const float* T;            // n x 12
   long long n;
   long long n_bulk;          // fine kernel: hypotheses [0, n_bulk) are one work unit each, the rest are split into `split` model chunks
-  const uint32_t* ready;     // streamed upload: number of hypotheses whose transforms have arrived (nullptr: all of them)
+  uint32_t* ready;           // streamed upload: number of hypotheses whose transforms have arrived (nullptr: all of them)
   int split;                 // (so that the last wave of the persistent grid ends on quarter-sized units, not whole hypotheses)
   const float4* pts;
   const float4* aux;
@@ -547,8 +547,15 @@ __global__ void __launch_bounds__(FTHREADS, 1) k3_fine_kernel(const __grid_const
       if (p.ready) {
         // the transforms are still being uploaded chunk by chunk on another stream (pgp_score_lcp); the counter is written by
         // the copy engine after each chunk, chunks end on 384-byte boundaries so no cache line of T spans two of them
-        const volatile uint32_t* rd = p.ready;
-        for (int spin = 0; (long long)*rd <= h && spin < (1 << 23); ++spin) __nanosleep(200);   // bounded (> 1.5 s): never hang the device
+        // rd[0] = hypotheses uploaded, rd[1] = abort flag.  A wait that exceeds ~20 ms (the copy stream is not making progress:
+        // a profiler serialising streams, a wedged DMA engine) raises the flag; every other wait then falls through at once, the
+        // launch ends with garbage and the host re-scores the batch un-streamed (pgp_score_lcp).  The device never hangs.
+        volatile uint32_t* rd = p.ready;
+        for (int spin = 0; (long long)rd[0] <= h; ++spin) {
+          if (rd[1]) break;
+          if (spin > 100000) { rd[1] = 1u; __threadfence(); break; }
+          __nanosleep(200);
+        }
       }
       // bound on the transform's intermediates: decides whether the FMA fast path's error budget holds
       float bound = 0.f;
@@ -683,7 +690,7 @@ bool k3_streams_upload(pgp_ctx* ctx, int mode) {
   return true;
 }
 
-int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mode, uint32_t* counts_dev, float* scores_dev, const uint32_t* ready_dev) {
+int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mode, uint32_t* counts_dev, float* scores_dev, uint32_t* ready_dev) {
   if (n == 0) return PGP_OK;
   Scene& s = ctx->scene;
   LcpParams p = make_params(ctx, m, T_dev, n, counts_dev, scores_dev);

@@ -140,6 +140,7 @@ int64_t pgp_launch_count(const pgp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int pgp_set_option(pgp_ctx* ctx, const char* name, int value) {
   CHECK_CTX(ctx);
   if (name && !strcmp(name, "force_coarse")) { ctx->force_coarse = value; return PGP_OK; }
+  if (name && !strcmp(name, "stream_upload")) { ctx->stream_upload = value ? 1 : 0; return PGP_OK; }
   if (name && !strcmp(name, "tail_split")) { ctx->tail_split = value < 1 ? 1 : (value > 16 ? 16 : value); return PGP_OK; }
   return pgp_fail(ctx, PGP_E_INVALID, "unknown option %s", name ? name : "(null)");
 }
@@ -398,7 +399,7 @@ int pgp_score_lcp(pgp_ctx* ctx, int obj, const float* T, int64_t n, int mode, ui
   uint32_t* dC = ctx->batch_counts.as<uint32_t>();
   float* dS = ctx->batch_scores.as<float>();
   const int chunks = 4;
-  if (n >= 32768 && n < (1ll << 31) && k3_streams_upload(ctx, mode)) {
+  if (ctx->stream_upload && n >= 32768 && n < (1ll << 31) && k3_streams_upload(ctx, mode)) {
     if (!ctx->pinned) { PGP_CUDA(ctx, cudaMallocHost(&ctx->pinned, 256)); ctx->pinned_cap = 256; }
     uint32_t* marks = static_cast<uint32_t*>(ctx->pinned);                      // [0] = 0, [1..4] = hypotheses uploaded after chunk c
     uint32_t* ready = reinterpret_cast<uint32_t*>(ctx->work.as<char>() + 320);
@@ -406,7 +407,8 @@ int pgp_score_lcp(pgp_ctx* ctx, int obj, const float* T, int64_t n, int mode, ui
     for (int c = 0; c < chunks; ++c) marks[c + 1] = (uint32_t)(c + 1 == chunks ? n : ((n * (c + 1) / chunks) & ~7ll));
     PGP_CUDA(ctx, cudaEventRecord(ctx->ev[8], ctx->stream));                    // everything queued on the caller's stream so far
     PGP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[8], 0));
-    PGP_CUDA(ctx, cudaMemcpyAsync(ready, marks, 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+    marks[6] = 0; marks[7] = 0;
+    PGP_CUDA(ctx, cudaMemcpyAsync(ready, marks + 6, 8, cudaMemcpyHostToDevice, ctx->copy_stream));      // {uploaded = 0, abort = 0}
     for (int c = 0; c < chunks; ++c) {
       const int64_t lo = marks[c], hi = marks[c + 1];
       PGP_CUDA(ctx, cudaMemcpyAsync(dT + 12 * lo, T + 12 * lo, (size_t)(hi - lo) * 48, cudaMemcpyHostToDevice, ctx->copy_stream));
@@ -419,6 +421,14 @@ int pgp_score_lcp(pgp_ctx* ctx, int obj, const float* T, int64_t n, int mode, ui
       }
     }
     ctx->last.T = dT; ctx->last.counts = dC; ctx->last.scores = dS; ctx->last.n = n; ctx->last.mode = mode; ctx->last.obj = obj;
+    // did the kernel give up waiting for the upload (see k3_fine_kernel)?  Then the copies are done by now: score again, plainly.
+    PGP_CUDA(ctx, cudaMemcpyAsync(marks + 8, ready + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    if (marks[8]) {
+      rc = k3_score(ctx, *m, dT, n, mode, dC, dS, nullptr);
+      if (rc) return rc;
+    }
   } else {
     PGP_CUDA(ctx, cudaMemcpyAsync(dT, T, (size_t)n * 48, cudaMemcpyHostToDevice, ctx->stream));
     rc = pgp_score_lcp_dev(ctx, obj, dT, n, mode, dC, dS);
@@ -675,4 +685,20 @@ int pgp_mcts_tricp(pgp_ctx* ctx, int obj, const float* seg, int ns, const double
   if (n_unexplained) *n_unexplained = kept;
   if (kept == 0) { for (int i = 0; i < k; ++i) { if (iters) iters[i] = 0; if (energy) energy[i] = 0.f; } return PGP_OK; }
   return k5_tricp(ctx, *m, un.data(), kept, poses, k, trim, ratio, max_iter, iters, energy);
+}
+
+int pgp_prepare_segment(pgp_ctx* ctx, const uint16_t* depth_raw, const uint8_t* class_mask, int rows, int cols, int class_id, const float* K9,
+                        float leaf, float normal_radius, float outlier_radius, int min_neighbors, float* xyz_out, float* nrm_out, int cap,
+                        int* n_valid_pixels) {
+  CHECK_CTX(ctx);
+  if (!depth_raw || !class_mask || rows <= 0 || cols <= 0 || !K9 || !xyz_out || !nrm_out || cap < 0)
+    return pgp_fail(ctx, PGP_E_INVALID, "pgp_prepare_segment: bad argument");
+  if (!(leaf > 0.f) || !(normal_radius > 0.f) || !(outlier_radius > 0.f) || !(K9[0] != 0.f) || !(K9[4] != 0.f))
+    return pgp_fail(ctx, PGP_E_INVALID, "pgp_prepare_segment: leaf, radii and focal lengths must be non-zero");
+  if ((double)normal_radius / leaf > 16.0 || (double)outlier_radius / leaf > 16.0)
+    return pgp_fail(ctx, PGP_E_INVALID, "pgp_prepare_segment: radius / leaf > 16");
+  int n = 0;
+  int rc = k7_prepare_segment(ctx, depth_raw, class_mask, rows, cols, class_id, K9, leaf, normal_radius, outlier_radius, min_neighbors, xyz_out, nrm_out,
+                              cap, &n, n_valid_pixels);
+  return rc ? rc : n;
 }

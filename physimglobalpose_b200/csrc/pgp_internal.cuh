@@ -147,6 +147,7 @@ struct pgp_ctx {
   DevBuf topk_out;
   void* pinned = nullptr; size_t pinned_cap = 0;
   int64_t launches = 0;
+  int stream_upload = 1;  // pgp_score_lcp: overlap the batch upload with the scoring launch (0: upload first; use under profilers)
   int tail_split = 4;     // K3 fine kernel: model chunks per hypothesis in the last wave (1 = off)
   int force_coarse = 0;   // test hook: score on the 27-cell path even when the fine grid exists
   std::string err;
@@ -170,7 +171,7 @@ int k1_build_wlists(pgp_ctx* ctx);
 int k1_fine_stats(pgp_ctx* ctx, int64_t* out8);
 int pgp_scan_exclusive_u32(pgp_ctx* ctx, uint32_t* data, int64_t n, uint32_t* scratch);
 // k3_lcp.cu
-int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mode, uint32_t* counts_dev, float* scores_dev, const uint32_t* ready_dev = nullptr);
+int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mode, uint32_t* counts_dev, float* scores_dev, uint32_t* ready_dev = nullptr);
 bool k3_streams_upload(pgp_ctx* ctx, int mode);
 int k3_nearest(pgp_ctx* ctx, const Model& m, const float* T_dev, int32_t* idx_dev, int gate);
 // k4_select.cu
@@ -214,3 +215,6 @@ __device__ __forceinline__ float cell_coord(float x, float lo, float inv_h) { re
 // k6_explained.cu
 int k6_remove_explained(pgp_ctx* ctx, Model& m, const float* seg_xyz_host, int ns, const double* placed16_host, int n_placed, float threshold,
                         uint8_t* flags_host, int* n_unexplained);
+// k7_segment.cu
+int k7_prepare_segment(pgp_ctx* ctx, const uint16_t* depth_host, const uint8_t* mask_host, int rows, int cols, int cls, const float* K9, float leaf,
+                       float normal_r, float outlier_r, int min_nb, float* xyz_host, float* nrm_host, int cap, int* n_out, int* n_raw_out);

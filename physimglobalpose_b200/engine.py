@@ -325,6 +325,22 @@ class PoseEngine:
                                              _ptr(P), len(P), float(trim), float(ratio), int(max_iter), _ptr(iters), _ptr(energy), C.byref(nun)))
         return P.reshape(-1, 4, 4), iters, energy, nun.value
 
+    # ------------------------------------------------------------------ K7
+    def prepare_segment(self, depth_raw_u16, class_mask_u8, class_id: int, K, leaf: float = 0.01, normal_radius: float = 0.02,
+                        outlier_radius: float = 0.03, min_neighbors: int = 10, cap: int = 1 << 20):
+        """Depth frame + class mask -> the object's segment cloud (points, unit normals) and the number of valid-depth pixels."""
+        d = np.ascontiguousarray(depth_raw_u16, np.uint16)
+        m = np.ascontiguousarray(class_mask_u8, np.uint8)
+        assert d.shape == m.shape and d.ndim == 2
+        K = _f32(K).reshape(9)
+        xyz = np.zeros((cap, 3), np.float32)
+        nrm = np.zeros((cap, 3), np.float32)
+        nraw = C.c_int(0)
+        n = self._check(self._lib.pgp_prepare_segment(self._ctx, _ptr(d), _ptr(m), d.shape[0], d.shape[1], int(class_id), _ptr(K), float(leaf),
+                                                      float(normal_radius), float(outlier_radius), int(min_neighbors), _ptr(xyz), _ptr(nrm), cap,
+                                                      C.byref(nraw)))
+        return xyz[:n].copy(), nrm[:n].copy(), nraw.value
+
 
 def topk_merge(lists: Sequence[np.ndarray], k: int) -> np.ndarray:
     """Deterministic merge of per-rank top-k record arrays (pgp_topk_merge)."""

@@ -23,13 +23,13 @@ import sys
 
 import numpy as np
 from PIL import Image
-from scipy.spatial import cKDTree
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 REF = "/root/reference"
 from oracle.pyoracle import RefOracle  # noqa: E402
+from oracle import segment_port  # noqa: E402
 
 K = np.array([[6.13998108e+02, 0.0, 3.22453583e+02], [0.0, 6.13998169e+02, 2.39678940e+02], [0.0, 0.0, 1.0]], np.float32)   # gt_info.yml:4
 OBJECTS = [(8, "kleenex_tissue_box"), (2, "expo_dry_erase_board_eraser"), (3, "folgers_classic_roast_coffee")]             # gt_info.yml:14-19, obj_config.yml
@@ -66,54 +66,23 @@ def sample_mesh(v, f, n, rng):
     return p.astype(np.float32), (nrm * np.where(s == 0, 1, s)[:, None]).astype(np.float32)
 
 
-def prepare_segment(depth_m, mask, cls):
-    rows, cols = depth_m.shape
-    obj = np.where(mask == cls, depth_m, np.float32(0))
-    u, v = np.nonzero((obj > 0.1) & (obj < 2.0))                     # row-major pixel order, like the double loop
-    d = obj[u, v].astype(np.float32)
-    x = ((v.astype(np.float32) - K[0, 2]) * d / K[0, 0]).astype(np.float32)
-    y = ((u.astype(np.float32) - K[1, 2]) * d / K[1, 1]).astype(np.float32)
-    pts = np.stack([x, y, d], axis=1)
-    n_raw = len(pts)
-    # 1 cm voxel centroids, output in voxel-index order (pcl::VoxelGrid sorts by index)
-    leaf = np.float32(0.01)
-    ijk = np.floor(pts / leaf).astype(np.int64)
-    ijk -= ijk.min(axis=0)
-    dims = ijk.max(axis=0) + 1
-    key = ijk[:, 0] + dims[0] * (ijk[:, 1] + dims[1] * ijk[:, 2])
-    order = np.argsort(key, kind="stable")
-    key, pts = key[order], pts[order]
-    starts = np.flatnonzero(np.r_[True, key[1:] != key[:-1]])
-    cnt = np.diff(np.r_[starts, len(key)])
-    cen = (np.add.reduceat(pts.astype(np.float64), starts, axis=0) / cnt[:, None]).astype(np.float32)
-    # normals: PCA of the neighbours within 2 cm, oriented towards the camera at the origin
-    tree = cKDTree(cen)
-    nrm = np.zeros_like(cen)
-    for i, nb in enumerate(tree.query_ball_point(cen, 0.02)):
-        q = cen[nb].astype(np.float64)
-        if len(nb) >= 3:
-            w, vec = np.linalg.eigh(np.cov((q - q.mean(axis=0)).T))
-            n = vec[:, 0]
-        else:
-            n = -cen[i].astype(np.float64)
-        if np.dot(n, cen[i]) > 0:
-            n = -n
-        nrm[i] = (n / np.linalg.norm(n)).astype(np.float32)
-    # radius-outlier removal: keep points with >= 10 neighbours within 3 cm (the point itself counts, as in PCL)
-    keep = np.array([len(nb) >= 10 for nb in tree.query_ball_point(cen, 0.03)])
-    return cen[keep], nrm[keep], n_raw
+def _rle(a):
+    """run-length encoding (values, run lengths) of a flat array"""
+    starts = np.flatnonzero(np.r_[True, a[1:] != a[:-1]])
+    return a[starts].astype(np.int32), np.diff(np.r_[starts, len(a)]).astype(np.int32)
 
 
 def main():
     raw = np.array(Image.open(os.path.join(REF, "test-scene", "frame-000000.depth.png"))).astype(np.uint16)
     dec = ((raw << np.uint16(13)) | (raw >> np.uint16(3))).astype(np.uint16)
-    depth_m = (dec.astype(np.float32) / np.float32(10000)).astype(np.float32)
+    depth_m = segment_port.decode_depth(raw)
     mask = np.array(Image.open(os.path.join(REF, "test-scene", "frame-000000.mask.png"))).astype(np.uint8)
     assert depth_m.shape == mask.shape == (480, 640)
     rng = np.random.default_rng(2024)
-    out = dict(K=K, delta=np.float64(0.005), depth_raw_crop=raw[200:216, 300:316], depth_dec_crop=dec[200:216, 300:316])
+    out = dict(K=K, delta=np.float64(0.005), depth_raw_crop=raw[200:216, 300:316], depth_dec_crop=dec[200:216, 300:316],
+               depth_raw_rle=np.stack(_rle(raw.ravel())), mask_all_rle=np.stack(_rle(mask.ravel())))
     for cls, name in OBJECTS:
-        seg_xyz, seg_nrm, n_raw = prepare_segment(depth_m, mask, cls)
+        seg_xyz, seg_nrm, n_raw = segment_port.prepare_segment(depth_m, mask, cls, K)
         v, f = read_mesh(os.path.join(REF, "src/physim_pose_estimation/models_visualization", name + ".ply"))
         mod_xyz, mod_nrm = sample_mesh(v, f, 1500, rng)
         prior_img = np.where(mask == cls, 10000, 0).astype(np.uint16)

@@ -163,3 +163,28 @@ def test_c1_test_scene_golden(engine):
         engine.generate_pcs(0, seed=7, max_hyp=20000)
         engine.score_generated(0, "weighted")
         assert engine.topk(0, 1)["score"][0] >= 0.6 * ws.max()
+
+
+C1_CLASSES = {"kleenex_tissue_box": 8, "expo_dry_erase_board_eraser": 2, "folgers_classic_roast_coffee": 3}
+
+
+def test_segment_preparation_on_device(engine):
+    """K7 (depth decode, mask, back-projection, 1 cm voxel centroids, PCA normals, radius-outlier removal) on the test-scene frame
+    against the numpy restatement the configs[0] fixture was prepared with: same pixel count, same points bit for bit, same
+    normals (the eigenvector of a nearly isotropic neighbourhood is ill-conditioned, hence a tolerance on a few of them); and the
+    device-prepared segment scores exactly like the fixture's."""
+    g = np.load(os.path.join(G, "c1_test_scene.npz"))
+    raw = np.repeat(g["depth_raw_rle"][0], g["depth_raw_rle"][1]).astype(np.uint16).reshape(480, 640)
+    mask = np.repeat(g["mask_all_rle"][0], g["mask_all_rle"][1]).astype(np.uint8).reshape(480, 640)
+    for name in g["names"]:
+        xyz, nrm, n_raw = engine.prepare_segment(raw, mask, C1_CLASSES[str(name)], g["K"])
+        want_xyz, want_nrm = g[f"{name}_seg_xyz"], g[f"{name}_seg_nrm"]
+        assert n_raw == int(g[f"{name}_n_raw"])
+        assert xyz.shape == want_xyz.shape
+        assert np.array_equal(xyz, want_xyz)
+        cosang = np.einsum("ij,ij->i", nrm.astype(np.float64), want_nrm.astype(np.float64))
+        assert np.all(np.abs(np.linalg.norm(nrm, axis=1) - 1) < 1e-6)
+        assert (cosang > 1 - 1e-6).mean() > 0.98 and cosang.min() > 0.99, (cosang.min(), (cosang > 1 - 1e-6).mean())     # fp32 unit vectors
+    # a class that is not in the mask: empty segment, no error
+    xyz, nrm, n_raw = engine.prepare_segment(raw, mask, 77, g["K"])
+    assert len(xyz) == 0 and n_raw == 0

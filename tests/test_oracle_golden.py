@@ -177,3 +177,28 @@ def _c1_mask(g, name):
     np.add.at(flat, edges[0::2], 1)
     np.add.at(flat, edges[1::2], -1)
     return (np.cumsum(flat)[:-1] > 0).reshape(480, 640)
+
+
+C1_CLASSES = {"kleenex_tissue_box": 8, "expo_dry_erase_board_eraser": 2, "folgers_classic_roast_coffee": 3}     # gt_info.yml / obj_config.yml
+
+
+def _c1_images(g):
+    raw = np.repeat(g["depth_raw_rle"][0], g["depth_raw_rle"][1]).astype(np.uint16).reshape(480, 640)
+    mask = np.repeat(g["mask_all_rle"][0], g["mask_all_rle"][1]).astype(np.uint8).reshape(480, 640)
+    return raw, mask
+
+
+def test_segment_port_reproduces_the_fixture_clouds():
+    """The segment-preparation restatement (oracle/segment_port.py), run on the test-scene's depth + mask images stored in the
+    fixture, yields exactly the segment clouds the configs[0] vectors were minted on; the bit-twiddled depth decode matches the
+    stored crop."""
+    from oracle import segment_port
+    g = np.load(os.path.join(G, "c1_test_scene.npz"))
+    raw, mask = _c1_images(g)
+    assert np.array_equal(raw[200:216, 300:316], g["depth_raw_crop"])
+    dec = segment_port.decode_depth(raw)
+    assert np.array_equal((dec[200:216, 300:316] * np.float32(10000)).round().astype(np.uint16), g["depth_dec_crop"])
+    for name in g["names"]:
+        xyz, nrm, n_raw = segment_port.prepare_segment(dec, mask, C1_CLASSES[str(name)], g["K"])
+        assert n_raw == int(g[f"{name}_n_raw"])
+        assert np.array_equal(xyz, g[f"{name}_seg_xyz"]) and np.array_equal(nrm, g[f"{name}_seg_nrm"])

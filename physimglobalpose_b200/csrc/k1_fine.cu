@@ -379,6 +379,39 @@ __global__ void k1f_stats(const uint32_t* __restrict__ codes, int n_blocks, unsi
   }
 }
 
+
+// ---- K1d: per-cell lower bound of the distance to the nearest scene point ----------------------
+// For a cell C and an occupied cell C' that differ by (kx, ky, kz) cells, every point of C is at least
+// h * sqrt(gx^2 + gy^2 + gz^2) away from every point of C', g = max(|k| - 1, 0).  S(C) = min over the
+// occupied cells of gx^2 + gy^2 + gz^2 separates per axis (a min-plus pass along x, then y, then z,
+// window +-DIST_W cells; nothing occupied inside the window -> S = DIST_W^2, still a lower bound).
+// K3 uses it to drop whole groups of model points whose bounding sphere cannot reach the scene.
+constexpr int DIST_W = 15;     // DIST_W^2 must fit a byte
+
+template <int PASS>   // 0: occupancy -> S along x, 1: += y, 2: += z and conversion to metres
+__global__ void k1d_pass(const uint32_t* __restrict__ cell_start, const unsigned char* __restrict__ in, unsigned char* __restrict__ out,
+                         float* __restrict__ dist, GridParams g) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= g.n_cells) return;
+  const int cx = (int)(c % g.dim[0]), cy = (int)((c / g.dim[0]) % g.dim[1]), cz = (int)(c / ((int64_t)g.dim[0] * g.dim[1]));
+  const int pos = PASS == 0 ? cx : PASS == 1 ? cy : cz;
+  const int dim = g.dim[PASS];
+  const int64_t stride = PASS == 0 ? 1 : PASS == 1 ? g.dim[0] : (int64_t)g.dim[0] * g.dim[1];
+  int best = DIST_W * DIST_W;
+  const int t0 = max(-DIST_W, -pos), t1 = min(DIST_W, dim - 1 - pos);
+  for (int t = t0; t <= t1; ++t) {
+    const int64_t cc = c + t * stride;
+    const int gap = max(abs(t) - 1, 0);
+    int v;
+    if (PASS == 0) v = cell_start[cc + 1] > cell_start[cc] ? 0 : DIST_W * DIST_W;
+    else v = in[cc];
+    best = min(best, v + gap * gap);
+  }
+  if (PASS < 2) out[c] = (unsigned char)best;
+  // 0.02 h: the cell of a point is computed in fp32 (error < 1e-3 cells per axis), (1 - 1e-4): sqrtf / product rounding
+  else dist[c] = fmaxf(0.f, g.h * sqrtf((float)best) * (1.0f - 1e-4f) - 0.02f * g.h);
+}
+
 }  // namespace
 
 int k1_build_fine(pgp_ctx* ctx) {
@@ -452,6 +485,19 @@ int k1_build_fine(pgp_ctx* ctx) {
                                                s.near_cnt.as<uint16_t>(), s.hdr.as<uint32_t>(), region, s.lists.as<uint32_t>());
     ctx->launches++;
     s.n_list_words = total;
+  }
+  // K1d distance field (two byte planes of scratch in `cursor`, which is free again by now)
+  {
+    const int64_t nc = g.n_cells;
+    PGP_CUDA(ctx, s.dist.reserve((size_t)nc * 4));
+    PGP_CUDA(ctx, s.cursor.reserve((size_t)nc * 2 + 16));
+    unsigned char* pa = s.cursor.as<unsigned char>();
+    unsigned char* pb = pa + nc;
+    const unsigned blocks = (unsigned)((nc + 255) / 256);
+    k1d_pass<0><<<blocks, 256, 0, st>>>(s.cell_start.as<uint32_t>(), nullptr, pa, nullptr, g);
+    k1d_pass<1><<<blocks, 256, 0, st>>>(nullptr, pa, pb, nullptr, g);
+    k1d_pass<2><<<blocks, 256, 0, st>>>(nullptr, pb, nullptr, s.dist.as<float>(), g);
+    ctx->launches += 3;
   }
   PGP_CUDA(ctx, cudaGetLastError());
   g.n_blocks = (int)nb;

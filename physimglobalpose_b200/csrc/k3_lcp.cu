@@ -57,6 +57,9 @@ struct LcpParams {
   const uint32_t* wbase;     // K1c: per block first entry of its region
   const float4* wlists;      // K1c: candidate records {x, y, z, original index}
   const float4* aux_orig;    // unit normal + prior by ORIGINAL scene index
+  const float4* groups;      // bounding sphere {centre, radius} of every aligned run of 32 validation points (pgp_set_model)
+  const float* dist;         // K1d: per cell, lower bound of the distance to the nearest scene point (nullptr: no group cull)
+  float cull_add;            // delta (1 + 1e-5) + rounding margin: a group is dropped when dist > |A| r + cull_add
 };
 
 // ---- mbarrier + TMA bulk copy (global -> shared), sm_90+/sm_100a PTX ---------------------------
@@ -296,17 +299,19 @@ __global__ void __launch_bounds__(THREADS, 2) k3_lcp_kernel(const __grid_constan
 // and resolved by the exact, non-fused test of the reference in phase 2.  The labels are
 // conservative with respect to the difference between the fast transform and the reference's
 // rounding sequence (GridParams::inflate), so counts stay bit-exact.
-constexpr int FWARPS = 32;
-constexpr int FTHREADS = FWARPS * 32;
+// warps per CTA (one CTA per SM) is a template parameter of the kernel: 32 (64 registers per thread) or 16 (128 registers)
 constexpr int FUNROLL = 4;           // model points per lane per step (their label gathers are issued together)
 constexpr int FQCAP = 32 + 32 * FUNROLL;   // queue slots per warp: < 32 left over + the new ones of one step
 
 struct FineCtx {
   const float4* s_model;
   const float4* s_nrm;       // weighted mode only
+  const float4* s_groups;    // bounding spheres of the tile's 32-point groups
   const uint2* table;        // bmrank: shared (SMEM_TABLE) or global
   uint16_t* q;
-  int dimx, dimy;
+  uint16_t* glist;           // per warp: the groups of the current hypothesis that survived the cull (+ FUNROLL pad slots)
+  int dummy_group;           // a group of NaN points behind the tile
+  int dimx, dimy, dimz;
   unsigned rx, ry, rz;
   int lane;
   unsigned lt_mask;
@@ -369,55 +374,81 @@ __device__ __forceinline__ const float4* wlist_of(const LcpParams& p, const Fine
   return p.wlists + base + (e >> 10);
 }
 
-// phase 2 for one queued query: the reference's exact test against the voxel's candidate list
-template <bool SMEM_TABLE>
+// phase 2 for one queued query: the reference's exact test against the voxel's candidate list, U candidates per round with
+// their id and point loads issued together (U > 1 needs the register budget of the 16- / 24-warp CTA shapes)
+template <bool SMEM_TABLE, int U>
 __device__ __forceinline__ int resolve_ambiguous(const LcpParams& p, const FineCtx& f, const Xf& x, const float4 m, int ix, int iy, int iz) {
   uint32_t s0, s1;
   const uint32_t* reg = list_range<SMEM_TABLE>(p, f, ix, iy, iz, s0, s1);
   float tx, ty, tz;
   apply_xf(x, m, tx, ty, tz);
   const float r2 = p.g.r2;
-  for (uint32_t j = s0; j < s1; ++j) {
-    const float4 sp = __ldg(p.pts + __ldg(reg + j));
-    if (sqdist3(tx, ty, tz, sp.x, sp.y, sp.z) <= r2) return 1;
+  for (uint32_t j = s0; j < s1; j += U) {
+    uint32_t id[U];
+    float4 sp[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) if (u == 0 || j + u < s1) id[u] = __ldg(reg + j + u);
+#pragma unroll
+    for (int u = 0; u < U; ++u) if (u == 0 || j + u < s1) sp[u] = __ldg(p.pts + id[u]);
+    bool hit = false;
+#pragma unroll
+    for (int u = 0; u < U; ++u) if (u == 0 || j + u < s1) hit |= sqdist3(tx, ty, tz, sp[u].x, sp[u].y, sp[u].z) <= r2;
+    if (hit) return 1;
   }
   return 0;
 }
 
 // nearest in-range scene point among the voxel's K1c candidates (same acceptance / tie rule as
-// nearest_within: d2 <= delta^2, exact ties to the smaller original index): original index or -1
+// nearest_within: d2 <= delta^2, exact ties to the smaller original index): original index or -1.
+// U records per round are loaded together: the list lives in DRAM at the benchmark sizes and a one-at-a-time loop pays a
+// memory latency per record.
+template <int U>
 __device__ __forceinline__ int nearest_in_list(const LcpParams& p, const float4* __restrict__ l, uint32_t cnt, float tx, float ty, float tz) {
   float best = p.g.r2;
   int best_orig = 0x7fffffff;
-  for (uint32_t j = 0; j < cnt; ++j) {
-    const float4 sp = __ldg(l + j);
-    const float d2 = sqdist3(tx, ty, tz, sp.x, sp.y, sp.z);
-    const int orig = __float_as_int(sp.w);
-    if (d2 < best || (d2 == best && orig < best_orig)) { best = d2; best_orig = orig; }
+  for (uint32_t j = 0; j < cnt; j += U) {
+    float4 sp[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) if (u == 0 || j + u < cnt) sp[u] = __ldg(l + j + u);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (u == 0 || j + u < cnt) {
+        const float d2 = sqdist3(tx, ty, tz, sp[u].x, sp[u].y, sp[u].z);
+        const int orig = __float_as_int(sp[u].w);
+        if (d2 < best || (d2 == best && orig < best_orig)) { best = d2; best_orig = orig; }
+      }
+    }
   }
   return best_orig == 0x7fffffff ? -1 : best_orig;
 }
 
 // phase 2 of the weighted mode: nearest in-range point, then the normal gate.  0x10001: gated and prior == 1, 0x1: gated
-template <bool SMEM_TABLE>
+template <bool SMEM_TABLE, int U>
 __device__ __forceinline__ int resolve_nearest(const LcpParams& p, const FineCtx& f, const Xf& x, const float4 m, const float4 nm, int ix, int iy, int iz) {
   uint32_t cnt;
   const float4* l = wlist_of<SMEM_TABLE>(p, f, ix, iy, iz, cnt);
   float tx, ty, tz;
   apply_xf(x, m, tx, ty, tz);
-  const int orig = nearest_in_list(p, l, cnt, tx, ty, tz);
+  const int orig = nearest_in_list<U>(p, l, cnt, tx, ty, tz);
   if (orig < 0) return 0;
   const float4 ns = __ldg(p.aux_orig + orig);
   if (!normal_gate(x, nm, ns)) return 0;
   return (ns.w != 0.f) ? 0x10001 : 0x1;
 }
 
-// one hypothesis, all model points of the staged tile (tn_pad = tile size rounded up to 64; the pad
-// slots hold NaN points, which convert to voxel 0 and fail the range test).
+// one hypothesis, the 32-point groups [g_begin, g_end) of the staged tile (the slots behind the last point hold NaN points, which
+// convert to voxel 0 and fail the range test; `dummy_group` is a whole group of them).
 // FAST: voxel coordinates from the pre-scaled FMA transform a[]; otherwise the reference's
 // rounding sequence followed by the grid's own cell_coord (huge / non-finite matrices).
-template <bool SMEM_TABLE, bool FAST, int MODE>
-__device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCtx& f, const float* __restrict__ T, long long h, int m_begin, int m_end) {
+//
+// Group cull (FAST only).  All points of a group lie within r of its centre c, so their images lie within |A| r of T c
+// (|A| = spectral norm of the 3x3 part, bounded by the square root of the largest absolute row sum of A^T A: 1 for a rotation).
+// dist[cell of T c] is a lower bound of the distance from T c to every scene point (cells outside the grid clamp to the border
+// cell: the projection onto the grid box only moves T c closer to the scene).  If that exceeds |A| r + delta + margins, no point
+// of the group can have a scene point within delta: the whole group is skipped -- one test instead of 32 label look-ups.
+template <bool SMEM_TABLE, bool FAST, int MODE, int U>
+__device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCtx& f, const float* __restrict__ T, long long h, int g_begin, int g_end) {
+  static_assert(FUNROLL == 4, "the survivor list is read four entries at a time");
   const Xf x = load_xf(T, h);
   float a[12];
 #pragma unroll
@@ -440,6 +471,38 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
     }
     ix = __float2int_rz(ux); iy = __float2int_rz(uy); iz = __float2int_rz(uz);   // saturating, NaN -> 0
   };
+  // ---- survivor list of this hypothesis
+  int ns = 0;
+  {
+    const bool cull = FAST && p.dist != nullptr;
+    float snorm = 0.f;
+    if (cull) {
+      const float g00 = x.m[0] * x.m[0] + x.m[4] * x.m[4] + x.m[8] * x.m[8], g11 = x.m[1] * x.m[1] + x.m[5] * x.m[5] + x.m[9] * x.m[9],
+                  g22 = x.m[2] * x.m[2] + x.m[6] * x.m[6] + x.m[10] * x.m[10];
+      const float g01 = fabsf(x.m[0] * x.m[1] + x.m[4] * x.m[5] + x.m[8] * x.m[9]), g02 = fabsf(x.m[0] * x.m[2] + x.m[4] * x.m[6] + x.m[8] * x.m[10]),
+                  g12 = fabsf(x.m[1] * x.m[2] + x.m[5] * x.m[6] + x.m[9] * x.m[10]);
+      snorm = sqrtf(fmaxf(fmaxf(g00 + g01 + g02, g01 + g11 + g12), g02 + g12 + g22)) * (1.0f + 1e-5f);
+    }
+    for (int g0 = g_begin; g0 < g_end; g0 += 32) {
+      const int g = g0 + f.lane;
+      bool keep = g < g_end;
+      if (cull && keep) {
+        const float4 sp = f.s_groups[g];
+        const float ux = __fmaf_rn(a[0], sp.x, __fmaf_rn(a[1], sp.y, __fmaf_rn(a[2], sp.z, a[3]))) * 0.125f;
+        const float uy = __fmaf_rn(a[4], sp.x, __fmaf_rn(a[5], sp.y, __fmaf_rn(a[6], sp.z, a[7]))) * 0.125f;
+        const float uz = __fmaf_rn(a[8], sp.x, __fmaf_rn(a[9], sp.y, __fmaf_rn(a[10], sp.z, a[11]))) * 0.125f;
+        const int cx = min(max(__float2int_rd(ux), 0), f.dimx - 1), cy = min(max(__float2int_rd(uy), 0), f.dimy - 1),
+                  cz = min(max(__float2int_rd(uz), 0), f.dimz - 1);
+        const float d = __ldg(p.dist + ((size_t)cz * f.dimy + cy) * f.dimx + cx);
+        keep = !(d > __fmaf_rn(snorm, sp.w, p.cull_add));
+      }
+      const unsigned bb = __ballot_sync(0xffffffffu, keep);
+      if (keep) f.glist[ns + __popc(bb & f.lt_mask)] = (uint16_t)g;
+      ns += __popc(bb);
+    }
+    if (f.lane < FUNROLL) f.glist[ns + f.lane] = (uint16_t)f.dummy_group;
+    __syncwarp();
+  }
   int good = 0, qn = 0;
   auto drain = [&](int take) {
     if (f.lane < take) {
@@ -448,18 +511,20 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
       int ix, iy, iz;
       voxel_of(m, ix, iy, iz);                      // same arithmetic as phase 1 -> same voxel
       const Xf xe = FAST ? load_xf(T, h) : x;       // FAST keeps only a[] live across the loop; the exact matrix is re-read (L1)
-      if (MODE == 0) good += resolve_ambiguous<SMEM_TABLE>(p, f, xe, m, ix, iy, iz);
-      else good += resolve_nearest<SMEM_TABLE>(p, f, xe, m, f.s_nrm[i], ix, iy, iz);
+      if (MODE == 0) good += resolve_ambiguous<SMEM_TABLE, U>(p, f, xe, m, ix, iy, iz);
+      else good += resolve_nearest<SMEM_TABLE, U>(p, f, xe, m, f.s_nrm[i], ix, iy, iz);
     }
     qn -= take;
   };
   const float4* mp = f.s_model + f.lane;
-  for (int base = m_begin; base < m_end; base += 32 * FUNROLL) {
+  for (int k = 0; k < ns; k += FUNROLL) {
+    const uint2 gg = *reinterpret_cast<const uint2*>(f.glist + k);
+    const int gb[FUNROLL] = {(int)(gg.x & 0xffffu) << 5, (int)(gg.x >> 16) << 5, (int)(gg.y & 0xffffu) << 5, (int)(gg.y >> 16) << 5};
     uint32_t off[FUNROLL], sh[FUNROLL], code[FUNROLL];
 #pragma unroll
     for (int u = 0; u < FUNROLL; ++u) {
       int ix, iy, iz;
-      voxel_of(mp[base + 32 * u], ix, iy, iz);
+      voxel_of(mp[gb[u]], ix, iy, iz);
       off[u] = label_slot<SMEM_TABLE>(p, f, ix, iy, iz, sh[u]);
     }
 #pragma unroll
@@ -479,7 +544,7 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
 #pragma unroll
       for (int u = 0; u < FUNROLL; ++u) {
         const unsigned bb = __ballot_sync(0xffffffffu, code[u] == 2u);
-        if (code[u] == 2u) f.q[qn + __popc(bb & f.lt_mask)] = (uint16_t)(base + 32 * u + f.lane);
+        if (code[u] == 2u) f.q[qn + __popc(bb & f.lt_mask)] = (uint16_t)(gb[u] + f.lane);
         qn += __popc(bb);
       }
       __syncwarp();
@@ -490,21 +555,28 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
   return __reduce_add_sync(0xffffffffu, good);
 }
 
-template <bool SMEM_TABLE, int MODE>   // MODE 0 = count (Verify), 1 = weighted with binary priors (WeightedVerify)
-__global__ void __launch_bounds__(FTHREADS, 1) k3_fine_kernel(const __grid_constant__ LcpParams p) {
+template <bool SMEM_TABLE, int MODE, int FWARPS>   // MODE 0 = count (Verify), 1 = weighted with binary priors (WeightedVerify)
+__global__ void __launch_bounds__(FWARPS * 32, 1) k3_fine_kernel(const __grid_constant__ LcpParams p) {
+  constexpr int PU = FWARPS == 32 ? 1 : 4;     // candidates in flight per lane in phase 2
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t mbar;
+  // shared-memory plan (k3_fine_smem on the host): model tile + one NaN group | normals (weighted) | bmrank | group spheres | survivor lists | queues
+  const int cap_groups = p.tile_cap >> 5;
   float4* s_model = reinterpret_cast<float4*>(smem);
-  float4* s_nrm = s_model + p.tile_cap;                                   // only MODE 1
-  uint2* s_bmrank = reinterpret_cast<uint2*>(smem + (size_t)p.tile_cap * 16 * (MODE == 1 ? 2 : 1));
-  uint16_t* s_queue = reinterpret_cast<uint16_t*>(s_bmrank + p.bmrank_words);
+  float4* s_nrm = s_model + p.tile_cap + 32;                              // only MODE 1
+  uint2* s_bmrank = reinterpret_cast<uint2*>(s_nrm + (MODE == 1 ? p.tile_cap : 0));
+  float4* s_groups = reinterpret_cast<float4*>(s_bmrank + p.bmrank_words);
+  uint16_t* s_glist = reinterpret_cast<uint16_t*>(s_groups + cap_groups);
+  uint16_t* s_queue = s_glist + (((FWARPS * (cap_groups + FUNROLL)) + 7) & ~7);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   FineCtx f;
   f.s_model = s_model;
   f.s_nrm = s_nrm;
+  f.s_groups = s_groups;
   f.table = SMEM_TABLE ? s_bmrank : p.bmrank;
   f.q = s_queue + warp * FQCAP;
-  f.dimx = p.g.dim[0]; f.dimy = p.g.dim[1];
+  f.glist = s_glist + warp * (cap_groups + FUNROLL);
+  f.dimx = p.g.dim[0]; f.dimy = p.g.dim[1]; f.dimz = p.g.dim[2];
   f.rx = (unsigned)(p.g.dim[0] - 2) * 8u; f.ry = (unsigned)(p.g.dim[1] - 2) * 8u; f.rz = (unsigned)(p.g.dim[2] - 2) * 8u;
   f.lane = lane; f.lt_mask = (1u << lane) - 1u;
   f.dummy_word = (uint32_t)p.g.n_blocks * 32u;
@@ -515,34 +587,36 @@ __global__ void __launch_bounds__(FTHREADS, 1) k3_fine_kernel(const __grid_const
   for (int tile = 0; tile < p.n_tiles; ++tile) {
     const int t0 = tile * p.tile_cap;
     const int tn = min(p.tile_cap, p.nv - t0);
-    const int tn_pad = (tn + 32 * FUNROLL - 1) / (32 * FUNROLL) * (32 * FUNROLL);
+    const int ng = (tn + 31) >> 5;                 // groups of this tile; group `ng` is the NaN dummy
+    f.dummy_group = ng;
     if (threadIdx.x == 0) {
       uint32_t bytes = (uint32_t)tn * 16u;
       uint32_t bm = (SMEM_TABLE && tile == 0) ? (uint32_t)p.bmrank_words * 8u : 0u;
-      mbar_expect_tx(&mbar, bytes * (MODE == 1 ? 2u : 1u) + bm);
+      mbar_expect_tx(&mbar, bytes * (MODE == 1 ? 2u : 1u) + bm + (uint32_t)ng * 16u);
       tma_bulk_g2s(s_model, p.model + t0, bytes, &mbar);
       if (MODE == 1) tma_bulk_g2s(s_nrm, p.model_nrm + t0, bytes, &mbar);
       if (bm) tma_bulk_g2s(s_bmrank, p.bmrank, bm, &mbar);
+      tma_bulk_g2s(s_groups, p.groups + (t0 >> 5), (uint32_t)ng * 16u, &mbar);
     }
     // pad slots: NaN points (their voxel converts to 0 and fails the range test); disjoint from the bulk copy's bytes
-    for (int i = tn + (int)threadIdx.x; i < tn_pad; i += FTHREADS) s_model[i] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
+    for (int i = tn + (int)threadIdx.x; i < ng * 32 + 32; i += FWARPS * 32) s_model[i] = make_float4(__int_as_float(0x7fc00000), 0.f, 0.f, 0.f);
     mbar_wait(&mbar, tile & 1);
     __syncthreads();
 
     const long long n_units = p.n_bulk + (p.n - p.n_bulk) * p.split;
-    const int chunk = ((tn_pad / (32 * FUNROLL) + p.split - 1) / p.split) * (32 * FUNROLL);
+    const int chunk = (ng + p.split - 1) / p.split;
     for (;;) {
       long long h = 0;
       if (lane == 0) h = (long long)atomicAdd(p.work + tile, 1ull);
       h = __shfl_sync(0xffffffffu, h, 0);
       if (h >= n_units) break;
-      int m_begin = 0, m_end = tn_pad;
+      int m_begin = 0, m_end = ng;
       const bool whole = h < p.n_bulk;
       if (!whole) {
         const long long u = h - p.n_bulk;
         h = p.n_bulk + u / p.split;
         m_begin = (int)(u % p.split) * chunk;
-        m_end = min(tn_pad, m_begin + chunk);
+        m_end = min(ng, m_begin + chunk);
       }
       if (p.ready) {
         // the transforms are still being uploaded chunk by chunk on another stream (pgp_score_lcp); the counter is written by
@@ -566,7 +640,7 @@ __global__ void __launch_bounds__(FTHREADS, 1) k3_fine_kernel(const __grid_const
           bound = fmaxf(bound, (fabsf(x.m[4 * r]) + fabsf(x.m[4 * r + 1]) + fabsf(x.m[4 * r + 2])) * p.model_rinf + fabsf(x.m[4 * r + 3]));
       }
       const bool fast = bound <= p.g.pos_bound;     // false for NaN / huge matrices: those take the reference's arithmetic
-      const int tot = m_begin >= m_end ? 0 : fast ? score_hypothesis<SMEM_TABLE, true, MODE>(p, f, p.T, h, m_begin, m_end) : score_hypothesis<SMEM_TABLE, false, MODE>(p, f, p.T, h, m_begin, m_end);
+      const int tot = m_begin >= m_end ? 0 : fast ? score_hypothesis<SMEM_TABLE, true, MODE, PU>(p, f, p.T, h, m_begin, m_end) : score_hypothesis<SMEM_TABLE, false, MODE, 1>(p, f, p.T, h, m_begin, m_end);
       if (lane == 0) {
         if (MODE == 0) {
           if (p.n_tiles == 1 && whole) {
@@ -635,7 +709,7 @@ __global__ void __launch_bounds__(256) k3_weighted_ordered(const LcpParams p, in
         if ((__ldg(p.codes + off) >> sh) & 3u) {
           uint32_t cnt;
           const float4* l = wlist_of<false>(p, f, ix, iy, iz, cnt);
-          const int o = nearest_in_list(p, l, cnt, tx, ty, tz);
+          const int o = nearest_in_list<1>(p, l, cnt, tx, ty, tz);
           if (o >= 0) {
             float4 ns = __ldg(p.aux_orig + o);
             if (!gate || normal_gate(x, __ldg(p.model_nrm + i), ns)) {
@@ -724,12 +798,17 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
   }
   const bool fine_ok = s.g.fine == 8 && !ctx->force_coarse && (mode == PGP_LCP_COUNT || s.wlists_ready);
   if (fine_ok) {
-    const int per_pt = mode == PGP_LCP_WEIGHTED ? 32 : 16;
-    const size_t smem_max = 200 * 1024, qb = (size_t)FWARPS * FQCAP * 2;
+    // shared-memory plan of k3_fine_kernel: model tile + one NaN group | normals (weighted) | bmrank | group spheres | survivor lists | queues
+    const size_t smem_max = 200 * 1024;
+    const int FWARPS = mode == PGP_LCP_WEIGHTED ? ctx->k3_warps_weighted : ctx->k3_warps_count;
+    auto smem_need = [&](int cap, size_t table) {
+      return (size_t)(cap + 32) * 16 + (mode == PGP_LCP_WEIGHTED ? (size_t)cap * 16 : 0) + table + (size_t)(cap >> 5) * 16 +
+             (size_t)(((FWARPS * ((cap >> 5) + FUNROLL)) + 7) & ~7) * 2 + (size_t)FWARPS * FQCAP * 2;
+    };
     size_t bm = (size_t)s.bitmap_words * 8;
     int tile_cap = std::min((m.nv + 127) & ~127, 8192);
-    if (bm + qb + (size_t)std::min(tile_cap, 2048) * per_pt > smem_max) bm = 0;          // table too big for smem: read it through L1
-    if ((size_t)tile_cap * per_pt + bm + qb > smem_max) tile_cap = (int)((smem_max - bm - qb) / per_pt) & ~127;
+    if (smem_need(std::min(tile_cap, 2048), bm) > smem_max) bm = 0;          // table too big for smem: read it through L1
+    while (tile_cap > 128 && smem_need(tile_cap, bm) > smem_max) tile_cap -= 128;
     p.tile_cap = tile_cap;
     p.n_tiles = (m.nv + tile_cap - 1) / tile_cap;
     if (p.n_tiles > 256) return pgp_fail(ctx, PGP_E_INVALID, "validation model too large (%d points)", m.nv);
@@ -739,7 +818,10 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     p.bmrank_words = (int)(bm / 8);
     p.model_rinf = m.val_rinf;
     p.ready = ready_dev;
-    const size_t smem = (size_t)tile_cap * per_pt + bm + qb;
+    p.groups = m.val_groups.as<float4>();
+    p.dist = ctx->group_cull ? s.dist.as<float>() : nullptr;
+    p.cull_add = s.delta * (1.0f + 1e-5f) + 4.0f * s.g.inflate;
+    const size_t smem = smem_need(tile_cap, bm);
     PGP_CUDA(ctx, cudaMemsetAsync(p.work, 0, 8 * (size_t)p.n_tiles, st));
     int grid = (int)std::min<long long>((n + FWARPS - 1) / FWARPS, ctx->sm_count);
     // the last two hypotheses' worth of work per warp is handed out in quarter-model units (shorter tail of the persistent grid)
@@ -752,12 +834,19 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     }
     auto launch = [&](auto kern) -> int {
       PGP_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<grid, FTHREADS, smem, st>>>(p);
+      kern<<<grid, FWARPS * 32, smem, st>>>(p);
       return PGP_OK;
     };
     int rc;
-    if (mode == PGP_LCP_COUNT) rc = bm ? launch(k3_fine_kernel<true, 0>) : launch(k3_fine_kernel<false, 0>);
-    else rc = bm ? launch(k3_fine_kernel<true, 1>) : launch(k3_fine_kernel<false, 1>);
+    if (mode == PGP_LCP_COUNT) {
+      if (FWARPS == 32) rc = bm ? launch(k3_fine_kernel<true, 0, 32>) : launch(k3_fine_kernel<false, 0, 32>);
+      else if (FWARPS == 24) rc = bm ? launch(k3_fine_kernel<true, 0, 24>) : launch(k3_fine_kernel<false, 0, 24>);
+      else rc = bm ? launch(k3_fine_kernel<true, 0, 16>) : launch(k3_fine_kernel<false, 0, 16>);
+    } else {
+      if (FWARPS == 32) rc = bm ? launch(k3_fine_kernel<true, 1, 32>) : launch(k3_fine_kernel<false, 1, 32>);
+      else if (FWARPS == 24) rc = bm ? launch(k3_fine_kernel<true, 1, 24>) : launch(k3_fine_kernel<false, 1, 24>);
+      else rc = bm ? launch(k3_fine_kernel<true, 1, 16>) : launch(k3_fine_kernel<false, 1, 16>);
+    }
     if (rc) return rc;
     ctx->launches++;
     if (zero_from < n && scores_dev) {

@@ -47,15 +47,6 @@ void unit_normal(const float* n, float out[3]) {
   out[0] = n[0] / len; out[1] = n[1] / len; out[2] = n[2] / len;
 }
 
-uint32_t spread10(uint32_t v) {
-  v &= 1023u;
-  v = (v | (v << 16)) & 0x030000FFu;
-  v = (v | (v << 8)) & 0x0300F00Fu;
-  v = (v | (v << 4)) & 0x030C30C3u;
-  v = (v | (v << 2)) & 0x09249249u;
-  return v;
-}
-
 int upload_cloud4(pgp_ctx* ctx, DevBuf& buf, const std::vector<float>& v4) {
   PGP_CUDA(ctx, buf.reserve(std::max<size_t>(v4.size() * 4, 64)));
   if (!v4.empty()) PGP_CUDA(ctx, cudaMemcpyAsync(buf.p, v4.data(), v4.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -107,11 +98,11 @@ void pgp_destroy(pgp_ctx* ctx) {
   cudaDeviceSynchronize();
   Scene& s = ctx->scene;
   for (DevBuf* b : {&s.xyz_raw, &s.nrm_raw, &s.unsorted, &s.cursor, &s.pts, &s.aux, &s.cell_start, &s.cell_of, &s.bitmap, &s.bmrank,
-                    &s.block_cell, &s.codes, &s.near_cnt, &s.hdr, &s.region, &s.lists, &s.wvox, &s.wbase, &s.wlists, &s.aux_orig, &s.prior, &s.scratch, &ctx->batch_T, &ctx->batch_counts, &ctx->batch_scores, &ctx->work, &ctx->topk_out})
+                    &s.block_cell, &s.codes, &s.near_cnt, &s.hdr, &s.region, &s.lists, &s.wvox, &s.wbase, &s.wlists, &s.aux_orig, &s.dist, &s.prior, &s.scratch, &ctx->batch_T, &ctx->batch_counts, &ctx->batch_scores, &ctx->work, &ctx->topk_out})
     b->release();
   for (Model& m : ctx->models)
     for (DevBuf* b : {&m.search, &m.search_nrm, &m.search_unit, &m.val, &m.val_nrm, &m.val_orig, &m.val_nrm_orig, &m.gen_T, &m.gen_counts, &m.gen_scores,
-                      &m.tgrid_pts, &m.tgrid_start, &m.val_raw})
+                      &m.tgrid_pts, &m.tgrid_start, &m.val_raw, &m.val_groups, &m.ppf_keys, &m.ppf_offsets, &m.ppf_pairs, &m.ppf_bits})
       b->release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -140,6 +131,12 @@ int64_t pgp_launch_count(const pgp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int pgp_set_option(pgp_ctx* ctx, const char* name, int value) {
   CHECK_CTX(ctx);
   if (name && !strcmp(name, "force_coarse")) { ctx->force_coarse = value; return PGP_OK; }
+  if (name && (!strcmp(name, "k3_warps_count") || !strcmp(name, "k3_warps_weighted"))) {
+    if (value != 16 && value != 24 && value != 32) return pgp_fail(ctx, PGP_E_INVALID, "%s must be 16, 24 or 32", name);
+    (strcmp(name, "k3_warps_count") ? ctx->k3_warps_weighted : ctx->k3_warps_count) = value;
+    return PGP_OK;
+  }
+  if (name && !strcmp(name, "group_cull")) { ctx->group_cull = value ? 1 : 0; return PGP_OK; }
   if (name && !strcmp(name, "stream_upload")) { ctx->stream_upload = value ? 1 : 0; return PGP_OK; }
   if (name && !strcmp(name, "tail_split")) { ctx->tail_split = value < 1 ? 1 : (value > 16 ? 16 : value); return PGP_OK; }
   return pgp_fail(ctx, PGP_E_INVALID, "unknown option %s", name ? name : "(null)");
@@ -243,32 +240,60 @@ int pgp_set_model(pgp_ctx* ctx, int obj, const float* sx, const float* sn, int n
       m.search_diameter = std::max(m.search_diameter, sqrtf(d2));
     }
   }
-  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
   for (int i = 0; i < nv; ++i) {
     for (int k = 0; k < 3; ++k) {
       float c = vx[3 * i + k] - m.cQ[k];
       v4[4 * (size_t)i + k] = c;
-      lo[k] = std::min(lo[k], c); hi[k] = std::max(hi[k], c);
       m.val_rinf = std::max(m.val_rinf, fabsf(c));
     }
     int idx = i; memcpy(&v4[4 * (size_t)i + 3], &idx, 4);
     unit_normal(vn ? vn + 3 * i : nullptr, &vn4[4 * (size_t)i]);
   }
-  // scoring order of the validation cloud: Morton order, so the 32 points a warp handles per step
-  // are neighbours and their queries fall into neighbouring cells (counts are order-free).
-  std::vector<uint32_t> code(nv);
+  // scoring order of the validation cloud: leaves of a balanced kd split (widest axis, cut at a multiple of 32 points), so every
+  // aligned run of 32 points -- what a warp handles per step -- is a compact patch: its queries fall into neighbouring cells, and
+  // its bounding sphere is small enough for K3's group cull to fire (counts are order-free).
   std::vector<int> order(nv);
-  for (int i = 0; i < nv; ++i) {
-    uint32_t q[3];
-    for (int k = 0; k < 3; ++k) {
-      float ext = hi[k] - lo[k];
-      float u = ext > 0.f ? (v4[4 * (size_t)i + k] - lo[k]) / ext : 0.f;
-      q[k] = (uint32_t)std::min(1023.f, std::max(0.f, u * 1023.f));
-    }
-    code[i] = spread10(q[0]) | (spread10(q[1]) << 1) | (spread10(q[2]) << 2);
-  }
   std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return code[a] < code[b]; });
+  {
+    struct Range { int b, e; };
+    std::vector<Range> stack{{0, nv}};
+    while (!stack.empty()) {
+      const Range r = stack.back(); stack.pop_back();
+      const int n = r.e - r.b;
+      if (n <= 32) continue;
+      float rlo[3] = {INFINITY, INFINITY, INFINITY}, rhi[3] = {-INFINITY, -INFINITY, -INFINITY};
+      for (int i = r.b; i < r.e; ++i)
+        for (int k = 0; k < 3; ++k) { const float c = v4[4 * (size_t)order[i] + k]; rlo[k] = std::min(rlo[k], c); rhi[k] = std::max(rhi[k], c); }
+      int ax = 0;
+      for (int k = 1; k < 3; ++k) if (rhi[k] - rlo[k] > rhi[ax] - rlo[ax]) ax = k;
+      const int half = ((n + 31) / 32 / 2) * 32;
+      std::nth_element(order.begin() + r.b, order.begin() + r.b + half, order.begin() + r.e, [&](int a, int b) {
+        const float ca = v4[4 * (size_t)a + ax], cb = v4[4 * (size_t)b + ax];
+        return ca < cb || (ca == cb && a < b);
+      });
+      stack.push_back({r.b, r.b + half});
+      stack.push_back({r.b + half, r.e});
+    }
+    for (int b = 0; b < nv; b += 32) std::sort(order.begin() + b, order.begin() + std::min(nv, b + 32));   // deterministic inside a leaf
+  }
+  // bounding sphere of each run of 32 points (centre = AABB centre, radius rounded up)
+  std::vector<float> grp((size_t)((nv + 31) / 32) * 4);
+  for (int b = 0, gi = 0; b < nv; b += 32, ++gi) {
+    const int e = std::min(nv, b + 32);
+    double glo[3] = {1e300, 1e300, 1e300}, ghi[3] = {-1e300, -1e300, -1e300};
+    for (int i = b; i < e; ++i)
+      for (int k = 0; k < 3; ++k) { const double c = v4[4 * (size_t)order[i] + k]; glo[k] = std::min(glo[k], c); ghi[k] = std::max(ghi[k], c); }
+    float cf[3];
+    for (int k = 0; k < 3; ++k) cf[k] = (float)(0.5 * (glo[k] + ghi[k]));
+    double r2 = 0.0;
+    for (int i = b; i < e; ++i) {
+      double d2 = 0.0;
+      for (int k = 0; k < 3; ++k) { const double d = (double)v4[4 * (size_t)order[i] + k] - (double)cf[k]; d2 += d * d; }
+      r2 = std::max(r2, d2);
+    }
+    for (int k = 0; k < 3; ++k) grp[4 * (size_t)gi + k] = cf[k];
+    grp[4 * (size_t)gi + 3] = (float)(sqrt(r2) * (1.0 + 1e-6)) + 1e-12f;
+  }
   std::vector<float> vs4((size_t)nv * 4), vsn4((size_t)nv * 4);
   for (int i = 0; i < nv; ++i) {
     memcpy(&vs4[4 * (size_t)i], &v4[4 * (size_t)order[i]], 16);
@@ -291,6 +316,7 @@ int pgp_set_model(pgp_ctx* ctx, int obj, const float* sx, const float* sn, int n
   if ((rc = upload_cloud4(ctx, m.val_orig, v4))) return rc;
   if ((rc = upload_cloud4(ctx, m.val_nrm_orig, vn4))) return rc;
   if ((rc = upload_cloud4(ctx, m.val, vs4))) return rc;
+  if ((rc = upload_cloud4(ctx, m.val_groups, grp))) return rc;
   if ((rc = upload_cloud4(ctx, m.val_nrm, vsn4))) return rc;
   PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the staging vectors die here
   m.ready = true;

@@ -78,6 +78,7 @@ struct Scene {
   DevBuf wbase;        // K1c: n_blocks u32: first wlists entry of the block's region
   DevBuf wlists;       // K1c: float4 copies {x,y,z,original index} of the nearest-neighbour candidates of every non-OUT voxel
   int64_t n_wlist_entries = 0;
+  DevBuf dist;         // K1d: n_cells x f32, lower bound of the distance from any point of the cell to the nearest scene point
   DevBuf aux_orig;     // n x float4 in ORIGINAL order: unit normal, prior (the K1c records carry original indices)
   bool wlists_ready = false, wlists_tried = false;
   DevBuf prior;        // n x f32 in ORIGINAL order
@@ -100,6 +101,7 @@ struct Model {
   float search_diameter = 0.f; // P_diameter_ estimate (match4pcsBase.cc:274-283)
   DevBuf val;          // nv x float4 centred, in a cache-friendly order; w = original index bits
   DevBuf val_nrm;      // nv x float4 unit normal, same order
+  DevBuf val_groups;   // ceil(nv/32) x float4: bounding sphere {centre, radius} of each run of 32 points of `val` (K3 group cull)
   DevBuf val_orig;     // nv x float4 centred, ORIGINAL order (weighted mode with general priors, TrICP target)
   DevBuf val_nrm_orig;
   // model-space grid for TrICP (K5): nearest validation-model point of any query
@@ -149,6 +151,8 @@ struct pgp_ctx {
   int64_t launches = 0;
   int stream_upload = 1;  // pgp_score_lcp: overlap the batch upload with the scoring launch (0: upload first; use under profilers)
   int tail_split = 4;     // K3 fine kernel: model chunks per hypothesis in the last wave (1 = off)
+  int k3_warps_count = 32, k3_warps_weighted = 24;   // warps per CTA of k3_fine_kernel (32 -> 64 registers/thread, 24 -> 80, 16 -> 128)
+  int group_cull = 1;     // K3 fine kernel: drop groups of 32 model points whose bounding sphere cannot reach the scene (0 = off, test hook)
   int force_coarse = 0;   // test hook: score on the 27-cell path even when the fine grid exists
   std::string err;
 };

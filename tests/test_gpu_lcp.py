@@ -191,3 +191,32 @@ def test_tail_split_units(engine, port_lib):
     assert np.array_equal(res[4][0][0][sel], o.verify(T[sel]))
     ws, wn = o.weighted_verify(T[sel])
     assert np.array_equal(res[4][1][1][sel], ws) and np.array_equal(res[4][1][0][sel], wn.astype(np.uint32))
+
+
+def test_group_cull_is_exact(engine, port_lib):
+    """K3 drops whole 32-point groups whose bounding sphere cannot reach the scene (K1d distance field).  The cull must never
+    change a count: rigid poses, poses far outside the grid, and non-rigid matrices (scaled / sheared: the sphere radius is
+    stretched by the matrix norm) give the oracle's counts with the cull on, and the same counts with it off; both modes."""
+    prob = synth.make_problem(1500, 40000, 0.01, seed=31)
+    T = synth.make_hypotheses(prob, 4000, seed=32).copy()
+    rng = np.random.default_rng(7)
+    for i in range(20, 120):                      # anisotropic scale / shear around poses near the ground truth and random ones
+        A = np.eye(3) + rng.normal(scale=0.4, size=(3, 3))
+        T[i, :, :3] = (A @ T[i, :, :3].astype(np.float64)).astype(np.float32)
+    T[120:160, :, 3] += rng.normal(scale=2.0, size=(40, 3)).astype(np.float32)      # far outside the scene grid
+    T[160:200, :, :3] *= rng.uniform(0.05, 3.0, size=(40, 1, 1)).astype(np.float32)  # uniform scales
+    _setup(engine, prob)
+    o = _oracle(port_lib, prob)
+    want = o.verify(T)
+    ws, wn = o.weighted_verify(T)
+    on_c, _ = engine.score_lcp(0, T, "count")
+    on_w, on_ws = engine.score_lcp(0, T, "weighted")
+    engine.set_option("group_cull", 0)
+    try:
+        off_c, _ = engine.score_lcp(0, T, "count")
+        off_w, off_ws = engine.score_lcp(0, T, "weighted")
+    finally:
+        engine.set_option("group_cull", 1)
+    assert np.array_equal(off_c, want) and np.array_equal(on_c, want)
+    assert np.array_equal(off_w, wn.astype(np.uint32)) and np.array_equal(on_w, wn.astype(np.uint32))
+    assert np.array_equal(on_ws, ws) and np.array_equal(off_ws, ws)

@@ -40,7 +40,8 @@ __global__ void k1f_bmrank(const uint32_t* __restrict__ bitmap, const uint32_t* 
 __global__ void __launch_bounds__(CLS_THREADS) k1f_classify(const uint32_t* __restrict__ block_cell, const uint32_t* __restrict__ cell_start,
                                                             const float4* __restrict__ pts, GridParams g, uint32_t* __restrict__ codes,
                                                             uint16_t* __restrict__ near_cnt, uint32_t* __restrict__ hdr,
-                                                            uint32_t* __restrict__ region_words, int* __restrict__ overflow) {
+                                                            uint32_t* __restrict__ region_recs, uint32_t* __restrict__ region_amb,
+                                                            unsigned long long* __restrict__ total_recs, int* __restrict__ overflow) {
   __shared__ float4 s_p[CLS_CHUNK];
   __shared__ unsigned char s_code[F * F * F];
   __shared__ uint32_t s_tot;
@@ -114,46 +115,53 @@ __global__ void __launch_bounds__(CLS_THREADS) k1f_classify(const uint32_t* __re
     const uint32_t g_hi = __shfl_sync(0xffffffffu, excl, (threadIdx.x & 3) * 8 + 4);   // groups 1,3,5,7
     if (threadIdx.x < 4) hdr[(size_t)b * 8 + threadIdx.x] = g_lo | (g_hi << 16);
     if (threadIdx.x == 0) {
-      hdr[(size_t)b * 8 + 4] = 0;                 // region base, filled after the scan
+      hdr[(size_t)b * 8 + 4] = 0;
       hdr[(size_t)b * 8 + 5] = n_amb;
       hdr[(size_t)b * 8 + 6] = s_tot;
       hdr[(size_t)b * 8 + 7] = 0;
-      region_words[b] = n_amb ? n_amb + 1 + s_tot : 0;
+      region_recs[b] = s_tot;
+      region_amb[b] = n_amb;
+      if (s_tot) atomicAdd(total_recs, (unsigned long long)s_tot);
     }
   }
 }
 
-// Pass B: candidate lists of the AMBIG voxels.  Region of block b in `lists` (u32 words):
-//   [n_amb + 1 offsets relative to the region][ids...]; offsets[r] .. offsets[r+1] delimit the ids
-// (positions in the cell-sorted point array) of the r-th AMBIG voxel of the block.
+// Pass B: candidate lists of the AMBIG voxels, laid out for K3's phase 2:
+//   hdrw[b * 32 + w]  = global rank of the first AMBIG voxel of label word w of block b (ranks run over all blocks, voxel order),
+//   adesc[rank]       = {first record, number of records} of that AMBIG voxel,
+//   arec[...]         = float4 COPIES {x, y, z, original index} of its candidates -- every scene point whose distance to the
+//                       (inflated) voxel is <= delta (1 + 1e-5) -- with the candidate closest to the voxel centre FIRST (the
+//                       most likely hit: K3's existence test stops at the first point within delta).
+// A query that fell into an AMBIG voxel reaches its candidates with two indexed loads (hdrw, adesc) and no second indirection.
 __global__ void __launch_bounds__(CLS_THREADS) k1f_fill_lists(const uint32_t* __restrict__ block_cell, const uint32_t* __restrict__ cell_start,
                                                               const float4* __restrict__ pts, GridParams g, const uint32_t* __restrict__ codes,
-                                                              const uint16_t* __restrict__ near_cnt, uint32_t* __restrict__ hdr,
-                                                              const uint32_t* __restrict__ region_base, uint32_t* __restrict__ lists) {
+                                                              const uint16_t* __restrict__ near_cnt, const uint32_t* __restrict__ hdr,
+                                                              const uint32_t* __restrict__ rec_base, const uint32_t* __restrict__ amb_base,
+                                                              uint32_t* __restrict__ hdrw, uint2* __restrict__ adesc, float4* __restrict__ arec) {
   __shared__ float4 s_p[CLS_CHUNK];
   __shared__ uint16_t s_av[F * F * F];       // AMBIG voxels in rank order
-  __shared__ uint32_t s_off[F * F * F + 1];  // their list offsets
+  __shared__ uint32_t s_off[F * F * F + 1];  // their list offsets within the block's record region
   const int b = blockIdx.x;
   const uint32_t n_amb = hdr[(size_t)b * 8 + 5];
-  if (threadIdx.x == 0) hdr[(size_t)b * 8 + 4] = region_base[b];
-  if (n_amb == 0) return;
-  const uint32_t base_w = region_base[b];
-  const uint32_t c = block_cell[b];
-  const int cx = (int)(c % g.dim[0]), cy = (int)((c / g.dim[0]) % g.dim[1]), cz = (int)(c / ((uint32_t)g.dim[0] * g.dim[1]));
-  const float hs = 0.5f * g.hf + g.inflate;
-  // rank order = voxel order; build the compact voxel list from the code words
+  const uint32_t abase = amb_base[b], rbase = rec_base[b];
+  // rank order = voxel order; per-word rank prefixes + the compact voxel list from the code words
   if (threadIdx.x < 32) {
     const uint32_t w = codes[(size_t)b * 32 + threadIdx.x] & 0xAAAAAAAAu;
     uint32_t cnt = __popc(w), incl = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)threadIdx.x >= o) incl += t; }
     uint32_t r = incl - cnt, ww = w;
+    hdrw[(size_t)b * 32 + threadIdx.x] = abase + r;
     while (ww) { int bit = __ffs(ww) - 1; ww &= ww - 1; s_av[r++] = (uint16_t)(threadIdx.x * 16 + (bit >> 1)); }
   }
+  if (n_amb == 0) return;
+  const uint32_t c = block_cell[b];
+  const int cx = (int)(c % g.dim[0]), cy = (int)((c / g.dim[0]) % g.dim[1]), cz = (int)(c / ((uint32_t)g.dim[0] * g.dim[1]));
+  const float hs = 0.5f * g.hf + g.inflate;
   __syncthreads();
   // offsets: serial scan by one warp over <= 512 entries (tiny)
   if (threadIdx.x < 32) {
-    uint32_t run = n_amb + 1;     // ids start after the offset table
+    uint32_t run = 0;
     for (uint32_t r0 = 0; r0 < n_amb; r0 += 32) {
       const uint32_t r = r0 + threadIdx.x;
       uint32_t cnt = r < n_amb ? near_cnt[(size_t)b * 512 + s_av[r]] : 0u, incl = cnt;
@@ -165,10 +173,10 @@ __global__ void __launch_bounds__(CLS_THREADS) k1f_fill_lists(const uint32_t* __
     if (threadIdx.x == 0) s_off[n_amb] = run;
   }
   __syncthreads();
-  for (uint32_t r = threadIdx.x; r <= n_amb; r += CLS_THREADS) lists[base_w + r] = s_off[r];
+  for (uint32_t r = threadIdx.x; r < n_amb; r += CLS_THREADS) adesc[abase + r] = make_uint2(rbase + s_off[r], s_off[r + 1] - s_off[r]);
   // fill: thread t owns AMBIG voxels t, t+128, ... (up to 4)
-  float vx[4], vy[4], vz[4];
-  uint32_t wr[4];
+  float vx[4], vy[4], vz[4], bd2[4];
+  uint32_t wr[4], first[4], bpos[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const uint32_t r = threadIdx.x + CLS_THREADS * j;
@@ -176,7 +184,8 @@ __global__ void __launch_bounds__(CLS_THREADS) k1f_fill_lists(const uint32_t* __
     vx[j] = __fmaf_rn((float)(cx * F + (v & 7)) + 0.5f, g.hf, g.lo[0]);
     vy[j] = __fmaf_rn((float)(cy * F + ((v >> 3) & 7)) + 0.5f, g.hf, g.lo[1]);
     vz[j] = __fmaf_rn((float)(cz * F + (v >> 6)) + 0.5f, g.hf, g.lo[2]);
-    wr[j] = r < n_amb ? base_w + s_off[r] : 0xffffffffu;
+    wr[j] = r < n_amb ? rbase + s_off[r] : 0xffffffffu;
+    first[j] = wr[j]; bpos[j] = wr[j]; bd2[j] = INFINITY;
   }
   const uint32_t active_j = (n_amb + CLS_THREADS - 1) / CLS_THREADS;
   for (int row = 0; row < 9; ++row) {
@@ -193,13 +202,26 @@ __global__ void __launch_bounds__(CLS_THREADS) k1f_fill_lists(const uint32_t* __
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           if ((uint32_t)j < active_j && wr[j] != 0xffffffffu) {
-            const float ax = fabsf(p.x - vx[j]), ay = fabsf(p.y - vy[j]), az = fabsf(p.z - vz[j]);
+            const float dx = p.x - vx[j], dy = p.y - vy[j], dz = p.z - vz[j];
+            const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
             const float lx = fmaxf(ax - hs, 0.f), ly = fmaxf(ay - hs, 0.f), lz = fmaxf(az - hs, 0.f);
             const float mind2 = __fmaf_rn(lx, lx, __fmaf_rn(ly, ly, lz * lz));
-            if (mind2 <= g.dhi2) lists[wr[j]++] = base + (uint32_t)t;
+            if (mind2 <= g.dhi2) {
+              const float c2 = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, dz * dz));
+              if (c2 < bd2[j]) { bd2[j] = c2; bpos[j] = wr[j]; }    // strict <: the first of equals in sweep order (deterministic)
+              arec[wr[j]++] = p;
+            }
           }
         }
       }
+    }
+  }
+  // the candidate closest to the voxel centre goes first (own writes, same thread: program order)
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if ((uint32_t)j < active_j && first[j] != 0xffffffffu && bpos[j] != first[j]) {
+      const float4 a = arec[first[j]], bb = arec[bpos[j]];
+      arec[first[j]] = bb; arec[bpos[j]] = a;
     }
   }
 }
@@ -461,30 +483,45 @@ int k1_build_fine(pgp_ctx* ctx) {
   // the OUT label also needs: everything within delta(1+1e-5) + inflate of a cell lies in its 27 cells
   if (!((double)g.h * (1.0 - 4e-4) >= d * (1.0 + 1e-5) + (double)g.inflate)) return PGP_OK;   // margins do not close: no fine grid
   s.n_list_words = 0;
+  if ((size_t)nb * 32 >= ((size_t)1 << 28)) return PGP_OK;          // K3 packs (label word index, rank) into one 32-bit queue entry
   if (nb > 0) {
     PGP_CUDA(ctx, s.near_cnt.reserve((size_t)nb * 512 * 2));
     PGP_CUDA(ctx, s.hdr.reserve((size_t)nb * 32));
-    PGP_CUDA(ctx, s.region.reserve((size_t)(nb + 1) * 4));
+    PGP_CUDA(ctx, s.hdrw.reserve((size_t)nb * 128));
+    PGP_CUDA(ctx, s.region.reserve((size_t)(nb + 1) * 8));
     PGP_CUDA(ctx, s.scratch.reserve((size_t)((nb + 1) / 2048 + 4096) * 4));
-    uint32_t* region = s.region.as<uint32_t>();
-    PGP_CUDA(ctx, cudaMemsetAsync(region, 0, (size_t)(nb + 1) * 4, st));
+    uint32_t* region = s.region.as<uint32_t>();            // records per block -> first record of the block
+    uint32_t* region_amb = region + (nb + 1);              // AMBIG voxels per block -> global rank of the block's first one
+    unsigned long long* d_total = reinterpret_cast<unsigned long long*>(ctx->work.as<char>() + 192);
+    PGP_CUDA(ctx, cudaMemsetAsync(region, 0, (size_t)(nb + 1) * 8, st));
+    PGP_CUDA(ctx, cudaMemsetAsync(d_total, 0, 8, st));
     PGP_CUDA(ctx, cudaMemsetAsync(ctx->work.as<int>() + 40, 0, 4, st));
     k1f_classify<<<nb, CLS_THREADS, 0, st>>>(s.block_cell.as<uint32_t>(), s.cell_start.as<uint32_t>(), s.pts.as<float4>(), g, s.codes.as<uint32_t>(),
-                                             s.near_cnt.as<uint16_t>(), s.hdr.as<uint32_t>(), region, ctx->work.as<int>() + 40);
+                                             s.near_cnt.as<uint16_t>(), s.hdr.as<uint32_t>(), region, region_amb, d_total, ctx->work.as<int>() + 40);
     ctx->launches++;
     rc = pgp_scan_exclusive_u32(ctx, region, (int64_t)nb + 1, s.scratch.as<uint32_t>());
     if (rc) return rc;
-    uint32_t total = 0;
+    rc = pgp_scan_exclusive_u32(ctx, region_amb, (int64_t)nb + 1, s.scratch.as<uint32_t>());
+    if (rc) return rc;
+    unsigned long long total = 0;
+    uint32_t n_amb_total = 0;
     int overflow = 0;
-    PGP_CUDA(ctx, cudaMemcpyAsync(&total, region + nb, 4, cudaMemcpyDeviceToHost, st));
+    PGP_CUDA(ctx, cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, st));
+    PGP_CUDA(ctx, cudaMemcpyAsync(&n_amb_total, region_amb + nb, 4, cudaMemcpyDeviceToHost, st));
     PGP_CUDA(ctx, cudaMemcpyAsync(&overflow, ctx->work.as<int>() + 40, 4, cudaMemcpyDeviceToHost, st));
     PGP_CUDA(ctx, cudaStreamSynchronize(st));
-    if (overflow) return PGP_OK;     // g.fine stays 0: scoring uses the 27-cell path
-    PGP_CUDA(ctx, s.lists.reserve((size_t)total * 4 + 16));
+    if (overflow || total >= (1ull << 32) - 64) return PGP_OK;     // g.fine stays 0: scoring uses the 27-cell path
+    size_t free_b = 0, total_b = 0;
+    PGP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    if ((size_t)total * 16 + (size_t)n_amb_total * 8 + ((size_t)256 << 20) > free_b + s.arec.cap + s.adesc.cap) return PGP_OK;
+    PGP_CUDA(ctx, s.arec.reserve((size_t)total * 16 + 16));
+    PGP_CUDA(ctx, s.adesc.reserve((size_t)n_amb_total * 8 + 16));
     k1f_fill_lists<<<nb, CLS_THREADS, 0, st>>>(s.block_cell.as<uint32_t>(), s.cell_start.as<uint32_t>(), s.pts.as<float4>(), g, s.codes.as<uint32_t>(),
-                                               s.near_cnt.as<uint16_t>(), s.hdr.as<uint32_t>(), region, s.lists.as<uint32_t>());
+                                               s.near_cnt.as<uint16_t>(), s.hdr.as<uint32_t>(), region, region_amb, s.hdrw.as<uint32_t>(),
+                                               s.adesc.as<uint2>(), s.arec.as<float4>());
     ctx->launches++;
-    s.n_list_words = total;
+    s.n_list_words = (int64_t)total;
+    s.n_ambig_voxels = (int64_t)n_amb_total;
   }
   // K1d distance field (two byte planes of scratch in `cursor`, which is free again by now)
   {

@@ -50,8 +50,9 @@ struct LcpParams {
   const uint2* bmrank;       // per bitmap word {bits, rank prefix}
   const uint32_t* codes;     // n_blocks x 32 words
   int bmrank_words;          // words staged in smem (0: read from global/L1)
-  const uint4* hdr;          // n_blocks x 2 uint4: {u16 ambig-rank prefix per 64-voxel group x 8}, {list region base, #ambig, #ids, 0}
-  const uint32_t* lists;     // candidate ids of the AMBIG voxels (K1b pass B)
+  const uint32_t* hdrw;      // n_blocks x 32: global rank of the first AMBIG voxel of each label word (K1b pass B)
+  const uint2* adesc;        // per AMBIG voxel: {first record, number of records}
+  const float4* arec;        // candidate records {x, y, z, original index}, closest to the voxel centre first
   float model_rinf;          // max |coordinate| of the validation model (bounds the transform's intermediates)
   const uint32_t* wvox;      // K1c: per voxel (offset in the block's region << 10) | candidate count
   const uint32_t* wbase;     // K1c: per block first entry of its region
@@ -308,7 +309,8 @@ struct FineCtx {
   const float4* s_nrm;       // weighted mode only
   const float4* s_groups;    // bounding spheres of the tile's 32-point groups
   const uint2* table;        // bmrank: shared (SMEM_TABLE) or global
-  uint16_t* q;
+  uint16_t* q;               // per warp: queued model-point indices
+  uint32_t* qe;              // count mode: (label word index << 4) | rank of the voxel among the word's AMBIG voxels
   uint16_t* glist;           // per warp: the groups of the current hypothesis that survived the cull (+ FUNROLL pad slots)
   int dummy_group;           // a group of NaN points behind the tile
   int dimx, dimy, dimz;
@@ -339,28 +341,6 @@ __device__ __forceinline__ uint32_t label_slot(const LcpParams& p, const FineCtx
   return (wr.x & bit) ? blk * 32u + (uint32_t)(v >> 4) : f.dummy_word;
 }
 
-// AMBIG candidate list (K1b) of the voxel a queued query fell into: [s0, s1) word offsets into the block's region `reg`.
-template <bool SMEM_TABLE>
-__device__ __forceinline__ const uint32_t* list_range(const LcpParams& p, const FineCtx& f, int ix, int iy, int iz, uint32_t& s0, uint32_t& s1) {
-  const int c = ((iz >> 3) * f.dimy + (iy >> 3)) * f.dimx + (ix >> 3);
-  const uint2 wr = table_word<SMEM_TABLE>(f, c >> 5);
-  const unsigned blk = wr.y + __popc(wr.x & ((1u << (c & 31)) - 1u));
-  const int v = ((iz & 7) << 6) | ((iy & 7) << 3) | (ix & 7);
-  const uint4 gp = __ldg(p.hdr + (size_t)blk * 2);
-  const uint4 h1 = __ldg(p.hdr + (size_t)blk * 2 + 1);
-  const uint4 grp = __ldg(reinterpret_cast<const uint4*>(p.codes) + (size_t)blk * 8 + (v >> 6));
-  const int g8 = v >> 6, wi = (v >> 4) & 3;
-  const uint32_t gw = g8 < 2 ? gp.x : g8 < 4 ? gp.y : g8 < 6 ? gp.z : gp.w;
-  uint32_t r = (gw >> ((g8 & 1) * 16)) & 0xffffu;
-  const uint32_t A = 0xAAAAAAAAu;
-  r += (wi > 0 ? __popc(grp.x & A) : 0) + (wi > 1 ? __popc(grp.y & A) : 0) + (wi > 2 ? __popc(grp.z & A) : 0);
-  const uint32_t word = wi == 0 ? grp.x : wi == 1 ? grp.y : wi == 2 ? grp.z : grp.w;
-  r += __popc(word & A & ((1u << ((v & 15) * 2)) - 1u));
-  const uint32_t* reg = p.lists + h1.x;
-  s0 = __ldg(reg + r); s1 = __ldg(reg + r + 1);
-  return reg;
-}
-
 // K1c nearest-candidate records of the voxel: one indexed load, no rank arithmetic
 template <bool SMEM_TABLE>
 __device__ __forceinline__ const float4* wlist_of(const LcpParams& p, const FineCtx& f, int ix, int iy, int iz, uint32_t& cnt) {
@@ -374,26 +354,18 @@ __device__ __forceinline__ const float4* wlist_of(const LcpParams& p, const Fine
   return p.wlists + base + (e >> 10);
 }
 
-// phase 2 for one queued query: the reference's exact test against the voxel's candidate list, U candidates per round with
-// their id and point loads issued together (U > 1 needs the register budget of the 16- / 24-warp CTA shapes)
-template <bool SMEM_TABLE, int U>
-__device__ __forceinline__ int resolve_ambiguous(const LcpParams& p, const FineCtx& f, const Xf& x, const float4 m, int ix, int iy, int iz) {
-  uint32_t s0, s1;
-  const uint32_t* reg = list_range<SMEM_TABLE>(p, f, ix, iy, iz, s0, s1);
+// phase 2 (count mode) for one queued query: the reference's exact test against the candidate records of its AMBIG voxel.
+// `e` = (label word index << 4) | rank of the voxel among the AMBIG voxels of that word, packed by phase 1.
+__device__ __forceinline__ int resolve_ambiguous(const LcpParams& p, const Xf& x, const float4 m, uint32_t e) {
+  const uint32_t r = __ldg(p.hdrw + (e >> 4)) + (e & 15u);
+  const uint2 d = __ldg(p.adesc + r);
   float tx, ty, tz;
   apply_xf(x, m, tx, ty, tz);
   const float r2 = p.g.r2;
-  for (uint32_t j = s0; j < s1; j += U) {
-    uint32_t id[U];
-    float4 sp[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) if (u == 0 || j + u < s1) id[u] = __ldg(reg + j + u);
-#pragma unroll
-    for (int u = 0; u < U; ++u) if (u == 0 || j + u < s1) sp[u] = __ldg(p.pts + id[u]);
-    bool hit = false;
-#pragma unroll
-    for (int u = 0; u < U; ++u) if (u == 0 || j + u < s1) hit |= sqdist3(tx, ty, tz, sp[u].x, sp[u].y, sp[u].z) <= r2;
-    if (hit) return 1;
+  const float4* __restrict__ rec = p.arec + d.x;
+  for (uint32_t j = 0; j < d.y; ++j) {
+    const float4 sp = __ldg(rec + j);
+    if (sqdist3(tx, ty, tz, sp.x, sp.y, sp.z) <= r2) return 1;
   }
   return 0;
 }
@@ -508,11 +480,14 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
     if (f.lane < take) {
       const int i = f.q[qn - take + f.lane];
       const float4 m = f.s_model[i];
-      int ix, iy, iz;
-      voxel_of(m, ix, iy, iz);                      // same arithmetic as phase 1 -> same voxel
       const Xf xe = FAST ? load_xf(T, h) : x;       // FAST keeps only a[] live across the loop; the exact matrix is re-read (L1)
-      if (MODE == 0) good += resolve_ambiguous<SMEM_TABLE, U>(p, f, xe, m, ix, iy, iz);
-      else good += resolve_nearest<SMEM_TABLE, U>(p, f, xe, m, f.s_nrm[i], ix, iy, iz);
+      if (MODE == 0) {
+        good += resolve_ambiguous(p, xe, m, f.qe[qn - take + f.lane]);
+      } else {
+        int ix, iy, iz;
+        voxel_of(m, ix, iy, iz);                    // same arithmetic as phase 1 -> same voxel
+        good += resolve_nearest<SMEM_TABLE, U>(p, f, xe, m, f.s_nrm[i], ix, iy, iz);
+      }
     }
     qn -= take;
   };
@@ -532,19 +507,26 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
     unsigned any = 0;
 #pragma unroll
     for (int u = 0; u < FUNROLL; ++u) {
-      code[u] = (code[u] >> sh[u]) & 3u;
+      const uint32_t lab = (code[u] >> sh[u]) & 3u;
       if (MODE == 0) {
-        good += (code[u] == 1u);
+        good += (lab == 1u);
+        any |= (lab == 2u);
       } else {
-        code[u] = code[u] ? 2u : 0u;       // weighted: IN voxels need the nearest point's identity too
+        any |= (lab != 0u);                 // weighted: IN voxels need the nearest point's identity too
       }
-      any |= (code[u] == 2u);
     }
     if (__any_sync(0xffffffffu, any)) {
 #pragma unroll
       for (int u = 0; u < FUNROLL; ++u) {
-        const unsigned bb = __ballot_sync(0xffffffffu, code[u] == 2u);
-        if (code[u] == 2u) f.q[qn + __popc(bb & f.lt_mask)] = (uint16_t)(gb[u] + f.lane);
+        const uint32_t lab = (code[u] >> sh[u]) & 3u;
+        const bool push = MODE == 0 ? lab == 2u : lab != 0u;
+        const unsigned bb = __ballot_sync(0xffffffffu, push);
+        if (push) {
+          const int slot = qn + __popc(bb & f.lt_mask);
+          f.q[slot] = (uint16_t)(gb[u] + f.lane);
+          // rank of this voxel among the AMBIG voxels (high bit of the 2-bit label set) of its label word
+          if (MODE == 0) f.qe[slot] = (off[u] << 4) | (uint32_t)__popc(code[u] & 0xAAAAAAAAu & ((1u << sh[u]) - 1u));
+        }
         qn += __popc(bb);
       }
       __syncwarp();
@@ -568,6 +550,7 @@ __global__ void __launch_bounds__(FWARPS * 32, 1) k3_fine_kernel(const __grid_co
   float4* s_groups = reinterpret_cast<float4*>(s_bmrank + p.bmrank_words);
   uint16_t* s_glist = reinterpret_cast<uint16_t*>(s_groups + cap_groups);
   uint16_t* s_queue = s_glist + (((FWARPS * (cap_groups + FUNROLL)) + 7) & ~7);
+  uint32_t* s_qe = reinterpret_cast<uint32_t*>(s_queue + FWARPS * FQCAP);       // count mode only
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   FineCtx f;
   f.s_model = s_model;
@@ -575,6 +558,7 @@ __global__ void __launch_bounds__(FWARPS * 32, 1) k3_fine_kernel(const __grid_co
   f.s_groups = s_groups;
   f.table = SMEM_TABLE ? s_bmrank : p.bmrank;
   f.q = s_queue + warp * FQCAP;
+  f.qe = s_qe + warp * FQCAP;
   f.glist = s_glist + warp * (cap_groups + FUNROLL);
   f.dimx = p.g.dim[0]; f.dimy = p.g.dim[1]; f.dimz = p.g.dim[2];
   f.rx = (unsigned)(p.g.dim[0] - 2) * 8u; f.ry = (unsigned)(p.g.dim[1] - 2) * 8u; f.rz = (unsigned)(p.g.dim[2] - 2) * 8u;
@@ -803,7 +787,7 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     const int FWARPS = mode == PGP_LCP_WEIGHTED ? ctx->k3_warps_weighted : ctx->k3_warps_count;
     auto smem_need = [&](int cap, size_t table) {
       return (size_t)(cap + 32) * 16 + (mode == PGP_LCP_WEIGHTED ? (size_t)cap * 16 : 0) + table + (size_t)(cap >> 5) * 16 +
-             (size_t)(((FWARPS * ((cap >> 5) + FUNROLL)) + 7) & ~7) * 2 + (size_t)FWARPS * FQCAP * 2;
+             (size_t)(((FWARPS * ((cap >> 5) + FUNROLL)) + 7) & ~7) * 2 + (size_t)FWARPS * FQCAP * (mode == PGP_LCP_WEIGHTED ? 2 : 6);
     };
     size_t bm = (size_t)s.bitmap_words * 8;
     int tile_cap = std::min((m.nv + 127) & ~127, 8192);
@@ -813,7 +797,7 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     p.n_tiles = (m.nv + tile_cap - 1) / tile_cap;
     if (p.n_tiles > 256) return pgp_fail(ctx, PGP_E_INVALID, "validation model too large (%d points)", m.nv);
     p.bmrank = s.bmrank.as<uint2>(); p.codes = s.codes.as<uint32_t>();
-    p.hdr = s.hdr.as<uint4>(); p.lists = s.lists.as<uint32_t>();
+    p.hdrw = s.hdrw.as<uint32_t>(); p.adesc = s.adesc.as<uint2>(); p.arec = s.arec.as<float4>();
     p.wvox = s.wvox.as<uint32_t>(); p.wbase = s.wbase.as<uint32_t>(); p.wlists = s.wlists.as<float4>(); p.aux_orig = s.aux_orig.as<float4>();
     p.bmrank_words = (int)(bm / 8);
     p.model_rinf = m.val_rinf;

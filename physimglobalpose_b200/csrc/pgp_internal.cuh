@@ -70,10 +70,13 @@ struct Scene {
   DevBuf block_cell;   // n_blocks x u32: cell of block b
   DevBuf codes;        // n_blocks x 32 words: 512 2-bit voxel states, voxel v = (sz*8+sy)*8+sx at bits 2(v&15) of word v>>4
   DevBuf near_cnt;     // build scratch: n_blocks x 512 u16 candidate counts
-  DevBuf hdr;          // n_blocks x 8 u32: {4 words of u16 ambig-rank prefixes per 64-voxel group, list region base, #ambig, #ids, 0}
+  DevBuf hdr;          // build scratch: n_blocks x 8 u32: {.., #ambig voxels at [5], #candidate records at [6], ..}
   DevBuf region;       // build scratch: region sizes / bases
-  DevBuf lists;        // per-block regions: offsets + candidate ids of the AMBIG voxels
-  int64_t n_list_words = 0;
+  DevBuf hdrw;         // n_blocks x 32 u32: global rank of the first AMBIG voxel of each label word
+  DevBuf adesc;        // per AMBIG voxel (rank order): {first record, number of records}
+  DevBuf arec;         // float4 copies {x, y, z, original index} of the AMBIG voxels' candidate points, closest to the voxel centre first
+  int64_t n_list_words = 0;    // records in arec
+  int64_t n_ambig_voxels = 0;
   DevBuf wvox;         // K1c: n_blocks x 512 u32: (offset in the block's region << 10) | candidate count, 0 for OUT voxels
   DevBuf wbase;        // K1c: n_blocks u32: first wlists entry of the block's region
   DevBuf wlists;       // K1c: float4 copies {x,y,z,original index} of the nearest-neighbour candidates of every non-OUT voxel

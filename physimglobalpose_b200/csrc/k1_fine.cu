@@ -21,6 +21,19 @@ constexpr int F = 8;
 constexpr int CLS_THREADS = 128;
 constexpr int CLS_CHUNK = 512;
 
+// Domination pruning of candidate lists.  For a voxel with centre c and half-size hs (inflated), a scene point p is DOMINATED by a
+// scene point b when b is strictly closer than p to every query q = c + e, |e_i| <= hs, that can land in the voxel:
+//     |q-p|^2 - |q-b|^2 = (|c-p|^2 - |c-b|^2) + 2 e.(b-p) >= (c2p - c2b) - 2 hs |b-p|_1 > margin.
+// Then p can never be the nearest in-range point of such a query, nor tie with it, and whenever p passes d2 <= delta^2 so does b:
+// p is dropped from the voxel's list (b stays, or is itself dominated by a point that stays).  `margin` = 1e-5 delta^2 is > 10x the
+// rounding of the two fp32 squared distances K3 compares (relative 3e-7 of <= 2 delta^2 each); the 1e-5 (c2p + c2b) term covers
+// the rounding of this test itself.  With 1.25 mm voxels and a few mm between scene points this leaves the 2-3 points whose
+// bisector planes cross the voxel instead of every point within delta + voxel diagonal.
+__device__ __forceinline__ bool dominated(const float4 p, float bx, float by, float bz, float hs, float c2p, float c2b, float margin) {
+  const float spread = 2.0f * hs * (fabsf(bx - p.x) + fabsf(by - p.y) + fabsf(bz - p.z));
+  return (c2p - c2b) - spread > margin + 1e-5f * (c2p + c2b);
+}
+
 __global__ void k1f_popc(const uint32_t* __restrict__ bitmap, int64_t n_words, uint32_t* __restrict__ out) {
   int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w < n_words) out[w] = __popc(bitmap[w]);
@@ -52,6 +65,8 @@ __global__ void __launch_bounds__(CLS_THREADS) k1f_classify(const uint32_t* __re
   float vx[4], vy[4], vz[4];
   bool in[4] = {false, false, false, false};
   int near[4] = {0, 0, 0, 0};
+  float bx[4], by[4], bz[4], bc2[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+  const float dom_margin = 1e-5f * g.dhi2;
   if (threadIdx.x == 0) s_tot = 0;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -78,7 +93,13 @@ __global__ void __launch_bounds__(CLS_THREADS) k1f_classify(const uint32_t* __re
           const float hx = ax + hs, hy = ay + hs, hz = az + hs;
           const float mind2 = __fmaf_rn(lx, lx, __fmaf_rn(ly, ly, lz * lz));
           const float maxd2 = __fmaf_rn(hx, hx, __fmaf_rn(hy, hy, hz * hz));
-          near[j] += (mind2 <= g.dhi2) ? 1 : 0;
+          if (mind2 <= g.dhi2) {
+            // candidate of the exact test unless the closest-to-centre candidate seen so far dominates it (k1f_fill_lists makes the
+            // same decisions in the same sweep order)
+            const float c2 = __fmaf_rn(p.x - vx[j], p.x - vx[j], __fmaf_rn(p.y - vy[j], p.y - vy[j], (p.z - vz[j]) * (p.z - vz[j])));
+            if (!(bc2[j] < INFINITY && dominated(p, bx[j], by[j], bz[j], hs, c2, bc2[j], dom_margin))) near[j] += 1;
+            if (c2 < bc2[j]) { bc2[j] = c2; bx[j] = p.x; by[j] = p.y; bz[j] = p.z; }
+          }
           in[j] |= maxd2 <= g.dlo2;
         }
       }
@@ -173,9 +194,9 @@ __global__ void __launch_bounds__(CLS_THREADS) k1f_fill_lists(const uint32_t* __
     if (threadIdx.x == 0) s_off[n_amb] = run;
   }
   __syncthreads();
-  for (uint32_t r = threadIdx.x; r < n_amb; r += CLS_THREADS) adesc[abase + r] = make_uint2(rbase + s_off[r], s_off[r + 1] - s_off[r]);
   // fill: thread t owns AMBIG voxels t, t+128, ... (up to 4)
-  float vx[4], vy[4], vz[4], bd2[4];
+  float vx[4], vy[4], vz[4], bd2[4], bx[4], by[4], bz[4];
+  const float dom_margin = 1e-5f * g.dhi2;
   uint32_t wr[4], first[4], bpos[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -208,20 +229,24 @@ __global__ void __launch_bounds__(CLS_THREADS) k1f_fill_lists(const uint32_t* __
             const float mind2 = __fmaf_rn(lx, lx, __fmaf_rn(ly, ly, lz * lz));
             if (mind2 <= g.dhi2) {
               const float c2 = __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, dz * dz));
-              if (c2 < bd2[j]) { bd2[j] = c2; bpos[j] = wr[j]; }    // strict <: the first of equals in sweep order (deterministic)
-              arec[wr[j]++] = p;
+              const bool keep = !(bd2[j] < INFINITY && dominated(p, bx[j], by[j], bz[j], hs, c2, bd2[j], dom_margin));   // as k1f_classify counted
+              if (c2 < bd2[j]) { bd2[j] = c2; bx[j] = p.x; by[j] = p.y; bz[j] = p.z; if (keep) bpos[j] = wr[j]; }    // strict <: first of equals
+              if (keep) arec[wr[j]++] = p;
             }
           }
         }
       }
     }
   }
-  // the candidate closest to the voxel centre goes first (own writes, same thread: program order)
+  // the candidate closest to the voxel centre goes first (own writes, same thread: program order); descriptor = what was written
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    if ((uint32_t)j < active_j && first[j] != 0xffffffffu && bpos[j] != first[j]) {
-      const float4 a = arec[first[j]], bb = arec[bpos[j]];
-      arec[first[j]] = bb; arec[bpos[j]] = a;
+    if ((uint32_t)j < active_j && first[j] != 0xffffffffu) {
+      if (bpos[j] != first[j]) {
+        const float4 a = arec[first[j]], bb = arec[bpos[j]];
+        arec[first[j]] = bb; arec[bpos[j]] = a;
+      }
+      adesc[abase + threadIdx.x + CLS_THREADS * j] = make_uint2(first[j], wr[j] - first[j]);
     }
   }
 }
@@ -246,6 +271,11 @@ __device__ __forceinline__ void box_d2(const float4 p, float vx, float vy, float
   const float hx = ax + hs, hy = ay + hs, hz = az + hs;
   mind2 = __fmaf_rn(lx, lx, __fmaf_rn(ly, ly, lz * lz));
   maxd2 = __fmaf_rn(hx, hx, __fmaf_rn(hy, hy, hz * hz));
+}
+
+__device__ __forceinline__ float centre_d2(const float4 p, float vx, float vy, float vz) {
+  const float dx = p.x - vx, dy = p.y - vy, dz = p.z - vz;
+  return __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, dz * dz));
 }
 
 // all scene points of the 27 cells around cell (cx,cy,cz), staged through shared memory; every
@@ -296,15 +326,24 @@ __global__ void __launch_bounds__(CLS_THREADS) k1w_count(const uint32_t* __restr
     u2[j] = INFINITY;
     live[j] = ((codes[(size_t)b * 32 + (v >> 4)] >> ((v & 15) * 2)) & 3u) != 0u;
   }
+  float bx[4], by[4], bz[4], bc2[4] = {INFINITY, INFINITY, INFINITY, INFINITY};     // the scene point closest to the voxel centre
+  const float dom_margin = 1e-5f * g.dhi2;
   sweep27(cell_start, pts, g, cx, cy, cz, s_p, [&](const float4 p, uint32_t) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { float lo2, hi2; box_d2(p, vx[j], vy[j], vz[j], hs, lo2, hi2); u2[j] = fminf(u2[j], hi2); }
+    for (int j = 0; j < 4; ++j) {
+      float lo2, hi2; box_d2(p, vx[j], vy[j], vz[j], hs, lo2, hi2); u2[j] = fminf(u2[j], hi2);
+      const float c2 = centre_d2(p, vx[j], vy[j], vz[j]);
+      if (c2 < bc2[j]) { bc2[j] = c2; bx[j] = p.x; by[j] = p.y; bz[j] = p.z; }
+    }
   });
 #pragma unroll
   for (int j = 0; j < 4; ++j) thr[j] = wlist_threshold(u2[j], g.dhi2);
   sweep27(cell_start, pts, g, cx, cy, cz, s_p, [&](const float4 p, uint32_t) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { float lo2, hi2; box_d2(p, vx[j], vy[j], vz[j], hs, lo2, hi2); cnt[j] += (lo2 <= thr[j]) ? 1 : 0; }
+    for (int j = 0; j < 4; ++j) {
+      float lo2, hi2; box_d2(p, vx[j], vy[j], vz[j], hs, lo2, hi2);
+      cnt[j] += (lo2 <= thr[j] && !dominated(p, bx[j], by[j], bz[j], hs, centre_d2(p, vx[j], vy[j], vz[j]), bc2[j], dom_margin)) ? 1 : 0;
+    }
   });
   uint32_t mine = 0;
 #pragma unroll
@@ -367,9 +406,15 @@ __global__ void __launch_bounds__(CLS_THREADS) k1w_fill(const uint32_t* __restri
     u2[j] = INFINITY;
     wr[j] = cnt[j] ? base + rel[j] : 0xffffffffu;
   }
+  float bx[4], by[4], bz[4], bc2[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+  const float dom_margin = 1e-5f * g.dhi2;
   sweep27(cell_start, pts, g, cx, cy, cz, s_p, [&](const float4 p, uint32_t) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { float lo2, hi2; box_d2(p, vx[j], vy[j], vz[j], hs, lo2, hi2); u2[j] = fminf(u2[j], hi2); }
+    for (int j = 0; j < 4; ++j) {
+      float lo2, hi2; box_d2(p, vx[j], vy[j], vz[j], hs, lo2, hi2); u2[j] = fminf(u2[j], hi2);
+      const float c2 = centre_d2(p, vx[j], vy[j], vz[j]);
+      if (c2 < bc2[j]) { bc2[j] = c2; bx[j] = p.x; by[j] = p.y; bz[j] = p.z; }
+    }
   });
 #pragma unroll
   for (int j = 0; j < 4; ++j) thr[j] = wlist_threshold(u2[j], g.dhi2);
@@ -379,7 +424,7 @@ __global__ void __launch_bounds__(CLS_THREADS) k1w_fill(const uint32_t* __restri
       if (wr[j] != 0xffffffffu) {
         float lo2, hi2;
         box_d2(p, vx[j], vy[j], vz[j], hs, lo2, hi2);
-        if (lo2 <= thr[j]) wlists[wr[j]++] = p;
+        if (lo2 <= thr[j] && !dominated(p, bx[j], by[j], bz[j], hs, centre_d2(p, vx[j], vy[j], vz[j]), bc2[j], dom_margin)) wlists[wr[j]++] = p;   // as k1w_count counted
       }
     }
   });

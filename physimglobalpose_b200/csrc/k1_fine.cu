@@ -447,36 +447,42 @@ __global__ void k1f_stats(const uint32_t* __restrict__ codes, int n_blocks, unsi
 }
 
 
-// ---- K1d: per-cell lower bound of the distance to the nearest scene point ----------------------
-// For a cell C and an occupied cell C' that differ by (kx, ky, kz) cells, every point of C is at least
-// h * sqrt(gx^2 + gy^2 + gz^2) away from every point of C', g = max(|k| - 1, 0).  S(C) = min over the
-// occupied cells of gx^2 + gy^2 + gz^2 separates per axis (a min-plus pass along x, then y, then z,
-// window +-DIST_W cells; nothing occupied inside the window -> S = DIST_W^2, still a lower bound).
-// K3 uses it to drop whole groups of model points whose bounding sphere cannot reach the scene.
-constexpr int DIST_W = 15;     // DIST_W^2 must fit a byte
+// ---- K1d: lower bound of the distance to the nearest scene point, on a lattice of R sub-cells per cell edge ----------------
+// For a sub-cell C and an occupied sub-cell C' that differ by (kx, ky, kz) sub-cells, every point of C is at least
+// (h/R) sqrt(gx^2 + gy^2 + gz^2) away from every point of C', g = max(|k| - 1, 0).  S(C) = min over the occupied sub-cells of
+// gx^2 + gy^2 + gz^2 separates per axis (a min-plus pass along x, then y, then z, window +-W sub-cells; nothing occupied inside
+// the window -> S = W^2, still a lower bound).  K3 uses it to drop whole groups of model points whose bounding sphere cannot
+// reach the scene; R = 2 halves what the "|k| - 1" rule gives away (up to one sub-cell per axis).
+__global__ void k1d_mark(const float4* __restrict__ pts, int n, GridParams g, int R, unsigned char* __restrict__ occ) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pts[i];
+  const float fr = (float)R;
+  int sx = (int)(cell_coord(p.x, g.lo[0], g.inv_h) * fr), sy = (int)(cell_coord(p.y, g.lo[1], g.inv_h) * fr), sz = (int)(cell_coord(p.z, g.lo[2], g.inv_h) * fr);
+  sx = min(max(sx, 0), g.dim[0] * R - 1); sy = min(max(sy, 0), g.dim[1] * R - 1); sz = min(max(sz, 0), g.dim[2] * R - 1);
+  occ[((size_t)sz * (g.dim[1] * R) + sy) * (g.dim[0] * R) + sx] = 1;
+}
 
 template <int PASS>   // 0: occupancy -> S along x, 1: += y, 2: += z and conversion to metres
-__global__ void k1d_pass(const uint32_t* __restrict__ cell_start, const unsigned char* __restrict__ in, unsigned char* __restrict__ out,
-                         float* __restrict__ dist, GridParams g) {
+__global__ void k1d_pass(const unsigned char* __restrict__ occ, const uint16_t* __restrict__ in, uint16_t* __restrict__ out, float* __restrict__ dist,
+                         int dx, int dy, int dz, int W, float sub_h) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= g.n_cells) return;
-  const int cx = (int)(c % g.dim[0]), cy = (int)((c / g.dim[0]) % g.dim[1]), cz = (int)(c / ((int64_t)g.dim[0] * g.dim[1]));
+  if (c >= (int64_t)dx * dy * dz) return;
+  const int cx = (int)(c % dx), cy = (int)((c / dx) % dy), cz = (int)(c / ((int64_t)dx * dy));
   const int pos = PASS == 0 ? cx : PASS == 1 ? cy : cz;
-  const int dim = g.dim[PASS];
-  const int64_t stride = PASS == 0 ? 1 : PASS == 1 ? g.dim[0] : (int64_t)g.dim[0] * g.dim[1];
-  int best = DIST_W * DIST_W;
-  const int t0 = max(-DIST_W, -pos), t1 = min(DIST_W, dim - 1 - pos);
+  const int dim = PASS == 0 ? dx : PASS == 1 ? dy : dz;
+  const int64_t stride = PASS == 0 ? 1 : PASS == 1 ? dx : (int64_t)dx * dy;
+  int best = W * W;
+  const int t0 = max(-W, -pos), t1 = min(W, dim - 1 - pos);
   for (int t = t0; t <= t1; ++t) {
     const int64_t cc = c + t * stride;
     const int gap = max(abs(t) - 1, 0);
-    int v;
-    if (PASS == 0) v = cell_start[cc + 1] > cell_start[cc] ? 0 : DIST_W * DIST_W;
-    else v = in[cc];
+    const int v = PASS == 0 ? (occ[cc] ? 0 : W * W) : (int)in[cc];
     best = min(best, v + gap * gap);
   }
-  if (PASS < 2) out[c] = (unsigned char)best;
-  // 0.02 h: the cell of a point is computed in fp32 (error < 1e-3 cells per axis), (1 - 1e-4): sqrtf / product rounding
-  else dist[c] = fmaxf(0.f, g.h * sqrtf((float)best) * (1.0f - 1e-4f) - 0.02f * g.h);
+  if (PASS < 2) out[c] = (uint16_t)best;
+  // 0.04 sub-cells: the sub-cell of a point is computed in fp32 (error < 2e-3 sub-cells per axis), (1 - 1e-4): sqrtf / product rounding
+  else dist[c] = fmaxf(0.f, sub_h * sqrtf((float)best) * (1.0f - 1e-4f) - 0.04f * sub_h);
 }
 
 }  // namespace
@@ -568,18 +574,26 @@ int k1_build_fine(pgp_ctx* ctx) {
     s.n_list_words = (int64_t)total;
     s.n_ambig_voxels = (int64_t)n_amb_total;
   }
-  // K1d distance field (two byte planes of scratch in `cursor`, which is free again by now)
+  // K1d distance field on the R-times refined lattice (R = 2 unless the grid is huge)
   {
-    const int64_t nc = g.n_cells;
-    PGP_CUDA(ctx, s.dist.reserve((size_t)nc * 4));
-    PGP_CUDA(ctx, s.cursor.reserve((size_t)nc * 2 + 16));
-    unsigned char* pa = s.cursor.as<unsigned char>();
-    unsigned char* pb = pa + nc;
-    const unsigned blocks = (unsigned)((nc + 255) / 256);
-    k1d_pass<0><<<blocks, 256, 0, st>>>(s.cell_start.as<uint32_t>(), nullptr, pa, nullptr, g);
-    k1d_pass<1><<<blocks, 256, 0, st>>>(nullptr, pa, pb, nullptr, g);
-    k1d_pass<2><<<blocks, 256, 0, st>>>(nullptr, pb, nullptr, s.dist.as<float>(), g);
-    ctx->launches += 3;
+    const int R = g.n_cells <= (16ll << 20) ? 2 : 1;
+    const int dx = g.dim[0] * R, dy = g.dim[1] * R, dz = g.dim[2] * R;
+    const int64_t ns = (int64_t)dx * dy * dz;
+    const int W = 12 * R;                                   // 12 cells: beyond that a group is culled whatever its radius
+    PGP_CUDA(ctx, s.dist.reserve((size_t)ns * 4));
+    PGP_CUDA(ctx, s.dist_tmp.reserve((size_t)ns * 5 + 64));
+    unsigned char* occ = s.dist_tmp.as<unsigned char>();
+    uint16_t* pa = reinterpret_cast<uint16_t*>(occ + ((ns + 63) & ~63ll));
+    uint16_t* pb = pa + ns;
+    PGP_CUDA(ctx, cudaMemsetAsync(occ, 0, (size_t)ns, st));
+    k1d_mark<<<(s.n + 255) / 256, 256, 0, st>>>(s.pts.as<float4>(), s.n, g, R, occ);
+    const unsigned blocks = (unsigned)((ns + 255) / 256);
+    const float sub_h = g.h / (float)R;
+    k1d_pass<0><<<blocks, 256, 0, st>>>(occ, nullptr, pa, nullptr, dx, dy, dz, W, sub_h);
+    k1d_pass<1><<<blocks, 256, 0, st>>>(nullptr, pa, pb, nullptr, dx, dy, dz, W, sub_h);
+    k1d_pass<2><<<blocks, 256, 0, st>>>(nullptr, pb, nullptr, s.dist.as<float>(), dx, dy, dz, W, sub_h);
+    ctx->launches += 4;
+    s.dist_r = R;
   }
   PGP_CUDA(ctx, cudaGetLastError());
   g.n_blocks = (int)nb;

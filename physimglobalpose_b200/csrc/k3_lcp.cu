@@ -61,6 +61,9 @@ struct LcpParams {
   const float4* groups;      // bounding sphere {centre, radius} of every aligned run of 32 validation points (pgp_set_model)
   const float* dist;         // K1d: per cell, lower bound of the distance to the nearest scene point (nullptr: no group cull)
   float cull_add;            // delta (1 + 1e-5) + rounding margin: a group is dropped when dist > |A| r + cull_add
+  float dist_scale;          // voxel units -> sub-cells of the K1d lattice (dist_r / 8)
+  float sub_h2;              // (edge of a K1d sub-cell)^2, shrunk by 1e-4
+  int ddx, ddy, ddz;         // K1d lattice dimensions
 };
 
 // ---- mbarrier + TMA bulk copy (global -> shared), sm_90+/sm_100a PTX ---------------------------
@@ -460,13 +463,18 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
       bool keep = g < g_end;
       if (cull && keep) {
         const float4 sp = f.s_groups[g];
-        const float ux = __fmaf_rn(a[0], sp.x, __fmaf_rn(a[1], sp.y, __fmaf_rn(a[2], sp.z, a[3]))) * 0.125f;
-        const float uy = __fmaf_rn(a[4], sp.x, __fmaf_rn(a[5], sp.y, __fmaf_rn(a[6], sp.z, a[7]))) * 0.125f;
-        const float uz = __fmaf_rn(a[8], sp.x, __fmaf_rn(a[9], sp.y, __fmaf_rn(a[10], sp.z, a[11]))) * 0.125f;
-        const int cx = min(max(__float2int_rd(ux), 0), f.dimx - 1), cy = min(max(__float2int_rd(uy), 0), f.dimy - 1),
-                  cz = min(max(__float2int_rd(uz), 0), f.dimz - 1);
-        const float d = __ldg(p.dist + ((size_t)cz * f.dimy + cy) * f.dimx + cx);
-        keep = !(d > __fmaf_rn(snorm, sp.w, p.cull_add));
+        const float ux = __fmaf_rn(a[0], sp.x, __fmaf_rn(a[1], sp.y, __fmaf_rn(a[2], sp.z, a[3]))) * p.dist_scale;
+        const float uy = __fmaf_rn(a[4], sp.x, __fmaf_rn(a[5], sp.y, __fmaf_rn(a[6], sp.z, a[7]))) * p.dist_scale;
+        const float uz = __fmaf_rn(a[8], sp.x, __fmaf_rn(a[9], sp.y, __fmaf_rn(a[10], sp.z, a[11]))) * p.dist_scale;
+        const int cx = min(max(__float2int_rd(ux), 0), p.ddx - 1), cy = min(max(__float2int_rd(uy), 0), p.ddy - 1),
+                  cz = min(max(__float2int_rd(uz), 0), p.ddz - 1);
+        const float d = __ldg(p.dist + ((size_t)cz * p.ddy + cy) * p.ddx + cx);
+        // a centre outside the grid box: the scene lies inside the (convex) box, so |q - s|^2 >= |q - q'|^2 + |q' - s|^2 for the
+        // projection q' of q onto the box; (ex, ey, ez) = q - q' in sub-cells
+        const float ex = fmaxf(fmaxf(-ux, ux - (float)p.ddx), 0.f), ey = fmaxf(fmaxf(-uy, uy - (float)p.ddy), 0.f), ez = fmaxf(fmaxf(-uz, uz - (float)p.ddz), 0.f);
+        const float e2 = (ex * ex + ey * ey + ez * ez) * p.sub_h2;
+        const float thr = __fmaf_rn(snorm, sp.w, p.cull_add);
+        keep = !(__fmaf_rn(d, d, e2) > thr * thr * (1.0f + 1e-5f));
       }
       const unsigned bb = __ballot_sync(0xffffffffu, keep);
       if (keep) f.glist[ns + __popc(bb & f.lt_mask)] = (uint16_t)g;
@@ -805,6 +813,9 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     p.groups = m.val_groups.as<float4>();
     p.dist = ctx->group_cull ? s.dist.as<float>() : nullptr;
     p.cull_add = s.delta * (1.0f + 1e-5f) + 4.0f * s.g.inflate;
+    p.dist_scale = (float)s.dist_r * 0.125f;
+    p.sub_h2 = (s.g.h / (float)s.dist_r) * (s.g.h / (float)s.dist_r) * (1.0f - 1e-4f);
+    p.ddx = s.g.dim[0] * s.dist_r; p.ddy = s.g.dim[1] * s.dist_r; p.ddz = s.g.dim[2] * s.dist_r;
     const size_t smem = smem_need(tile_cap, bm);
     PGP_CUDA(ctx, cudaMemsetAsync(p.work, 0, 8 * (size_t)p.n_tiles, st));
     int grid = (int)std::min<long long>((n + FWARPS - 1) / FWARPS, ctx->sm_count);

@@ -81,7 +81,9 @@ struct Scene {
   DevBuf wbase;        // K1c: n_blocks u32: first wlists entry of the block's region
   DevBuf wlists;       // K1c: float4 copies {x,y,z,original index} of the nearest-neighbour candidates of every non-OUT voxel
   int64_t n_wlist_entries = 0;
-  DevBuf dist;         // K1d: n_cells x f32, lower bound of the distance from any point of the cell to the nearest scene point
+  DevBuf dist;         // K1d: f32 per sub-cell (dist_r per cell edge), lower bound of the distance from any point of the sub-cell to the nearest scene point
+  DevBuf dist_tmp;     // K1d build scratch
+  int dist_r = 1;
   DevBuf aux_orig;     // n x float4 in ORIGINAL order: unit normal, prior (the K1c records carry original indices)
   bool wlists_ready = false, wlists_tried = false;
   DevBuf prior;        // n x f32 in ORIGINAL order

@@ -234,8 +234,14 @@ def run_ours(args, rank, local_rank, world):
         return gather(0, index_base)
 
     def step_e2e():
-        eng.score_lcp_ptr(0, T_host.data_ptr(), N_HYP, counts_host.data_ptr(), scores_host.data_ptr(), "count", host=True)
-        return gather(0, index_base)
+        # host buffers in, host buffers out: upload (streamed under the scoring launch) -> K3 -> {download of counts / scores on the
+        # copy-back stream  ||  K4 top-k -> all-gather -> download of the records}, one wait at the end
+        eng.score_lcp_begin(0, T_host.data_ptr(), N_HYP, counts_host.data_ptr(), scores_host.data_ptr(), "count")
+        ticket = gather.submit(0, index_base)
+        if eng.score_lcp_end():                      # the streamed upload stalled and the batch was re-scored: select again
+            gather.collect(ticket)
+            ticket = gather.submit(0, index_base)
+        return gather.collect(ticket)
 
     def barrier():
         torch.cuda.synchronize()

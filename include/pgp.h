@@ -128,6 +128,15 @@ PGP_API int pgp_label_stats(pgp_ctx* ctx, int64_t* out8);
  * device for pgp_topk / pgp_improving_chain. */
 PGP_API int pgp_score_lcp(pgp_ctx* ctx, int obj, const float* T_host, int64_t n, int mode,
                           uint32_t* counts_host, float* scores_host);
+/* The same call in two halves, for callers that want to queue the selection (pgp_topk_dev) and their collective behind the
+ * scoring launch before waiting: _begin enqueues upload + scoring + the downloads (T_host and the two output buffers should be
+ * pinned and must stay valid until _end) and returns at once; _end waits until counts_host / scores_host are filled.  _end
+ * returns 1 (not an error) in the one case where the batch had to be scored a second time -- the upload that is streamed under
+ * the scoring launch stalled (a profiler serialising streams) -- and work queued in between must be repeated; 0 otherwise.
+ * One batch at a time per context.  Replaces the same loop of the reference as pgp_score_lcp (match4pcsBase.cc:1888-1901). */
+PGP_API int pgp_score_lcp_begin(pgp_ctx* ctx, int obj, const float* T_host, int64_t n, int mode,
+                                uint32_t* counts_host, float* scores_host);
+PGP_API int pgp_score_lcp_end(pgp_ctx* ctx);
 /* Same with everything already in device memory; asynchronous on the context's stream.
  * counts_dev (n x u32) and scores_dev (n x f32) are caller-owned and must stay alive until the
  * top-k / chain calls that follow. */

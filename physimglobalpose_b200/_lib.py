@@ -51,6 +51,8 @@ _SIGNATURES = {
     "pgp_label_stats": (_i, [_vp, _vp]),
     "pgp_score_lcp": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp]),
     "pgp_score_lcp_dev": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp]),
+    "pgp_score_lcp_begin": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp]),
+    "pgp_score_lcp_end": (_i, [_vp]),
     "pgp_registered_points": (_i, [_vp, _i, _vp, _vp, _i]),
     "pgp_nearest_in_range": (_i, [_vp, _i, _vp, _vp]),
     "pgp_set_option": (_i, [_vp, C.c_char_p, _i]),

@@ -407,11 +407,14 @@ int pgp_score_lcp_dev(pgp_ctx* ctx, int obj, const float* T_dev, int64_t n, int 
   return PGP_OK;
 }
 
-int pgp_score_lcp(pgp_ctx* ctx, int obj, const float* T, int64_t n, int mode, uint32_t* counts, float* scores) {
+// Host-buffer scoring, split in two so that the caller can queue more work (top-k, the all-gather) behind the scoring launch
+// before it waits: pgp_score_lcp_begin enqueues upload + K3 + the downloads and returns, pgp_score_lcp_end waits for them.
+int pgp_score_lcp_begin(pgp_ctx* ctx, int obj, const float* T, int64_t n, int mode, uint32_t* counts, float* scores) {
   CHECK_CTX(ctx);
   Model* m = nullptr;
   int rc = check_score_args(ctx, obj, n, mode, &m);
   if (rc) return rc;
+  if (ctx->pending.active) return pgp_fail(ctx, PGP_E_INVALID, "pgp_score_lcp_begin: the previous batch has not been ended");
   if (n == 0) { ctx->last = LastBatch(); return PGP_OK; }
   if (!T) return pgp_fail(ctx, PGP_E_INVALID, "null transforms");
   PGP_CUDA(ctx, ctx->batch_T.reserve((size_t)n * 48));
@@ -425,9 +428,11 @@ int pgp_score_lcp(pgp_ctx* ctx, int obj, const float* T, int64_t n, int mode, ui
   uint32_t* dC = ctx->batch_counts.as<uint32_t>();
   float* dS = ctx->batch_scores.as<float>();
   const int chunks = 4;
-  if (ctx->stream_upload && n >= 32768 && n < (1ll << 31) && k3_streams_upload(ctx, mode)) {
-    if (!ctx->pinned) { PGP_CUDA(ctx, cudaMallocHost(&ctx->pinned, 256)); ctx->pinned_cap = 256; }
-    uint32_t* marks = static_cast<uint32_t*>(ctx->pinned);                      // [0] = 0, [1..4] = hypotheses uploaded after chunk c
+  if (!ctx->pinned) { PGP_CUDA(ctx, cudaMallocHost(&ctx->pinned, 256)); ctx->pinned_cap = 256; }
+  uint32_t* marks = static_cast<uint32_t*>(ctx->pinned);                        // [0] = 0, [1..4] = hypotheses uploaded after chunk c
+  marks[8] = 0;                                                                 // abort flag read back by pgp_score_lcp_end
+  const bool streamed = ctx->stream_upload && n >= 32768 && n < (1ll << 31) && k3_streams_upload(ctx, mode);
+  if (streamed) {
     uint32_t* ready = reinterpret_cast<uint32_t*>(ctx->work.as<char>() + 320);
     marks[0] = 0;
     for (int c = 0; c < chunks; ++c) marks[c + 1] = (uint32_t)(c + 1 == chunks ? n : ((n * (c + 1) / chunks) & ~7ll));
@@ -447,23 +452,52 @@ int pgp_score_lcp(pgp_ctx* ctx, int obj, const float* T, int64_t n, int mode, ui
       }
     }
     ctx->last.T = dT; ctx->last.counts = dC; ctx->last.scores = dS; ctx->last.n = n; ctx->last.mode = mode; ctx->last.obj = obj;
-    // did the kernel give up waiting for the upload (see k3_fine_kernel)?  Then the copies are done by now: score again, plainly.
-    PGP_CUDA(ctx, cudaMemcpyAsync(marks + 8, ready + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
-    if (marks[8]) {
-      rc = k3_score(ctx, *m, dT, n, mode, dC, dS, nullptr);
-      if (rc) return rc;
-    }
   } else {
     PGP_CUDA(ctx, cudaMemcpyAsync(dT, T, (size_t)n * 48, cudaMemcpyHostToDevice, ctx->stream));
     rc = pgp_score_lcp_dev(ctx, obj, dT, n, mode, dC, dS);
     if (rc) return rc;
   }
-  if (counts) PGP_CUDA(ctx, cudaMemcpyAsync(counts, dC, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  if (scores) PGP_CUDA(ctx, cudaMemcpyAsync(scores, dS, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // downloads on their own stream (PCIe is full duplex, and the caller's stream stays free for K4 / the all-gather)
+  PGP_CUDA(ctx, cudaEventRecord(ctx->ev[9], ctx->stream));
+  PGP_CUDA(ctx, cudaStreamWaitEvent(ctx->back_stream, ctx->ev[9], 0));
+  if (streamed) PGP_CUDA(ctx, cudaMemcpyAsync(marks + 8, reinterpret_cast<uint32_t*>(ctx->work.as<char>() + 320) + 1, 4, cudaMemcpyDeviceToHost, ctx->back_stream));
+  if (counts) PGP_CUDA(ctx, cudaMemcpyAsync(counts, dC, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->back_stream));
+  if (scores) PGP_CUDA(ctx, cudaMemcpyAsync(scores, dS, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->back_stream));
+  ctx->pending.active = true; ctx->pending.obj = obj; ctx->pending.n = n; ctx->pending.mode = mode;
+  ctx->pending.counts = counts; ctx->pending.scores = scores; ctx->pending.streamed = streamed;
+  return PGP_OK;
+}
+
+int pgp_score_lcp_end(pgp_ctx* ctx) {
+  CHECK_CTX(ctx);
+  if (!ctx->pending.active) return PGP_OK;
+  ctx->pending.active = false;
+  PGP_CUDA(ctx, cudaStreamSynchronize(ctx->back_stream));
   PGP_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  const uint32_t* marks = static_cast<const uint32_t*>(ctx->pinned);
+  if (ctx->pending.streamed && marks[8]) {
+    // the kernel gave up waiting for the upload (see k3_fine_kernel); the copies are done by now: score again, plainly
+    Model* m = get_model(ctx, ctx->pending.obj);
+    if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", ctx->pending.obj);
+    const int64_t n = ctx->pending.n;
+    uint32_t* dC = ctx->batch_counts.as<uint32_t>();
+    float* dS = ctx->batch_scores.as<float>();
+    int rc = k3_score(ctx, *m, ctx->batch_T.as<float>(), n, ctx->pending.mode, dC, dS, nullptr);
+    if (rc) return rc;
+    if (ctx->pending.counts) PGP_CUDA(ctx, cudaMemcpyAsync(ctx->pending.counts, dC, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->pending.scores) PGP_CUDA(ctx, cudaMemcpyAsync(ctx->pending.scores, dS, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 1;        // > 0: the batch was re-scored; anything the caller queued behind the first launch (pgp_topk_dev) must be redone
+  }
+  return PGP_OK;
+}
+
+int pgp_score_lcp(pgp_ctx* ctx, int obj, const float* T, int64_t n, int mode, uint32_t* counts, float* scores) {
+  int rc = pgp_score_lcp_begin(ctx, obj, T, n, mode, counts, scores);
+  if (rc) return rc;
+  rc = pgp_score_lcp_end(ctx);
+  if (rc < 0) return rc;
+  PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return PGP_OK;
 }
 

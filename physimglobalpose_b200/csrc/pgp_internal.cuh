@@ -138,6 +138,14 @@ struct LastBatch {
   int obj = -1;
 };
 
+struct PendingBatch {            // pgp_score_lcp_begin ... pgp_score_lcp_end
+  bool active = false, streamed = false;
+  int obj = -1, mode = 0;
+  int64_t n = 0;
+  uint32_t* counts = nullptr;    // host
+  float* scores = nullptr;       // host
+};
+
 struct pgp_ctx {
   int device = 0;
   int sm_count = 148;
@@ -145,10 +153,11 @@ struct pgp_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;      // host -> device of the host-buffer API
   cudaStream_t back_stream = nullptr;      // device -> host of the host-buffer API (PCIe is full duplex: its own stream)
-  cudaEvent_t ev[12] = {};                 // [0..3] chunk uploaded, [4..7] chunk scored, [8] batch start
+  cudaEvent_t ev[12] = {};                 // [0] first chunk uploaded, [8] batch start, [9] batch scored, [10] batch downloaded
   Scene scene;
   std::vector<Model> models;
   LastBatch last;
+  PendingBatch pending;
   DevBuf batch_T, batch_counts, batch_scores;   // device residency for the host-buffer API
   DevBuf work;                                   // counters / select scratch
   DevBuf topk_out;

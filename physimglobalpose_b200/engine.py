@@ -169,6 +169,14 @@ class PoseEngine:
         fn = self._lib.pgp_score_lcp if host else self._lib.pgp_score_lcp_dev
         self._check(fn(self._ctx, obj, T_ptr, n, MODES[mode], counts_ptr, scores_ptr))
 
+    def score_lcp_begin(self, obj: int, T_ptr: int, n: int, counts_ptr: int, scores_ptr: int, mode="count"):
+        """pgp_score_lcp_begin: enqueue upload + scoring + downloads of a pinned host batch and return (see include/pgp.h)."""
+        self._check(self._lib.pgp_score_lcp_begin(self._ctx, obj, T_ptr, n, MODES[mode], counts_ptr, scores_ptr))
+
+    def score_lcp_end(self) -> bool:
+        """pgp_score_lcp_end: wait for the batch; True when it had to be re-scored (work queued in between must be redone)."""
+        return self._check(self._lib.pgp_score_lcp_end(self._ctx)) > 0
+
     def score_lcp_device(self, obj: int, T_dev, counts_dev, scores_dev, mode="count"):
         """torch CUDA tensors: T (n,12) f32, counts (n,) i32/u32-as-int32, scores (n,) f32.  Asynchronous."""
         n = T_dev.shape[0]

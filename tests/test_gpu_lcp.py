@@ -220,3 +220,25 @@ def test_group_cull_is_exact(engine, port_lib):
     assert np.array_equal(off_c, want) and np.array_equal(on_c, want)
     assert np.array_equal(off_w, wn.astype(np.uint32)) and np.array_equal(on_w, wn.astype(np.uint32))
     assert np.array_equal(on_ws, ws) and np.array_equal(off_ws, ws)
+
+
+def test_score_begin_end_equals_blocking_call(engine, port_lib):
+    """pgp_score_lcp_begin / _end (the pipelined host-buffer call bench.py's e2e step uses) fills the same counts and scores as
+    pgp_score_lcp, with the top-k queued between the two halves; large enough for the streamed-upload path (>= 32768)."""
+    import torch
+    prob = synth.make_problem(600, 20000, 0.01, seed=41)
+    T = synth.make_hypotheses(prob, 40000, seed=42)
+    _setup(engine, prob)
+    want_c, want_s = engine.score_lcp(0, T, "count")
+    want_top = engine.topk(0, 16)
+    Th = torch.from_numpy(T.reshape(-1, 12).copy()).pin_memory()
+    ch = torch.zeros(len(T), dtype=torch.int32).pin_memory()
+    sh = torch.zeros(len(T), dtype=torch.float32).pin_memory()
+    engine.score_lcp_begin(0, Th.data_ptr(), len(T), ch.data_ptr(), sh.data_ptr(), "count")
+    top = engine.topk(0, 16)                      # queued behind the scoring launch, before the wait
+    if engine.score_lcp_end():
+        top = engine.topk(0, 16)
+    assert np.array_equal(ch.numpy().astype(np.uint32), want_c)
+    assert np.array_equal(sh.numpy(), want_s)
+    assert np.array_equal(top["index"], want_top["index"]) and np.array_equal(top["count"], want_top["count"])
+    assert np.array_equal(want_c[:2000], _oracle(port_lib, prob).verify(T[:2000]))

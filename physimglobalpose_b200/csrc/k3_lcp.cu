@@ -314,10 +314,10 @@ struct FineCtx {
   const uint2* table;        // bmrank: shared (SMEM_TABLE) or global
   uint16_t* q;               // per warp: queued model-point indices
   uint32_t* qe;              // count mode: (label word index << 4) | rank of the voxel among the word's AMBIG voxels
-  uint16_t* glist;           // per warp: the groups of the current hypothesis that survived the cull (+ FUNROLL pad slots)
+  uint32_t* glist;           // per warp: byte offsets (into the staged model) of the groups of the current hypothesis that survived the cull (+ FUNROLL pad slots)
   int dummy_group;           // a group of NaN points behind the tile
   int dimx, dimy, dimz;
-  unsigned rx, ry, rz;
+  unsigned limx, limy, limz;   // last voxel index per axis
   int lane;
   unsigned lt_mask;
   uint32_t dummy_word;       // offset of a zero word in `codes`
@@ -334,8 +334,8 @@ __device__ __forceinline__ uint2 table_word(const FineCtx& f, int w) {
 // queries outside the grid or in cells with an empty neighbourhood) and the bit shift.
 template <bool SMEM_TABLE>
 __device__ __forceinline__ uint32_t label_slot(const LcpParams& p, const FineCtx& f, int ix, int iy, int iz, uint32_t& shift) {
-  const bool inr = (unsigned)(ix - 8) < f.rx && (unsigned)(iy - 8) < f.ry && (unsigned)(iz - 8) < f.rz;   // cells 1 .. dim-2
-  const int c = inr ? ((iz >> 3) * f.dimy + (iy >> 3)) * f.dimx + (ix >> 3) : 0;                        // cell 0 is apron: bit clear
+  // ix, iy, iz are clamped to the grid (voxel_of): a query outside lands in an apron cell (0 or dim-1 on some axis), whose bit is clear
+  const int c = ((iz >> 3) * f.dimy + (iy >> 3)) * f.dimx + (ix >> 3);
   const uint2 wr = table_word<SMEM_TABLE>(f, c >> 5);
   const unsigned bit = 1u << (c & 31);
   const unsigned blk = wr.y + __popc(wr.x & (bit - 1u));
@@ -444,7 +444,8 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
       apply_xf(x, m, tx, ty, tz);
       ux = cell_coord(tx, p.g.lo[0], p.g.inv_hf); uy = cell_coord(ty, p.g.lo[1], p.g.inv_hf); uz = cell_coord(tz, p.g.lo[2], p.g.inv_hf);
     }
-    ix = __float2int_rz(ux); iy = __float2int_rz(uy); iz = __float2int_rz(uz);   // saturating, NaN -> 0
+    // float -> unsigned saturates (negative and NaN -> 0), one min clamps the high side: always a valid voxel of the grid
+    ix = (int)min(__float2uint_rz(ux), f.limx); iy = (int)min(__float2uint_rz(uy), f.limy); iz = (int)min(__float2uint_rz(uz), f.limz);
   };
   // ---- survivor list of this hypothesis
   int ns = 0;
@@ -477,10 +478,10 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
         keep = !(__fmaf_rn(d, d, e2) > thr * thr * (1.0f + 1e-5f));
       }
       const unsigned bb = __ballot_sync(0xffffffffu, keep);
-      if (keep) f.glist[ns + __popc(bb & f.lt_mask)] = (uint16_t)g;
+      if (keep) f.glist[ns + __popc(bb & f.lt_mask)] = (uint32_t)g << 9;
       ns += __popc(bb);
     }
-    if (f.lane < FUNROLL) f.glist[ns + f.lane] = (uint16_t)f.dummy_group;
+    if (f.lane < FUNROLL) f.glist[ns + f.lane] = (uint32_t)f.dummy_group << 9;
     __syncwarp();
   }
   int good = 0, qn = 0;
@@ -501,29 +502,27 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
   };
   const float4* mp = f.s_model + f.lane;
   for (int k = 0; k < ns; k += FUNROLL) {
-    const uint2 gg = *reinterpret_cast<const uint2*>(f.glist + k);
-    const int gb[FUNROLL] = {(int)(gg.x & 0xffffu) << 5, (int)(gg.x >> 16) << 5, (int)(gg.y & 0xffffu) << 5, (int)(gg.y >> 16) << 5};
+    const uint4 gg = *reinterpret_cast<const uint4*>(f.glist + k);
+    const uint32_t gb[FUNROLL] = {gg.x, gg.y, gg.z, gg.w};
     uint32_t off[FUNROLL], sh[FUNROLL], code[FUNROLL];
 #pragma unroll
     for (int u = 0; u < FUNROLL; ++u) {
       int ix, iy, iz;
-      voxel_of(mp[gb[u]], ix, iy, iz);
+      voxel_of(*reinterpret_cast<const float4*>(reinterpret_cast<const char*>(mp) + gb[u]), ix, iy, iz);
       off[u] = label_slot<SMEM_TABLE>(p, f, ix, iy, iz, sh[u]);
     }
 #pragma unroll
     for (int u = 0; u < FUNROLL; ++u) code[u] = __ldg(p.codes + off[u]);
+    // labels: OUT = 00, IN = 01, AMBIG = 10 -> bit 0 counts, bit 1 (count mode) / either bit (weighted: IN voxels need the
+    // nearest point's identity too) sends the query to phase 2
     unsigned any = 0;
 #pragma unroll
     for (int u = 0; u < FUNROLL; ++u) {
-      const uint32_t lab = (code[u] >> sh[u]) & 3u;
-      if (MODE == 0) {
-        good += (lab == 1u);
-        any |= (lab == 2u);
-      } else {
-        any |= (lab != 0u);                 // weighted: IN voxels need the nearest point's identity too
-      }
+      const uint32_t t = code[u] >> sh[u];
+      if (MODE == 0) good += t & 1u;
+      any |= t;
     }
-    if (__any_sync(0xffffffffu, any)) {
+    if (__any_sync(0xffffffffu, (any & (MODE == 0 ? 2u : 3u)) != 0u)) {
 #pragma unroll
       for (int u = 0; u < FUNROLL; ++u) {
         const uint32_t lab = (code[u] >> sh[u]) & 3u;
@@ -531,7 +530,7 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
         const unsigned bb = __ballot_sync(0xffffffffu, push);
         if (push) {
           const int slot = qn + __popc(bb & f.lt_mask);
-          f.q[slot] = (uint16_t)(gb[u] + f.lane);
+          f.q[slot] = (uint16_t)((gb[u] >> 4) + f.lane);
           // rank of this voxel among the AMBIG voxels (high bit of the 2-bit label set) of its label word
           if (MODE == 0) f.qe[slot] = (off[u] << 4) | (uint32_t)__popc(code[u] & 0xAAAAAAAAu & ((1u << sh[u]) - 1u));
         }
@@ -556,8 +555,8 @@ __global__ void __launch_bounds__(FWARPS * 32, 1) k3_fine_kernel(const __grid_co
   float4* s_nrm = s_model + p.tile_cap + 32;                              // only MODE 1
   uint2* s_bmrank = reinterpret_cast<uint2*>(s_nrm + (MODE == 1 ? p.tile_cap : 0));
   float4* s_groups = reinterpret_cast<float4*>(s_bmrank + p.bmrank_words);
-  uint16_t* s_glist = reinterpret_cast<uint16_t*>(s_groups + cap_groups);
-  uint16_t* s_queue = s_glist + (((FWARPS * (cap_groups + FUNROLL)) + 7) & ~7);
+  uint32_t* s_glist = reinterpret_cast<uint32_t*>(s_groups + cap_groups);
+  uint16_t* s_queue = reinterpret_cast<uint16_t*>(s_glist + FWARPS * (cap_groups + FUNROLL));
   uint32_t* s_qe = reinterpret_cast<uint32_t*>(s_queue + FWARPS * FQCAP);       // count mode only
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   FineCtx f;
@@ -569,7 +568,7 @@ __global__ void __launch_bounds__(FWARPS * 32, 1) k3_fine_kernel(const __grid_co
   f.qe = s_qe + warp * FQCAP;
   f.glist = s_glist + warp * (cap_groups + FUNROLL);
   f.dimx = p.g.dim[0]; f.dimy = p.g.dim[1]; f.dimz = p.g.dim[2];
-  f.rx = (unsigned)(p.g.dim[0] - 2) * 8u; f.ry = (unsigned)(p.g.dim[1] - 2) * 8u; f.rz = (unsigned)(p.g.dim[2] - 2) * 8u;
+  f.limx = (unsigned)p.g.dim[0] * 8u - 1u; f.limy = (unsigned)p.g.dim[1] * 8u - 1u; f.limz = (unsigned)p.g.dim[2] * 8u - 1u;
   f.lane = lane; f.lt_mask = (1u << lane) - 1u;
   f.dummy_word = (uint32_t)p.g.n_blocks * 32u;
 
@@ -679,7 +678,7 @@ __global__ void __launch_bounds__(256) k3_weighted_ordered(const LcpParams p, in
   FineCtx f;
   f.table = p.bmrank;
   f.dimx = p.g.dim[0]; f.dimy = p.g.dim[1];
-  f.rx = (unsigned)(p.g.dim[0] - 2) * 8u; f.ry = (unsigned)(p.g.dim[1] - 2) * 8u; f.rz = (unsigned)(p.g.dim[2] - 2) * 8u;
+  f.limx = (unsigned)p.g.dim[0] * 8u - 1u; f.limy = (unsigned)p.g.dim[1] * 8u - 1u; f.limz = (unsigned)p.g.dim[2] * 8u - 1u;
   f.dummy_word = (uint32_t)p.g.n_blocks * 32u;
   float acc = 0.f;
   int gated = 0;
@@ -694,8 +693,8 @@ __global__ void __launch_bounds__(256) k3_weighted_ordered(const LcpParams p, in
       apply_xf(x, __ldg(p.model + i), tx, ty, tz);
       if (LISTS) {
         // the reference's own rounding sequence, then the grid's cell_coord: exactly the non-FAST voxel of the fine kernel
-        const int ix = __float2int_rz(cell_coord(tx, p.g.lo[0], p.g.inv_hf)), iy = __float2int_rz(cell_coord(ty, p.g.lo[1], p.g.inv_hf)),
-                  iz = __float2int_rz(cell_coord(tz, p.g.lo[2], p.g.inv_hf));
+        const int ix = (int)min(__float2uint_rz(cell_coord(tx, p.g.lo[0], p.g.inv_hf)), f.limx), iy = (int)min(__float2uint_rz(cell_coord(ty, p.g.lo[1], p.g.inv_hf)), f.limy),
+                  iz = (int)min(__float2uint_rz(cell_coord(tz, p.g.lo[2], p.g.inv_hf)), f.limz);
         uint32_t sh;
         const uint32_t off = label_slot<false>(p, f, ix, iy, iz, sh);
         if ((__ldg(p.codes + off) >> sh) & 3u) {
@@ -795,7 +794,7 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     const int FWARPS = mode == PGP_LCP_WEIGHTED ? ctx->k3_warps_weighted : ctx->k3_warps_count;
     auto smem_need = [&](int cap, size_t table) {
       return (size_t)(cap + 32) * 16 + (mode == PGP_LCP_WEIGHTED ? (size_t)cap * 16 : 0) + table + (size_t)(cap >> 5) * 16 +
-             (size_t)(((FWARPS * ((cap >> 5) + FUNROLL)) + 7) & ~7) * 2 + (size_t)FWARPS * FQCAP * (mode == PGP_LCP_WEIGHTED ? 2 : 6);
+             (size_t)(FWARPS * ((cap >> 5) + FUNROLL)) * 4 + (size_t)FWARPS * FQCAP * (mode == PGP_LCP_WEIGHTED ? 2 : 6);
     };
     size_t bm = (size_t)s.bitmap_words * 8;
     int tile_cap = std::min((m.nv + 127) & ~127, 8192);

@@ -146,7 +146,7 @@ def run_reference(args, rank):
             "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "hypotheses_per_step": sample, "device": "host CPU"},
             "cpu_baseline": base, "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------ GPU
@@ -344,13 +344,34 @@ def run_ours(args, rank, local_rank, world):
             line["cpu_baseline"] = base
             got = counts_host.numpy()[:sample].astype(np.uint32)
             line["parity"] = {"checked": int(sample), "mismatches": int((got != cpu_counts).sum())}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     eng.close()
 
 
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries (the NCCL version banner under NCCL_DEBUG=VERSION, torchrun's OMP notice)
+    write to file descriptor 1 directly, so fd 1 is pointed at stderr for the whole run and the result goes to a saved duplicate."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -46,7 +46,7 @@ class ClockSampler:
 
     def __init__(self, uuid: str | None):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        cmd = ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"]
+        cmd = ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"]
         if uuid:
             cmd += ["-i", uuid]
         try:
@@ -256,17 +256,19 @@ def run_ours(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- warm-up, then the timed region: K steps, device-timed, L2 flushed between steps
-    for _ in range(max(args.warmup, 3)):
-        flush.zero_()
-        top = step_resident()
+    # ---- warm-up, then the timed region: K steps, device-timed, L2 flushed between steps.  The clock sampler (nvidia-smi, 20 ms
+    # period) needs ~0.1 s to deliver its first line and the timed region is ~12 ms, so it runs from the warm-up to the end of
+    # the end-to-end loop: every sample is taken under this benchmark's load.
     uuid = None
     try:
         uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
     except Exception:
         pass
-    barrier()
     sampler = ClockSampler(uuid) if rank == 0 else None
+    for _ in range(max(args.warmup, 3) + 300):     # + 300 steps (~0.25 s) of lead-in for the sampler; the same count on every rank
+        flush.zero_()
+        top = step_resident()
+    barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = eng.launch_count
     # K steps, pipelined: a step = K3 (score) -> K4 (top-k) -> NCCL all-gather -> async D2H of the gathered records, all on
@@ -300,7 +302,6 @@ def run_ours(args, rank, local_rank, world):
         b.record(stream)
     torch.cuda.synchronize()
     kernel_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
-    clocks = sampler.stop() if sampler else None
 
     # ---- end to end through the host-buffer API (H2D of the transforms + D2H of counts/scores/top-k inside)
     for _ in range(2):
@@ -316,6 +317,7 @@ def run_ours(args, rank, local_rank, world):
     e2e_s = max_over_ranks(e2e_s)
     barrier()
     e2e_value = world * N_HYP * args.steps / e2e_s
+    clocks = sampler.stop() if sampler else None
 
     if rank == 0:
         b_hyp, kbar, nonempty = algorithmic_bytes_per_hyp(prob, T)

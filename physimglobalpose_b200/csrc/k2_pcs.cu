@@ -177,11 +177,45 @@ __global__ void k2_join_scatter(long long n1, const uint32_t* __restrict__ bucke
 // B side: one thread per pair of the second edge; rasterise the cone of directions at angle alpha
 // around the pair's direction (normalset.hpp:160-214) and collect the A pairs in the same position
 // cell whose direction cell is coloured.
+// Which B-side pairs can produce a quad at all: the pair's intermediate point lies in the unit cube and its position cell holds at
+// least one A-side pair.  Their indices are compacted (warp ballot + one atomic per warp) so that the expensive cone rasterisation of
+// k2_join_query runs on dense warps; the order of the list is arbitrary, results are indexed by the pair itself.
+__global__ void __launch_bounds__(256) k2_join_probe(JoinParams p, const uint32_t* __restrict__ bucket_start, const uint32_t* __restrict__ sorted,
+                                                     const uint32_t* __restrict__ key_of, uint32_t* __restrict__ list, uint32_t* __restrict__ n_list) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  bool live = false;
+  float inv1, inv2, cos_alpha; uint32_t bkt_base;
+  if (i < p.n2 && join_ctx(p, i, 1, inv1, inv2, cos_alpha, bkt_base)) {
+    const int2 pr = p.B[i];
+    const float4 a = p.Qn[pr.x], b = p.Qn[pr.y];
+    const float dx = __fsub_rn(b.x, a.x), dy = __fsub_rn(b.y, a.y), dz = __fsub_rn(b.z, a.z);
+    const float fx = __fadd_rn(a.x, __fmul_rn(inv2, dx)), fy = __fadd_rn(a.y, __fmul_rn(inv2, dy)), fz = __fadd_rn(a.z, __fmul_rn(inv2, dz));
+    if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < 1.f && fy < 1.f && fz < 1.f) {
+      const int pc = pos_cell(p, fx, fy, fz);
+      const uint32_t bkt = bkt_base + ((uint32_t)pc & (p.n_buckets - 1));
+      const uint32_t s = bucket_start[bkt], e = bucket_start[bkt + 1];
+      for (uint32_t t = s; t < e && !live; ++t) live = (int)(key_of[sorted[t]] >> 9) == pc;
+    }
+  }
+  const unsigned bb = __ballot_sync(0xffffffffu, live);
+  if (bb) {
+    uint32_t base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(n_list, (uint32_t)__popc(bb));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (live) list[base + __popc(bb & ((1u << (threadIdx.x & 31)) - 1u))] = (uint32_t)i;
+  }
+}
+
+// `list` (optional): indices of the pairs to process, `*n_list` of them (k2_join_probe, or the count pass's own list of pairs that
+// found something); without it thread i handles pair i.
 template <bool FILL>
 __global__ void __launch_bounds__(128) k2_join_query(JoinParams p, const uint32_t* __restrict__ bucket_start, const uint32_t* __restrict__ sorted,
-                                                     const uint32_t* __restrict__ key_of, uint32_t* __restrict__ cnt, int4* __restrict__ out, long long cap) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= p.n2) return;
+                                                     const uint32_t* __restrict__ key_of, uint32_t* __restrict__ cnt, int4* __restrict__ out, long long cap,
+                                                     const uint32_t* __restrict__ list = nullptr, const uint32_t* __restrict__ n_list = nullptr,
+                                                     uint32_t* __restrict__ list_out = nullptr, uint32_t* __restrict__ n_list_out = nullptr) {
+  const long long t_id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (list ? t_id >= (long long)*n_list : t_id >= p.n2) return;
+  const long long i = list ? (long long)list[t_id] : t_id;
   float inv1, inv2, cos_alpha; uint32_t bkt_base;
   if (FILL && cnt[i + 1] == cnt[i]) return;                // the count pass found nothing for this pair: skip the cone rasterisation
   if (!join_ctx(p, i, 1, inv1, inv2, cos_alpha, bkt_base)) { if (!FILL) cnt[i] = 0; return; }
@@ -261,7 +295,10 @@ __global__ void __launch_bounds__(128) k2_join_query(JoinParams p, const uint32_
       out[b2] = v;
     }
   }
-  if (!FILL) cnt[i] = n;
+  if (!FILL) {
+    cnt[i] = n;
+    if (list_out && n) list_out[atomicAdd(n_list_out, 1u)] = (uint32_t)i;     // the fill pass runs on these only
+  }
 }
 
 // ------------------------------------------------------------------------------- rigid transforms
@@ -734,7 +771,7 @@ __global__ void k2s_combo_copy(PpfMapDev m, const int* __restrict__ slot, const 
 }
 
 struct Scratch {
-  DevBuf cnt, cnt2, off, flag, curr, pairs1, pairs2, quads, bucket_of, key_of, bucket_start, sorted, T, ok, base, qn;
+  DevBuf list1, list2, cnt, cnt2, off, flag, curr, pairs1, pairs2, quads, bucket_of, key_of, bucket_start, sorted, T, ok, base, qn;
 };
 Scratch g_scratch[16];   // per device
 
@@ -1071,10 +1108,18 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
     PGP_CUDA(ctx, cudaGetLastError());
     PGP_CUDA(ctx, sc.cnt2.reserve((size_t)(ntot + 1) * 4));
     uint32_t* cnt2 = sc.cnt2.as<uint32_t>();
-    PGP_CUDA(ctx, cudaMemsetAsync(cnt2 + ntot, 0, 4, st));
+    PGP_CUDA(ctx, cudaMemsetAsync(cnt2, 0, (size_t)(ntot + 1) * 4, st));
+    // probe -> list of the B pairs with an A pair in their position cell -> count pass on those (dense warps) -> list of the pairs
+    // that found quads -> fill pass on those
+    PGP_CUDA(ctx, sc.list1.reserve((size_t)ntot * 4 + 16));
+    PGP_CUDA(ctx, sc.list2.reserve((size_t)ntot * 4 + 16));
+    uint32_t* n_lists = reinterpret_cast<uint32_t*>(ctx->work.as<char>() + 384);      // [0] = |list1|, [1] = |list2|
+    PGP_CUDA(ctx, cudaMemsetAsync(n_lists, 0, 8, st));
+    k2_join_probe<<<gk, 256, 0, st>>>(p, bs, sc.sorted.as<uint32_t>(), sc.key_of.as<uint32_t>(), sc.list1.as<uint32_t>(), n_lists);
     const unsigned gq = (unsigned)((ntot + 127) / 128);
-    k2_join_query<false><<<gq, 128, 0, st>>>(p, bs, sc.sorted.as<uint32_t>(), sc.key_of.as<uint32_t>(), cnt2, nullptr, 0);
-    ctx->launches++;
+    k2_join_query<false><<<gq, 128, 0, st>>>(p, bs, sc.sorted.as<uint32_t>(), sc.key_of.as<uint32_t>(), cnt2, nullptr, 0, sc.list1.as<uint32_t>(), n_lists,
+                                             sc.list2.as<uint32_t>(), n_lists + 1);
+    ctx->launches += 2;
     PGP_CUDA(ctx, cudaGetLastError());
     uint64_t nquads = 0;
     rc = scan_u32(ctx, cnt2, ntot, &nquads);                                // sync 2
@@ -1084,7 +1129,8 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
     PGP_CUDA(ctx, sc.quads.reserve((size_t)nquads * 16));
     PGP_CUDA(ctx, sc.T.reserve((size_t)nquads * 48));
     PGP_CUDA(ctx, sc.flag.reserve((size_t)(nquads + 1) * 4));
-    k2_join_query<true><<<gq, 128, 0, st>>>(p, bs, sc.sorted.as<uint32_t>(), sc.key_of.as<uint32_t>(), cnt2, sc.quads.as<int4>(), (long long)nquads);
+    k2_join_query<true><<<gq, 128, 0, st>>>(p, bs, sc.sorted.as<uint32_t>(), sc.key_of.as<uint32_t>(), cnt2, sc.quads.as<int4>(), (long long)nquads,
+                                            sc.list2.as<uint32_t>(), n_lists + 1);
     k2b_quad_offsets<<<(nb + 256) / 256, 256, 0, st>>>(cnt2, coff, nb, qoff);
     // ---- transforms, subset, compaction behind the hypotheses already generated
     uint32_t* flag = sc.flag.as<uint32_t>();

@@ -174,6 +174,32 @@ __global__ void k2_join_scatter(long long n1, const uint32_t* __restrict__ bucke
   sorted[atomicAdd(cursor + bucket_of[k], 1u)] = (uint32_t)k;
 }
 
+// The scatter above is atomic-ordered.  Every bucket of up to SORT_MAX entries is put into the order of its pairs' point ids (first,
+// second) once, so that every query that walks it emits its quads in that order: deterministic output without a sort per query.
+// Larger buckets (rare, skewed inputs) keep the atomic order and are flagged: a query that walks one orders its own quads.
+constexpr uint32_t SORT_MAX = 32;
+__global__ void k2_join_sort_buckets(const int2* __restrict__ A, const uint32_t* __restrict__ bucket_start, long long n_buckets, uint32_t* __restrict__ sorted,
+                                     unsigned char* __restrict__ in_order) {
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_buckets) return;
+  const uint32_t s = bucket_start[b], e = bucket_start[b + 1];
+  const bool small = e - s <= SORT_MAX;
+  in_order[b] = small ? 1 : 0;
+  if (!small) return;
+  for (uint32_t i = s + 1; i < e; ++i) {
+    const uint32_t k = sorted[i];
+    const int2 v = A[k];
+    uint32_t j = i;
+    while (j > s) {
+      const uint32_t kp = sorted[j - 1];
+      const int2 w = A[kp];
+      if (!(w.x > v.x || (w.x == v.x && (w.y > v.y || (w.y == v.y && kp > k))))) break;
+      sorted[j] = kp; --j;
+    }
+    sorted[j] = k;
+  }
+}
+
 // B side: one thread per pair of the second edge; rasterise the cone of directions at angle alpha
 // around the pair's direction (normalset.hpp:160-214) and collect the A pairs in the same position
 // cell whose direction cell is coloured.
@@ -211,8 +237,9 @@ __global__ void __launch_bounds__(256) k2_join_probe(JoinParams p, const uint32_
 template <bool FILL>
 __global__ void __launch_bounds__(128) k2_join_query(JoinParams p, const uint32_t* __restrict__ bucket_start, const uint32_t* __restrict__ sorted,
                                                      const uint32_t* __restrict__ key_of, uint32_t* __restrict__ cnt, int4* __restrict__ out, long long cap,
-                                                     const uint32_t* __restrict__ list = nullptr, const uint32_t* __restrict__ n_list = nullptr,
-                                                     uint32_t* __restrict__ list_out = nullptr, uint32_t* __restrict__ n_list_out = nullptr) {
+                                                     const unsigned char* __restrict__ in_order, const uint32_t* __restrict__ list = nullptr,
+                                                     const uint32_t* __restrict__ n_list = nullptr, uint32_t* __restrict__ list_out = nullptr,
+                                                     uint32_t* __restrict__ n_list_out = nullptr) {
   const long long t_id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (list ? t_id >= (long long)*n_list : t_id >= p.n2) return;
   const long long i = list ? (long long)list[t_id] : t_id;
@@ -225,9 +252,11 @@ __global__ void __launch_bounds__(128) k2_join_query(JoinParams p, const uint32_
   const float fx = __fadd_rn(a.x, __fmul_rn(inv2, dx)), fy = __fadd_rn(a.y, __fmul_rn(inv2, dy)), fz = __fadd_rn(a.z, __fmul_rn(inv2, dz));
   uint32_t n = 0;
   long long w = FILL ? (long long)cnt[i] : 0;
+  bool ordered = true;
   if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < 1.f && fy < 1.f && fz < 1.f) {
     const int pc = pos_cell(p, fx, fy, fz);
     const uint32_t bkt = bkt_base + ((uint32_t)pc & (p.n_buckets - 1));
+    if (FILL) ordered = in_order[bkt] != 0;
     const uint32_t s = bucket_start[bkt], e = bucket_start[bkt + 1];
     if (e > s) {
       normalize3(dx, dy, dz);                      // queryn
@@ -285,8 +314,8 @@ __global__ void __launch_bounds__(128) k2_join_query(JoinParams p, const uint32_
       }
     }
   }
-  if (FILL && n > 1) {
-    // the bucket order comes from atomics: order this query's quads by their first pair (unique key) so the output is deterministic
+  if (FILL && n > 1 && !ordered) {
+    // an over-long bucket kept its atomic order: order this query's quads by their first pair (unique key)
     const long long s0 = (long long)cnt[i], e0 = min(cap, s0 + (long long)n);
     for (long long a2 = s0 + 1; a2 < e0; ++a2) {
       const int4 v = out[a2];
@@ -771,7 +800,7 @@ __global__ void k2s_combo_copy(PpfMapDev m, const int* __restrict__ slot, const 
 }
 
 struct Scratch {
-  DevBuf list1, list2, cnt, cnt2, off, flag, curr, pairs1, pairs2, quads, bucket_of, key_of, bucket_start, sorted, T, ok, base, qn;
+  DevBuf in_order, list1, list2, cnt, cnt2, off, flag, curr, pairs1, pairs2, quads, bucket_of, key_of, bucket_start, sorted, T, ok, base, qn;
 };
 Scratch g_scratch[16];   // per device
 
@@ -839,11 +868,13 @@ int find_quads_dev(pgp_ctx* ctx, const Model& m, float cos_alpha, float inv1, fl
   if (rc) return rc;
   PGP_CUDA(ctx, cudaMemcpyAsync(cursor, bs, (size_t)p.n_buckets * 4, cudaMemcpyDeviceToDevice, ctx->stream));
   k2_join_scatter<<<(unsigned)((n1 + 255) / 256), 256, 0, ctx->stream>>>(n1, sc.bucket_of.as<uint32_t>(), cursor, sc.sorted.as<uint32_t>());
-  ctx->launches++;
+  PGP_CUDA(ctx, sc.in_order.reserve((size_t)p.n_buckets + 16));
+  k2_join_sort_buckets<<<(unsigned)((p.n_buckets + 255) / 256), 256, 0, ctx->stream>>>(p.A, bs, (long long)p.n_buckets, sc.sorted.as<uint32_t>(), sc.in_order.as<unsigned char>());
+  ctx->launches += 2;
   PGP_CUDA(ctx, sc.cnt.reserve((size_t)(n2 + 1) * 4));
   uint32_t* cnt = sc.cnt.as<uint32_t>();
   PGP_CUDA(ctx, cudaMemsetAsync(cnt, 0, (size_t)(n2 + 1) * 4, ctx->stream));
-  k2_join_query<false><<<(unsigned)((n2 + 127) / 128), 128, 0, ctx->stream>>>(p, bs, sc.sorted.as<uint32_t>(), sc.key_of.as<uint32_t>(), cnt, nullptr, 0);
+  k2_join_query<false><<<(unsigned)((n2 + 127) / 128), 128, 0, ctx->stream>>>(p, bs, sc.sorted.as<uint32_t>(), sc.key_of.as<uint32_t>(), cnt, nullptr, 0, sc.in_order.as<unsigned char>());
   ctx->launches++;
   uint64_t nquads = 0;
   rc = scan_u32(ctx, cnt, n2, &nquads);
@@ -852,7 +883,7 @@ int find_quads_dev(pgp_ctx* ctx, const Model& m, float cos_alpha, float inv1, fl
   PGP_CUDA(ctx, out.reserve((size_t)std::max<uint64_t>(nquads, 1) * 16));
   if (nquads) {
     k2_join_query<true><<<(unsigned)((n2 + 127) / 128), 128, 0, ctx->stream>>>(p, bs, sc.sorted.as<uint32_t>(), sc.key_of.as<uint32_t>(), cnt, out.as<int4>(),
-                                                                              (long long)nquads);
+                                                                              (long long)nquads, sc.in_order.as<unsigned char>());
     ctx->launches++;
   }
   PGP_CUDA(ctx, cudaGetLastError());
@@ -1104,7 +1135,9 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
     if (rc) return rc;
     PGP_CUDA(ctx, cudaMemcpyAsync(cursor, bs, nbuckets * 4, cudaMemcpyDeviceToDevice, st));
     k2_join_scatter<<<gk, 256, 0, st>>>(ntot, sc.bucket_of.as<uint32_t>(), cursor, sc.sorted.as<uint32_t>());
-    ctx->launches++;
+    PGP_CUDA(ctx, sc.in_order.reserve(nbuckets + 16));
+    k2_join_sort_buckets<<<(unsigned)((nbuckets + 255) / 256), 256, 0, st>>>(p.A, bs, (long long)nbuckets, sc.sorted.as<uint32_t>(), sc.in_order.as<unsigned char>());
+    ctx->launches += 2;
     PGP_CUDA(ctx, cudaGetLastError());
     PGP_CUDA(ctx, sc.cnt2.reserve((size_t)(ntot + 1) * 4));
     uint32_t* cnt2 = sc.cnt2.as<uint32_t>();
@@ -1117,7 +1150,7 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
     PGP_CUDA(ctx, cudaMemsetAsync(n_lists, 0, 8, st));
     k2_join_probe<<<gk, 256, 0, st>>>(p, bs, sc.sorted.as<uint32_t>(), sc.key_of.as<uint32_t>(), sc.list1.as<uint32_t>(), n_lists);
     const unsigned gq = (unsigned)((ntot + 127) / 128);
-    k2_join_query<false><<<gq, 128, 0, st>>>(p, bs, sc.sorted.as<uint32_t>(), sc.key_of.as<uint32_t>(), cnt2, nullptr, 0, sc.list1.as<uint32_t>(), n_lists,
+    k2_join_query<false><<<gq, 128, 0, st>>>(p, bs, sc.sorted.as<uint32_t>(), sc.key_of.as<uint32_t>(), cnt2, nullptr, 0, sc.in_order.as<unsigned char>(), sc.list1.as<uint32_t>(), n_lists,
                                              sc.list2.as<uint32_t>(), n_lists + 1);
     ctx->launches += 2;
     PGP_CUDA(ctx, cudaGetLastError());
@@ -1130,7 +1163,7 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
     PGP_CUDA(ctx, sc.T.reserve((size_t)nquads * 48));
     PGP_CUDA(ctx, sc.flag.reserve((size_t)(nquads + 1) * 4));
     k2_join_query<true><<<gq, 128, 0, st>>>(p, bs, sc.sorted.as<uint32_t>(), sc.key_of.as<uint32_t>(), cnt2, sc.quads.as<int4>(), (long long)nquads,
-                                            sc.list2.as<uint32_t>(), n_lists + 1);
+                                            sc.in_order.as<unsigned char>(), sc.list2.as<uint32_t>(), n_lists + 1);
     k2b_quad_offsets<<<(nb + 256) / 256, 256, 0, st>>>(cnt2, coff, nb, qoff);
     // ---- transforms, subset, compaction behind the hypotheses already generated
     uint32_t* flag = sc.flag.as<uint32_t>();

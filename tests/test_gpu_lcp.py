@@ -242,3 +242,42 @@ def test_score_begin_end_equals_blocking_call(engine, port_lib):
     assert np.array_equal(sh.numpy(), want_s)
     assert np.array_equal(top["index"], want_top["index"]) and np.array_equal(top["count"], want_top["count"])
     assert np.array_equal(want_c[:2000], _oracle(port_lib, prob).verify(T[:2000]))
+
+
+@pytest.mark.parametrize("n_model", [1, 5, 31, 32, 33, 65])
+def test_ragged_model_sizes(engine, port_lib, n_model):
+    """Validation models that are not a multiple of the 32-point group / 128-point step (a single point, a partial group, one
+    group plus one point): the NaN-padded tail and the dummy group must never count.  Both modes against the oracle."""
+    prob = synth.make_problem(200, 8000, 0.01, seed=51)
+    rng = np.random.default_rng(n_model)
+    sel = rng.choice(len(prob.model_xyz), n_model, replace=False)
+    mx, mn = prob.model_xyz[sel].copy(), prob.model_nrm[sel].copy()
+    T = synth.make_hypotheses(prob, 600, seed=52)
+    engine.set_scene(prob.scene_xyz, prob.scene_nrm, prob.delta)
+    engine.set_model(0, prob.model_xyz, prob.model_nrm, mx, mn)              # search cloud (centroid) as usual, ragged validation cloud
+    o = port_lib.PortOracle(prob.scene_xyz, prob.scene_nrm, prob.model_xyz, prob.model_nrm, mx, mn, prob.delta)
+    want = o.verify(T)
+    ws, wn = o.weighted_verify(T)
+    c, _ = engine.score_lcp(0, T, "count")
+    wc, wsc = engine.score_lcp(0, T, "weighted")
+    assert np.array_equal(c, want) and c.max() <= n_model
+    assert np.array_equal(wc, wn.astype(np.uint32)) and np.array_equal(wsc, ws)
+
+
+def test_empty_batch_and_tiny_scene(engine, port_lib):
+    """Zero hypotheses is a no-op; a scene of one / two points still builds its grid and scores exactly."""
+    prob = synth.make_problem(300, 5000, 0.01, seed=61)
+    _setup(engine, prob)
+    c, s = engine.score_lcp(0, np.zeros((0, 3, 4), np.float32), "count")
+    assert len(c) == 0 and len(s) == 0
+    T = synth.make_hypotheses(prob, 300, seed=62)
+    for n_scene in (1, 2):
+        sx, sn = prob.scene_xyz[:n_scene].copy(), prob.scene_nrm[:n_scene].copy()
+        engine.set_scene(sx, sn, prob.delta)
+        engine.set_model(0, prob.model_xyz, prob.model_nrm)
+        o = port_lib.PortOracle(sx, sn, prob.model_xyz, prob.model_nrm, prob.model_xyz, prob.model_nrm, prob.delta)
+        # poses that drop the model onto the lone scene point(s), plus the generic ones
+        Tn = T.copy()
+        Tn[:100, :, 3] = (sx[0] - o.centroids()[0])[None, :] + np.random.default_rng(3).normal(scale=0.02, size=(100, 3)).astype(np.float32)
+        c, _ = engine.score_lcp(0, Tn, "count")
+        assert np.array_equal(c, o.verify(Tn))

@@ -802,7 +802,12 @@ __global__ void k2s_combo_copy(PpfMapDev m, const int* __restrict__ slot, const 
 struct Scratch {
   DevBuf in_order, list1, list2, cnt, cnt2, off, flag, curr, pairs1, pairs2, quads, bucket_of, key_of, bucket_start, sorted, T, ok, base, qn;
 };
-Scratch g_scratch[16];   // per device
+// the generator's device scratch belongs to the context (two contexts on one device must not share it); created on first use,
+// released by k2_release (pgp_destroy)
+Scratch& scratch_of(pgp_ctx* ctx) {
+  if (!ctx->k2_scratch) ctx->k2_scratch = new Scratch();
+  return *static_cast<Scratch*>(ctx->k2_scratch);
+}
 
 int scan_u32(pgp_ctx* ctx, uint32_t* data, int64_t n, uint64_t* total) {
   PGP_CUDA(ctx, ctx->scene.scratch.reserve((size_t)((n + 1) / 2048 + 4096) * 4));
@@ -817,7 +822,7 @@ int scan_u32(pgp_ctx* ctx, uint32_t* data, int64_t n, uint64_t* total) {
 
 // all ordered pairs into `out` (device, grown as needed); returns the number of ORDERED pairs
 int extract_pairs_dev(pgp_ctx* ctx, const Model& m, float dist, float eps, DevBuf& out, int64_t* n_pairs) {
-  Scratch& sc = g_scratch[ctx->device & 15];
+  Scratch& sc = scratch_of(ctx);
   const int nq = m.nq, B = (nq + 255) / 256;
   PGP_CUDA(ctx, sc.cnt.reserve((size_t)(nq + 1) * 4));
   uint32_t* cnt = sc.cnt.as<uint32_t>();
@@ -839,7 +844,7 @@ int extract_pairs_dev(pgp_ctx* ctx, const Model& m, float dist, float eps, DevBu
 
 int find_quads_dev(pgp_ctx* ctx, const Model& m, float cos_alpha, float inv1, float inv2, float eps, const int2* A, int64_t n1, const int2* B,
                    int64_t n2, DevBuf& out, int64_t* n_quads) {
-  Scratch& sc = g_scratch[ctx->device & 15];
+  Scratch& sc = scratch_of(ctx);
   *n_quads = 0;
   if (n1 <= 0 || n2 <= 0) return PGP_OK;
   JoinParams p{};
@@ -893,7 +898,7 @@ int find_quads_dev(pgp_ctx* ctx, const Model& m, float cos_alpha, float inv1, fl
 }  // namespace
 
 int k2_extract_pairs(pgp_ctx* ctx, const Model& m, float dist, float eps, int32_t* pairs_host, int64_t cap, int64_t* n_pairs) {
-  Scratch& sc = g_scratch[ctx->device & 15];
+  Scratch& sc = scratch_of(ctx);
   int rc = extract_pairs_dev(ctx, m, dist, eps, sc.pairs1, n_pairs);
   if (rc) return rc;
   const int64_t n = std::min(cap, *n_pairs);
@@ -906,7 +911,7 @@ int k2_extract_pairs(pgp_ctx* ctx, const Model& m, float dist, float eps, int32_
 
 int k2_find_quads(pgp_ctx* ctx, const Model& m, const int32_t* base4, float inv1, float inv2, float eps, const int32_t* p1, int64_t n1,
                   const int32_t* p2, int64_t n2, int32_t* quads_host, int64_t cap, int64_t* n_quads) {
-  Scratch& sc = g_scratch[ctx->device & 15];
+  Scratch& sc = scratch_of(ctx);
   const Scene& s = ctx->scene;
   for (int k = 0; k < 4; ++k)
     if (base4[k] < 0 || base4[k] >= s.n) return pgp_fail(ctx, PGP_E_INVALID, "base id out of range");
@@ -940,7 +945,7 @@ int k2_find_quads(pgp_ctx* ctx, const Model& m, const int32_t* base4, float inv1
 }
 
 int k2_rigid_from_quads(pgp_ctx* ctx, const Model& m, const int32_t* base4, const int32_t* quads_host, int64_t n, float* T_host, uint8_t* ok_host) {
-  Scratch& sc = g_scratch[ctx->device & 15];
+  Scratch& sc = scratch_of(ctx);
   if (n == 0) return PGP_OK;
   for (int k = 0; k < 4; ++k)
     if (base4[k] < 0 || base4[k] >= ctx->scene.n) return pgp_fail(ctx, PGP_E_INVALID, "base id out of range");
@@ -1024,7 +1029,7 @@ __global__ void k2b_append(const float* __restrict__ T, const uint32_t* __restri
 }  // namespace
 
 int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, int64_t max_hyp, int64_t* n_hyp) {
-  Scratch& sc = g_scratch[ctx->device & 15];
+  Scratch& sc = scratch_of(ctx);
   const Scene& s = ctx->scene;
   cudaStream_t st = ctx->stream;
   *n_hyp = 0;
@@ -1197,7 +1202,7 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
 // bases of the last k2_generate call on this device (they stay in the scratch buffer): ids (n x 4 scene indices,
 // in the pairing TryQuadrilateral chose), inv (n x 2), ok flags
 int k2_get_bases(pgp_ctx* ctx, int n_bases, int32_t* ids_host, float* inv_host, uint8_t* ok_host) {
-  Scratch& sc = g_scratch[ctx->device & 15];
+  Scratch& sc = scratch_of(ctx);
   if (n_bases <= 0 || sc.base.cap < (size_t)n_bases * sizeof(BaseOut) + 64) return pgp_fail(ctx, PGP_E_INVALID, "no bases generated");
   std::vector<BaseOut> b(n_bases);
   PGP_CUDA(ctx, cudaMemcpyAsync(b.data(), sc.base.as<char>() + 64, (size_t)n_bases * sizeof(BaseOut), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1261,7 +1266,7 @@ int k2_set_ppf_map(pgp_ctx* ctx, Model& m, const int32_t* keys4, const int64_t* 
 // of the SEARCH cloud under the key computePPF gives it -- keys on the device (the same function that keys the scene side),
 // grouping on the host (stable: rows in (i, j) order inside a key).
 int k2_build_ppf_map(pgp_ctx* ctx, Model& m) {
-  Scratch& sc = g_scratch[ctx->device & 15];
+  Scratch& sc = scratch_of(ctx);
   const int n = m.nq;
   if (n > 16384) return pgp_fail(ctx, PGP_E_TOO_LARGE, "PPF map builder: search cloud of %d points (limit 16384)", n);
   const long long np = (long long)n * n;
@@ -1294,7 +1299,7 @@ int k2_build_ppf_map(pgp_ctx* ctx, Model& m) {
 
 // computePPF of arbitrary scene index pairs (parity hook): keys4_host n x 4
 int k2_scene_ppf_keys(pgp_ctx* ctx, const int32_t* pairs_host, int64_t n, int32_t* keys4_host) {
-  Scratch& sc = g_scratch[ctx->device & 15];
+  Scratch& sc = scratch_of(ctx);
   const Scene& s = ctx->scene;
   if (n <= 0) return PGP_OK;
   for (int64_t t = 0; t < 2 * n; ++t)
@@ -1312,3 +1317,13 @@ int k2_scene_ppf_keys(pgp_ctx* ctx, const int32_t* pairs_host, int64_t n, int32_
 }
 
 uint32_t k2_stocs_engine_seed(uint64_t seed, int base, int attempt) { return stocs_base_seed(seed, base, attempt); }
+
+void k2_release(pgp_ctx* ctx) {
+  if (!ctx->k2_scratch) return;
+  Scratch* sc = static_cast<Scratch*>(ctx->k2_scratch);
+  for (DevBuf* b : {&sc->in_order, &sc->list1, &sc->list2, &sc->cnt, &sc->cnt2, &sc->off, &sc->flag, &sc->curr, &sc->pairs1, &sc->pairs2, &sc->quads,
+                    &sc->bucket_of, &sc->key_of, &sc->bucket_start, &sc->sorted, &sc->T, &sc->ok, &sc->base, &sc->qn})
+    b->release();
+  delete sc;
+  ctx->k2_scratch = nullptr;
+}

@@ -104,6 +104,7 @@ void pgp_destroy(pgp_ctx* ctx) {
     for (DevBuf* b : {&m.search, &m.search_nrm, &m.search_unit, &m.val, &m.val_nrm, &m.val_orig, &m.val_nrm_orig, &m.gen_T, &m.gen_counts, &m.gen_scores,
                       &m.tgrid_pts, &m.tgrid_start, &m.val_raw, &m.val_groups, &m.ppf_keys, &m.ppf_offsets, &m.ppf_pairs, &m.ppf_bits})
       b->release();
+  k2_release(ctx);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(ctx->own_stream);

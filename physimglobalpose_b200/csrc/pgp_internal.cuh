@@ -163,6 +163,7 @@ struct pgp_ctx {
   DevBuf topk_out;
   void* pinned = nullptr; size_t pinned_cap = 0;
   int64_t launches = 0;
+  void* k2_scratch = nullptr;              // k2_pcs.cu: the generator's device scratch (k2_release)
   int stream_upload = 1;  // pgp_score_lcp: overlap the batch upload with the scoring launch (0: upload first; use under profilers)
   int tail_split = 4;     // K3 fine kernel: model chunks per hypothesis in the last wave (1 = off)
   int k3_warps_count = 32, k3_warps_weighted = 24;   // warps per CTA of k3_fine_kernel (32 -> 64 registers/thread, 24 -> 80, 16 -> 128)
@@ -207,6 +208,7 @@ int k2_build_ppf_map(pgp_ctx* ctx, Model& m);
 int k2_scene_ppf_keys(pgp_ctx* ctx, const int32_t* pairs_host, int64_t n, int32_t* keys4_host);
 uint32_t k2_stocs_engine_seed(uint64_t seed, int base, int attempt);
 int k2_get_bases(pgp_ctx* ctx, int n_bases, int32_t* ids_host, float* inv_host, uint8_t* ok_host);
+void k2_release(pgp_ctx* ctx);
 // k5_tricp.cu
 int k5_tricp(pgp_ctx* ctx, Model& m, const float* seg_xyz_host, int ns, double* poses16_host, int k, float trim, float ratio,
              int max_iter, int* iters_out, float* energy_out);

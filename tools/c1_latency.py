@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""configs[0] (the reference's test-scene, three objects) end to end, per object: the request the ROS node makes of
+getProbableTransformsSuper4PCS -- scene segment + prior image + model in, improving chain of poses + registered points out --
+through the in-memory C ABI (operMode 1 = StoCS + PPF map, the shipped mode, and operMode 0), optionally next to the reference's own
+Perform_N_steps (oracle/_ref, one CPU thread) on the same clouds.  Parity is NOT claimed here (different random draws): this is the
+latency line of DESIGN.md.   python tools/c1_latency.py [--reference]"""
+import json, os, sys, time
+sys.path.insert(0, '.')
+import numpy as np, torch
+from physimglobalpose_b200.engine import PoseEngine
+from oracle import pyoracle
+
+g = np.load(os.path.join('tests', 'golden', 'c1_test_scene.npz'))
+sys.path.insert(0, 'tests')
+from test_gpu_golden import _c1_mask
+
+e = PoseEngine(0)
+out = {}
+for k, name in enumerate(g['names']):
+    seg, nrm, mx, mn = g[f'{name}_seg_xyz'], g[f'{name}_seg_nrm'], g[f'{name}_model_xyz'], g[f'{name}_model_nrm']
+    img = np.where(_c1_mask(g, name), 10000, 0).astype(np.uint16)
+    delta = float(g['delta'])
+    # one-off per model (GlobalCfg::loadObjects loads models once): upload + PPF map
+    e.set_scene(seg, nrm, delta)
+    t0 = time.perf_counter(); e.set_model(k, mx, mn); e.build_ppf_map(k); torch.cuda.synchronize(); t_model = time.perf_counter() - t0
+    keys, offs, pairs = e.get_ppf_map(k)
+    def request(seed, mode=1):
+        e.set_scene(seg, nrm, delta)
+        e.set_scene_prior_image(img, g['K'])
+        n = e.generate_pcs(k, seed=seed, max_hyp=10000, n_bases=100, max_quads_per_base=100, mode=mode)
+        e.score_generated(k, 'weighted')
+        chain = e.improving_chain(k)
+        reg = e.registered_points(k, chain['T'][-1]) if len(chain) else np.zeros(0, np.int32)
+        return n, chain, reg
+    request(1)                                          # warm-up (allocations)
+    ts = []
+    for seed in range(2, 7):
+        torch.cuda.synchronize(); t0 = time.perf_counter(); n, chain, reg = request(seed); ts.append(time.perf_counter() - t0)
+    t0s = []
+    for seed in range(2, 5):
+        torch.cuda.synchronize(); t0 = time.perf_counter(); n0, chain0, _ = request(seed, mode=0); t0s.append(time.perf_counter() - t0)
+    res = dict(mode0_request_ms=float(np.median(t0s) * 1e3), mode0_hypotheses=int(n0), mode0_best_score=float(chain0['score'][-1]) if len(chain0) else 0.0)
+    res.update(dict(segment_points=int(len(seg)), model_points=int(len(mx)), hypotheses=int(n), request_ms=float(np.median(ts) * 1e3),
+               best_score=float(chain['score'][-1]) if len(chain) else 0.0, chain=int(len(chain)), registered=int(len(reg)), model_setup_ms=t_model * 1e3))
+    if "--reference" in sys.argv and pyoracle.have_ref():
+        # the reference's own Perform_N_steps, operMode 0 (its operMode 1 does not finish on these clouds: minutes per base with a
+        # 2.2 M-pair PPF map).  Slow: 9 s / 82 s / 367 s for the three objects on an 8-vCPU Xeon -- run it on the CPU, not under gpurun.
+        t0 = time.perf_counter()
+        ref = pyoracle.RefOracle(seg, nrm, mx, mn, mx, mn, delta, K=g['K'], prior_img=img)
+        t1 = time.perf_counter()
+        r = ref.perform_n_steps(mode=0, seed=7, cap=4096)
+        t2 = time.perf_counter()
+        res.update(reference_init_ms=(t1 - t0) * 1e3, reference_perform_ms=(t2 - t1) * 1e3, reference_hypotheses=int(len(r['transforms'])),
+                   reference_best=float(r['best_lcp']), reference_stage_s=[float(x) for x in r['stage_s']])
+    out[str(name)] = res
+print(json.dumps(out))

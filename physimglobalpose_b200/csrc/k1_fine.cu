@@ -299,7 +299,7 @@ __device__ __forceinline__ void sweep27(const uint32_t* __restrict__ cell_start,
 
 __device__ __forceinline__ float wlist_threshold(float u2, float dhi2) { return fminf(u2 * (1.0f + 4e-5f), dhi2); }
 
-constexpr uint32_t WV_CNT_BITS = 10, WV_CNT_MAX = (1u << WV_CNT_BITS) - 1u, WV_REL_MAX = (1u << (32 - WV_CNT_BITS)) - 1u;
+constexpr uint32_t WV_CNT_BITS = 8, WV_CNT_MAX = (1u << WV_CNT_BITS) - 1u, WV_REL_MAX = (1u << (32 - WV_CNT_BITS)) - 1u;   // counts are stored as bytes
 
 // Pass A: list length of every voxel of the block (0 for OUT voxels) -> wvox (count only), block total -> region.
 // 4 voxels per thread (v = tid + 128 j).
@@ -368,7 +368,8 @@ __global__ void __launch_bounds__(CLS_THREADS) k1w_count(const uint32_t* __restr
 // candidates' float4 records {x, y, z, original index}, so that scoring needs no second indirection).
 __global__ void __launch_bounds__(CLS_THREADS) k1w_fill(const uint32_t* __restrict__ block_cell, const uint32_t* __restrict__ cell_start,
                                                         const float4* __restrict__ pts, GridParams g, uint32_t* __restrict__ wvox,
-                                                        const uint32_t* __restrict__ region_base, float4* __restrict__ wlists) {
+                                                        const uint32_t* __restrict__ region_base, float4* __restrict__ wlists,
+                                                        unsigned char* __restrict__ wcnt, uint32_t* __restrict__ wword) {
   __shared__ float4 s_p[CLS_CHUNK];
   __shared__ uint32_t s_warp[CLS_THREADS / 32];
   const int b = blockIdx.x;
@@ -394,6 +395,10 @@ __global__ void __launch_bounds__(CLS_THREADS) k1w_fill(const uint32_t* __restri
     rel[j] = run; run += cnt[j];
     wvox[(size_t)b * 512 + threadIdx.x * 4 + j] = (rel[j] << WV_CNT_BITS) | cnt[j];
   }
+  // what scoring reads (L2-resident: 512 + 128 bytes per block instead of 2 KB): the count of every voxel as a byte, and the first
+  // record of every label word's 16 voxels; a voxel's first record = that + the counts of the voxels before it in the word
+  *reinterpret_cast<uchar4*>(wcnt + (size_t)b * 512 + threadIdx.x * 4) = make_uchar4((unsigned char)cnt[0], (unsigned char)cnt[1], (unsigned char)cnt[2], (unsigned char)cnt[3]);
+  if ((threadIdx.x & 3) == 0) wword[(size_t)b * 32 + (threadIdx.x >> 2)] = base + rel[0];
   if (total == 0) return;      // uniform over the CTA
   float vx[4], vy[4], vz[4], u2[4], thr[4];
   uint32_t wr[4];
@@ -616,6 +621,8 @@ int k1_build_wlists(pgp_ctx* ctx) {
   if ((size_t)nb * 2048 + (64u << 20) > free_b + s.wvox.cap) return PGP_OK;
   PGP_CUDA(ctx, s.wvox.reserve((size_t)nb * 512 * 4));
   PGP_CUDA(ctx, s.wbase.reserve((size_t)(nb + 1) * 4));
+  PGP_CUDA(ctx, s.wcnt.reserve((size_t)nb * 512 + 64));
+  PGP_CUDA(ctx, s.wword.reserve((size_t)nb * 128 + 64));
   PGP_CUDA(ctx, s.scratch.reserve((size_t)((nb + 1) / 2048 + 4096) * 4));
   uint32_t* region = s.wbase.as<uint32_t>();
   unsigned long long* d_total = reinterpret_cast<unsigned long long*>(ctx->work.as<char>() + 192);
@@ -638,7 +645,7 @@ int k1_build_wlists(pgp_ctx* ctx) {
   if (rc) return rc;
   PGP_CUDA(ctx, s.wlists.reserve((size_t)total * 16 + 16));
   k1w_fill<<<nb, CLS_THREADS, 0, st>>>(s.block_cell.as<uint32_t>(), s.cell_start.as<uint32_t>(), s.pts.as<float4>(), g, s.wvox.as<uint32_t>(), region,
-                                       s.wlists.as<float4>());
+                                       s.wlists.as<float4>(), s.wcnt.as<unsigned char>(), s.wword.as<uint32_t>());
   ctx->launches++;
   PGP_CUDA(ctx, cudaGetLastError());
   s.n_wlist_entries = (int64_t)total;

@@ -54,8 +54,8 @@ struct LcpParams {
   const uint2* adesc;        // per AMBIG voxel: {first record, number of records}
   const float4* arec;        // candidate records {x, y, z, original index}, closest to the voxel centre first
   float model_rinf;          // max |coordinate| of the validation model (bounds the transform's intermediates)
-  const uint32_t* wvox;      // K1c: per voxel (offset in the block's region << 10) | candidate count
-  const uint32_t* wbase;     // K1c: per block first entry of its region
+  const unsigned char* wcnt; // K1c: per voxel candidate count (a byte)
+  const uint32_t* wword;     // K1c: per label word (16 voxels) the first record
   const float4* wlists;      // K1c: candidate records {x, y, z, original index}
   const float4* aux_orig;    // unit normal + prior by ORIGINAL scene index
   const float4* groups;      // bounding sphere {centre, radius} of every aligned run of 32 validation points (pgp_set_model)
@@ -344,17 +344,22 @@ __device__ __forceinline__ uint32_t label_slot(const LcpParams& p, const FineCtx
   return (wr.x & bit) ? blk * 32u + (uint32_t)(v >> 4) : f.dummy_word;
 }
 
-// K1c nearest-candidate records of the voxel: one indexed load, no rank arithmetic
+// K1c nearest-candidate records of the voxel: the 16 byte counts of its label word and the word's first record (two independent
+// loads from tables that stay L2-resident: 640 bytes per block), then first record = word base + the counts of the voxels before it
 template <bool SMEM_TABLE>
 __device__ __forceinline__ const float4* wlist_of(const LcpParams& p, const FineCtx& f, int ix, int iy, int iz, uint32_t& cnt) {
   const int c = ((iz >> 3) * f.dimy + (iy >> 3)) * f.dimx + (ix >> 3);
   const uint2 wr = table_word<SMEM_TABLE>(f, c >> 5);
   const unsigned blk = wr.y + __popc(wr.x & ((1u << (c & 31)) - 1u));
   const int v = ((iz & 7) << 6) | ((iy & 7) << 3) | (ix & 7);
-  const uint32_t e = __ldg(p.wvox + (size_t)blk * 512 + v);
-  const uint32_t base = __ldg(p.wbase + blk);
-  cnt = e & 1023u;
-  return p.wlists + base + (e >> 10);
+  const uint4 cw = __ldg(reinterpret_cast<const uint4*>(p.wcnt + (size_t)blk * 512) + (v >> 4));
+  const uint32_t base = __ldg(p.wword + (size_t)blk * 32 + (v >> 4));
+  const int wi = (v >> 2) & 3, bi = v & 3;
+  const uint32_t mine = wi == 0 ? cw.x : wi == 1 ? cw.y : wi == 2 ? cw.z : cw.w;
+  uint32_t before = __dp4a(mine & ((1u << (8 * bi)) - 1u), 0x01010101u, 0u);
+  before += (wi > 0 ? __dp4a(cw.x, 0x01010101u, 0u) : 0u) + (wi > 1 ? __dp4a(cw.y, 0x01010101u, 0u) : 0u) + (wi > 2 ? __dp4a(cw.z, 0x01010101u, 0u) : 0u);
+  cnt = (mine >> (8 * bi)) & 255u;
+  return p.wlists + base + before;
 }
 
 // phase 2 (count mode) for one queued query: the reference's exact test against the candidate records of its AMBIG voxel.
@@ -769,7 +774,7 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     if (s.g.fine == 8 && !ctx->force_coarse && !s.wlists_tried) { int rc = k1_build_wlists(ctx); if (rc) return rc; }
     if (s.g.fine == 8 && !ctx->force_coarse && s.wlists_ready) {
       p.bmrank = s.bmrank.as<uint2>(); p.codes = s.codes.as<uint32_t>();
-      p.wvox = s.wvox.as<uint32_t>(); p.wbase = s.wbase.as<uint32_t>(); p.wlists = s.wlists.as<float4>(); p.aux_orig = s.aux_orig.as<float4>();
+      p.wcnt = s.wcnt.as<unsigned char>(); p.wword = s.wword.as<uint32_t>(); p.wlists = s.wlists.as<float4>(); p.aux_orig = s.aux_orig.as<float4>();
       k3_weighted_ordered<true><<<(unsigned)blocks, T, 0, st>>>(p, nullptr, 1);
     } else {
       k3_weighted_ordered<false><<<(unsigned)blocks, T, 0, st>>>(p, nullptr, 1);
@@ -805,7 +810,7 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     if (p.n_tiles > 256) return pgp_fail(ctx, PGP_E_INVALID, "validation model too large (%d points)", m.nv);
     p.bmrank = s.bmrank.as<uint2>(); p.codes = s.codes.as<uint32_t>();
     p.hdrw = s.hdrw.as<uint32_t>(); p.adesc = s.adesc.as<uint2>(); p.arec = s.arec.as<float4>();
-    p.wvox = s.wvox.as<uint32_t>(); p.wbase = s.wbase.as<uint32_t>(); p.wlists = s.wlists.as<float4>(); p.aux_orig = s.aux_orig.as<float4>();
+    p.wcnt = s.wcnt.as<unsigned char>(); p.wword = s.wword.as<uint32_t>(); p.wlists = s.wlists.as<float4>(); p.aux_orig = s.aux_orig.as<float4>();
     p.bmrank_words = (int)(bm / 8);
     p.model_rinf = m.val_rinf;
     p.ready = ready_dev;

@@ -98,7 +98,7 @@ void pgp_destroy(pgp_ctx* ctx) {
   cudaDeviceSynchronize();
   Scene& s = ctx->scene;
   for (DevBuf* b : {&s.xyz_raw, &s.nrm_raw, &s.unsorted, &s.cursor, &s.pts, &s.aux, &s.cell_start, &s.cell_of, &s.bitmap, &s.bmrank,
-                    &s.block_cell, &s.codes, &s.near_cnt, &s.hdr, &s.region, &s.hdrw, &s.adesc, &s.arec, &s.wvox, &s.wbase, &s.wlists, &s.aux_orig, &s.dist, &s.dist_tmp, &s.prior, &s.scratch, &ctx->batch_T, &ctx->batch_counts, &ctx->batch_scores, &ctx->work, &ctx->topk_out})
+                    &s.block_cell, &s.codes, &s.near_cnt, &s.hdr, &s.region, &s.hdrw, &s.adesc, &s.arec, &s.wvox, &s.wbase, &s.wcnt, &s.wword, &s.wlists, &s.aux_orig, &s.dist, &s.dist_tmp, &s.prior, &s.scratch, &ctx->batch_T, &ctx->batch_counts, &ctx->batch_scores, &ctx->work, &ctx->topk_out})
     b->release();
   for (Model& m : ctx->models)
     for (DevBuf* b : {&m.search, &m.search_nrm, &m.search_unit, &m.val, &m.val_nrm, &m.val_orig, &m.val_nrm_orig, &m.gen_T, &m.gen_counts, &m.gen_scores,
@@ -373,7 +373,7 @@ int pgp_grid_info(pgp_ctx* ctx, int* dims3, int64_t* n_cells, int64_t* n_occupie
   if (bytes) {
     *bytes = (int64_t)s.n * 32 + (s.g.n_cells + 1) * 4 + s.bitmap_words * 4;
     if (s.g.fine) *bytes += s.bitmap_words * 8 + (int64_t)s.g.n_blocks * (128 + 128) + s.n_ambig_voxels * 8 + s.n_list_words * 16 + s.g.n_cells * 4 * s.dist_r * s.dist_r * s.dist_r;   // K1b: bmrank, codes, hdrw, adesc, arec; K1d: dist
-    if (s.wlists_ready) *bytes += (int64_t)s.g.n_blocks * 2052 + s.n_wlist_entries * 16 + (int64_t)s.n * 16;               // K1c: wvox, wbase, wlists, aux_orig
+    if (s.wlists_ready) *bytes += (int64_t)s.g.n_blocks * (2052 + 640) + s.n_wlist_entries * 16 + (int64_t)s.n * 16;               // K1c: wvox, wbase, wlists, aux_orig
   }
   return PGP_OK;
 }

@@ -77,8 +77,10 @@ struct Scene {
   DevBuf arec;         // float4 copies {x, y, z, original index} of the AMBIG voxels' candidate points, closest to the voxel centre first
   int64_t n_list_words = 0;    // records in arec
   int64_t n_ambig_voxels = 0;
-  DevBuf wvox;         // K1c: n_blocks x 512 u32: (offset in the block's region << 10) | candidate count, 0 for OUT voxels
-  DevBuf wbase;        // K1c: n_blocks u32: first wlists entry of the block's region
+  DevBuf wvox;         // K1c build scratch: n_blocks x 512 u32 counts / offsets
+  DevBuf wbase;        // K1c build scratch: n_blocks u32: first wlists entry of the block's region
+  DevBuf wcnt;         // K1c: n_blocks x 512 bytes: candidate count of every voxel (0 for OUT voxels)
+  DevBuf wword;        // K1c: n_blocks x 32 u32: first wlists entry of the 16 voxels of each label word
   DevBuf wlists;       // K1c: float4 copies {x,y,z,original index} of the nearest-neighbour candidates of every non-OUT voxel
   int64_t n_wlist_entries = 0;
   DevBuf dist;         // K1d: f32 per sub-cell (dist_r per cell edge), lower bound of the distance from any point of the sub-cell to the nearest scene point

@@ -5,17 +5,23 @@
 // (S4/accelerators/kdtree.h:394-459) per validation-model point, and the loop over hypotheses of
 // Perform_N_steps (:1888-1901).
 //
-// Mapping: persistent CTAs; the validation model is staged ONCE per CTA into shared memory with a
-// 1-D TMA bulk copy (cp.async.bulk -> SASS UBLKCP) together with the dilated-occupancy bitmap; each
-// warp pulls one hypothesis at a time from a global work counter, keeps its 3x4 transform in
-// registers, and walks the model 32 points per step:
-//   phase 1 (uniform control flow)  exact fp32 transform, cell, one bitmap bit: queries whose 27
-//           cells hold no scene point are done; survivors go to a per-warp shared-memory queue
-//           (warp-ballot compaction);
-//   phase 2 (dense)  whenever 32 survivors are queued, every lane takes one and runs the exact
-//           d2 <= delta^2 test over the 9 contiguous x-rows of the 27 cells.
+// Two kernels.  k3_fine_kernel (below, the one that runs) works on the tri-state label structure of K1b/K1c/K1d:
+//   persistent CTAs, one per SM; the validation model (kd-leaf order: every aligned run of 32 points is a compact patch), its
+//   group spheres and the bitmap+rank table are staged ONCE per CTA into shared memory with 1-D TMA bulk copies (cp.async.bulk
+//   -> SASS UBLKCP) on an mbarrier; each warp pulls one hypothesis at a time from a global work counter, keeps its 3x4 transform
+//   in registers and runs
+//     group cull   one lane per 32-point group: distance-field lower bound at the image of the group's centre vs the (norm-
+//                  stretched) group radius + delta -> groups that cannot reach the scene are never looked at,
+//     phase 1      128 points per step (uniform control flow): FMA voxel transform, shared-memory bitmap+rank word, ONE 4-byte
+//                  gather of the 2-bit label; IN counts, OUT is done, AMBIG (weighted: IN too) goes to a per-warp queue
+//                  (warp-ballot compaction),
+//     phase 2      whenever 32 are queued, every lane takes one and runs the reference's exact non-fused test against the
+//                  voxel's few candidate records.
+// k3_lcp_kernel (first in this file) is the plain 27-cell probe the fine structure was derived from: exact fp32 transform, cell,
+// one dilated-occupancy bit, then the exact d2 <= delta^2 test over the 9 contiguous x-rows of the 27 cells.  It is the
+// fallback when the fine grid cannot be built (margins do not close, absurd densities) and the cross-check of the tests.
 // Inlier counts are warp-reduced (REDUX) -- integer, hence order-free and bit-exact.
-// All float math is the reference's association, non-fused (pgp_internal.cuh).
+// All float math that decides a count is the reference's association, non-fused (pgp_internal.cuh).
 #include <math.h>
 
 #include "pgp_internal.cuh"

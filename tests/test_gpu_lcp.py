@@ -281,3 +281,32 @@ def test_empty_batch_and_tiny_scene(engine, port_lib):
         Tn[:100, :, 3] = (sx[0] - o.centroids()[0])[None, :] + np.random.default_rng(3).normal(scale=0.02, size=(100, 3)).astype(np.float32)
         c, _ = engine.score_lcp(0, Tn, "count")
         assert np.array_equal(c, o.verify(Tn))
+
+
+def test_full_size_properties(engine, port_lib):
+    """BASELINE.json configs[1] at its full size (2k-pt model, 100k-pt scene, 100k hypotheses), through properties that do not
+    need the oracle on every hypothesis: permutation equivariance, shard independence (two halves == whole: what the multi-GPU
+    split relies on), weighted <= count, the ground-truth pose at index 0 scores every model point and is the arg-max, the
+    top-k is the sorted prefix; plus the oracle itself on a 1 500-hypothesis sample spread over the batch."""
+    prob = synth.make_problem(2000, 100000, 0.01, seed=1234)
+    T = synth.make_hypotheses(prob, 100000, seed=4321)
+    _setup(engine, prob)
+    c, s = engine.score_lcp(0, T, "count")
+    top = engine.topk(0, 64)
+    order = np.lexsort((np.arange(len(c)), -c.astype(np.int64)))[:64]
+    assert np.array_equal(top["index"], order) and np.array_equal(top["count"], c[order])
+    assert c[0] == 2000 and int(c.argmax()) == 0 and c.max() <= 2000
+    rng = np.random.default_rng(9)
+    perm = rng.permutation(len(T))
+    cp, _ = engine.score_lcp(0, T[perm], "count")
+    assert np.array_equal(cp, c[perm])
+    ca, _ = engine.score_lcp(0, T[:50000], "count")
+    cb, _ = engine.score_lcp(0, T[50000:], "count")
+    assert np.array_equal(np.concatenate([ca, cb]), c)
+    wc, ws = engine.score_lcp(0, T, "weighted")
+    assert np.all(wc <= c) and np.array_equal(ws, wc.astype(np.float32) / np.float32(2000))      # priors are all 1: score = gated count / n
+    sample = np.sort(rng.choice(len(T), 1500, replace=False))
+    o = _oracle(port_lib, prob)
+    assert np.array_equal(c[sample], o.verify(T[sample]))
+    wso, wno = o.weighted_verify(T[sample[:500]])
+    assert np.array_equal(wc[sample[:500]], wno.astype(np.uint32)) and np.array_equal(ws[sample[:500]], wso)

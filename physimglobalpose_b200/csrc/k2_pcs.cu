@@ -1047,7 +1047,7 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
   if (depth > 7) return pgp_fail(ctx, PGP_E_TOO_LARGE, "quad join: model diameter / delta too large (grid depth %d > 7)", depth);
   const uint32_t nbk = 1u << std::min(3 * depth, 15);
   // bases per chunk: bound the pair buffer (~ 10 % of nq^2 ordered pairs per edge) to about 1 GB
-  const int chunk = (int)std::max<double>(1.0, std::min<double>(32.0, 6.0e8 / ((double)nq * (double)nq)));
+  int chunk = (int)std::max<double>(1.0, std::min<double>(32.0, 6.0e8 / ((double)nq * (double)nq)));
   PGP_CUDA(ctx, sc.base.reserve((size_t)nb_total * sizeof(BaseOut) + 64));
   PGP_CUDA(ctx, m.gen_T.reserve((size_t)std::max<int64_t>(max_hyp, 1) * 48));
   BaseOut* d_bases_all = reinterpret_cast<BaseOut*>(sc.base.as<char>() + 64);
@@ -1068,8 +1068,15 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
   ctx->launches++;
   PGP_CUDA(ctx, cudaGetLastError());
   int64_t cur = 0;
-  for (int base0 = 0; base0 < nb_total && cur < max_hyp; base0 += chunk) {
-    const int nb = std::min(chunk, nb_total - base0), ncombo = 2 * nb;
+  // A chunk whose pair lists or congruent quads outgrow the 32-bit offsets / the free device memory (highly symmetric models: very
+  // many pairs at one distance) is retried with half as many bases; one base alone that does not fit is an error.
+  size_t mem_free = 0, mem_total = 0;
+  PGP_CUDA(ctx, cudaMemGetInfo(&mem_free, &mem_total));
+  int nb = 0;
+  for (int base0 = 0; base0 < nb_total && cur < max_hyp; base0 += nb) {
+    nb = std::min(chunk, nb_total - base0);
+    const int ncombo = 2 * nb;
+    auto shrink = [&]() { if (nb <= 1) return false; chunk = std::max(1, nb / 2); nb = 0; return true; };   // nb = 0: the loop repeats base0
     const BaseOut* d_bases = d_bases_all + base0;
     // ---- pairs of all 2 nb (base, edge) combos
     const size_t ncnt = (size_t)ncombo * nq;
@@ -1093,7 +1100,10 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
       if (rc) return rc;
       ntot = (int64_t)tot;
       if (ntot == 0) continue;
-      if (ntot >= (1ll << 31)) return pgp_fail(ctx, PGP_E_TOO_LARGE, "pair lists of one chunk exceed 2^31 entries");
+      if (ntot >= (1ll << 31) || (size_t)ntot * 24 > mem_free / 2) {
+        if (shrink()) continue;
+        return pgp_fail(ctx, PGP_E_TOO_LARGE, "pair lists of one base exceed 2^31 entries / the device memory");
+      }
       PGP_CUDA(ctx, sc.pairs1.reserve((size_t)ntot * 8));
       k2s_combo_copy<<<dim3(64, (unsigned)ncombo), 256, 0, st>>>(pm, slot, coff, sc.pairs1.as<int2>());
       ctx->launches++;
@@ -1109,7 +1119,10 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
       if (rc) return rc;
       ntot = (int64_t)unordered * 2;
       if (ntot == 0) continue;
-      if (ntot >= (1ll << 31)) return pgp_fail(ctx, PGP_E_TOO_LARGE, "pair lists of one chunk exceed 2^31 entries");
+      if (ntot >= (1ll << 31) || (size_t)ntot * 24 > mem_free / 2) {
+        if (shrink()) continue;
+        return pgp_fail(ctx, PGP_E_TOO_LARGE, "pair lists of one base exceed 2^31 entries / the device memory");
+      }
       PGP_CUDA(ctx, sc.pairs1.reserve((size_t)ntot * 8));
       k2b_pairs<true><<<pgrid, 256, 0, st>>>(m.search.as<float4>(), nq, d_bases, eps, cnt, sc.pairs1.as<int2>());
       k2b_combo_offsets<<<(ncombo + 256) / 256, 256, 0, st>>>(cnt, nq, ncombo, coff);
@@ -1163,7 +1176,10 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
     rc = scan_u32(ctx, cnt2, ntot, &nquads);                                // sync 2
     if (rc) return rc;
     if (nquads == 0) continue;
-    if (nquads >= (1ull << 31)) return pgp_fail(ctx, PGP_E_TOO_LARGE, "congruent quads of one chunk exceed 2^31");
+    if (nquads >= (1ull << 31) || (size_t)nquads * 68 > mem_free / 2) {
+      if (shrink()) continue;
+      return pgp_fail(ctx, PGP_E_TOO_LARGE, "congruent quads of one base exceed 2^31 / the device memory");
+    }
     PGP_CUDA(ctx, sc.quads.reserve((size_t)nquads * 16));
     PGP_CUDA(ctx, sc.T.reserve((size_t)nquads * 48));
     PGP_CUDA(ctx, sc.flag.reserve((size_t)(nquads + 1) * 4));

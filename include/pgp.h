@@ -67,7 +67,8 @@ typedef struct pgp_pcs_opts {
   float overlap;             /* overlap_estimation (only scales the wide-base target), default 0.5 */
   int base_trials;           /* kNumberOfDiameterTrials = 1000 random triangles per base, :377-410 */
   int mode;                  /* operMode (match4pcsBase.cc:300): 0 = wide random base + Super4PCS pair extraction (default here),
-                                1 = StoCS base sampling + PPF-map pair lookup (what the reference ships; needs a PPF map) */
+                                1 = StoCS base sampling + PPF-map pair lookup (what the reference ships; needs a PPF map),
+                                2 = V4PCS: tetrahedron base (SelectTetrahedronBase :466-503) + six-distance join (:978-1044) */
 } pgp_pcs_opts;
 
 /* ---------------------------------------------------------------- context ------------------ */
@@ -193,6 +194,11 @@ PGP_API int pgp_extract_pairs(pgp_ctx* ctx, int obj, float dist, float eps, int3
 PGP_API int pgp_find_quads(pgp_ctx* ctx, int obj, const int32_t* base4, float inv1, float inv2, float eps,
                            const int32_t* pairs1_host, int64_t n1, const int32_t* pairs2_host, int64_t n2,
                            int32_t* quads_host, int64_t cap, int64_t* n_quads);
+/* Congruent quads for one base in operMode 2 (V4PCS): ExtractCongruentSet (match4pcsBase.cc:1929-2039) with its six
+ * ExtractPairs calls and FindCongruentQuadrilateralsV4PCS (:978-1044) -- every ordered 4-tuple of search-cloud points whose
+ * six pairwise distances match the base's within eps (the pair filter of S4/pairCreationFunctor.h:167-253).  base4: scene
+ * ids.  quads_host: cap x 4, sorted by (v1, v2, v3, v4) (the reference's order is an unordered_set iteration: compare as sets). */
+PGP_API int pgp_find_quads_v4pcs(pgp_ctx* ctx, int obj, const int32_t* base4, float eps, int32_t* quads_host, int64_t cap, int64_t* n_quads);
 /* Rigid transform of one (base, quad): ComputeRigidTransformFromCongruentPair
  * (match4pcsBase.cc:1411-1488) + ComputeRigidTransformation (:1504-1614).  n quads of the same
  * base; T_host: n x 12 centred; ok_host: n flags (0 = rejected: degenerate or non-orthogonal). */

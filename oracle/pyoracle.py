@@ -303,6 +303,50 @@ class RefOracle(_Base):
         return out[: min(n, cap)].copy()
 
 
+    # ---- operMode 2 (V4PCS: tetrahedron base, six-distance join)
+    def congruent_set_mode2(self, base, cap=1 << 22):
+        """ExtractCongruentSet in operMode 2 for one base (4 scene ids): (n, 4) model ids, in the reference's own order
+        (an unordered_set iteration: compare as sets)."""
+        b = np.ascontiguousarray(base, np.int32)
+        out = np.zeros((cap, 4), np.int32)
+        n = self._fn("congruent_set_mode2", C.c_int64, [C.c_void_p, _i32p, _i32p, C.c_int64])(self.h, _p(b, _i32p), _p(out, _i32p), cap)
+        return out[: min(n, cap)].copy()
+
+    def select_tetrahedron(self, seed):
+        b = np.zeros(4, np.int32)
+        ok = self._fn("select_tetrahedron", C.c_int, [C.c_void_p, C.c_uint, _i32p])(self.h, int(seed), _p(b, _i32p))
+        return bool(ok), b
+
+
+def v4pcs_quads_port(P_centred, Q_centred, base, eps):
+    """numpy restatement of ExtractCongruentSet in operMode 2 (match4pcsBase.cc:1929-2039): the six pair extractions
+    (pairCreationFunctor.h:167-253: |float norm - d| <= eps compared in double, both orientations, no self pairs) and the
+    connectivity join of FindCongruentQuadrilateralsV4PCS (:978-1044).  Returns the quads (v1, v2, v3, v4) sorted."""
+    P = np.asarray(P_centred, np.float32); Q = np.asarray(Q_centred, np.float32)
+    b = [P[i] for i in base]
+    def norm32(v):
+        v = v.astype(np.float32)
+        return np.sqrt((v[..., 0] * v[..., 0] + (v[..., 1] * v[..., 1] + v[..., 2] * v[..., 2])).astype(np.float32)).astype(np.float32)
+    def dist(i, j):                                     # (base_3D_[i].pos() - base_3D_[j].pos()).norm(), Eigen: x^2 + y^2 + z^2 left to right
+        v = (b[i] - b[j]).astype(np.float32)
+        return np.float32(np.sqrt(np.float32(np.float32(v[0] * v[0] + v[1] * v[1]) + v[2] * v[2])))
+    d = {1: dist(0, 1), 2: dist(0, 2), 3: dist(0, 3), 4: dist(1, 2), 5: dist(1, 3), 6: dist(2, 3)}
+    D = norm32(Q[:, None, :] - Q[None, :, :])           # (q_i - q_j).norm() in the accelerator's association dx^2 + (dy^2 + dz^2)
+    n = len(Q)
+    off = ~np.eye(n, dtype=bool)
+    A = {k: (np.abs(D.astype(np.float64) - np.float64(d[k])) <= np.float64(np.float32(eps))) & off for k in d}
+    quads = []
+    for v1, v2 in np.argwhere(A[1]):
+        v3s = np.flatnonzero(A[2][v1] & A[4][:, v2])    # (v1, v3) in pairs2 and (v3, v2) in pairs4
+        if len(v3s) == 0:
+            continue
+        c4 = A[3][v1] & A[5][:, v2]                     # (v1, v4) in pairs3 and (v4, v2) in pairs5
+        for v3 in v3s:
+            for v4 in np.flatnonzero(c4 & A[6][:, v3]): # (v4, v3) in pairs6
+                quads.append((v1, v2, v3, v4))
+    return np.array(sorted(quads), np.int32).reshape(-1, 4)
+
+
 def group_ppf_keys(keys4_all, n):
     """All-ordered-pairs keys (n*n, 4; row t = pair (t // n, t % n)) -> map rows (keys4, offsets, pairs) in key order,
     pairs inside a key in (i, j) order; the diagonal is skipped."""

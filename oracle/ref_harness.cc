@@ -402,4 +402,27 @@ int64_t ref_congruent_set_mode1(void* h, const int* b, float inv1, float inv2, i
   return n;
 }
 
+// ExtractCongruentSet (:1929-2039) in operMode 2: six pair extractions + FindCongruentQuadrilateralsV4PCS (:978-1044)
+int64_t ref_congruent_set_mode2(void* h, const int* b, int32_t* quads, int64_t cap) {
+  Oracle* o = static_cast<Oracle*>(h);
+  o->operMode = 2;
+  std::vector<int> ids(b, b + 4);
+  Super4PCS::BaseGraph g(ids, 0.f, 0.f, 1.0f);
+  o->ExtractCongruentSet(&g);
+  int64_t n = int64_t(g.congruent_quads.size());
+  for (int64_t i = 0; i < std::min(n, cap); ++i) {
+    quads[4 * i] = g.congruent_quads[i].vertices[0]; quads[4 * i + 1] = g.congruent_quads[i].vertices[1];
+    quads[4 * i + 2] = g.congruent_quads[i].vertices[2]; quads[4 * i + 3] = g.congruent_quads[i].vertices[3];
+  }
+  return n;
+}
+
+// SelectTetrahedronBase (:466-503) after srand(seed): widest random triangle + the most voluminous of 100 random 4th points
+int ref_select_tetrahedron(void* h, unsigned seed, int* b) {
+  Oracle* o = static_cast<Oracle*>(h);
+  srand(seed);
+  Oracle::Scalar i1 = 0, i2 = 0;
+  return o->SelectTetrahedronBase(i1, i2, b[0], b[1], b[2], b[3]) ? 1 : 0;
+}
+
 }  // extern "C"

@@ -64,6 +64,7 @@ _SIGNATURES = {
     "pgp_pcs_default_opts": (None, [_vp]),
     "pgp_extract_pairs": (_i, [_vp, _i, _f, _f, _vp, _i64, _vp]),
     "pgp_find_quads": (_i, [_vp, _i, _vp, _f, _f, _f, _vp, _i64, _vp, _i64, _vp, _i64, _vp]),
+    "pgp_find_quads_v4pcs": (_i, [_vp, _i, _vp, _f, _vp, _i64, _vp]),
     "pgp_rigid_from_quads": (_i, [_vp, _i, _vp, _vp, _i64, _vp, _vp]),
     "pgp_generate_pcs": (_i, [_vp, _i, _vp, C.c_uint64, _i64, _vp]),
     "pgp_score_generated": (_i, [_vp, _i, _i]),

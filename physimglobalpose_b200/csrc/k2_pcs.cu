@@ -800,7 +800,7 @@ __global__ void k2s_combo_copy(PpfMapDev m, const int* __restrict__ slot, const 
 }
 
 struct Scratch {
-  DevBuf in_order, list1, list2, cnt, cnt2, off, flag, curr, pairs1, pairs2, quads, bucket_of, key_of, bucket_start, sorted, T, ok, base, qn;
+  DevBuf adj, dist6, in_order, list1, list2, cnt, cnt2, off, flag, curr, pairs1, pairs2, quads, bucket_of, key_of, bucket_start, sorted, T, ok, base, qn;
 };
 // the generator's device scratch belongs to the context (two contexts on one device must not share it); created on first use,
 // released by k2_release (pgp_destroy)
@@ -1000,6 +1000,195 @@ __global__ void k2b_rigid(const float4* __restrict__ P_unsorted, const float4* _
   flag[i] = good ? 1u : 0u;
 }
 
+// ------------------------------------------------------------------------------- operMode 2: V4PCS (tetrahedron base, six-distance join)
+// ExtractCongruentSet in operMode 2 (match4pcsBase.cc:1929-2039) runs ExtractPairs for the six edge lengths d1 = |b1 b2|,
+// d2 = |b1 b3|, d3 = |b1 b4|, d4 = |b2 b3|, d5 = |b2 b4|, d6 = |b3 b4| of the base and FindCongruentQuadrilateralsV4PCS
+// (:978-1044) joins them through (vertex, distance) connectivity maps: the result is every ordered 4-tuple (v1, v2, v3, v4) of
+// model points with (v1,v2) in pairs1, (v1,v3) in pairs2, (v3,v2) in pairs4, (v1,v4) in pairs3, (v4,v2) in pairs5, (v4,v3) in
+// pairs6.  On the device the six pair sets are bit matrices (row i, bit j: the pair filter of pairCreationFunctor.h:167-253 --
+// float norm, |norm - d| <= eps compared in double, no self pairs; the filter is symmetric, so column v of a matrix is its row v),
+// and the join is row ANDs + popcounts, one warp per (base, v1).  Quads come out sorted by (v1, v2, v3, v4); the reference's own
+// order is an unordered_set iteration, so parity is on the set.
+
+// widest random triangle as operMode 0 (SelectRandomTriangle :377-410), then the most voluminous of 100 random fourth points
+// (SelectTetrahedronBase :466-503).  Counter-based RNG like k2_select_bases (the reference draws from rand()).
+__global__ void __launch_bounds__(256) k2v_select_bases(const float4* __restrict__ P, int n, float max_diam, int trials, uint64_t seed, BaseOut* __restrict__ out) {
+  __shared__ float s_val[256];
+  __shared__ int s_idx[256];
+  const int base = blockIdx.x, tid = threadIdx.x;
+  BaseOut o{};
+  for (int attempt = 0; attempt < 16 && !o.ok; ++attempt) {
+    const uint64_t s0 = mix64(seed ^ mix64(0x7E7A00000000ull | ((uint64_t)base << 8) | (uint64_t)attempt));
+    const int first = (int)(mix64(s0) % (uint64_t)n);
+    const float4 p0 = P[first];
+    const float sqmax = max_diam * max_diam;
+    float best = 0.f; int best_t = 0x7fffffff;
+    for (int t = tid; t < trials; t += 256) {
+      const uint64_t r = mix64(s0 + 2 * (uint64_t)t + 1), r2 = mix64(s0 + 2 * (uint64_t)t + 2);
+      const float4 a = P[(int)(r % (uint64_t)n)], b = P[(int)(r2 % (uint64_t)n)];
+      const V3 u = {a.x - p0.x, a.y - p0.y, a.z - p0.z}, w = {b.x - p0.x, b.y - p0.y, b.z - p0.z};
+      const V3 cr = cross(u, w);
+      const float wide = sqrtf(dot(cr, cr));
+      if (wide > best && dot(u, u) < sqmax && dot(w, w) < sqmax) { best = wide; best_t = t; }
+    }
+    s_val[tid] = best; s_idx[tid] = best_t;
+    __syncthreads();
+    for (int o2 = 128; o2 > 0; o2 >>= 1) {
+      if (tid < o2) {
+        const float v = s_val[tid + o2]; const int ix = s_idx[tid + o2];
+        if (v > s_val[tid] || (v == s_val[tid] && ix < s_idx[tid])) { s_val[tid] = v; s_idx[tid] = ix; }
+      }
+      __syncthreads();
+    }
+    const int bt = s_idx[0];
+    const bool have_tri = s_val[0] > 0.f && bt != 0x7fffffff;
+    __syncthreads();
+    if (!have_tri) continue;
+    const int i1 = first, i2 = (int)(mix64(s0 + 2 * (uint64_t)bt + 1) % (uint64_t)n), i3 = (int)(mix64(s0 + 2 * (uint64_t)bt + 2) % (uint64_t)n);
+    const float4 p1 = P[i1], p2 = P[i2], p3 = P[i3];
+    const V3 v1 = {p2.x - p1.x, p2.y - p1.y, p2.z - p1.z}, v2 = {p3.x - p1.x, p3.y - p1.y, p3.z - p1.z};
+    const V3 nrm = cross(v1, v2);
+    float vol = 0.f; int vt = 0x7fffffff, vi = -1;
+    if (tid < 100) {                                    // 100 random fourth points, first maximum in trial order wins (strict '>')
+      vi = (int)(mix64(s0 ^ (0x4444000000000000ull + (uint64_t)tid)) % (uint64_t)n);
+      const float4 q = P[vi];
+      const V3 v3 = {q.x - p1.x, q.y - p1.y, q.z - p1.z};
+      vol = fabsf(dot(nrm, v3)) / 6.0f;
+      vt = tid;
+    }
+    s_val[tid] = vol; s_idx[tid] = vt;
+    __syncthreads();
+    for (int o2 = 128; o2 > 0; o2 >>= 1) {
+      if (tid < o2) {
+        const float v = s_val[tid + o2]; const int ix = s_idx[tid + o2];
+        if (v > s_val[tid] || (v == s_val[tid] && ix < s_idx[tid])) { s_val[tid] = v; s_idx[tid] = ix; }
+      }
+      __syncthreads();
+    }
+    const int wt = s_idx[0];
+    const bool have4 = s_val[0] > 0.f && wt < 100;
+    __syncthreads();
+    if (!have4) continue;
+    const int i4 = (int)(mix64(s0 ^ (0x4444000000000000ull + (uint64_t)wt)) % (uint64_t)n);
+    o.id[0] = i1; o.id[1] = i2; o.id[2] = i3; o.id[3] = i4; o.ok = 1;
+  }
+  if (tid == 0) out[base] = o;
+}
+
+// the six edge lengths of every base: (a - b).norm() as Eigen evaluates it for a Vector3f, sqrt((x^2 + y^2) + z^2)
+__global__ void k2v_base_dists(const float4* __restrict__ P, const BaseOut* __restrict__ bases, int nb, float* __restrict__ dist6) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nb * 6) return;
+  const int b = t / 6, k = t % 6;
+  const int ia = k < 3 ? 0 : k < 5 ? 1 : 2, ib = k == 0 ? 1 : k == 1 ? 2 : k == 2 ? 3 : k == 3 ? 2 : 3;    // (0,1) (0,2) (0,3) (1,2) (1,3) (2,3)
+  const float4 a = P[bases[b].id[ia]], c = P[bases[b].id[ib]];
+  const float x = __fsub_rn(a.x, c.x), y = __fsub_rn(a.y, c.y), z = __fsub_rn(a.z, c.z);
+  dist6[t] = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+}
+
+// bit matrices A[((b * 6 + k) * nq + i) * W + w]: bit (j & 31) of word j >> 5 = pair (i, j) passes the filter for distance k of base b
+__global__ void __launch_bounds__(256) k2v_adjacency(const float4* __restrict__ Q, int nq, int W, const BaseOut* __restrict__ bases,
+                                                     const float* __restrict__ dist6, float eps, uint32_t* __restrict__ A) {
+  const int b = blockIdx.y;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nq * W) return;
+  const int i = (int)(idx % nq), w = (int)(idx / nq);           // consecutive lanes: consecutive i, the same 32 columns
+  uint32_t bits[6] = {0, 0, 0, 0, 0, 0};
+  if (bases[b].ok) {
+    double d[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) d[k] = (double)dist6[b * 6 + k];
+    const double e = (double)eps;
+    const float4 qi = Q[i];
+    const int j0 = w * 32, j1 = min(nq, j0 + 32);
+    for (int j = j0; j < j1; ++j) {
+      if (j == i) continue;
+      const float4 p = Q[j];
+      const float dx = __fsub_rn(qi.x, p.x), dy = __fsub_rn(qi.y, p.y), dz = __fsub_rn(qi.z, p.z);
+      const double dd = (double)__fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fadd_rn(__fmul_rn(dy, dy), __fmul_rn(dz, dz))));
+#pragma unroll
+      for (int k = 0; k < 6; ++k) if (!(fabs(dd - d[k]) > e)) bits[k] |= 1u << (j - j0);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) A[(((size_t)b * 6 + k) * nq + i) * W + w] = bits[k];
+}
+
+// one warp per (base, v1): count (FILL = false) or write (FILL = true, at the scanned offset) the quads that start with v1
+template <bool FILL>
+__global__ void __launch_bounds__(256) k2v_join(int nq, int W, int nb, const BaseOut* __restrict__ bases, const uint32_t* __restrict__ A,
+                                                uint32_t* __restrict__ cnt, int4* __restrict__ out, long long cap) {
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (gw >= (long long)nb * nq) return;
+  const int b = (int)(gw / nq), v1 = (int)(gw % nq);
+  if (!bases[b].ok) { if (!FILL && lane == 0) cnt[gw] = 0; return; }
+  if (FILL && cnt[gw + 1] == cnt[gw]) return;
+  const size_t mat = (size_t)nq * W;
+  const uint32_t* A1 = A + ((size_t)b * 6 + 0) * mat + (size_t)v1 * W;
+  const uint32_t* A2 = A + ((size_t)b * 6 + 1) * mat + (size_t)v1 * W;
+  const uint32_t* A3 = A + ((size_t)b * 6 + 2) * mat + (size_t)v1 * W;
+  const uint32_t* M4 = A + ((size_t)b * 6 + 3) * mat;
+  const uint32_t* M5 = A + ((size_t)b * 6 + 4) * mat;
+  const uint32_t* M6 = A + ((size_t)b * 6 + 5) * mat;
+  uint32_t n = 0;
+  long long wpos = FILL ? (long long)cnt[gw] : 0;
+  for (int w1 = 0; w1 < W; ++w1) {
+    uint32_t word1 = A1[w1];                                   // uniform
+    while (word1) {
+      const int v2 = 32 * w1 + __ffs(word1) - 1;
+      word1 &= word1 - 1;
+      const uint32_t* A4 = M4 + (size_t)v2 * W;                // (v3, v2) in pairs4  <=>  bit v3 of row v2 (symmetric filter)
+      const uint32_t* A5 = M5 + (size_t)v2 * W;
+      for (int c3 = 0; c3 < W; c3 += 32) {
+        const int l3 = c3 + lane;
+        const uint32_t m3 = l3 < W ? (A2[l3] & A4[l3]) : 0u;
+        unsigned nz = __ballot_sync(0xffffffffu, m3 != 0u);
+        while (nz) {
+          const int src = __ffs(nz) - 1;
+          nz &= nz - 1;
+          uint32_t bits3 = __shfl_sync(0xffffffffu, m3, src);
+          while (bits3) {
+            const int v3 = 32 * (c3 + src) + __ffs(bits3) - 1;
+            bits3 &= bits3 - 1;
+            const uint32_t* A6 = M6 + (size_t)v3 * W;          // (v4, v3) in pairs6
+            for (int c4 = 0; c4 < W; c4 += 32) {
+              const int l4 = c4 + lane;
+              const uint32_t m4 = l4 < W ? (A3[l4] & A5[l4] & A6[l4]) : 0u;
+              const uint32_t c = (uint32_t)__popc(m4);
+              if (!FILL) {
+                n += c;
+              } else {
+                uint32_t incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                long long w = wpos + (long long)(incl - c);
+                uint32_t mm = m4;
+                while (mm) {
+                  const int v4 = 32 * l4 + __ffs(mm) - 1;
+                  mm &= mm - 1;
+                  if (w < cap) out[w] = make_int4(v1, v2, v3, v4);
+                  ++w;
+                }
+                wpos += (long long)__shfl_sync(0xffffffffu, incl, 31);
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!FILL) {
+    n = __reduce_add_sync(0xffffffffu, n);
+    if (lane == 0) cnt[gw] = n;
+  }
+}
+
+__global__ void k2v_quad_offsets(const uint32_t* __restrict__ scan, int nq, int nb, uint32_t* __restrict__ qoff) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b <= nb) qoff[b] = scan[(size_t)b * nq];
+}
+
 // one thread: per-base kept counts (capped) -> output offsets
 __global__ void k2b_base_out(const uint32_t* __restrict__ fscan, const uint32_t* __restrict__ qoff, int nb, int max_quads, uint32_t* __restrict__ outoff) {
   if (blockIdx.x || threadIdx.x) return;
@@ -1028,6 +1217,127 @@ __global__ void k2b_append(const float* __restrict__ T, const uint32_t* __restri
 
 }  // namespace
 
+namespace {
+
+// operMode 2, one chunk of bases (device array, `ok` set): six bit matrices per base, count, scan, fill.  Leaves the quads in
+// sc.quads (sorted by base, v1, v2, v3, v4), qoff[0..nb] (device) = first quad of each base, *nquads = their number.
+int v4pcs_chunk(pgp_ctx* ctx, const Model& m, const BaseOut* d_bases, int nb, float eps, uint32_t* qoff, uint64_t* nquads) {
+  Scratch& sc = scratch_of(ctx);
+  const Scene& s = ctx->scene;
+  cudaStream_t st = ctx->stream;
+  const int nq = m.nq, W = (nq + 31) / 32;
+  const size_t rows = (size_t)nb * nq;
+  PGP_CUDA(ctx, sc.adj.reserve(rows * 6 * W * 4 + 64));
+  PGP_CUDA(ctx, sc.dist6.reserve((size_t)nb * 6 * 4 + 64));
+  PGP_CUDA(ctx, sc.cnt.reserve((rows + 1) * 4));
+  uint32_t* cnt = sc.cnt.as<uint32_t>();
+  k2v_base_dists<<<(nb * 6 + 127) / 128, 128, 0, st>>>(s.unsorted.as<float4>(), d_bases, nb, sc.dist6.as<float>());
+  k2v_adjacency<<<dim3((unsigned)(((size_t)nq * W + 255) / 256), (unsigned)nb), 256, 0, st>>>(m.search.as<float4>(), nq, W, d_bases, sc.dist6.as<float>(), eps,
+                                                                                              sc.adj.as<uint32_t>());
+  PGP_CUDA(ctx, cudaMemsetAsync(cnt + rows, 0, 4, st));
+  const unsigned gj = (unsigned)((rows * 32 + 255) / 256);
+  k2v_join<false><<<gj, 256, 0, st>>>(nq, W, nb, d_bases, sc.adj.as<uint32_t>(), cnt, nullptr, 0);
+  ctx->launches += 3;
+  PGP_CUDA(ctx, cudaGetLastError());
+  int rc = scan_u32(ctx, cnt, (int64_t)rows, nquads);
+  if (rc) return rc;
+  if (*nquads == 0 || *nquads >= (1ull << 31)) return PGP_OK;
+  PGP_CUDA(ctx, sc.quads.reserve((size_t)*nquads * 16));
+  k2v_join<true><<<gj, 256, 0, st>>>(nq, W, nb, d_bases, sc.adj.as<uint32_t>(), cnt, sc.quads.as<int4>(), (long long)*nquads);
+  k2v_quad_offsets<<<(nb + 256) / 256, 256, 0, st>>>(cnt, nq, nb, qoff);
+  ctx->launches += 2;
+  PGP_CUDA(ctx, cudaGetLastError());
+  return PGP_OK;
+}
+
+// pgp_generate_pcs in operMode 2: tetrahedron bases -> V4PCS quads -> rigid transforms -> per-base subset -> append
+int generate_v4pcs(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, int64_t max_hyp, float max_diam, int64_t* n_hyp) {
+  Scratch& sc = scratch_of(ctx);
+  const Scene& s = ctx->scene;
+  cudaStream_t st = ctx->stream;
+  const int nb_total = std::max(1, o->n_bases), nq = m.nq, W = (nq + 31) / 32;
+  const float eps = s.delta;
+  PGP_CUDA(ctx, sc.base.reserve((size_t)nb_total * sizeof(BaseOut) + 64));
+  PGP_CUDA(ctx, m.gen_T.reserve((size_t)std::max<int64_t>(max_hyp, 1) * 48));
+  BaseOut* d_bases_all = reinterpret_cast<BaseOut*>(sc.base.as<char>() + 64);
+  k2v_select_bases<<<nb_total, 256, 0, st>>>(s.unsorted.as<float4>(), s.n, max_diam, std::max(1, o->base_trials), seed, d_bases_all);
+  ctx->launches++;
+  PGP_CUDA(ctx, cudaGetLastError());
+  // bases per chunk: six nq x nq bit matrices each, about 1 GB in all
+  int chunk = (int)std::max<double>(1.0, std::min<double>(64.0, 1.0e9 / (24.0 * (double)nq * (double)W)));
+  int64_t cur = 0;
+  int nb = 0;
+  for (int base0 = 0; base0 < nb_total && cur < max_hyp; base0 += nb) {
+    nb = std::min(chunk, nb_total - base0);
+    const BaseOut* d_bases = d_bases_all + base0;
+    PGP_CUDA(ctx, sc.off.reserve((size_t)(4 * nb + 16) * 4 + 64));
+    uint32_t* qoff = sc.off.as<uint32_t>();            // nb + 1
+    uint32_t* outoff = qoff + nb + 2;                  // nb + 1
+    uint64_t nquads = 0;
+    int rc = v4pcs_chunk(ctx, m, d_bases, nb, eps, qoff, &nquads);
+    if (rc) return rc;
+    if (nquads == 0) continue;
+    if (nquads >= (1ull << 31)) {
+      if (nb > 1) { chunk = std::max(1, nb / 2); nb = 0; continue; }
+      return pgp_fail(ctx, PGP_E_TOO_LARGE, "congruent quads of one base exceed 2^31");
+    }
+    PGP_CUDA(ctx, sc.T.reserve((size_t)nquads * 48));
+    PGP_CUDA(ctx, sc.flag.reserve((size_t)(nquads + 1) * 4));
+    uint32_t* flag = sc.flag.as<uint32_t>();
+    PGP_CUDA(ctx, cudaMemsetAsync(flag + nquads, 0, 4, st));
+    const unsigned gr = (unsigned)((nquads + 127) / 128);
+    k2b_rigid<<<gr, 128, 0, st>>>(s.unsorted.as<float4>(), m.search.as<float4>(), d_bases, base0, qoff, nb, sc.quads.as<int4>(), (long long)nquads,
+                                  o->max_quads_per_base, seed, sc.T.as<float>(), flag);
+    ctx->launches++;
+    PGP_CUDA(ctx, cudaGetLastError());
+    PGP_CUDA(ctx, ctx->scene.scratch.reserve((size_t)((nquads + 1) / 2048 + 4096) * 4));
+    rc = pgp_scan_exclusive_u32(ctx, flag, (int64_t)nquads + 1, ctx->scene.scratch.as<uint32_t>());
+    if (rc) return rc;
+    k2b_base_out<<<1, 32, 0, st>>>(flag, qoff, nb, o->max_quads_per_base, outoff);
+    const int64_t room = max_hyp - cur;
+    k2b_append<<<gr, 128, 0, st>>>(sc.T.as<float>(), flag, qoff, nb, o->max_quads_per_base, outoff, (long long)nquads, m.gen_T.as<float>() + 12 * cur, room);
+    ctx->launches += 2;
+    PGP_CUDA(ctx, cudaGetLastError());
+    uint32_t added = 0;
+    PGP_CUDA(ctx, cudaMemcpyAsync(&added, outoff + nb, 4, cudaMemcpyDeviceToHost, st));
+    PGP_CUDA(ctx, cudaStreamSynchronize(st));
+    cur += std::min<int64_t>(room, (int64_t)added);
+  }
+  PGP_CUDA(ctx, cudaStreamSynchronize(st));
+  PGP_CUDA(ctx, cudaGetLastError());
+  m.n_gen = std::min<int64_t>(cur, max_hyp);
+  m.n_gen_bases = nb_total;
+  *n_hyp = m.n_gen;
+  return PGP_OK;
+}
+
+}  // namespace
+
+// Congruent quads of ONE base in operMode 2 (parity hook): base4 = scene ids, quads_host: cap x 4, sorted by (v1, v2, v3, v4)
+int k2_find_quads_v4pcs(pgp_ctx* ctx, const Model& m, const int32_t* base4, float eps, int32_t* quads_host, int64_t cap, int64_t* n_quads) {
+  Scratch& sc = scratch_of(ctx);
+  const Scene& s = ctx->scene;
+  for (int k = 0; k < 4; ++k)
+    if (base4[k] < 0 || base4[k] >= s.n) return pgp_fail(ctx, PGP_E_INVALID, "base id out of range");
+  PGP_CUDA(ctx, sc.base.reserve(sizeof(BaseOut) + 64));
+  PGP_CUDA(ctx, sc.off.reserve(64 * 4));
+  BaseOut h{};
+  for (int k = 0; k < 4; ++k) h.id[k] = base4[k];
+  h.ok = 1;
+  BaseOut* d_base = reinterpret_cast<BaseOut*>(sc.base.as<char>() + 64);
+  PGP_CUDA(ctx, cudaMemcpyAsync(d_base, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+  PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // h is a local
+  uint64_t nquads = 0;
+  int rc = v4pcs_chunk(ctx, m, d_base, 1, eps, sc.off.as<uint32_t>(), &nquads);
+  if (rc) return rc;
+  if (nquads >= (1ull << 31)) return pgp_fail(ctx, PGP_E_TOO_LARGE, "congruent quads of one base exceed 2^31");
+  *n_quads = (int64_t)nquads;
+  const int64_t k = std::min<int64_t>((int64_t)nquads, cap);
+  if (k > 0 && quads_host) PGP_CUDA(ctx, cudaMemcpyAsync(quads_host, sc.quads.p, (size_t)k * 16, cudaMemcpyDeviceToHost, ctx->stream));
+  PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PGP_OK;
+}
+
 int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, int64_t max_hyp, int64_t* n_hyp) {
   Scratch& sc = scratch_of(ctx);
   const Scene& s = ctx->scene;
@@ -1039,6 +1349,7 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
   const int nq = m.nq;
   float max_diam = o->max_base_diameter;
   if (!(max_diam > 0.f)) max_diam = m.search_diameter;   // P_diameter_ estimate of init() (:274-283)
+  if (o->mode == 2) return generate_v4pcs(ctx, m, o, seed, max_hyp, max_diam, n_hyp);
   const float eps = s.delta;          // distance_factor * options_.delta, distance_factor = 1 (match4pcsBase.h:99)
   // join grid (IndexedNormalSet, normalset.h:117-123); buckets per base capped at 2^15 (collisions are filtered by the key)
   const float eps_n = eps / m.unit_ratio;
@@ -1337,7 +1648,7 @@ uint32_t k2_stocs_engine_seed(uint64_t seed, int base, int attempt) { return sto
 void k2_release(pgp_ctx* ctx) {
   if (!ctx->k2_scratch) return;
   Scratch* sc = static_cast<Scratch*>(ctx->k2_scratch);
-  for (DevBuf* b : {&sc->in_order, &sc->list1, &sc->list2, &sc->cnt, &sc->cnt2, &sc->off, &sc->flag, &sc->curr, &sc->pairs1, &sc->pairs2, &sc->quads,
+  for (DevBuf* b : {&sc->adj, &sc->dist6, &sc->in_order, &sc->list1, &sc->list2, &sc->cnt, &sc->cnt2, &sc->off, &sc->flag, &sc->curr, &sc->pairs1, &sc->pairs2, &sc->quads,
                     &sc->bucket_of, &sc->key_of, &sc->bucket_start, &sc->sorted, &sc->T, &sc->ok, &sc->base, &sc->qn})
     b->release();
   delete sc;

@@ -606,6 +606,15 @@ int pgp_find_quads(pgp_ctx* ctx, int obj, const int32_t* base4, float inv1, floa
   return k2_find_quads(ctx, *m, base4, inv1, inv2, eps, p1, n1, p2, n2, quads, cap, n_quads);
 }
 
+int pgp_find_quads_v4pcs(pgp_ctx* ctx, int obj, const int32_t* base4, float eps, int32_t* quads, int64_t cap, int64_t* n_quads) {
+  CHECK_CTX(ctx);
+  Model* m = get_model(ctx, obj);
+  if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", obj);
+  if (!ctx->scene.ready) return pgp_fail(ctx, PGP_E_NO_SCENE, "pgp_set_scene first");
+  if (!base4 || !n_quads || cap < 0) return pgp_fail(ctx, PGP_E_INVALID, "bad argument");
+  return k2_find_quads_v4pcs(ctx, *m, base4, eps, quads, cap, n_quads);
+}
+
 int pgp_rigid_from_quads(pgp_ctx* ctx, int obj, const int32_t* base4, const int32_t* quads, int64_t n, float* T, uint8_t* ok) {
   CHECK_CTX(ctx);
   Model* m = get_model(ctx, obj);

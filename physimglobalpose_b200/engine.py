@@ -233,6 +233,14 @@ class PoseEngine:
             return self.find_quads(obj, base4, inv1, inv2, eps, pairs1, pairs2, cap=int(n.value))
         return out[: n.value].copy()
 
+    def find_quads_v4pcs(self, obj: int, base4, eps: float, cap: int = 1 << 22) -> np.ndarray:
+        """operMode 2: congruent quads of one base (4 scene ids), sorted by (v1, v2, v3, v4)."""
+        b = np.ascontiguousarray(base4, np.int32)
+        out = np.zeros((cap, 4), np.int32)
+        n = C.c_int64(0)
+        self._check(self._lib.pgp_find_quads_v4pcs(self._ctx, obj, _ptr(b), float(eps), _ptr(out), cap, C.byref(n)))
+        return out[: min(n.value, cap)].copy()
+
     def rigid_from_quads(self, obj: int, base4, quads):
         b = np.ascontiguousarray(base4, np.int32)
         q = np.ascontiguousarray(quads, np.int32).reshape(-1, 4)

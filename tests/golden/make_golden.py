@@ -89,6 +89,7 @@ def main():
                         model_nrm=seg.model_nrm, delta=np.float64(seg.delta), cP=scP, cQ=scQ, bases=np.array(bases, np.int32), invariants=np.array(invs, np.float32),
                         **pairs_out, **quads_out, **rigid_out)
     mint_stocs()
+    mint_mode2()
     print("golden vectors written:", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 
@@ -132,6 +133,24 @@ def mint_stocs():
                         model_nrm=seg.model_nrm, delta=np.float64(seg.delta), map_keys=keys4, map_offsets=offsets, map_pairs=pairs,
                         scene_pairs=sp, scene_keys=scene_keys, user_seed=np.int64(user_seed), base_ok=np.array(ok_l, bool),
                         base_ids=np.array(ids_l, np.int32), base_inv=np.array(inv_l, np.float32), base_attempts=np.array(att_l, np.int32), **quads)
+
+
+def mint_mode2():
+    """operMode 2 (V4PCS): tetrahedron bases drawn by the reference's SelectTetrahedronBase after srand(seed), and the congruent
+    quads its ExtractCongruentSet finds for them (six ExtractPairs + FindCongruentQuadrilateralsV4PCS) -- from the reference itself."""
+    seg = synth.make_segment_problem(300, 400, 0.005, seed=401)
+    ref = RefOracle(seg.scene_xyz, seg.scene_nrm, seg.model_xyz, seg.model_nrm, seg.model_xyz, seg.model_nrm, seg.delta)
+    bases, quads, offs = [], [], [0]
+    for seed in range(1, 13):
+        ok, b = ref.select_tetrahedron(seed)
+        assert ok
+        q = ref.congruent_set_mode2(b)
+        q = np.array(sorted(map(tuple, q.tolist())), np.int32).reshape(-1, 4)      # the reference's order is an unordered_set iteration
+        bases.append(b); quads.append(q); offs.append(offs[-1] + len(q))
+    out = os.path.join(HERE, "mode2_small.npz")
+    np.savez_compressed(out, scene_xyz=seg.scene_xyz, scene_nrm=seg.scene_nrm, model_xyz=seg.model_xyz, model_nrm=seg.model_nrm,
+                        delta=np.float64(seg.delta), bases=np.array(bases, np.int32), quads=np.concatenate(quads), quad_offsets=np.array(offs, np.int64))
+    print("mode2_small.npz:", len(bases), "bases,", offs[-1], "quads,", os.path.getsize(out), "bytes")
 
 
 if __name__ == "__main__":

@@ -188,3 +188,42 @@ def test_segment_preparation_on_device(engine):
     # a class that is not in the mask: empty segment, no error
     xyz, nrm, n_raw = engine.prepare_segment(raw, mask, 77, g["K"])
     assert len(xyz) == 0 and n_raw == 0
+
+
+def test_v4pcs_golden(engine):
+    """operMode 2: the device's bit-matrix join returns, for the reference's own tetrahedron bases, exactly the quads of the
+    reference's ExtractCongruentSet / FindCongruentQuadrilateralsV4PCS (tests/golden/mode2_small.npz), and every quad's rigid
+    transform is what pgp_rigid_from_quads gives for the operMode-0 path (same function of the reference)."""
+    g = np.load(os.path.join(G, "mode2_small.npz"))
+    engine.set_scene(g["scene_xyz"], g["scene_nrm"], float(g["delta"]))
+    engine.set_model(0, g["model_xyz"], g["model_nrm"])
+    offs = g["quad_offsets"]
+    for k, b in enumerate(g["bases"]):
+        want = g["quads"][offs[k]:offs[k + 1]]
+        got = engine.find_quads_v4pcs(0, b, float(g["delta"]))
+        assert np.array_equal(got, want)
+
+
+def test_generate_v4pcs_finds_the_pose(engine, port_lib):
+    """pgp_generate_pcs in operMode 2 end to end on a segment problem: tetrahedron bases -> quads -> rigid transforms.  The
+    best-scoring hypothesis reaches (most of) the LCP of the ground-truth pose -- the objective the search maximises; a partial
+    view of a box admits other alignments of the same quality, so the pose itself is not asserted -- the generated transforms are
+    rigid, the device scores equal the oracle's, and a seed reproduces the batch bit for bit."""
+    from physimglobalpose_b200 import synth
+    seg = synth.make_segment_problem(600, 800, 0.005, seed=411)
+    engine.set_scene(seg.scene_xyz, seg.scene_nrm, seg.delta)
+    engine.set_model(0, seg.model_xyz, seg.model_nrm)
+    n = engine.generate_pcs(0, seed=3, max_hyp=20000, n_bases=60, max_quads_per_base=100, mode=2)
+    assert n > 100
+    T1 = engine.get_generated(0)[0].copy()
+    R = T1[:, :, :3].astype(np.float64)
+    assert np.allclose(R @ R.transpose(0, 2, 1), np.eye(3), atol=1e-4)
+    engine.score_generated(0, "count")
+    _, counts, _ = engine.get_generated(0)
+    o = port_lib.PortOracle(seg.scene_xyz, seg.scene_nrm, seg.model_xyz, seg.model_nrm, seg.model_xyz, seg.model_nrm, seg.delta)
+    assert np.array_equal(counts[:300], o.verify(T1[:300]))
+    gt_count = int(o.verify(engine.pose_to_centred(0, seg.gt_pose[None]))[0])
+    top = engine.topk(0, 1)
+    assert top["count"][0] >= 0.7 * gt_count, (int(top["count"][0]), gt_count)
+    n2 = engine.generate_pcs(0, seed=3, max_hyp=20000, n_bases=60, max_quads_per_base=100, mode=2)
+    assert n2 == n and np.array_equal(engine.get_generated(0)[0], T1)

@@ -202,3 +202,29 @@ def test_segment_port_reproduces_the_fixture_clouds():
         xyz, nrm, n_raw = segment_port.prepare_segment(dec, mask, C1_CLASSES[str(name)], g["K"])
         assert n_raw == int(g[f"{name}_n_raw"])
         assert np.array_equal(xyz, g[f"{name}_seg_xyz"]) and np.array_equal(nrm, g[f"{name}_seg_nrm"])
+
+
+# ---------------------------------------------------------------- operMode 2 (V4PCS)
+def test_v4pcs_port_matches_reference_golden():
+    """The numpy restatement of ExtractCongruentSet in operMode 2 (six pair extractions + FindCongruentQuadrilateralsV4PCS,
+    match4pcsBase.cc:978-1044,1929-2039) gives the reference's quads for the reference's own tetrahedron bases
+    (tests/golden/mode2_small.npz, minted from oracle/_ref); live against the reference too where it is built."""
+    from oracle import pyoracle
+    from physimglobalpose_b200 import synth
+    g = np.load(os.path.join(G, "mode2_small.npz"))
+    cP = synth.seq_centroid_f32(g["scene_xyz"]); cQ = synth.seq_centroid_f32(g["model_xyz"])
+    P = (g["scene_xyz"] - cP).astype(np.float32); Q = (g["model_xyz"] - cQ).astype(np.float32)
+    offs = g["quad_offsets"]
+    for k, b in enumerate(g["bases"]):
+        want = g["quads"][offs[k]:offs[k + 1]]
+        got = pyoracle.v4pcs_quads_port(P, Q, b, float(g["delta"]))
+        assert np.array_equal(got, want)
+    if pyoracle.have_ref():
+        ref = pyoracle.RefOracle(g["scene_xyz"], g["scene_nrm"], g["model_xyz"], g["model_nrm"], g["model_xyz"], g["model_nrm"], float(g["delta"]))
+        assert np.array_equal(ref.centred(0)[0], P) and np.array_equal(ref.centred(1)[0], Q)
+        for seed in (21, 22, 23):
+            ok, b = ref.select_tetrahedron(seed)
+            assert ok
+            q = ref.congruent_set_mode2(b)
+            assert len(set(map(tuple, q.tolist()))) == len(q)
+            assert np.array_equal(np.array(sorted(map(tuple, q.tolist())), np.int32).reshape(-1, 4), pyoracle.v4pcs_quads_port(P, Q, b, float(g["delta"])))

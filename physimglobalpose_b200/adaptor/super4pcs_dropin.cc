@@ -14,8 +14,9 @@
 // empty (the reference: exit(-1) on unreadable input, uninitialised outputs on exceptions).
 //
 // Environment: PGP_DEVICE (CUDA device, default 0), PGP_LCP_MODE = weighted (default, the shipped
-// WeightedVerify) | count, PGP_DELTA (default 0.005 = S4/super4pcs_test.cc:20), PGP_SEED, PGP_PCS_MODE = stocs | super4pcs
-// (default: stocs when the caller's PPFMap is not empty -- the reference hard-sets operMode 1, match4pcsBase.cc:300).
+// WeightedVerify) | count, PGP_DELTA (default 0.005 = S4/super4pcs_test.cc:20), PGP_SEED, PGP_PCS_MODE = stocs | super4pcs | v4pcs
+// (operMode 1 / 0 / 2; default: stocs when the caller's PPFMap is not empty -- the reference hard-sets operMode 1,
+// match4pcsBase.cc:300; operMode 2 is scored with Verify like the reference does, :1498-1499).
 #include <zlib.h>
 
 #include <cmath>
@@ -228,7 +229,8 @@ void getProbableTransformsSuper4PCS(std::string input1, std::string input2, std:
     pgp_pcs_default_opts(&opts);                    // 100 bases x <= 100 congruent quads (match4pcsBase.cc:290,1858)
     const char* pe = getenv("PGP_PCS_MODE");
     bool stocs = !PPFMap.empty() && !seg.nrm.empty() && !search.nrm.empty();
-    if (pe && !strcmp(pe, "super4pcs")) stocs = false;
+    const bool v4pcs = pe && !strcmp(pe, "v4pcs");
+    if (pe && (!strcmp(pe, "super4pcs") || v4pcs)) stocs = false;
     if (pe && !strcmp(pe, "stocs") && PPFMap.empty()) {
       if (pgp_build_ppf_map(ctx, 0)) return fail("build_ppf_map");      // no PPFMap.txt was loaded: build the map from the search cloud
       stocs = !seg.nrm.empty() && !search.nrm.empty();
@@ -247,7 +249,8 @@ void getProbableTransformsSuper4PCS(std::string input1, std::string input2, std:
       offs.push_back((int64_t)prs.size() / 2);
       if (pgp_set_ppf_map(ctx, 0, keys4.data(), offs.data(), prs.data(), (int64_t)keys4.size() / 4)) return fail("set_ppf_map");
     }
-    opts.mode = stocs ? 1 : 0;
+    opts.mode = v4pcs ? 2 : stocs ? 1 : 0;
+    if (v4pcs) mode = PGP_LCP_COUNT;                // verifyRigidTransform uses Verify in operMode 2 (match4pcsBase.cc:1498-1499)
     int64_t n_hyp = 0;
     if (pgp_generate_pcs(ctx, 0, &opts, seed, 10000, &n_hyp)) return fail("generate_pcs");
     if (n_hyp == 0) return;

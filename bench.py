@@ -153,6 +153,24 @@ def cpu_reference_run(prob, T, seconds_per_step: float, steps: int, warmup: int)
         total / steps * 1e3, counts, sample
 
 
+def cpu_secondary(prob, T) -> dict:
+    """BASELINE.md 3: the reference's WeightedVerify (the shipped scorer) and its kd-tree build (Match4PCSBase::init), timed on one
+    host thread next to the device figures of `secondary` (weighted_lcp, scene_grid_build_ms).  A bounded sample: ~2 s."""
+    from oracle import pyoracle
+    if not pyoracle.have_ref():
+        return {}
+    args = (prob.scene_xyz, prob.scene_nrm, prob.model_xyz, prob.model_nrm, prob.model_xyz, prob.model_nrm, prob.delta)
+    t0 = time.perf_counter()
+    o = pyoracle.RefOracle(*args)
+    init_ms = (time.perf_counter() - t0) * 1e3
+    n = 1000
+    t0 = time.perf_counter()
+    o.weighted_verify(T[:n])
+    dt = time.perf_counter() - t0
+    return {"cpu_weighted_verify": {"value": n / dt, "unit": UNIT, "cores": 1, "kind": "reference", "sample": f"first {n} hypotheses, WeightedVerify, 1 thread"},
+            "cpu_init_kdtree_ms": {"value": init_ms, "unit": "ms", "what": "Match4PCSBase::init incl. the kd-tree build, 100k-pt scene, 1 thread"}}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -362,6 +380,7 @@ def run_ours(args, rank, local_rank, world):
             line["secondary"] = secondary_metrics(eng, prob, T_dev, counts_dev, scores_dev, flush, stream)
             base, _, cpu_counts, sample = cpu_reference_run(prob, T, seconds_per_step=12.0, steps=1, warmup=0)
             line["cpu_baseline"] = base
+            line["secondary"].update(cpu_secondary(prob, T))
             got = counts_host.numpy()[:sample].astype(np.uint32)
             line["parity"] = {"checked": int(sample), "mismatches": int((got != cpu_counts).sum())}
         emit(line)

@@ -1,9 +1,10 @@
-"""CPU property tests of the three conservative bounds the CUDA path relies on (numpy restatements of the device formulas, fp32
+"""CPU property tests of the conservative bounds the CUDA path relies on (numpy restatements of the device formulas, fp32
 where the device uses fp32).  They do not run the kernels -- tests/test_gpu_lcp.py does, against the oracle -- they check that
 the MATH of the bounds is sound on random inputs:
   * domination pruning of candidate lists   (physimglobalpose_b200/csrc/k1_fine.cu: dominated(), k1f_classify / k1w_count)
   * spectral-norm bound of the group cull    (physimglobalpose_b200/csrc/k3_lcp.cu: score_hypothesis, `snorm`)
-  * separable gap distance field K1d         (physimglobalpose_b200/csrc/k1_fine.cu: k1d_pass)"""
+  * separable gap distance field K1d         (physimglobalpose_b200/csrc/k1_fine.cu: k1d_pass)
+  * tri-state voxel labels K1b               (physimglobalpose_b200/csrc/k1_fine.cu: k1f_classify, k1_build_fine)"""
 import numpy as np
 
 f32 = np.float32
@@ -115,3 +116,49 @@ def test_gap_distance_field_is_a_lower_bound():
         true = np.sqrt(((q[:, None, :] - pts[None]) ** 2).sum(-1)).min(1)
         lower = h * np.sqrt(S[qc[:, 0], qc[:, 1], qc[:, 2]])
         assert np.all(lower <= true + 1e-12)
+
+
+def test_tristate_labels_are_conservative():
+    """The IN / OUT labels of K1b (k1_fine.cu: k1f_classify, thresholds and `inflate` from k1_build_fine) restated in numpy on a
+    small scene: for queries anywhere inside a voxel's INFLATED box -- where K3's fast FMA transform may place a query whose
+    reference-rounded position the exact test uses -- an IN voxel always has a scene point with fp32 d2 <= delta^2 and an OUT voxel
+    never has one, so only AMBIG voxels need the exact test."""
+    rng = np.random.default_rng(5)
+    delta = f32(0.01)
+    r2 = f32(delta * delta)
+    # scene: a jittered plane patch and a small box corner, centred like the engine does
+    n = 400
+    pts = np.c_[rng.uniform(-0.06, 0.06, (n, 2)), rng.uniform(-0.001, 0.001, n)]
+    pts[: n // 3, 2] += 0.03 + rng.uniform(0, 0.02, n // 3)
+    pts = (pts - pts.mean(0)).astype(f32)
+    h = f32(delta * f32(1.0 + 1.0 / 256.0))
+    lo = (pts.min(0) - f32(2.5) * h).astype(f32)
+    dim = ((pts.max(0).astype(np.float64) - lo) / h).astype(int) + 4
+    F = 8
+    hf = f32(h / F)
+    maxabs = f32(max(np.abs(lo).max(), np.abs(lo + h * dim.astype(f32)).max()))
+    pos_bound = f32(3.0) * maxabs
+    eps_pos = f32(32.0 * 5.9604645e-8) * (pos_bound + maxabs)
+    inflate = hf * (f32(2e-3) + f32(16.0 * 5.9604645e-8) * f32(dim.max() * F)) + eps_pos
+    dlo2 = f32((0.01 * (1 - 1e-5)) ** 2)
+    dhi2 = f32((0.01 * (1 + 1e-5)) ** 2)
+    hs = f32(0.5) * hf + inflate
+    # voxels: a random sample of those within ~2 delta of some scene point (elsewhere everything is trivially OUT)
+    seeds = pts[rng.integers(0, n, 6000)] + rng.uniform(-0.02, 0.02, (6000, 3)).astype(f32)
+    vidx = np.floor((seeds - lo) / hf).astype(np.int64)
+    c = (lo + (vidx.astype(f32) + f32(0.5)) * hf).astype(f32)                           # voxel centres
+    a = np.abs(pts[None, :, :] - c[:, None, :]).astype(f32)                             # (voxels, points, 3)
+    lo_d = np.maximum(a - hs, 0).astype(f32)
+    hi_d = (a + hs).astype(f32)
+    mind2 = (lo_d * lo_d).sum(2).astype(f32)
+    maxd2 = (hi_d * hi_d).sum(2).astype(f32)
+    is_in = (maxd2 <= dlo2).any(1)
+    is_out = (mind2 > dhi2).all(1)
+    assert is_in.sum() > 500 and is_out.sum() > 500 and (~is_in & ~is_out).sum() > 200    # all three classes are exercised
+    # queries anywhere in the inflated box, including its corners
+    for rep in range(6):
+        e = rng.uniform(-1, 1, c.shape) if rep else np.sign(rng.uniform(-1, 1, c.shape))
+        q = (c + e.astype(f32) * hs).astype(f32)
+        exists = (_d2(q[:, None, :], pts[None, :, :]) <= r2).any(1)
+        assert exists[is_in].all()
+        assert not exists[is_out].any()

@@ -49,7 +49,12 @@ def test_domination_pruning_keeps_existence_and_the_nearest_point():
                 bc2, best = c2[i], i
         # exact-dominator rule of k1w_count: dominator = the closest-to-centre point of all
         star = int(np.argmin(c2))
-        kept_w = [i for i in range(n) if not _dominated(pts[i], pts[star], hs, c2[i], c2[star], margin)]
+        # ... on top of K1c's own bound: lo(p)^2 <= min(min_p' hi(p')^2 (1 + 4e-5), (delta (1 + 1e-5))^2)   (wlist_threshold)
+        a_all = np.abs(pts - c).astype(f32)
+        lo_all = np.maximum(a_all - hs, 0).astype(f32); hi_all = (a_all + hs).astype(f32)
+        lo2 = (lo_all * lo_all).sum(1).astype(f32); hi2 = (hi_all * hi_all).sum(1).astype(f32)
+        thr = min(f32(hi2.min() * f32(1.0 + 4e-5)), dhi2)
+        kept_w = [i for i in range(n) if lo2[i] <= thr and not _dominated(pts[i], pts[star], hs, c2[i], c2[star], margin)]
         removed_total += n - len(kept_w); kept_total += len(kept_w)
         q = (c + rng.uniform(-float(hs), float(hs), (400, 3))).astype(f32)
         d2 = _d2(q[:, None, :], pts[None, :, :])                               # (400, n)

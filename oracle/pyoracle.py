@@ -2,6 +2,8 @@
 
   RefOracle   oracle/_ref/libs4ref.so       the reference engine compiled in place (oracle/Makefile `ref`)
   PortOracle  oracle/_build/liblcp_oracle.so  the plain-C restatement (oracle/lcp_oracle.c)
+  v4pcs_quads_port                          numpy restatement of ExtractCongruentSet in operMode 2 (V4PCS), pinned against
+                                            tests/golden/mode2_small.npz and live against RefOracle
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 import this module.  The product package (physimglobalpose_b200/) never does.

@@ -90,6 +90,7 @@ def main():
                         **pairs_out, **quads_out, **rigid_out)
     mint_stocs()
     mint_mode2()
+    mint_full_shapes()
     print("golden vectors written:", sorted(f for f in os.listdir(HERE) if f.endswith(".npz")))
 
 
@@ -151,6 +152,24 @@ def mint_mode2():
     np.savez_compressed(out, scene_xyz=seg.scene_xyz, scene_nrm=seg.scene_nrm, model_xyz=seg.model_xyz, model_nrm=seg.model_nrm,
                         delta=np.float64(seg.delta), bases=np.array(bases, np.int32), quads=np.concatenate(quads), quad_offsets=np.array(offs, np.int64))
     print("mode2_small.npz:", len(bases), "bases,", offs[-1], "quads,", os.path.getsize(out), "bytes")
+
+
+def mint_full_shapes():
+    """BASELINE configs[1] and configs[4] shapes at FULL cloud sizes, from the reference itself: the clouds come from the seeded
+    generator (synth.make_problem, numpy only: identical on every machine), so only the hypothesis sample and the reference's
+    numbers are stored.  Verify / WeightedVerify of Match4PCSBase on a sample of hypotheses spread over the benchmark's batch."""
+    out = {}
+    for tag, (nm, ns, n_hyp, n_sample, seed_p, seed_t) in {"c2": (2000, 100000, 100000, 400, 1234, 4321), "c5": (30000, 300000, 2000, 60, 51, 52)}.items():
+        prob = synth.make_problem(nm, ns, 0.01, seed=seed_p)
+        T = synth.make_hypotheses(prob, n_hyp, seed=seed_t)
+        idx = np.unique(np.r_[0, 1, 2, np.random.default_rng(7).choice(n_hyp, n_sample - 3, replace=False)]).astype(np.int64)
+        ref = RefOracle(prob.scene_xyz, prob.scene_nrm, prob.model_xyz, prob.model_nrm, prob.model_xyz, prob.model_nrm, prob.delta)
+        counts = ref.verify(T[idx])
+        ws, wn = ref.weighted_verify(T[idx])
+        out.update({f"{tag}_shape": np.array([nm, ns, n_hyp, seed_p, seed_t], np.int64), f"{tag}_idx": idx, f"{tag}_counts": counts,
+                    f"{tag}_wscore": ws, f"{tag}_wnreg": wn, f"{tag}_T_check": T[idx[:4]]})
+        print(tag, "reference counts on", len(idx), "hypotheses; max", counts.max(), "at", idx[counts.argmax()])
+    np.savez_compressed(os.path.join(HERE, "lcp_full_shapes.npz"), **out)
 
 
 if __name__ == "__main__":

@@ -227,3 +227,27 @@ def test_generate_v4pcs_finds_the_pose(engine, port_lib):
     assert top["count"][0] >= 0.7 * gt_count, (int(top["count"][0]), gt_count)
     n2 = engine.generate_pcs(0, seed=3, max_hyp=20000, n_bases=60, max_quads_per_base=100, mode=2)
     assert n2 == n and np.array_equal(engine.get_generated(0)[0], T1)
+
+
+def test_lcp_full_shapes_golden(engine):
+    """BASELINE configs[1] (2k / 100k) and configs[4] (30k / 300k) at full cloud sizes against numbers minted from the reference
+    itself (tests/golden/lcp_full_shapes.npz): inlier counts, weighted scores and gated counts bit for bit."""
+    from physimglobalpose_b200 import synth
+
+    def _full_shape(g, tag):          # the clouds and hypotheses come from the seeded generator; the file holds the reference's numbers
+        nm, ns, n_hyp, seed_p, seed_t = (int(x) for x in g[f"{tag}_shape"])
+        prob = synth.make_problem(nm, ns, 0.01, seed=seed_p)
+        T = synth.make_hypotheses(prob, n_hyp, seed=seed_t)
+        idx = g[f"{tag}_idx"]
+        assert np.array_equal(T[idx[:4]], g[f"{tag}_T_check"])
+        return prob, T[idx]
+
+    g = np.load(os.path.join(G, "lcp_full_shapes.npz"))
+    for tag in ("c2", "c5"):
+        prob, T = _full_shape(g, tag)
+        engine.set_scene(prob.scene_xyz, prob.scene_nrm, prob.delta)
+        engine.set_model(0, prob.model_xyz, prob.model_nrm)
+        counts, _ = engine.score_lcp(0, T, "count")
+        assert np.array_equal(counts, g[f"{tag}_counts"])
+        wn, ws = engine.score_lcp(0, T, "weighted")
+        assert np.array_equal(ws, g[f"{tag}_wscore"]) and np.array_equal(wn, g[f"{tag}_wnreg"].astype(np.uint32))

@@ -228,3 +228,27 @@ def test_v4pcs_port_matches_reference_golden():
             q = ref.congruent_set_mode2(b)
             assert len(set(map(tuple, q.tolist()))) == len(q)
             assert np.array_equal(np.array(sorted(map(tuple, q.tolist())), np.int32).reshape(-1, 4), pyoracle.v4pcs_quads_port(P, Q, b, float(g["delta"])))
+
+
+# ---------------------------------------------------------------- full-size shapes (configs[1], configs[4])
+def _full_shape(g, tag):
+    from physimglobalpose_b200 import synth
+    nm, ns, n_hyp, seed_p, seed_t = (int(x) for x in g[f"{tag}_shape"])
+    prob = synth.make_problem(nm, ns, 0.01, seed=seed_p)
+    T = synth.make_hypotheses(prob, n_hyp, seed=seed_t)
+    idx = g[f"{tag}_idx"]
+    assert np.array_equal(T[idx[:4]], g[f"{tag}_T_check"])      # the seeded generator reproduces the hypotheses the vectors were minted on
+    return prob, T[idx]
+
+
+def test_port_matches_reference_golden_at_full_shapes(port_lib):
+    """The C restatement against the reference's own Verify / WeightedVerify at the FULL cloud sizes of BASELINE configs[1]
+    (2k / 100k) and configs[4] (30k / 300k): tests/golden/lcp_full_shapes.npz holds the reference's numbers for a hypothesis sample
+    spread over the benchmark's batch; the clouds are regenerated from the seeded generator."""
+    g = np.load(os.path.join(G, "lcp_full_shapes.npz"))
+    for tag, n_w in (("c2", 400), ("c5", 24)):
+        prob, T = _full_shape(g, tag)
+        o = port_lib.PortOracle(prob.scene_xyz, prob.scene_nrm, prob.model_xyz, prob.model_nrm, prob.model_xyz, prob.model_nrm, prob.delta)
+        assert np.array_equal(o.verify(T), g[f"{tag}_counts"])
+        ws, wn = o.weighted_verify(T[:n_w])
+        assert np.array_equal(ws, g[f"{tag}_wscore"][:n_w]) and np.array_equal(wn, g[f"{tag}_wnreg"][:n_w])

@@ -41,7 +41,8 @@ typedef enum pgp_status {
   PGP_E_NO_SCORES = -5,    /* top-k / chain requested before any scoring call */
   PGP_E_TOO_LARGE = -6,    /* scene extent / delta needs more grid cells than PGP_MAX_CELLS */
   PGP_E_NOMEM = -7,
-  PGP_E_CAPACITY = -8      /* an output list overflowed the capacity the caller gave */
+  PGP_E_CAPACITY = -8,     /* an output list overflowed the capacity the caller gave */
+  PGP_E_COMM = -9          /* NCCL could not be loaded or a collective failed (text in pgp_last_error) */
 } pgp_status;
 
 /* LCP scoring modes: which reference function a scoring call reproduces. */
@@ -73,7 +74,9 @@ typedef struct pgp_pcs_opts {
 
 /* ---------------------------------------------------------------- context ------------------ */
 
-/* Creates a context on CUDA device `device`.  Returns NULL when no CUDA device is usable (there
+/* One context drives ONE GPU.  Several GPUs: one context per GPU, joined by the communicator calls of the multi-GPU section
+ * below (one process per GPU), or pgp_group_create (one process, n devices) -- SURVEY.md 8(b) `pgp_create(n_devices, ids)`.
+ * Creates a context on CUDA device `device`.  Returns NULL when no CUDA device is usable (there
  * is no CPU path).  Replaces the construction of match_4pcs::MatchSuper4PCS
  * (S4/super4pcs_test.cc:100, S4/algorithms/super4pcs.cc:70-73). */
 PGP_API pgp_ctx* pgp_create(int device);
@@ -166,8 +169,23 @@ PGP_API int64_t pgp_launch_count(const pgp_ctx* ctx);
 
 /* Top-k of the last scored batch, ordered by (score desc, index asc); replaces the serial
  * best-so-far scan of Perform_N_steps (match4pcsBase.cc:1888-1901).  index_base is added to the
- * local indices (the rank's offset when hypotheses are sharded).  Returns the number written. */
+ * local indices (the rank's offset when hypotheses are sharded).  Returns the number written.
+ * On a context that belongs to a communicator (pgp_comm_init, world > 1) the call is COLLECTIVE: every rank calls it, K4 runs on
+ * every rank's shard, the per-rank records are all-gathered over NCCL and merged, and every rank receives the same global top-k
+ * -- identical to the single-GPU answer on the concatenated batch.  index_base = PGP_INDEX_AUTO numbers the hypotheses rank after
+ * rank (rank r's first index = the batch sizes of ranks < r, which travel in the same all-gather). */
 PGP_API int pgp_topk(pgp_ctx* ctx, int obj, int k, int64_t index_base, pgp_hyp* out_host);
+#define PGP_INDEX_AUTO (-1ll)
+/* The same in two halves, so that the collective never sits on the scoring stream: _begin enqueues K4 on the context's stream
+ * and -- behind an event, on the context's own exchange stream -- the all-gather and the download of the gathered records, and
+ * returns a ticket (>= 0) at once; the next batch can be scored while the exchange is in flight.  _end waits for the ticket and
+ * merges on the host (k records at most; returns the number written).  Up to 8 tickets may be in flight per context.  Works
+ * without a communicator too (then it is the local top-k). */
+PGP_API int pgp_topk_begin(pgp_ctx* ctx, int obj, int k, int64_t index_base);
+PGP_API int pgp_topk_end(pgp_ctx* ctx, int ticket, pgp_hyp* out_host);
+/* Makes the context's stream wait until the ticket's exchange has delivered its records to the host buffer (lets a caller time
+ * the exchange with events on its own stream; not needed for correctness). */
+PGP_API int pgp_topk_stream_wait(pgp_ctx* ctx, int ticket);
 /* Same, asynchronous, with the k records written straight into caller-owned DEVICE memory (the
  * send buffer of the multi-GPU all-gather); slots beyond the batch size get index = -1. */
 PGP_API int pgp_topk_dev(pgp_ctx* ctx, int obj, int k, int64_t index_base, pgp_hyp* out_dev);
@@ -176,7 +194,8 @@ PGP_API int pgp_topk_dev(pgp_ctx* ctx, int obj, int k, int64_t index_base, pgp_h
 PGP_API int pgp_topk_merge(const pgp_hyp* lists, int n_lists, int k_each, int k, pgp_hyp* out);
 /* The strictly-improving chain in generation order that Perform_N_steps returns as
  * hypothesisSet (match4pcsBase.cc:1888-1914); its last element is bestHypothesis.
- * Returns the chain length (<= cap) or PGP_E_CAPACITY. */
+ * Returns the chain length (<= cap) or PGP_E_CAPACITY.  Collective on a communicator context, like pgp_topk: the chain over the
+ * ranks' batches in rank order (each rank may contribute at most PGP_CHAIN_EXCHANGE_CAP elements). */
 PGP_API int pgp_improving_chain(pgp_ctx* ctx, int obj, int64_t index_base, pgp_hyp* out_host, int cap);
 
 /* ---------------------------------------------------------------- K2: PCS generation ------- */
@@ -208,6 +227,11 @@ PGP_API int pgp_rigid_from_quads(pgp_ctx* ctx, int obj, const int32_t* base4, co
  * pairs, quads, transforms -- written straight into the device buffer that pgp_score_generated
  * scores, no host round trip.  Returns the number of hypotheses generated through *n_hyp. */
 PGP_API int pgp_generate_pcs(pgp_ctx* ctx, int obj, const pgp_pcs_opts* opts, uint64_t seed, int64_t max_hyp, int64_t* n_hyp);
+/* The same for bases [base_lo, base_hi) of the opts->n_bases the request draws -- the unit bases shard by across GPUs (per-base
+ * independence of Perform_N_steps, match4pcsBase.cc:1855-1877).  Every random draw is keyed by (seed, GLOBAL base index), so the
+ * hypotheses of a base do not depend on which GPU generates it. */
+PGP_API int pgp_generate_pcs_range(pgp_ctx* ctx, int obj, const pgp_pcs_opts* opts, uint64_t seed, int base_lo, int base_hi, int64_t max_hyp,
+                                   int64_t* n_hyp);
 /* Scores the hypotheses pgp_generate_pcs left on the device. */
 PGP_API int pgp_score_generated(pgp_ctx* ctx, int obj, int mode);
 /* Copies generated transforms / their scores to the host (n x 12, n). */
@@ -234,6 +258,67 @@ PGP_API uint32_t pgp_stocs_engine_seed(uint64_t seed, int base, int attempt);
  * ids cap x 4 scene indices in the pairing TryQuadrilateral chose (:415-464), inv cap x 2 invariants, ok cap flags
  * (0 = no admissible base was found for that draw).  Returns the number of bases written. */
 PGP_API int pgp_get_bases(pgp_ctx* ctx, int obj, int32_t* ids, float* inv, uint8_t* ok, int cap);
+
+/* ---------------------------------------------------------------- multi-GPU - */
+
+/* Hypotheses (pgp_score_lcp* with a rank-specific index_base) or bases (pgp_generate_pcs_range) shard across the GPUs of one
+ * box; scene grid and models are replicated (every rank makes the same pgp_set_scene / pgp_set_model calls); the only exchange
+ * on the path is the all-gather of the selection records inside pgp_topk / pgp_improving_chain.  The reference is one thread
+ * (match4pcsBase.cc:1855-1877 per base, :1888-1901 per hypothesis, PPE/src/data_layer/SceneCfg.cpp:379-390 per object): these
+ * calls have no counterpart there; they keep its results.  NCCL is loaded with dlopen on first use.
+ *
+ * One process per GPU: rank 0 calls pgp_comm_unique_id, the PGP_COMM_ID_BYTES bytes reach the other ranks over any host channel,
+ * then every rank calls pgp_comm_init (collective; ncclCommInitRank on the context's device). */
+#define PGP_COMM_ID_BYTES 128
+#define PGP_CHAIN_EXCHANGE_CAP 255
+PGP_API int pgp_comm_unique_id(void* id128);
+PGP_API int pgp_comm_init(pgp_ctx* ctx, const void* id128, int rank, int world);
+/* One process, n contexts on n different devices (ncclCommInitAll); ctxs[i] becomes rank i. */
+PGP_API int pgp_comm_init_all(pgp_ctx** ctxs, int n);
+PGP_API int pgp_comm_rank(const pgp_ctx* ctx);
+PGP_API int pgp_comm_world(const pgp_ctx* ctx);
+PGP_API int pgp_comm_destroy(pgp_ctx* ctx);
+/* After pgp_generate_pcs_range on every rank (collective): exchanges the per-rank hypothesis counts, applies the request's global
+ * cap max_hyp in rank order (<= 0: no cap) -- the cut pgp_generate_pcs makes on one GPU -- and reports the global index of this
+ * rank's first hypothesis and the global total (either pointer may be NULL). */
+PGP_API int pgp_comm_sync_generated(pgp_ctx* ctx, int obj, int64_t max_hyp, int64_t* index_base, int64_t* n_total);
+
+/* The merge behind the collective pgp_topk / pgp_improving_chain, as a pure host function (no context): `wire` = world blocks of
+ * (k + 1) records as the all-gather delivers them -- per rank a header {index = the rank's batch size, count = valid records}
+ * and k records.  kind 0: global top-k by (score desc, index asc); kind 1: the strictly improving chain over the ranks in order
+ * (mode = the pgp_lcp_mode the batch was scored in).  auto_base != 0: records carry shard-local indices (PGP_INDEX_AUTO).
+ * Returns the number of records written (<= cap) or PGP_E_CAPACITY. */
+PGP_API int pgp_exchange_merge(const pgp_hyp* wire, int world, int k, int kind, int mode, int auto_base, pgp_hyp* out, int cap);
+
+/* One process, n devices: a group owns one context per device and a communicator over them.  Replicated state is set on every
+ * device, work is sharded, results are merged -- the calls below mirror their single-context namesakes.  (What SURVEY.md 8(b)
+ * sketches as pgp_create(n_devices, device_ids).) */
+typedef struct pgp_group pgp_group;
+PGP_API pgp_group* pgp_group_create(int n_devices, const int* device_ids /* NULL: 0 .. n-1 */);
+PGP_API void pgp_group_destroy(pgp_group* g);
+PGP_API int pgp_group_size(const pgp_group* g);
+PGP_API pgp_ctx* pgp_group_ctx(pgp_group* g, int i);          /* device i's context, for the per-device calls (pgp_registered_points ...) */
+PGP_API const char* pgp_group_last_error(const pgp_group* g);
+PGP_API int pgp_group_set_scene(pgp_group* g, const float* xyz_host, const float* nrm_host, int n, float delta);
+PGP_API int pgp_group_set_scene_prior_image(pgp_group* g, const uint16_t* img_host, int rows, int cols, const float* K9);
+PGP_API int pgp_group_set_scene_priors(pgp_group* g, const float* prior_host);
+PGP_API int pgp_group_set_model(pgp_group* g, int obj, const float* search_xyz, const float* search_nrm, int nq, const float* val_xyz,
+                                const float* val_nrm, int nv);
+PGP_API int pgp_group_set_ppf_map(pgp_group* g, int obj, const int32_t* keys4, const int64_t* offsets, const int32_t* pairs, int64_t n_keys);
+PGP_API int pgp_group_build_ppf_map(pgp_group* g, int obj);
+/* bases split across the devices: device i generates -- and pgp_group_score_generated scores -- bases [i B / n, (i+1) B / n) */
+PGP_API int pgp_group_generate_pcs(pgp_group* g, int obj, const pgp_pcs_opts* opts, uint64_t seed, int64_t max_hyp, int64_t* n_hyp);
+PGP_API int pgp_group_score_generated(pgp_group* g, int obj, int mode);
+/* hypotheses split across the devices: device i scores [i n / n_dev, (i+1) n / n_dev) */
+PGP_API int pgp_group_score_lcp(pgp_group* g, int obj, const float* T_host, int64_t n, int mode, uint32_t* counts_host, float* scores_host);
+/* K4 on every device -> one grouped ncclAllGather -> merge: the global answers, independent of the device count */
+PGP_API int pgp_group_topk(pgp_group* g, int obj, int k, pgp_hyp* out_host);
+PGP_API int pgp_group_improving_chain(pgp_group* g, int obj, pgp_hyp* out_host, int cap);
+
+/* Random 32-byte-sector gather micro-benchmark (the denominator of K3's moved-bytes roofline): every thread chases
+ * `loads_per_thread` pseudo-random 32-byte sectors of a `footprint_bytes` buffer (L2-resident when below ~100 MB), four
+ * independent chains per thread.  Returns the sustained sector traffic in GB/s through *gbps.  No reference counterpart. */
+PGP_API int pgp_bench_sector_gather(pgp_ctx* ctx, int64_t footprint_bytes, int loads_per_thread, float* gbps);
 
 /* ---------------------------------------------------------------- K5: trimmed ICP ---------- */
 

@@ -55,6 +55,50 @@ def compute_ppf(p1, n1, p2, n2):
     return (k0, k1, k2, k3)
 
 
+def ppf_keys_all_pairs(xyz, nrm) -> np.ndarray:
+    """compute_ppf of ALL ordered pairs (i, j) of a cloud, vectorised with the same fp32 operation order: (n*n, 4) int keys, row
+    i*n + j.  The generator of PPFMap.txt is not in the reference tree; this is the map the CPU arm of bench.py hands to the
+    reference's Perform_N_steps (rows are grouped by pyoracle.group_ppf_keys)."""
+    P = np.ascontiguousarray(xyz, f32)
+    N = np.ascontiguousarray(nrm, f32)
+    n = len(P)
+    u = (P[:, None, :] - P[None, :, :]).astype(f32)                      # p1 - p2
+    n1 = np.broadcast_to(N[:, None, :], (n, n, 3))
+    n2 = np.broadcast_to(N[None, :, :], (n, n, 3))
+
+    def dot(a, b):
+        return (a[..., 0] * b[..., 0]).astype(f32) + ((a[..., 1] * b[..., 1]).astype(f32) + (a[..., 2] * b[..., 2]).astype(f32)).astype(f32)
+
+    def cross(a, b):
+        return np.stack([(a[..., 1] * b[..., 2]).astype(f32) - (a[..., 2] * b[..., 1]).astype(f32),
+                         (a[..., 2] * b[..., 0]).astype(f32) - (a[..., 0] * b[..., 2]).astype(f32),
+                         (a[..., 0] * b[..., 1]).astype(f32) - (a[..., 1] * b[..., 0]).astype(f32)], axis=-1).astype(f32)
+
+    def norm(a):
+        return np.sqrt(dot(a, a).astype(f32)).astype(f32)
+
+    def angle(y, x):
+        a = np.arctan2(y.astype(np.float64), x.astype(np.float64)).astype(f32)
+        return ((a * f32(180.0)).astype(f32).astype(np.float64) / math.pi).astype(np.int64)      # C++ int(): truncation toward zero
+
+    def abin(val, disc):
+        lower = val - np.fmod(val, disc)
+        upper = lower + disc
+        return np.where((val - lower) < (upper - val), lower, upper)
+
+    k0 = abin((norm(u) * f32(1000.0)).astype(f32).astype(np.int64), 5)
+    k1 = abin(angle(norm(cross(n1, u)), dot(n1, u)), 10)
+    k2 = abin(angle(norm(cross(n2, u)), dot(n2, u)), 10)
+    k3 = abin(angle(norm(cross(n1, n2)), dot(n1, n2)), 10)
+    return np.stack([k0, k1, k2, k3], axis=-1).reshape(n * n, 4).astype(np.int32)
+
+
+def build_ppf_map(xyz, nrm):
+    """(keys4, offsets, pairs) of the cloud's PPF map, rows in key order (see ppf_keys_all_pairs)."""
+    from oracle import pyoracle
+    return pyoracle.group_ppf_keys(ppf_keys_all_pairs(xyz, nrm), len(xyz))
+
+
 class MinStd:
     M = 2147483647
 

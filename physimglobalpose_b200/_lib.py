@@ -12,7 +12,9 @@ PGP_LCP_COUNT = 0
 PGP_LCP_WEIGHTED = 1
 
 STATUS = {0: "PGP_OK", -1: "PGP_E_INVALID", -2: "PGP_E_CUDA", -3: "PGP_E_NO_SCENE", -4: "PGP_E_NO_MODEL",
-          -5: "PGP_E_NO_SCORES", -6: "PGP_E_TOO_LARGE", -7: "PGP_E_NOMEM", -8: "PGP_E_CAPACITY"}
+          -5: "PGP_E_NO_SCORES", -6: "PGP_E_TOO_LARGE", -7: "PGP_E_NOMEM", -8: "PGP_E_CAPACITY", -9: "PGP_E_COMM"}
+PGP_INDEX_AUTO = -1
+PGP_COMM_ID_BYTES = 128
 
 
 class PgpHyp(C.Structure):
@@ -79,6 +81,36 @@ _SIGNATURES = {
     "pgp_mcts_tricp": (_i, [_vp, _i, _vp, _i, _vp, _i, _f, _vp, _i, _f, _f, _i, _vp, _vp, _vp]),
     "pgp_prepare_segment": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _f, _f, _f, _i, _vp, _vp, _i, _vp]),
     "pgp_tricp": (_i, [_vp, _i, _vp, _i, _vp, _i, _f, _f, _i, _vp, _vp]),
+    # multi-GPU
+    "pgp_generate_pcs_range": (_i, [_vp, _i, _vp, C.c_uint64, _i, _i, _i64, _vp]),
+    "pgp_topk_begin": (_i, [_vp, _i, _i, _i64]),
+    "pgp_topk_end": (_i, [_vp, _i, _vp]),
+    "pgp_topk_stream_wait": (_i, [_vp, _i]),
+    "pgp_exchange_merge": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i]),
+    "pgp_comm_unique_id": (_i, [_vp]),
+    "pgp_comm_init": (_i, [_vp, _vp, _i, _i]),
+    "pgp_comm_init_all": (_i, [_vp, _i]),
+    "pgp_comm_rank": (_i, [_vp]),
+    "pgp_comm_world": (_i, [_vp]),
+    "pgp_comm_destroy": (_i, [_vp]),
+    "pgp_comm_sync_generated": (_i, [_vp, _i, _i64, _vp, _vp]),
+    "pgp_group_create": (_vp, [_i, _vp]),
+    "pgp_group_destroy": (None, [_vp]),
+    "pgp_group_size": (_i, [_vp]),
+    "pgp_group_ctx": (_vp, [_vp, _i]),
+    "pgp_group_last_error": (C.c_char_p, [_vp]),
+    "pgp_group_set_scene": (_i, [_vp, _vp, _vp, _i, _f]),
+    "pgp_group_set_scene_prior_image": (_i, [_vp, _vp, _i, _i, _vp]),
+    "pgp_group_set_scene_priors": (_i, [_vp, _vp]),
+    "pgp_group_set_model": (_i, [_vp, _i, _vp, _vp, _i, _vp, _vp, _i]),
+    "pgp_group_set_ppf_map": (_i, [_vp, _i, _vp, _vp, _vp, _i64]),
+    "pgp_group_build_ppf_map": (_i, [_vp, _i]),
+    "pgp_group_generate_pcs": (_i, [_vp, _i, _vp, C.c_uint64, _i64, _vp]),
+    "pgp_group_score_generated": (_i, [_vp, _i, _i]),
+    "pgp_group_score_lcp": (_i, [_vp, _i, _vp, _i64, _i, _vp, _vp]),
+    "pgp_group_topk": (_i, [_vp, _i, _i, _vp]),
+    "pgp_group_improving_chain": (_i, [_vp, _i, _vp, _i]),
+    "pgp_bench_sector_gather": (_i, [_vp, _i64, _i, _vp]),
 }
 
 _lib = None

@@ -465,11 +465,11 @@ __device__ void try_quadrilateral(const float4* __restrict__ P, const int ids[4]
   }
 }
 
-__global__ void __launch_bounds__(256) k2_select_bases(const float4* __restrict__ P, int n, float max_diam, int trials, uint64_t seed, BaseOut* __restrict__ out) {
+__global__ void __launch_bounds__(256) k2_select_bases(const float4* __restrict__ P, int n, float max_diam, int trials, uint64_t seed, int base_lo, BaseOut* __restrict__ out) {
   __shared__ float s_val[256];
   __shared__ int s_idx[256];
   __shared__ int s_tri[3];
-  const int base = blockIdx.x, tid = threadIdx.x;
+  const int base = base_lo + blockIdx.x, tid = threadIdx.x;      // the draws depend on the GLOBAL base index only (bases shard across GPUs)
   BaseOut o{};
   for (int attempt = 0; attempt < 16; ++attempt) {
     const uint64_t s0 = mix64(seed ^ mix64(((uint64_t)base << 8) | (uint64_t)attempt));
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(256) k2_select_bases(const float4* __restrict_
     __syncthreads();
     if (s_tri[0]) break;
   }
-  if (tid == 0) out[base] = o;
+  if (tid == 0) out[blockIdx.x] = o;
 }
 
 // ------------------------------------------------------------------------------- StoCS (operMode 1, the shipped generator)
@@ -801,6 +801,7 @@ __global__ void k2s_combo_copy(PpfMapDev m, const int* __restrict__ slot, const 
 
 struct Scratch {
   DevBuf adj, dist6, in_order, list1, list2, cnt, cnt2, off, flag, curr, pairs1, pairs2, quads, bucket_of, key_of, bucket_start, sorted, T, ok, base, qn;
+  const Model* bases_owner = nullptr;   // the model whose last k2_generate call left its bases in `base` (k2_get_bases)
 };
 // the generator's device scratch belongs to the context (two contexts on one device must not share it); created on first use,
 // released by k2_release (pgp_destroy)
@@ -1012,10 +1013,10 @@ __global__ void k2b_rigid(const float4* __restrict__ P_unsorted, const float4* _
 
 // widest random triangle as operMode 0 (SelectRandomTriangle :377-410), then the most voluminous of 100 random fourth points
 // (SelectTetrahedronBase :466-503).  Counter-based RNG like k2_select_bases (the reference draws from rand()).
-__global__ void __launch_bounds__(256) k2v_select_bases(const float4* __restrict__ P, int n, float max_diam, int trials, uint64_t seed, BaseOut* __restrict__ out) {
+__global__ void __launch_bounds__(256) k2v_select_bases(const float4* __restrict__ P, int n, float max_diam, int trials, uint64_t seed, int base_lo, BaseOut* __restrict__ out) {
   __shared__ float s_val[256];
   __shared__ int s_idx[256];
-  const int base = blockIdx.x, tid = threadIdx.x;
+  const int base = base_lo + blockIdx.x, tid = threadIdx.x;
   BaseOut o{};
   for (int attempt = 0; attempt < 16 && !o.ok; ++attempt) {
     const uint64_t s0 = mix64(seed ^ mix64(0x7E7A00000000ull | ((uint64_t)base << 8) | (uint64_t)attempt));
@@ -1072,7 +1073,7 @@ __global__ void __launch_bounds__(256) k2v_select_bases(const float4* __restrict
     const int i4 = (int)(mix64(s0 ^ (0x4444000000000000ull + (uint64_t)wt)) % (uint64_t)n);
     o.id[0] = i1; o.id[1] = i2; o.id[2] = i3; o.id[3] = i4; o.ok = 1;
   }
-  if (tid == 0) out[base] = o;
+  if (tid == 0) out[blockIdx.x] = o;
 }
 
 // the six edge lengths of every base: (a - b).norm() as Eigen evaluates it for a Vector3f, sqrt((x^2 + y^2) + z^2)
@@ -1251,16 +1252,17 @@ int v4pcs_chunk(pgp_ctx* ctx, const Model& m, const BaseOut* d_bases, int nb, fl
 }
 
 // pgp_generate_pcs in operMode 2: tetrahedron bases -> V4PCS quads -> rigid transforms -> per-base subset -> append
-int generate_v4pcs(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, int64_t max_hyp, float max_diam, int64_t* n_hyp) {
+int generate_v4pcs(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, int base_lo, int base_hi, int64_t max_hyp, float max_diam, int64_t* n_hyp) {
   Scratch& sc = scratch_of(ctx);
   const Scene& s = ctx->scene;
   cudaStream_t st = ctx->stream;
-  const int nb_total = std::max(1, o->n_bases), nq = m.nq, W = (nq + 31) / 32;
+  const int nb_total = base_hi - base_lo, nq = m.nq, W = (nq + 31) / 32;
+  sc.bases_owner = &m;
   const float eps = s.delta;
   PGP_CUDA(ctx, sc.base.reserve((size_t)nb_total * sizeof(BaseOut) + 64));
   PGP_CUDA(ctx, m.gen_T.reserve((size_t)std::max<int64_t>(max_hyp, 1) * 48));
   BaseOut* d_bases_all = reinterpret_cast<BaseOut*>(sc.base.as<char>() + 64);
-  k2v_select_bases<<<nb_total, 256, 0, st>>>(s.unsorted.as<float4>(), s.n, max_diam, std::max(1, o->base_trials), seed, d_bases_all);
+  k2v_select_bases<<<nb_total, 256, 0, st>>>(s.unsorted.as<float4>(), s.n, max_diam, std::max(1, o->base_trials), seed, base_lo, d_bases_all);
   ctx->launches++;
   PGP_CUDA(ctx, cudaGetLastError());
   // bases per chunk: six nq x nq bit matrices each, about 1 GB in all
@@ -1286,7 +1288,7 @@ int generate_v4pcs(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed,
     uint32_t* flag = sc.flag.as<uint32_t>();
     PGP_CUDA(ctx, cudaMemsetAsync(flag + nquads, 0, 4, st));
     const unsigned gr = (unsigned)((nquads + 127) / 128);
-    k2b_rigid<<<gr, 128, 0, st>>>(s.unsorted.as<float4>(), m.search.as<float4>(), d_bases, base0, qoff, nb, sc.quads.as<int4>(), (long long)nquads,
+    k2b_rigid<<<gr, 128, 0, st>>>(s.unsorted.as<float4>(), m.search.as<float4>(), d_bases, base_lo + base0, qoff, nb, sc.quads.as<int4>(), (long long)nquads,
                                   o->max_quads_per_base, seed, sc.T.as<float>(), flag);
     ctx->launches++;
     PGP_CUDA(ctx, cudaGetLastError());
@@ -1338,18 +1340,24 @@ int k2_find_quads_v4pcs(pgp_ctx* ctx, const Model& m, const int32_t* base4, floa
   return PGP_OK;
 }
 
-int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, int64_t max_hyp, int64_t* n_hyp) {
+// Bases [base_lo, base_hi) of the o->n_bases the request draws: every draw (base selection, per-base subset) is keyed by the GLOBAL
+// base index, so a base yields the same hypotheses whichever GPU generates it and however the bases are chunked (bases
+// shard across GPUs, per-base independence of match4pcsBase.cc:1855-1877).
+int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, int base_lo, int base_hi, int64_t max_hyp, int64_t* n_hyp) {
   Scratch& sc = scratch_of(ctx);
   const Scene& s = ctx->scene;
   cudaStream_t st = ctx->stream;
   *n_hyp = 0;
   m.n_gen = 0;
   m.gen_scored = false;
-  const int nb_total = std::max(1, o->n_bases);
+  m.n_gen_bases = 0;
+  if (base_hi <= base_lo) return PGP_OK;
+  const int nb_total = base_hi - base_lo;
+  sc.bases_owner = &m;
   const int nq = m.nq;
   float max_diam = o->max_base_diameter;
   if (!(max_diam > 0.f)) max_diam = m.search_diameter;   // P_diameter_ estimate of init() (:274-283)
-  if (o->mode == 2) return generate_v4pcs(ctx, m, o, seed, max_hyp, max_diam, n_hyp);
+  if (o->mode == 2) return generate_v4pcs(ctx, m, o, seed, base_lo, base_hi, max_hyp, max_diam, n_hyp);
   const float eps = s.delta;          // distance_factor * options_.delta, distance_factor = 1 (match4pcsBase.h:99)
   // join grid (IndexedNormalSet, normalset.h:117-123); buckets per base capped at 2^15 (collisions are filtered by the key)
   const float eps_n = eps / m.unit_ratio;
@@ -1368,13 +1376,19 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
     if (m.n_ppf_keys <= 0) return pgp_fail(ctx, PGP_E_INVALID, "PCS mode 1 (StoCS) needs the model's PPF map: pgp_set_ppf_map / pgp_build_ppf_map");
     if (!s.has_nrm) return pgp_fail(ctx, PGP_E_INVALID, "PCS mode 1 (StoCS) needs scene normals");
     pm.keys = m.ppf_keys.as<uint32_t>(); pm.offsets = m.ppf_offsets.as<uint32_t>(); pm.pairs = m.ppf_pairs.as<int2>(); pm.n_keys = m.n_ppf_keys;
-    PGP_CUDA(ctx, sc.curr.reserve((size_t)nb_total * s.n * 4));
+    // one weight vector of |P| floats per base in flight: the bases are selected in batches of at most ~1 GB of them
+    const int bsel = (int)std::max<int64_t>(1, std::min<int64_t>(nb_total, ((int64_t)1 << 28) / std::max(1, s.n)));
+    PGP_CUDA(ctx, sc.curr.reserve((size_t)bsel * s.n * 4));
     StocsParams sp{};
     sp.P = s.unsorted.as<float4>(); sp.aux = s.aux_orig.as<float4>(); sp.n = s.n; sp.bits = m.ppf_bits.as<uint32_t>();
-    sp.curr = sc.curr.as<float>(); sp.seed = seed; sp.base0 = 0;
-    k2s_select_bases<<<nb_total, 256, 0, st>>>(sp, d_bases_all);
+    sp.curr = sc.curr.as<float>(); sp.seed = seed;
+    for (int b0 = 0; b0 < nb_total; b0 += bsel) {
+      sp.base0 = base_lo + b0;
+      k2s_select_bases<<<std::min(bsel, nb_total - b0), 256, 0, st>>>(sp, d_bases_all + b0);
+      if (b0) ctx->launches++;
+    }
   } else {
-    k2_select_bases<<<nb_total, 256, 0, st>>>(s.unsorted.as<float4>(), s.n, max_diam, std::max(1, o->base_trials), seed, d_bases_all);
+    k2_select_bases<<<nb_total, 256, 0, st>>>(s.unsorted.as<float4>(), s.n, max_diam, std::max(1, o->base_trials), seed, base_lo, d_bases_all);
   }
   ctx->launches++;
   PGP_CUDA(ctx, cudaGetLastError());
@@ -1501,7 +1515,7 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
     uint32_t* flag = sc.flag.as<uint32_t>();
     PGP_CUDA(ctx, cudaMemsetAsync(flag + nquads, 0, 4, st));
     const unsigned gr = (unsigned)((nquads + 127) / 128);
-    k2b_rigid<<<gr, 128, 0, st>>>(s.unsorted.as<float4>(), m.search.as<float4>(), d_bases, base0, qoff, nb, sc.quads.as<int4>(), (long long)nquads,
+    k2b_rigid<<<gr, 128, 0, st>>>(s.unsorted.as<float4>(), m.search.as<float4>(), d_bases, base_lo + base0, qoff, nb, sc.quads.as<int4>(), (long long)nquads,
                                   o->max_quads_per_base, seed, sc.T.as<float>(), flag);
     ctx->launches += 3;
     PGP_CUDA(ctx, cudaGetLastError());
@@ -1528,8 +1542,9 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
 
 // bases of the last k2_generate call on this device (they stay in the scratch buffer): ids (n x 4 scene indices,
 // in the pairing TryQuadrilateral chose), inv (n x 2), ok flags
-int k2_get_bases(pgp_ctx* ctx, int n_bases, int32_t* ids_host, float* inv_host, uint8_t* ok_host) {
+int k2_get_bases(pgp_ctx* ctx, const Model& m, int n_bases, int32_t* ids_host, float* inv_host, uint8_t* ok_host) {
   Scratch& sc = scratch_of(ctx);
+  if (sc.bases_owner != &m) return pgp_fail(ctx, PGP_E_INVALID, "the bases on the device belong to another object's pgp_generate_pcs call");
   if (n_bases <= 0 || sc.base.cap < (size_t)n_bases * sizeof(BaseOut) + 64) return pgp_fail(ctx, PGP_E_INVALID, "no bases generated");
   std::vector<BaseOut> b(n_bases);
   PGP_CUDA(ctx, cudaMemcpyAsync(b.data(), sc.base.as<char>() + 64, (size_t)n_bases * sizeof(BaseOut), cudaMemcpyDeviceToHost, ctx->stream));

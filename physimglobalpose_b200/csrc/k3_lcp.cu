@@ -41,6 +41,7 @@ struct LcpParams {
   long long n;
   long long n_bulk;          // fine kernel: hypotheses [0, n_bulk) are one work unit each, the rest are split into `split` model chunks
   uint32_t* ready;           // streamed upload: number of hypotheses whose transforms have arrived (nullptr: all of them)
+  unsigned long long ready_timeout_ns;   // how long one wait on `ready` may last before the launch gives up (host re-scores)
   int split;                 // (so that the last wave of the persistent grid ends on quarter-sized units, not whole hypotheses)
   const float4* pts;
   const float4* aux;
@@ -97,9 +98,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 struct Xf { float m[12]; };
 
-__device__ __forceinline__ Xf load_xf(const float* __restrict__ T, long long h) {
+// The batch may still be being written by the copy engine while the kernel runs (streamed upload, LcpParams::ready), so T is not
+// read-only for the kernel's lifetime and must not go through the non-coherent path (ld.global.nc / __ldg): plain cached loads
+// (ld.global.ca), issued only after the acquire load of the upload counter has covered hypothesis h.  No line of T is touched
+// before its chunk has landed (chunks end on 384-byte boundaries), so L1 can never hold a stale copy.
+__device__ __forceinline__ Xf load_xf(const float* T, long long h) {
   const float4* t4 = reinterpret_cast<const float4*>(T + 12 * h);
-  float4 a = __ldg(t4), b = __ldg(t4 + 1), c = __ldg(t4 + 2);
+  const float4 a = __ldca(t4), b = __ldca(t4 + 1), c = __ldca(t4 + 2);
   Xf x;
   x.m[0] = a.x; x.m[1] = a.y; x.m[2] = a.z; x.m[3] = a.w;
   x.m[4] = b.x; x.m[5] = b.y; x.m[6] = b.z; x.m[7] = b.w;
@@ -623,13 +628,22 @@ __global__ void __launch_bounds__(FWARPS * 32, 1) k3_fine_kernel(const __grid_co
       if (p.ready) {
         // the transforms are still being uploaded chunk by chunk on another stream (pgp_score_lcp); the counter is written by
         // the copy engine after each chunk, chunks end on 384-byte boundaries so no cache line of T spans two of them
-        // rd[0] = hypotheses uploaded, rd[1] = abort flag.  A wait that exceeds ~20 ms (the copy stream is not making progress:
+        // ready[0] = hypotheses uploaded, ready[1] = abort flag.  A wait that exceeds ready_timeout_ns (20 ms + the time one chunk
+        // needs at a pessimistic 1 GB/s, set by the host from the chunk size; the copy stream is not making progress:
         // a profiler serialising streams, a wedged DMA engine) raises the flag; every other wait then falls through at once, the
         // launch ends with garbage and the host re-scores the batch un-streamed (pgp_score_lcp).  The device never hangs.
-        volatile uint32_t* rd = p.ready;
-        for (int spin = 0; (long long)rd[0] <= h; ++spin) {
-          if (rd[1]) break;
-          if (spin > 100000) { rd[1] = 1u; __threadfence(); break; }
+        // The counter is read with ld.acquire.sys (the writer is the copy engine), which orders the loads of T behind it.
+        unsigned long long t_start = 0;
+        for (;;) {
+          uint32_t have, stop;
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(p.ready) : "memory");
+          if ((long long)have > h) break;
+          asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(stop) : "l"(p.ready + 1) : "memory");
+          if (stop) break;
+          unsigned long long now;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+          if (!t_start) t_start = now;
+          else if (now - t_start > p.ready_timeout_ns) { atomicExch(p.ready + 1, 1u); __threadfence(); break; }
           __nanosleep(200);
         }
       }
@@ -820,6 +834,7 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     p.bmrank_words = (int)(bm / 8);
     p.model_rinf = m.val_rinf;
     p.ready = ready_dev;
+    p.ready_timeout_ns = 20000000ull + (unsigned long long)(n / 4 + 1) * 48ull;      // 20 ms + one of the four chunks at 1 GB/s (1 ns per byte)
     p.groups = m.val_groups.as<float4>();
     p.dist = ctx->group_cull ? s.dist.as<float>() : nullptr;
     p.cull_add = s.delta * (1.0f + 1e-5f) + 4.0f * s.g.inflate;

@@ -38,6 +38,8 @@ struct SelParams {
   unsigned* n_cand;          // zeroed before launch
   unsigned long long* cand;  // KMAX keys
   pgp_hyp* out;              // device, k records
+  pgp_hyp* hdr;              // may be null: one more record {index = batch size, count = records written} in front of the k
+                             // records, for the multi-GPU exchange (pgp_comm.cu)
   int* n_out;
   int mode;                  // 0: top-k, 1: improving chain
   unsigned long long* seg_max;   // chain: per-CTA segment maxima
@@ -167,7 +169,10 @@ __global__ void __launch_bounds__(ST, 1) k4_select_kernel(const SelParams p) {
         for (int c = 0; c < 12; ++c) r.T[c] = 0.f;
         p.out[t] = r;
       }
-      if (threadIdx.x == 0) *p.n_out = k;
+      if (threadIdx.x == 0) {
+        *p.n_out = k;
+        if (p.hdr) { pgp_hyp r{}; r.index = p.n; r.count = (uint32_t)k; *p.hdr = r; }
+      }
     }
   } else {
     // improving chain: i is kept iff key32[i] > max(key32[0..i)) and key32[i] > 0 (best_LCP_ starts at 0,
@@ -219,14 +224,18 @@ __global__ void __launch_bounds__(ST, 1) k4_select_kernel(const SelParams p) {
       const int keep = min(cnt, p.k);
       // generation order = ascending: reverse; if the chain is longer than the capacity keep its tail (the best)
       for (int t = threadIdx.x; t < keep; t += ST) write_record(p, keep - 1 - t, s_keys[t]);
-      if (threadIdx.x == 0) *p.n_out = (int)__ldcg(p.n_cand);
+      if (threadIdx.x == 0) {
+        *p.n_out = (int)__ldcg(p.n_cand);
+        if (p.hdr) { pgp_hyp r{}; r.index = p.n; r.count = (uint32_t)keep; r.score = __ldcg(p.n_cand) > (unsigned)p.k ? 1.f : 0.f; *p.hdr = r; }   // score = 1: chain overflowed the capacity
+      }
     }
   }
 }
 
 int bits_for(unsigned long long v) { int b = 1; while (b < 64 && (v >> b)) ++b; return b; }
 
-int run_select(pgp_ctx* ctx, const LastBatch& b, int k, int64_t index_base, pgp_hyp* out_host, int mode, int* n_out, pgp_hyp* out_dev = nullptr) {
+int run_select(pgp_ctx* ctx, const LastBatch& b, int k, int64_t index_base, pgp_hyp* out_host, int mode, int* n_out, pgp_hyp* out_dev = nullptr,
+               pgp_hyp* hdr_dev = nullptr) {
   if (n_out) *n_out = 0;
   if (b.n <= 0 || k <= 0) return PGP_OK;
   if (k > KMAX) return pgp_fail(ctx, PGP_E_INVALID, "k = %d exceeds %d", k, KMAX);
@@ -246,7 +255,8 @@ int run_select(pgp_ctx* ctx, const LastBatch& b, int k, int64_t index_base, pgp_
   if (p.ibits + p.kbits > 63) return pgp_fail(ctx, PGP_E_INVALID, "batch too large for a 64-bit selection key");
   const size_t off_hist = 2048, off_bar = off_hist + (size_t)MAX_PASSES * BINS * 4, off_ncand = off_bar + 64, off_nout = off_ncand + 64,
                off_cand = off_nout + 64, off_seg = off_cand + (size_t)KMAX * 8, off_out = off_seg + 8 * 1024, total = off_out + (size_t)KMAX * sizeof(pgp_hyp);
-  PGP_CUDA(ctx, ctx->work.reserve(total));
+  static_assert(2048 + (size_t)MAX_PASSES * BINS * 4 + 3 * 64 + (size_t)KMAX * 8 + 8 * 1024 + (size_t)KMAX * sizeof(pgp_hyp) <= PGP_WORK_BYTES, "K4 scratch exceeds pgp_ctx::work");
+  if (total > ctx->work.cap) return pgp_fail(ctx, PGP_E_NOMEM, "selection scratch (%zu bytes) exceeds the work buffer", total);
   char* w = ctx->work.as<char>();
   p.hist = reinterpret_cast<uint32_t*>(w + off_hist);
   p.barrier = reinterpret_cast<unsigned*>(w + off_bar);
@@ -255,6 +265,7 @@ int run_select(pgp_ctx* ctx, const LastBatch& b, int k, int64_t index_base, pgp_
   p.cand = reinterpret_cast<unsigned long long*>(w + off_cand);
   p.seg_max = reinterpret_cast<unsigned long long*>(w + off_seg);
   p.out = out_dev ? out_dev : reinterpret_cast<pgp_hyp*>(w + off_out);
+  p.hdr = hdr_dev;
   PGP_CUDA(ctx, cudaMemsetAsync(w + off_hist, 0, off_cand - off_hist, ctx->stream));
   int grid = (int)std::min<long long>(ctx->sm_count, (b.n + ST - 1) / ST);
   if (grid > 1024) grid = 1024;
@@ -282,4 +293,8 @@ int k4_topk_dev(pgp_ctx* ctx, const LastBatch& b, int k, int64_t index_base, pgp
 }
 int k4_chain(pgp_ctx* ctx, const LastBatch& b, int64_t index_base, pgp_hyp* out_host, int cap, int* n_out) {
   return run_select(ctx, b, cap, index_base, out_host, 1, n_out);
+}
+// asynchronous: header record + k records into device memory (the send buffer of the multi-GPU exchange); mode 0 = top-k, 1 = chain
+int k4_select_dev(pgp_ctx* ctx, const LastBatch& b, int k, int64_t index_base, int mode, pgp_hyp* hdr_dev, pgp_hyp* out_dev) {
+  return run_select(ctx, b, k, index_base, nullptr, mode, nullptr, out_dev, hdr_dev);
 }

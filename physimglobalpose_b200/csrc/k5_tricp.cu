@@ -252,13 +252,18 @@ __global__ void __launch_bounds__(TT, 1) k5_tricp_kernel(const TricpParams p) {
   if (tid == 0) { if (p.iters) p.iters[pose] = it; if (p.energy) p.energy[pose] = energy; }
 }
 
+// device scratch of the refinement: owned by the context (two contexts on one device must not share it), created on first
+// use, released by k5_release (pgp_destroy)
 struct TScratch { DevBuf seg, d2, nn, T, iters, energy, cell_of, cursor; };
-TScratch g_ts[16];
+TScratch& tscratch_of(pgp_ctx* ctx) {
+  if (!ctx->k5_scratch) ctx->k5_scratch = new TScratch();
+  return *static_cast<TScratch*>(ctx->k5_scratch);
+}
 
 // model-space grid over the raw validation cloud (the TrICP target)
 int build_target_grid(pgp_ctx* ctx, Model& m) {
   if (m.tgrid_ready) return PGP_OK;
-  TScratch& ts = g_ts[ctx->device & 15];
+  TScratch& ts = tscratch_of(ctx);
   const int n = m.nv;
   TGrid tg;
   float ext = 0.f;
@@ -305,7 +310,7 @@ void invert_pose(const double* P, double* I) {
 
 int k5_tricp(pgp_ctx* ctx, Model& m, const float* seg_xyz_host, int ns, double* poses16_host, int k, float trim, float ratio, int max_iter,
              int* iters_out, float* energy_out) {
-  TScratch& ts = g_ts[ctx->device & 15];
+  TScratch& ts = tscratch_of(ctx);
   int rc = build_target_grid(ctx, m);
   if (rc) return rc;
   const int n_keep = std::min(ns, (int)fabsf(trim * (float)ns));      // abs(numPoints) on a float, UCTState.cpp:181,194
@@ -354,4 +359,12 @@ int k5_tricp(pgp_ctx* ctx, Model& m, const float* seg_xyz_host, int ns, double* 
     if (energy_out) energy_out[i] = en[i];
   }
   return PGP_OK;
+}
+
+void k5_release(pgp_ctx* ctx) {
+  if (!ctx->k5_scratch) return;
+  TScratch* ts = static_cast<TScratch*>(ctx->k5_scratch);
+  for (DevBuf* b : {&ts->seg, &ts->d2, &ts->nn, &ts->T, &ts->iters, &ts->energy, &ts->cell_of, &ts->cursor}) b->release();
+  delete ts;
+  ctx->k5_scratch = nullptr;
 }

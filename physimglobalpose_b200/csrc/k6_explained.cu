@@ -47,15 +47,19 @@ __global__ void __launch_bounds__(K6_T) k6_mark(const float4* __restrict__ seg, 
   if (i < ns) flag[i] = hit ? 1 : 0;
 }
 
+// owned by the context, released by k6_release (pgp_destroy)
 struct K6Scratch { DevBuf seg, expl, T, flag; };
-K6Scratch g_k6[16];
+K6Scratch& k6_scratch_of(pgp_ctx* ctx) {
+  if (!ctx->k6_scratch) ctx->k6_scratch = new K6Scratch();
+  return *static_cast<K6Scratch*>(ctx->k6_scratch);
+}
 
 }  // namespace
 
 // flags_host[i] = 1 when segment point i is explained by a placed object.  Returns the number of UNEXPLAINED points.
 int k6_remove_explained(pgp_ctx* ctx, Model& m, const float* seg_xyz_host, int ns, const double* placed16_host, int n_placed, float threshold,
                         uint8_t* flags_host, int* n_unexplained) {
-  K6Scratch& sc = g_k6[ctx->device & 15];
+  K6Scratch& sc = k6_scratch_of(ctx);
   *n_unexplained = ns;
   if (ns <= 0) return PGP_OK;
   if (n_placed <= 0) { memset(flags_host, 0, (size_t)ns); return PGP_OK; }
@@ -81,4 +85,12 @@ int k6_remove_explained(pgp_ctx* ctx, Model& m, const float* seg_xyz_host, int n
   for (int i = 0; i < ns; ++i) kept += flags_host[i] ? 0 : 1;
   *n_unexplained = kept;
   return PGP_OK;
+}
+
+void k6_release(pgp_ctx* ctx) {
+  if (!ctx->k6_scratch) return;
+  K6Scratch* sc = static_cast<K6Scratch*>(ctx->k6_scratch);
+  for (DevBuf* b : {&sc->seg, &sc->expl, &sc->T, &sc->flag}) b->release();
+  delete sc;
+  ctx->k6_scratch = nullptr;
 }

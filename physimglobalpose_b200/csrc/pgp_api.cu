@@ -86,9 +86,21 @@ pgp_ctx* pgp_create(int device) {
     delete ctx;
     return nullptr;
   }
-  for (auto& ev : ctx->ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+  for (BatchSlot& bs : ctx->batch) {
+    cudaEventCreateWithFlags(&bs.ev_start, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&bs.ev_first, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&bs.ev_scored, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&bs.ev_done, cudaEventDisableTiming);
+  }
   ctx->stream = ctx->own_stream;
   ctx->models.resize(PGP_MAX_OBJECTS);
+  // `work` holds the counters kernel parameters point at (K3's work / ready counters, K4's histograms and records): it is sized
+  // once for its largest user (K4, ~350 KB) so that it is never reallocated while a launch that references it is in flight
+  if (ctx->work.reserve(PGP_WORK_BYTES) != cudaSuccess) {
+    pgp_fail(nullptr, PGP_E_NOMEM, "cudaMalloc of the %d-byte work buffer failed", PGP_WORK_BYTES);
+    pgp_destroy(ctx);
+    return nullptr;
+  }
   return ctx;
 }
 
@@ -98,15 +110,21 @@ void pgp_destroy(pgp_ctx* ctx) {
   cudaDeviceSynchronize();
   Scene& s = ctx->scene;
   for (DevBuf* b : {&s.xyz_raw, &s.nrm_raw, &s.unsorted, &s.cursor, &s.pts, &s.aux, &s.cell_start, &s.cell_of, &s.bitmap, &s.bmrank,
-                    &s.block_cell, &s.codes, &s.near_cnt, &s.hdr, &s.region, &s.hdrw, &s.adesc, &s.arec, &s.wvox, &s.wbase, &s.wcnt, &s.wword, &s.wlists, &s.aux_orig, &s.dist, &s.dist_tmp, &s.prior, &s.scratch, &ctx->batch_T, &ctx->batch_counts, &ctx->batch_scores, &ctx->work, &ctx->topk_out})
+                    &s.block_cell, &s.codes, &s.near_cnt, &s.hdr, &s.region, &s.hdrw, &s.adesc, &s.arec, &s.wvox, &s.wbase, &s.wcnt, &s.wword, &s.wlists, &s.aux_orig, &s.dist, &s.dist_tmp, &s.prior, &s.scratch, &ctx->work, &ctx->topk_out})
     b->release();
+  for (BatchSlot& bs : ctx->batch) {
+    bs.T.release(); bs.counts.release(); bs.scores.release();
+    for (cudaEvent_t e : {bs.ev_start, bs.ev_first, bs.ev_scored, bs.ev_done}) if (e) cudaEventDestroy(e);
+  }
   for (Model& m : ctx->models)
     for (DevBuf* b : {&m.search, &m.search_nrm, &m.search_unit, &m.val, &m.val_nrm, &m.val_orig, &m.val_nrm_orig, &m.gen_T, &m.gen_counts, &m.gen_scores,
                       &m.tgrid_pts, &m.tgrid_start, &m.val_raw, &m.val_groups, &m.ppf_keys, &m.ppf_offsets, &m.ppf_pairs, &m.ppf_bits})
       b->release();
+  pgp_comm_release(ctx);
   k2_release(ctx);
+  k5_release(ctx);
+  k6_release(ctx);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
-  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   cudaStreamDestroy(ctx->own_stream);
   cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->back_stream);
@@ -410,35 +428,44 @@ int pgp_score_lcp_dev(pgp_ctx* ctx, int obj, const float* T_dev, int64_t n, int 
 
 // Host-buffer scoring, split in two so that the caller can queue more work (top-k, the all-gather) behind the scoring launch
 // before it waits: pgp_score_lcp_begin enqueues upload + K3 + the downloads and returns, pgp_score_lcp_end waits for them.
+// PGP_BATCH_SLOTS batches may be in flight; _end ends the oldest.
 int pgp_score_lcp_begin(pgp_ctx* ctx, int obj, const float* T, int64_t n, int mode, uint32_t* counts, float* scores) {
   CHECK_CTX(ctx);
   Model* m = nullptr;
   int rc = check_score_args(ctx, obj, n, mode, &m);
   if (rc) return rc;
-  if (ctx->pending.active) return pgp_fail(ctx, PGP_E_INVALID, "pgp_score_lcp_begin: the previous batch has not been ended");
+  if (ctx->batch_head - ctx->batch_tail >= PGP_BATCH_SLOTS)
+    return pgp_fail(ctx, PGP_E_INVALID, "pgp_score_lcp_begin: %d batches are in flight already, end one first", PGP_BATCH_SLOTS);
+  if (n > 0 && !T) return pgp_fail(ctx, PGP_E_INVALID, "null transforms");
+  const int si = ctx->batch_head % PGP_BATCH_SLOTS;
+  BatchSlot& bs = ctx->batch[si];
+  bs.pending = PendingBatch();
+  bs.pending.active = true; bs.pending.obj = obj; bs.pending.n = n; bs.pending.mode = mode;
+  bs.pending.counts = counts; bs.pending.scores = scores;
+  ctx->batch_head++;
   if (n == 0) { ctx->last = LastBatch(); return PGP_OK; }
-  if (!T) return pgp_fail(ctx, PGP_E_INVALID, "null transforms");
-  PGP_CUDA(ctx, ctx->batch_T.reserve((size_t)n * 48));
-  PGP_CUDA(ctx, ctx->batch_counts.reserve((size_t)n * 4));
-  PGP_CUDA(ctx, ctx->batch_scores.reserve((size_t)n * 4));
+  auto fail = [&](int code) { bs.pending.active = false; ctx->batch_head--; return code; };
+  if (bs.T.reserve((size_t)n * 48) != cudaSuccess || bs.counts.reserve((size_t)n * 4) != cudaSuccess || bs.scores.reserve((size_t)n * 4) != cudaSuccess)
+    return fail(pgp_fail(ctx, PGP_E_NOMEM, "cudaMalloc of a %lld-hypothesis batch failed", (long long)n));
   // Large batches are uploaded in four chunks on the copy stream while ONE scoring launch is already consuming them: the kernel
   // hands out hypotheses in index order and, before touching hypothesis h, checks a device counter that the copy engine bumps
   // after every chunk (k3_fine_kernel, LcpParams::ready).  Chunk boundaries are multiples of 8 hypotheses = 384 bytes, so no
   // 128-byte line of T spans two chunks.  Only the first chunk's upload is exposed.
-  float* dT = ctx->batch_T.as<float>();
-  uint32_t* dC = ctx->batch_counts.as<uint32_t>();
-  float* dS = ctx->batch_scores.as<float>();
+  float* dT = bs.T.as<float>();
+  uint32_t* dC = bs.counts.as<uint32_t>();
+  float* dS = bs.scores.as<float>();
   const int chunks = 4;
   if (!ctx->pinned) { PGP_CUDA(ctx, cudaMallocHost(&ctx->pinned, 256)); ctx->pinned_cap = 256; }
-  uint32_t* marks = static_cast<uint32_t*>(ctx->pinned);                        // [0] = 0, [1..4] = hypotheses uploaded after chunk c
+  bs.marks = static_cast<uint32_t*>(ctx->pinned) + 16 * si;                     // [0] = 0, [1..4] = hypotheses uploaded after chunk c
+  uint32_t* marks = bs.marks;
   marks[8] = 0;                                                                 // abort flag read back by pgp_score_lcp_end
+  uint32_t* ready = reinterpret_cast<uint32_t*>(ctx->work.as<char>() + 320 + 16 * si);      // this slot's {uploaded, abort}
   const bool streamed = ctx->stream_upload && n >= 32768 && n < (1ll << 31) && k3_streams_upload(ctx, mode);
   if (streamed) {
-    uint32_t* ready = reinterpret_cast<uint32_t*>(ctx->work.as<char>() + 320);
     marks[0] = 0;
     for (int c = 0; c < chunks; ++c) marks[c + 1] = (uint32_t)(c + 1 == chunks ? n : ((n * (c + 1) / chunks) & ~7ll));
-    PGP_CUDA(ctx, cudaEventRecord(ctx->ev[8], ctx->stream));                    // everything queued on the caller's stream so far
-    PGP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[8], 0));
+    PGP_CUDA(ctx, cudaEventRecord(bs.ev_start, ctx->stream));                   // everything queued on the caller's stream so far
+    PGP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, bs.ev_start, 0));
     marks[6] = 0; marks[7] = 0;
     PGP_CUDA(ctx, cudaMemcpyAsync(ready, marks + 6, 8, cudaMemcpyHostToDevice, ctx->copy_stream));      // {uploaded = 0, abort = 0}
     for (int c = 0; c < chunks; ++c) {
@@ -446,54 +473,60 @@ int pgp_score_lcp_begin(pgp_ctx* ctx, int obj, const float* T, int64_t n, int mo
       PGP_CUDA(ctx, cudaMemcpyAsync(dT + 12 * lo, T + 12 * lo, (size_t)(hi - lo) * 48, cudaMemcpyHostToDevice, ctx->copy_stream));
       PGP_CUDA(ctx, cudaMemcpyAsync(ready, marks + c + 1, 4, cudaMemcpyHostToDevice, ctx->copy_stream));
       if (c == 0) {
-        PGP_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->copy_stream));
-        PGP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev[0], 0));
+        PGP_CUDA(ctx, cudaEventRecord(bs.ev_first, ctx->copy_stream));
+        PGP_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, bs.ev_first, 0));
         rc = k3_score(ctx, *m, dT, n, mode, dC, dS, ready);
-        if (rc) return rc;
+        if (rc) return fail(rc);
       }
     }
     ctx->last.T = dT; ctx->last.counts = dC; ctx->last.scores = dS; ctx->last.n = n; ctx->last.mode = mode; ctx->last.obj = obj;
   } else {
     PGP_CUDA(ctx, cudaMemcpyAsync(dT, T, (size_t)n * 48, cudaMemcpyHostToDevice, ctx->stream));
     rc = pgp_score_lcp_dev(ctx, obj, dT, n, mode, dC, dS);
-    if (rc) return rc;
+    if (rc) return fail(rc);
   }
-  // downloads on their own stream (PCIe is full duplex, and the caller's stream stays free for K4 / the all-gather)
-  PGP_CUDA(ctx, cudaEventRecord(ctx->ev[9], ctx->stream));
-  PGP_CUDA(ctx, cudaStreamWaitEvent(ctx->back_stream, ctx->ev[9], 0));
-  if (streamed) PGP_CUDA(ctx, cudaMemcpyAsync(marks + 8, reinterpret_cast<uint32_t*>(ctx->work.as<char>() + 320) + 1, 4, cudaMemcpyDeviceToHost, ctx->back_stream));
+  // downloads on their own stream (PCIe is full duplex, and the caller's stream stays free for K4 / the next batch)
+  PGP_CUDA(ctx, cudaEventRecord(bs.ev_scored, ctx->stream));
+  PGP_CUDA(ctx, cudaStreamWaitEvent(ctx->back_stream, bs.ev_scored, 0));
+  if (streamed) PGP_CUDA(ctx, cudaMemcpyAsync(marks + 8, ready + 1, 4, cudaMemcpyDeviceToHost, ctx->back_stream));
   if (counts) PGP_CUDA(ctx, cudaMemcpyAsync(counts, dC, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->back_stream));
   if (scores) PGP_CUDA(ctx, cudaMemcpyAsync(scores, dS, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->back_stream));
-  ctx->pending.active = true; ctx->pending.obj = obj; ctx->pending.n = n; ctx->pending.mode = mode;
-  ctx->pending.counts = counts; ctx->pending.scores = scores; ctx->pending.streamed = streamed;
+  PGP_CUDA(ctx, cudaEventRecord(bs.ev_done, ctx->back_stream));                // what pgp_score_lcp_end waits for
+  bs.pending.streamed = streamed;
   return PGP_OK;
 }
 
 int pgp_score_lcp_end(pgp_ctx* ctx) {
   CHECK_CTX(ctx);
-  if (!ctx->pending.active) return PGP_OK;
-  ctx->pending.active = false;
-  PGP_CUDA(ctx, cudaStreamSynchronize(ctx->back_stream));
-  PGP_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
-  const uint32_t* marks = static_cast<const uint32_t*>(ctx->pinned);
-  if (ctx->pending.streamed && marks[8]) {
+  if (ctx->batch_head == ctx->batch_tail) return PGP_OK;
+  BatchSlot& bs = ctx->batch[ctx->batch_tail % PGP_BATCH_SLOTS];
+  ctx->batch_tail++;
+  if (!bs.pending.active) return PGP_OK;
+  bs.pending.active = false;
+  if (bs.pending.n == 0) return PGP_OK;
+  PGP_CUDA(ctx, cudaEventSynchronize(bs.ev_done));           // this batch's downloads (and with them its upload and scoring) are done
+  if (bs.pending.streamed && bs.marks[8]) {
     // the kernel gave up waiting for the upload (see k3_fine_kernel); the copies are done by now: score again, plainly
-    Model* m = get_model(ctx, ctx->pending.obj);
-    if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", ctx->pending.obj);
-    const int64_t n = ctx->pending.n;
-    uint32_t* dC = ctx->batch_counts.as<uint32_t>();
-    float* dS = ctx->batch_scores.as<float>();
-    int rc = k3_score(ctx, *m, ctx->batch_T.as<float>(), n, ctx->pending.mode, dC, dS, nullptr);
+    Model* m = get_model(ctx, bs.pending.obj);
+    if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", bs.pending.obj);
+    const int64_t n = bs.pending.n;
+    uint32_t* dC = bs.counts.as<uint32_t>();
+    float* dS = bs.scores.as<float>();
+    PGP_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    int rc = k3_score(ctx, *m, bs.T.as<float>(), n, bs.pending.mode, dC, dS, nullptr);
     if (rc) return rc;
-    if (ctx->pending.counts) PGP_CUDA(ctx, cudaMemcpyAsync(ctx->pending.counts, dC, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (ctx->pending.scores) PGP_CUDA(ctx, cudaMemcpyAsync(ctx->pending.scores, dS, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (bs.pending.counts) PGP_CUDA(ctx, cudaMemcpyAsync(bs.pending.counts, dC, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (bs.pending.scores) PGP_CUDA(ctx, cudaMemcpyAsync(bs.pending.scores, dS, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return 1;        // > 0: the batch was re-scored; anything the caller queued behind the first launch (pgp_topk_dev) must be redone
+    ctx->last.T = bs.T.as<float>(); ctx->last.counts = dC; ctx->last.scores = dS; ctx->last.n = n; ctx->last.mode = bs.pending.mode; ctx->last.obj = bs.pending.obj;
+    return 1;        // > 0: the batch was re-scored; anything the caller queued behind the first launch (pgp_topk_begin) must be redone
   }
   return PGP_OK;
 }
 
 int pgp_score_lcp(pgp_ctx* ctx, int obj, const float* T, int64_t n, int mode, uint32_t* counts, float* scores) {
+  if (!ctx) return PGP_E_INVALID;
+  if (ctx->batch_head != ctx->batch_tail) return pgp_fail(ctx, PGP_E_INVALID, "pgp_score_lcp with batches of pgp_score_lcp_begin still in flight");
   int rc = pgp_score_lcp_begin(ctx, obj, T, n, mode, counts, scores);
   if (rc) return rc;
   rc = pgp_score_lcp_end(ctx);
@@ -542,6 +575,13 @@ int pgp_registered_points(pgp_ctx* ctx, int obj, const float* T12, int32_t* idx_
 
 int pgp_topk(pgp_ctx* ctx, int obj, int k, int64_t index_base, pgp_hyp* out) {
   CHECK_CTX(ctx);
+  if (pgp_comm_active(ctx)) {        // collective: K4 -> all-gather -> merge (pgp_comm.cu)
+    if (k < 0 || (k > 0 && !out)) return pgp_fail(ctx, PGP_E_INVALID, "bad k / output");
+    if (k == 0) return 0;
+    const int t = pgp_topk_begin(ctx, obj, k, index_base);
+    return t < 0 ? t : pgp_topk_end(ctx, t, out);
+  }
+  if (index_base == PGP_INDEX_AUTO) index_base = 0;
   if (ctx->last.obj != obj || ctx->last.n <= 0) return pgp_fail(ctx, PGP_E_NO_SCORES, "no scored batch for object %d", obj);
   if (k < 0 || (k > 0 && !out)) return pgp_fail(ctx, PGP_E_INVALID, "bad k / output");
   int n_out = 0;
@@ -558,6 +598,8 @@ int pgp_topk_dev(pgp_ctx* ctx, int obj, int k, int64_t index_base, pgp_hyp* out_
 
 int pgp_improving_chain(pgp_ctx* ctx, int obj, int64_t index_base, pgp_hyp* out, int cap) {
   CHECK_CTX(ctx);
+  if (pgp_comm_active(ctx)) return pgp_comm_improving_chain(ctx, obj, index_base, out, cap);
+  if (index_base == PGP_INDEX_AUTO) index_base = 0;
   if (ctx->last.obj != obj || ctx->last.n <= 0) return pgp_fail(ctx, PGP_E_NO_SCORES, "no scored batch for object %d", obj);
   if (cap <= 0 || !out) return pgp_fail(ctx, PGP_E_INVALID, "bad capacity / output");
   int n_out = 0;
@@ -624,7 +666,7 @@ int pgp_rigid_from_quads(pgp_ctx* ctx, int obj, const int32_t* base4, const int3
   return k2_rigid_from_quads(ctx, *m, base4, quads, n, T, ok);
 }
 
-int pgp_generate_pcs(pgp_ctx* ctx, int obj, const pgp_pcs_opts* opts, uint64_t seed, int64_t max_hyp, int64_t* n_hyp) {
+int pgp_generate_pcs_range(pgp_ctx* ctx, int obj, const pgp_pcs_opts* opts, uint64_t seed, int base_lo, int base_hi, int64_t max_hyp, int64_t* n_hyp) {
   CHECK_CTX(ctx);
   Model* m = get_model(ctx, obj);
   if (!m) return pgp_fail(ctx, PGP_E_NO_MODEL, "no model in slot %d", obj);
@@ -632,7 +674,17 @@ int pgp_generate_pcs(pgp_ctx* ctx, int obj, const pgp_pcs_opts* opts, uint64_t s
   pgp_pcs_opts o;
   if (opts) o = *opts; else pgp_pcs_default_opts(&o);
   if (!n_hyp || max_hyp <= 0) return pgp_fail(ctx, PGP_E_INVALID, "bad argument");
-  return k2_generate(ctx, *m, &o, seed, max_hyp, n_hyp);
+  const int nb = std::max(1, o.n_bases);
+  if (base_lo < 0 || base_hi > nb || base_lo > base_hi) return pgp_fail(ctx, PGP_E_INVALID, "base range [%d, %d) outside [0, %d)", base_lo, base_hi, nb);
+  m->gen_index_base = -1;
+  return k2_generate(ctx, *m, &o, seed, base_lo, base_hi, max_hyp, n_hyp);
+}
+
+int pgp_generate_pcs(pgp_ctx* ctx, int obj, const pgp_pcs_opts* opts, uint64_t seed, int64_t max_hyp, int64_t* n_hyp) {
+  const int nb = opts ? std::max(1, opts->n_bases) : 100;
+  int rc = pgp_generate_pcs_range(ctx, obj, opts, seed, 0, nb, max_hyp, n_hyp);
+  if (rc == PGP_OK) ctx->models[obj].gen_index_base = 0;
+  return rc;
 }
 
 int pgp_score_generated(pgp_ctx* ctx, int obj, int mode) {
@@ -709,7 +761,7 @@ int pgp_get_bases(pgp_ctx* ctx, int obj, int32_t* ids, float* inv, uint8_t* ok, 
   if (!ids || !inv || !ok) return pgp_fail(ctx, PGP_E_INVALID, "null output");
   const int n = std::min(cap, m->n_gen_bases);
   if (n <= 0) return 0;
-  int rc = k2_get_bases(ctx, n, ids, inv, ok);
+  int rc = k2_get_bases(ctx, *m, n, ids, inv, ok);
   return rc ? rc : n;
 }
 

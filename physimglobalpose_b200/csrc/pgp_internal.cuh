@@ -8,6 +8,7 @@
 
 #include "pgp.h"
 
+#define PGP_WORK_BYTES (512 << 10)   // pgp_ctx::work, allocated once in pgp_create (k4_select.cu static_asserts that its layout fits)
 #define PGP_WARPS_PER_CTA 8
 #define PGP_THREADS (32 * PGP_WARPS_PER_CTA)
 
@@ -121,6 +122,7 @@ struct Model {
   // generated hypotheses (K2)
   DevBuf gen_T, gen_counts, gen_scores;
   int64_t n_gen = 0;
+  int64_t gen_index_base = 0;   // global index of the first generated hypothesis (bases sharded over ranks: pgp_comm_sync_generated); -1 = not known yet
   int n_gen_bases = 0;
   bool gen_scored = false;
   // PPF map of the SEARCH cloud (operMode 1 / StoCS): sorted packed keys -> pair lists, + presence bitset
@@ -147,6 +149,15 @@ struct PendingBatch {            // pgp_score_lcp_begin ... pgp_score_lcp_end
   uint32_t* counts = nullptr;    // host
   float* scores = nullptr;       // host
 };
+// The host-buffer scoring API keeps TWO batches in flight (upload of batch i+1 under the scoring of batch i, download of batch i
+// under the scoring of batch i+1): each has its own device residency, upload counter and events.
+struct BatchSlot {
+  DevBuf T, counts, scores;      // device residency of the batch
+  PendingBatch pending;
+  uint32_t* marks = nullptr;     // pinned, 16 words: [0..4] chunk boundaries, [6] zero, [7] zero, [8] abort flag read back
+  cudaEvent_t ev_start = nullptr, ev_first = nullptr, ev_scored = nullptr, ev_done = nullptr;   // queued so far | first chunk up | K3 done | downloads done
+};
+#define PGP_BATCH_SLOTS 2
 
 struct pgp_ctx {
   int device = 0;
@@ -155,17 +166,19 @@ struct pgp_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;      // host -> device of the host-buffer API
   cudaStream_t back_stream = nullptr;      // device -> host of the host-buffer API (PCIe is full duplex: its own stream)
-  cudaEvent_t ev[12] = {};                 // [0] first chunk uploaded, [8] batch start, [9] batch scored, [10] batch downloaded
   Scene scene;
   std::vector<Model> models;
   LastBatch last;
-  PendingBatch pending;
-  DevBuf batch_T, batch_counts, batch_scores;   // device residency for the host-buffer API
+  BatchSlot batch[PGP_BATCH_SLOTS];        // host-buffer API: batches in flight (pgp_score_lcp_begin / _end)
+  int batch_head = 0, batch_tail = 0;      // next slot to begin / to end (counters, slot = value % PGP_BATCH_SLOTS)
   DevBuf work;                                   // counters / select scratch
   DevBuf topk_out;
   void* pinned = nullptr; size_t pinned_cap = 0;
   int64_t launches = 0;
+  void* comm = nullptr;                    // pgp_comm.cu: NCCL communicator, exchange stream and slots (pgp_comm_release)
   void* k2_scratch = nullptr;              // k2_pcs.cu: the generator's device scratch (k2_release)
+  void* k5_scratch = nullptr;              // k5_tricp.cu (k5_release)
+  void* k6_scratch = nullptr;              // k6_explained.cu (k6_release)
   int stream_upload = 1;  // pgp_score_lcp: overlap the batch upload with the scoring launch (0: upload first; use under profilers)
   int tail_split = 4;     // K3 fine kernel: model chunks per hypothesis in the last wave (1 = off)
   int k3_warps_count = 32, k3_warps_weighted = 24;   // warps per CTA of k3_fine_kernel (32 -> 64 registers/thread, 24 -> 80, 16 -> 128)
@@ -199,19 +212,26 @@ int k3_nearest(pgp_ctx* ctx, const Model& m, const float* T_dev, int32_t* idx_de
 int k4_topk(pgp_ctx* ctx, const LastBatch& b, int k, int64_t index_base, pgp_hyp* out_host, int* n_out);
 int k4_topk_dev(pgp_ctx* ctx, const LastBatch& b, int k, int64_t index_base, pgp_hyp* out_dev);
 int k4_chain(pgp_ctx* ctx, const LastBatch& b, int64_t index_base, pgp_hyp* out_host, int cap, int* n_out);
+int k4_select_dev(pgp_ctx* ctx, const LastBatch& b, int k, int64_t index_base, int mode, pgp_hyp* hdr_dev, pgp_hyp* out_dev);
+// pgp_comm.cu
+void pgp_comm_release(pgp_ctx* ctx);
+bool pgp_comm_active(const pgp_ctx* ctx);
+extern "C" int pgp_comm_improving_chain(pgp_ctx* ctx, int obj, int64_t index_base, pgp_hyp* out_host, int cap);
 // k2_pcs.cu
 int k2_extract_pairs(pgp_ctx* ctx, const Model& m, float dist, float eps, int32_t* pairs_host, int64_t cap, int64_t* n_pairs);
 int k2_find_quads(pgp_ctx* ctx, const Model& m, const int32_t* base4, float inv1, float inv2, float eps,
                   const int32_t* p1, int64_t n1, const int32_t* p2, int64_t n2, int32_t* quads_host, int64_t cap, int64_t* n_quads);
 int k2_find_quads_v4pcs(pgp_ctx* ctx, const Model& m, const int32_t* base4, float eps, int32_t* quads_host, int64_t cap, int64_t* n_quads);
 int k2_rigid_from_quads(pgp_ctx* ctx, const Model& m, const int32_t* base4, const int32_t* quads_host, int64_t n, float* T_host, uint8_t* ok_host);
-int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, int64_t max_hyp, int64_t* n_hyp);
+int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, int base_lo, int base_hi, int64_t max_hyp, int64_t* n_hyp);
 int k2_set_ppf_map(pgp_ctx* ctx, Model& m, const int32_t* keys4, const int64_t* offsets, const int32_t* pairs, int64_t n_keys);
 int k2_build_ppf_map(pgp_ctx* ctx, Model& m);
 int k2_scene_ppf_keys(pgp_ctx* ctx, const int32_t* pairs_host, int64_t n, int32_t* keys4_host);
 uint32_t k2_stocs_engine_seed(uint64_t seed, int base, int attempt);
-int k2_get_bases(pgp_ctx* ctx, int n_bases, int32_t* ids_host, float* inv_host, uint8_t* ok_host);
+int k2_get_bases(pgp_ctx* ctx, const Model& m, int n_bases, int32_t* ids_host, float* inv_host, uint8_t* ok_host);
 void k2_release(pgp_ctx* ctx);
+void k5_release(pgp_ctx* ctx);
+void k6_release(pgp_ctx* ctx);
 // k5_tricp.cu
 int k5_tricp(pgp_ctx* ctx, Model& m, const float* seg_xyz_host, int ns, double* poses16_host, int k, float trim, float ratio,
              int max_iter, int* iters_out, float* energy_out);

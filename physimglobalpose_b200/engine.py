@@ -12,7 +12,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import PGP_LCP_COUNT, PGP_LCP_WEIGHTED, PgpError, PgpHyp, PgpPcsOpts
+from ._lib import PGP_COMM_ID_BYTES, PGP_INDEX_AUTO, PGP_LCP_COUNT, PGP_LCP_WEIGHTED, PgpError, PgpHyp, PgpPcsOpts
 
 MODES = {"count": PGP_LCP_COUNT, "weighted": PGP_LCP_WEIGHTED, PGP_LCP_COUNT: PGP_LCP_COUNT, PGP_LCP_WEIGHTED: PGP_LCP_WEIGHTED}
 
@@ -37,9 +37,10 @@ class PoseEngine:
     """One context on one GPU.  Scene = the segmented cloud of one object request ("P"); model
     slots hold the search / validation clouds ("Q", "Q_validation")."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, _borrowed_ctx=None):
         self._lib = _lib.load()
-        self._ctx = self._lib.pgp_create(int(device))
+        self._owned = _borrowed_ctx is None
+        self._ctx = self._lib.pgp_create(int(device)) if self._owned else _borrowed_ctx
         if not self._ctx:
             raise PgpError(-2, self._lib.pgp_last_error(None).decode())
         self.device = int(device)
@@ -51,7 +52,8 @@ class PoseEngine:
     # ------------------------------------------------------------------ plumbing
     def close(self):
         if getattr(self, "_ctx", None):
-            self._lib.pgp_destroy(self._ctx)
+            if self._owned:
+                self._lib.pgp_destroy(self._ctx)
             self._ctx = None
 
     def __del__(self):
@@ -207,6 +209,72 @@ class PoseEngine:
         assert out_dev.is_cuda and out_dev.numel() * out_dev.element_size() >= 64 * k
         self._check(self._lib.pgp_topk_dev(self._ctx, obj, k, index_base, out_dev.data_ptr()))
 
+    def topk_begin(self, obj: int, k: int, index_base: int = 0) -> int:
+        """pgp_topk_begin: K4 on the context's stream, all-gather + download on its exchange stream; returns a ticket."""
+        self._tickets = getattr(self, "_tickets", {})
+        t = self._check(self._lib.pgp_topk_begin(self._ctx, obj, k, index_base))
+        self._tickets[t] = k
+        return t
+
+    def topk_stream_wait(self, ticket: int):
+        self._check(self._lib.pgp_topk_stream_wait(self._ctx, ticket))
+
+    def topk_end(self, ticket: int) -> np.ndarray:
+        """pgp_topk_end: wait for the ticket, merge -> the global top-k (the same on every rank)."""
+        out = np.zeros(max(self._tickets.pop(ticket), 1), HYP_DTYPE)
+        m = self._check(self._lib.pgp_topk_end(self._ctx, ticket, _ptr(out)))
+        return out[:m].copy()
+
+    # ------------------------------------------------------------------ multi-GPU (one process per GPU)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(PGP_COMM_ID_BYTES)
+        rc = _lib.load().pgp_comm_unique_id(buf)
+        if rc < 0:
+            raise PgpError(rc, _lib.load().pgp_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, unique_id: Optional[bytes], rank: int, world: int):
+        """pgp_comm_init (collective): joins this context to the communicator; pgp_topk / improving_chain become collective."""
+        buf = C.create_string_buffer(unique_id, PGP_COMM_ID_BYTES) if unique_id is not None else None
+        self._check(self._lib.pgp_comm_init(self._ctx, buf, int(rank), int(world)))
+
+    def comm_destroy(self):
+        self._check(self._lib.pgp_comm_destroy(self._ctx))
+
+    @property
+    def comm_rank(self) -> int:
+        return int(self._lib.pgp_comm_rank(self._ctx))
+
+    @property
+    def comm_world(self) -> int:
+        return int(self._lib.pgp_comm_world(self._ctx))
+
+    def generate_pcs_range(self, obj: int, base_lo: int, base_hi: int, seed: int = 1, max_hyp: int = 10000, **opts) -> int:
+        """pgp_generate_pcs_range: bases [base_lo, base_hi) of the request's n_bases (bases shard across GPUs)."""
+        o = PgpPcsOpts()
+        self._lib.pgp_pcs_default_opts(C.byref(o))
+        for k, v in opts.items():
+            setattr(o, k, v)
+        n = C.c_int64(0)
+        self._check(self._lib.pgp_generate_pcs_range(self._ctx, obj, C.byref(o), int(seed), int(base_lo), int(base_hi), int(max_hyp), C.byref(n)))
+        self._ngen = getattr(self, "_ngen", {})
+        self._ngen[obj] = n.value
+        return n.value
+
+    def sync_generated(self, obj: int, max_hyp: int = 0):
+        """pgp_comm_sync_generated (collective): global cap in rank order; returns (index_base of this rank, global total)."""
+        base, tot = C.c_int64(0), C.c_int64(0)
+        self._check(self._lib.pgp_comm_sync_generated(self._ctx, obj, int(max_hyp), C.byref(base), C.byref(tot)))
+        self._ngen = getattr(self, "_ngen", {})
+        return base.value, tot.value
+
+    def bench_sector_gather(self, footprint_bytes: int, loads_per_thread: int = 256) -> float:
+        """pgp_bench_sector_gather: random 32-byte-sector gather throughput in GB/s."""
+        g = C.c_float(0)
+        self._check(self._lib.pgp_bench_sector_gather(self._ctx, int(footprint_bytes), int(loads_per_thread), C.byref(g)))
+        return float(g.value)
+
     def improving_chain(self, obj: int, index_base: int = 0, cap: int = 4096) -> np.ndarray:
         out = np.zeros(cap, HYP_DTYPE)
         m = self._check(self._lib.pgp_improving_chain(self._ctx, obj, index_base, _ptr(out), cap))
@@ -356,6 +424,126 @@ class PoseEngine:
                                                       float(normal_radius), float(outlier_radius), int(min_neighbors), _ptr(xyz), _ptr(nrm), cap,
                                                       C.byref(nraw)))
         return xyz[:n].copy(), nrm[:n].copy(), nraw.value
+
+
+class PoseGroup:
+    """One process, n GPUs (pgp_group_*): replicated scene / models, bases or hypotheses sharded over the devices, NCCL
+    all-gather + deterministic merge of the selections.  `engine(i)` gives device i's context for the per-device calls."""
+
+    def __init__(self, devices: Sequence[int]):
+        self._lib = _lib.load()
+        ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+        self._g = self._lib.pgp_group_create(len(devices), ids)
+        if not self._g:
+            raise PgpError(-9, self._lib.pgp_last_error(None).decode())
+        self.devices = list(devices)
+        self._engines = [PoseEngine(d, _borrowed_ctx=self._lib.pgp_group_ctx(self._g, i)) for i, d in enumerate(devices)]
+
+    def close(self):
+        if getattr(self, "_g", None):
+            for e in self._engines:
+                e.close()
+            self._lib.pgp_group_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int) -> int:
+        if rc < 0:
+            raise PgpError(rc, self._lib.pgp_group_last_error(self._g).decode())
+        return rc
+
+    def __len__(self):
+        return len(self.devices)
+
+    def engine(self, i: int) -> PoseEngine:
+        return self._engines[i]
+
+    def set_scene(self, xyz, normals=None, delta: float = 0.005):
+        xyz, normals = _f32(xyz, 3), _f32(normals, 3)
+        self._check(self._lib.pgp_group_set_scene(self._g, _ptr(xyz), _ptr(normals), len(xyz), float(delta)))
+        for e in self._engines:
+            e._ns = len(xyz)
+
+    def set_scene_priors(self, prior):
+        prior = _f32(prior).reshape(-1)
+        self._check(self._lib.pgp_group_set_scene_priors(self._g, _ptr(prior)))
+
+    def set_scene_prior_image(self, img_u16, K):
+        img = np.ascontiguousarray(img_u16, dtype=np.uint16)
+        K = _f32(K).reshape(9)
+        self._check(self._lib.pgp_group_set_scene_prior_image(self._g, _ptr(img), img.shape[0], img.shape[1], _ptr(K)))
+
+    def set_model(self, obj: int, search_xyz, search_normals, val_xyz=None, val_normals=None):
+        sx, sn = _f32(search_xyz, 3), _f32(search_normals, 3)
+        vx = sx if val_xyz is None else _f32(val_xyz, 3)
+        vn = sn if val_xyz is None else _f32(val_normals, 3)
+        self._check(self._lib.pgp_group_set_model(self._g, obj, _ptr(sx), _ptr(sn), len(sx), _ptr(vx), _ptr(vn), len(vx)))
+        for e in self._engines:
+            e._nq[obj], e._nv[obj] = len(sx), len(vx)
+
+    def build_ppf_map(self, obj: int):
+        self._check(self._lib.pgp_group_build_ppf_map(self._g, obj))
+
+    def set_ppf_map(self, obj: int, keys4, offsets, pairs):
+        k = np.ascontiguousarray(keys4, np.int32).reshape(-1, 4)
+        o = np.ascontiguousarray(offsets, np.int64)
+        p = np.ascontiguousarray(pairs, np.int32).reshape(-1, 2)
+        self._check(self._lib.pgp_group_set_ppf_map(self._g, obj, _ptr(k), _ptr(o), _ptr(p), len(k)))
+
+    def generate_pcs(self, obj: int, seed: int = 1, max_hyp: int = 10000, **opts) -> int:
+        o = PgpPcsOpts()
+        self._lib.pgp_pcs_default_opts(C.byref(o))
+        for k, v in opts.items():
+            setattr(o, k, v)
+        n = C.c_int64(0)
+        self._check(self._lib.pgp_group_generate_pcs(self._g, obj, C.byref(o), int(seed), int(max_hyp), C.byref(n)))
+        return n.value
+
+    def score_generated(self, obj: int, mode="count"):
+        self._check(self._lib.pgp_group_score_generated(self._g, obj, MODES[mode]))
+
+    def score_lcp(self, obj: int, T, mode="count"):
+        T = _f32(T).reshape(-1, 12)
+        counts = np.zeros(len(T), np.uint32)
+        scores = np.zeros(len(T), np.float32)
+        self._check(self._lib.pgp_group_score_lcp(self._g, obj, _ptr(T), len(T), MODES[mode], _ptr(counts), _ptr(scores)))
+        return counts, scores
+
+    def topk(self, obj: int, k: int) -> np.ndarray:
+        out = np.zeros(max(k, 1), HYP_DTYPE)
+        m = self._check(self._lib.pgp_group_topk(self._g, obj, k, _ptr(out)))
+        return out[:m].copy()
+
+    def improving_chain(self, obj: int, cap: int = 4096) -> np.ndarray:
+        out = np.zeros(cap, HYP_DTYPE)
+        m = self._check(self._lib.pgp_group_improving_chain(self._g, obj, _ptr(out), cap))
+        return out[:m].copy()
+
+
+def exchange_merge(wire: np.ndarray, world: int, k: int, kind: int = 0, mode="count", auto_base: bool = False, cap: int = 4096) -> np.ndarray:
+    """pgp_exchange_merge: `wire` = world x (k + 1) records (header + k records per rank), as the all-gather delivers them."""
+    lib = _lib.load()
+    w = np.ascontiguousarray(wire, HYP_DTYPE).reshape(world, k + 1)
+    out = np.zeros(max(cap, 1), HYP_DTYPE)
+    m = lib.pgp_exchange_merge(w.ctypes.data, world, k, kind, MODES[mode], 1 if auto_base else 0, out.ctypes.data, cap)
+    if m < 0:
+        raise PgpError(m, "pgp_exchange_merge")
+    return out[:m].copy()
+
+
+def wire_block(records: np.ndarray, batch_size: int, k: int) -> np.ndarray:
+    """One rank's block of the exchange: header {batch size, number of records} + k record slots."""
+    blk = np.zeros(k + 1, HYP_DTYPE)
+    blk["index"][1:] = -1
+    n = min(len(records), k)
+    blk[0]["index"], blk[0]["count"] = batch_size, n
+    blk[1:1 + n] = records[:n]
+    return blk
 
 
 def topk_merge(lists: Sequence[np.ndarray], k: int) -> np.ndarray:

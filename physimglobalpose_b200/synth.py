@@ -210,6 +210,23 @@ def make_hypotheses(prob: Problem, n: int, seed: int = 4321, chunk: int = 1 << 2
     return out
 
 
+def make_hypotheses_range(prob: Problem, lo: int, hi: int, seed: int = 4321, block: int = 1 << 18) -> np.ndarray:
+    """Hypotheses [lo, hi) of an arbitrarily long list whose content depends only on (seed, index): the list is cut into blocks
+    of `block` hypotheses, block b drawn with its own generator seeded (seed, b) exactly like make_hypotheses draws one chunk.
+    Lets every rank of a sharded run build just its shard of the SAME global list (index 0 = GT)."""
+    out = np.empty((max(hi - lo, 0), 3, 4), dtype=np.float32)
+    b = lo // block
+    while b * block < hi:
+        s0, s1 = b * block, (b + 1) * block
+        full = make_hypotheses(prob, block, seed=(seed * 1_000_003 + b) & 0x7FFFFFFF, chunk=block)
+        if b != 0:                                  # only the list's first hypothesis is the exact GT
+            full[0] = make_hypotheses(prob, 2, seed=(seed * 1_000_003 + b + 77) & 0x7FFFFFFF)[1]
+        a, e = max(lo, s0), min(hi, s1)
+        out[a - lo:e - lo] = full[a - s0:e - s0]
+        b += 1
+    return out
+
+
 def kbar_27(prob: Problem, T: np.ndarray, max_hyp: int = 256) -> tuple[float, float]:
     """Mean number of scene points in the 27 delta-cells around a transformed model point
     (k-bar of SURVEY.md 8(d)) and the fraction of point-queries whose 27-neighbourhood is

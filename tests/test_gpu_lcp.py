@@ -7,8 +7,44 @@ from physimglobalpose_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
+class _Checker:
+    """The CPU checker of these tests: the reference engine itself (oracle/_ref/libs4ref.so -- built from /root/reference where
+    that exists and shipped to the GPU box as a built file) answers every question it can (Verify, WeightedVerify, centroids,
+    priors); the C restatement (pinned to it by tests/test_oracle_golden.py) only fills in what the reference does not expose
+    per call (per-point nearest ids, the chain scan, the multi-threaded driver)."""
+
+    def __init__(self, port_lib, args, kw):
+        self.port = port_lib.PortOracle(*args, **kw)
+        self.ref = port_lib.RefOracle(*args, **kw) if port_lib.have_ref() else None
+        self.first = self.ref or self.port
+
+    def verify(self, T):
+        return self.first.verify(T)
+
+    def weighted_verify(self, T, reg_of=-1):
+        return self.first.weighted_verify(T, reg_of=reg_of)
+
+    def centroids(self):
+        return self.first.centroids()
+
+    def priors(self):
+        return self.first.priors()
+
+    def __getattr__(self, name):
+        return getattr(self.port, name)
+
+
 def _oracle(port_lib, prob, **kw):
-    return port_lib.PortOracle(prob.scene_xyz, prob.scene_nrm, prob.model_xyz, prob.model_nrm, prob.model_xyz, prob.model_nrm, prob.delta, **kw)
+    return _Checker(port_lib, (prob.scene_xyz, prob.scene_nrm, prob.model_xyz, prob.model_nrm, prob.model_xyz, prob.model_nrm, prob.delta), kw)
+
+
+def test_gpu_tests_check_against_the_reference_engine_when_it_travelled(port_lib, small_problem):
+    """On the GPU box oracle/_ref/libs4ref.so is present (gpurun ships built files): the parity tests below then compare the CUDA
+    path with Match4PCSBase::Verify / WeightedVerify directly, not only with the C restatement."""
+    import os
+    prob, _ = small_problem
+    o = _oracle(port_lib, prob)
+    assert (o.ref is not None) == os.path.exists(port_lib.REF_SO)
 
 
 def _setup(engine, prob, obj=0):

@@ -261,10 +261,11 @@ __global__ void __launch_bounds__(CLS_THREADS) k1f_fill_lists(const uint32_t* __
 // scene point p* satisfies d(q,p*) <= d(q,p') <= hi(p') for every p', and d(q,p*) <= delta, hence
 //     lo(p*)^2 <= min( min_p' hi(p')^2 , delta^2 )      (+ rounding margins)
 // -- the list of all points passing that bound holds the nearest neighbour (and every point that
-// can tie with it) of every query of the voxel.  At 1/8-cell voxels that is ~5 points instead of
-// the ~60 in the 27 cells.  Layout: wvox[block * 512 + voxel] = (offset within the block's region << 10) | count,
-// wbase[block] = first entry of the region, wlists = float4 COPIES of the candidate points {x, y, z, original
-// index}: scoring reaches the candidates with one indexed load and no rank arithmetic.
+// can tie with it) of every query of the voxel.  At 1/8-cell voxels that is ~2 points (after the
+// domination pruning) instead of the ~60 in the 27 cells.  Layout: wcnt[block * 512 + voxel] = list length (a byte),
+// wword[block * 32 + w] = first entry of label word w's 16 voxels, wlists = the candidates' ORIGINAL indices (4 bytes each;
+// the points are read from the cloud in original order, 16 bytes per scene point and L2-resident), vrec = the per-voxel cone
+// record that lets scoring skip the search altogether when the candidates' normals agree (k1w_fill).
 __device__ __forceinline__ void box_d2(const float4 p, float vx, float vy, float vz, float hs, float& mind2, float& maxd2) {
   const float ax = fabsf(p.x - vx), ay = fabsf(p.y - vy), az = fabsf(p.z - vz);
   const float lx = fmaxf(ax - hs, 0.f), ly = fmaxf(ay - hs, 0.f), lz = fmaxf(az - hs, 0.f);
@@ -299,6 +300,7 @@ __device__ __forceinline__ void sweep27(const uint32_t* __restrict__ cell_start,
 
 __device__ __forceinline__ float wlist_threshold(float u2, float dhi2) { return fminf(u2 * (1.0f + 4e-5f), dhi2); }
 
+constexpr uint32_t VREC_UNDECIDED = 255u;
 constexpr uint32_t WV_CNT_BITS = 8, WV_CNT_MAX = (1u << WV_CNT_BITS) - 1u, WV_REL_MAX = (1u << (32 - WV_CNT_BITS)) - 1u;   // counts are stored as bytes
 
 // Pass A: list length of every voxel of the block (0 for OUT voxels) -> wvox (count only), block total -> region.
@@ -364,12 +366,21 @@ __global__ void __launch_bounds__(CLS_THREADS) k1w_count(const uint32_t* __restr
   }
 }
 
-// Pass B: per-block exclusive scan of the counts -> wvox = rel << 10 | count, then the fill (copies of the
-// candidates' float4 records {x, y, z, original index}, so that scoring needs no second indirection).
+// Pass B: per-block exclusive scan of the counts -> wvox = rel << 8 | count, then the fill: the ORIGINAL INDEX of every candidate
+// (4 bytes; scoring fetches the point itself from the L2-resident cloud in original order, Scene::unsorted) and, per voxel, the
+// cone record `vrec`:
+//     vrec[block * 512 + voxel] = code << 24 | rep
+// rep = original index of the voxel's first candidate; code tells how far the other candidates' normals are from rep's:
+//     0          every candidate has bit-identical (unit normal, prior): WeightedVerify's gate and weight do not depend on WHICH
+//                candidate is the nearest, so scoring evaluates the exact gate once on rep and never searches,
+//     1 .. 254   |n_i - n_rep| <= code * VREC_EPS_STEP for every candidate and all priors are equal: scoring decides the gate for
+//                all candidates at once whenever the dot product with rep's normal clears the 30-degree threshold by that margin,
+//     255        mixed priors, an empty list, more than 2^24 scene points: always the exact nearest search.
 __global__ void __launch_bounds__(CLS_THREADS) k1w_fill(const uint32_t* __restrict__ block_cell, const uint32_t* __restrict__ cell_start,
-                                                        const float4* __restrict__ pts, GridParams g, uint32_t* __restrict__ wvox,
-                                                        const uint32_t* __restrict__ region_base, float4* __restrict__ wlists,
-                                                        unsigned char* __restrict__ wcnt, uint32_t* __restrict__ wword) {
+                                                        const float4* __restrict__ pts, const float4* __restrict__ aux, GridParams g,
+                                                        uint32_t* __restrict__ wvox, const uint32_t* __restrict__ region_base,
+                                                        uint32_t* __restrict__ wlists, unsigned char* __restrict__ wcnt, uint32_t* __restrict__ wword,
+                                                        uint32_t* __restrict__ vrec, int rep_ok) {
   __shared__ float4 s_p[CLS_CHUNK];
   __shared__ uint32_t s_warp[CLS_THREADS / 32];
   const int b = blockIdx.x;
@@ -399,7 +410,8 @@ __global__ void __launch_bounds__(CLS_THREADS) k1w_fill(const uint32_t* __restri
   // record of every label word's 16 voxels; a voxel's first record = that + the counts of the voxels before it in the word
   *reinterpret_cast<uchar4*>(wcnt + (size_t)b * 512 + threadIdx.x * 4) = make_uchar4((unsigned char)cnt[0], (unsigned char)cnt[1], (unsigned char)cnt[2], (unsigned char)cnt[3]);
   if ((threadIdx.x & 3) == 0) wword[(size_t)b * 32 + (threadIdx.x >> 2)] = base + rel[0];
-  if (total == 0) return;      // uniform over the CTA
+  uint4* vout = reinterpret_cast<uint4*>(vrec + (size_t)b * 512 + threadIdx.x * 4);
+  if (total == 0) { *vout = make_uint4(VREC_UNDECIDED << 24, VREC_UNDECIDED << 24, VREC_UNDECIDED << 24, VREC_UNDECIDED << 24); return; }      // uniform over the CTA
   float vx[4], vy[4], vz[4], u2[4], thr[4];
   uint32_t wr[4];
 #pragma unroll
@@ -423,16 +435,45 @@ __global__ void __launch_bounds__(CLS_THREADS) k1w_fill(const uint32_t* __restri
   });
 #pragma unroll
   for (int j = 0; j < 4; ++j) thr[j] = wlist_threshold(u2[j], g.dhi2);
-  sweep27(cell_start, pts, g, cx, cy, cz, s_p, [&](const float4 p, uint32_t) {
+  // cone of the candidates' normals around the first candidate's (rep)
+  uint32_t rep[4] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+  float n0x[4], n0y[4], n0z[4], pr0[4], maxd2[4] = {0.f, 0.f, 0.f, 0.f};
+  bool mixed[4] = {false, false, false, false};
+  sweep27(cell_start, pts, g, cx, cy, cz, s_p, [&](const float4 p, uint32_t pos) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       if (wr[j] != 0xffffffffu) {
         float lo2, hi2;
         box_d2(p, vx[j], vy[j], vz[j], hs, lo2, hi2);
-        if (lo2 <= thr[j] && !dominated(p, bx[j], by[j], bz[j], hs, centre_d2(p, vx[j], vy[j], vz[j]), bc2[j], dom_margin)) wlists[wr[j]++] = p;   // as k1w_count counted
+        if (lo2 <= thr[j] && !dominated(p, bx[j], by[j], bz[j], hs, centre_d2(p, vx[j], vy[j], vz[j]), bc2[j], dom_margin)) {   // as k1w_count counted
+          const uint32_t orig = (uint32_t)__float_as_int(p.w);
+          wlists[wr[j]++] = orig;
+          const float4 a = __ldg(aux + pos);
+          if (rep[j] == 0xffffffffu) { rep[j] = orig; n0x[j] = a.x; n0y[j] = a.y; n0z[j] = a.z; pr0[j] = a.w; }
+          else {
+            const float dx = a.x - n0x[j], dy = a.y - n0y[j], dz = a.z - n0z[j];
+            maxd2[j] = fmaxf(maxd2[j], __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, dz * dz)));
+            mixed[j] |= a.w != pr0[j];
+          }
+        }
       }
     }
   });
+  uint32_t out[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint32_t code = VREC_UNDECIDED;
+    if (rep_ok && rep[j] != 0xffffffffu && !mixed[j]) {
+      if (maxd2[j] == 0.f) code = 0u;
+      else {
+        const float eps = sqrtf(maxd2[j]) * (1.0f + 1e-6f) + 1e-7f;
+        const float cf = ceilf(eps / VREC_EPS_STEP);
+        code = cf > 254.f ? VREC_UNDECIDED : (uint32_t)fmaxf(cf, 1.f);
+      }
+    }
+    out[j] = (code << 24) | (code == VREC_UNDECIDED ? 0u : rep[j]);
+  }
+  *vout = make_uint4(out[0], out[1], out[2], out[3]);
 }
 
 
@@ -640,12 +681,14 @@ int k1_build_wlists(pgp_ctx* ctx) {
   PGP_CUDA(ctx, cudaStreamSynchronize(st));
   if (overflow || total >= (1ull << 32) - 64) return PGP_OK;      // 32-bit entry offsets
   PGP_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-  if ((size_t)total * 16 + (64u << 20) > free_b + s.wlists.cap) return PGP_OK;
+  if ((size_t)total * 4 + (size_t)nb * 2048 + (64u << 20) > free_b + s.wlists.cap + s.vrec.cap) return PGP_OK;
   int rc = pgp_scan_exclusive_u32(ctx, region, (int64_t)nb + 1, s.scratch.as<uint32_t>());
   if (rc) return rc;
-  PGP_CUDA(ctx, s.wlists.reserve((size_t)total * 16 + 16));
-  k1w_fill<<<nb, CLS_THREADS, 0, st>>>(s.block_cell.as<uint32_t>(), s.cell_start.as<uint32_t>(), s.pts.as<float4>(), g, s.wvox.as<uint32_t>(), region,
-                                       s.wlists.as<float4>(), s.wcnt.as<unsigned char>(), s.wword.as<uint32_t>());
+  PGP_CUDA(ctx, s.wlists.reserve((size_t)total * 4 + 16));
+  PGP_CUDA(ctx, s.vrec.reserve((size_t)nb * 2048 + 16));
+  k1w_fill<<<nb, CLS_THREADS, 0, st>>>(s.block_cell.as<uint32_t>(), s.cell_start.as<uint32_t>(), s.pts.as<float4>(), s.aux.as<float4>(), g,
+                                       s.wvox.as<uint32_t>(), region, s.wlists.as<uint32_t>(), s.wcnt.as<unsigned char>(), s.wword.as<uint32_t>(),
+                                       s.vrec.as<uint32_t>(), s.n <= (1 << 24) ? 1 : 0);
   ctx->launches++;
   PGP_CUDA(ctx, cudaGetLastError());
   s.n_wlist_entries = (int64_t)total;

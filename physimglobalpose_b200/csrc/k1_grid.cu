@@ -330,6 +330,7 @@ int k1_refresh_sorted_priors(pgp_ctx* ctx) {
   PGP_CUDA(ctx, cudaMemcpyAsync(&h, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
   PGP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   s.priors_binary = (h == 0);
+  s.wlists_ready = false; s.wlists_tried = false;      // K1c's cone records depend on the priors: rebuilt by the next WEIGHTED call
   return PGP_OK;
 }
 

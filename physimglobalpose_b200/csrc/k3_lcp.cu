@@ -63,7 +63,9 @@ struct LcpParams {
   float model_rinf;          // max |coordinate| of the validation model (bounds the transform's intermediates)
   const unsigned char* wcnt; // K1c: per voxel candidate count (a byte)
   const uint32_t* wword;     // K1c: per label word (16 voxels) the first record
-  const float4* wlists;      // K1c: candidate records {x, y, z, original index}
+  const uint32_t* wlists;    // K1c: candidates' ORIGINAL indices
+  const uint32_t* vrec;      // K1c: per voxel (code << 24 | representative candidate): spread of the candidates' normals
+  const float4* pts_orig;    // centred scene points by ORIGINAL index (Scene::unsorted)
   const float4* aux_orig;    // unit normal + prior by ORIGINAL scene index
   const float4* groups;      // bounding sphere {centre, radius} of every aligned run of 32 validation points (pgp_set_model)
   const float* dist;         // K1d: per cell, lower bound of the distance to the nearest scene point (nullptr: no group cull)
@@ -316,6 +318,7 @@ __global__ void __launch_bounds__(THREADS, 2) k3_lcp_kernel(const __grid_constan
 // rounding sequence (GridParams::inflate), so counts stay bit-exact.
 // warps per CTA (one CTA per SM) is a template parameter of the kernel: 32 (64 registers per thread) or 16 (128 registers)
 constexpr int FUNROLL = 4;           // model points per lane per step (their label gathers are issued together)
+constexpr int SQCAP = 64;            // second-level (slow) queue slots per warp, weighted mode: < 32 left over + at most 32 new per drain
 constexpr int FQCAP = 32 + 32 * FUNROLL;   // queue slots per warp: < 32 left over + the new ones of one step
 
 struct FineCtx {
@@ -324,7 +327,12 @@ struct FineCtx {
   const float4* s_groups;    // bounding spheres of the tile's 32-point groups
   const uint2* table;        // bmrank: shared (SMEM_TABLE) or global
   uint16_t* q;               // per warp: queued model-point indices
-  uint32_t* qe;              // count mode: (label word index << 4) | rank of the voxel among the word's AMBIG voxels
+  uint32_t* qe;              // count mode: (label word index << 4) | rank of the voxel among the word's AMBIG voxels;
+                             // weighted mode: the voxel's address block * 512 + voxel = (label word index << 4) | (voxel & 15)
+  unsigned char* qr;         // weighted mode: rank of the voxel among the word's AMBIG voxels | (label == AMBIG) << 4
+  uint16_t* sq;              // weighted mode, second-level queue (SQCAP slots per warp) of the queries the cone record could not settle:
+  uint32_t* sqe;             //   model point, voxel address,
+  unsigned char* sqr;        //   info | gate_known << 5 -- resolved 32 at a time so that the rare, long exact path runs on full warps
   uint32_t* glist;           // per warp: byte offsets (into the staged model) of the groups of the current hypothesis that survived the cull (+ FUNROLL pad slots)
   int dummy_group;           // a group of NaN points behind the tile
   int dimx, dimy, dimz;
@@ -355,14 +363,10 @@ __device__ __forceinline__ uint32_t label_slot(const LcpParams& p, const FineCtx
   return (wr.x & bit) ? blk * 32u + (uint32_t)(v >> 4) : f.dummy_word;
 }
 
-// K1c nearest-candidate records of the voxel: the 16 byte counts of its label word and the word's first record (two independent
-// loads from tables that stay L2-resident: 640 bytes per block), then first record = word base + the counts of the voxels before it
-template <bool SMEM_TABLE>
-__device__ __forceinline__ const float4* wlist_of(const LcpParams& p, const FineCtx& f, int ix, int iy, int iz, uint32_t& cnt) {
-  const int c = ((iz >> 3) * f.dimy + (iy >> 3)) * f.dimx + (ix >> 3);
-  const uint2 wr = table_word<SMEM_TABLE>(f, c >> 5);
-  const unsigned blk = wr.y + __popc(wr.x & ((1u << (c & 31)) - 1u));
-  const int v = ((iz & 7) << 6) | ((iy & 7) << 3) | (ix & 7);
+// K1c nearest-candidate list of voxel v of block blk: the 16 byte counts of its label word and the word's first entry (two
+// independent loads from tables that stay L2-resident: 640 bytes per block), then first entry = word base + the counts of the voxels
+// before it
+__device__ __forceinline__ const uint32_t* wlist_at(const LcpParams& p, uint32_t blk, int v, uint32_t& cnt) {
   const uint4 cw = __ldg(reinterpret_cast<const uint4*>(p.wcnt + (size_t)blk * 512) + (v >> 4));
   const uint32_t base = __ldg(p.wword + (size_t)blk * 32 + (v >> 4));
   const int wi = (v >> 2) & 3, bi = v & 3;
@@ -371,6 +375,13 @@ __device__ __forceinline__ const float4* wlist_of(const LcpParams& p, const Fine
   before += (wi > 0 ? __dp4a(cw.x, 0x01010101u, 0u) : 0u) + (wi > 1 ? __dp4a(cw.y, 0x01010101u, 0u) : 0u) + (wi > 2 ? __dp4a(cw.z, 0x01010101u, 0u) : 0u);
   cnt = (mine >> (8 * bi)) & 255u;
   return p.wlists + base + before;
+}
+template <bool SMEM_TABLE>
+__device__ __forceinline__ const uint32_t* wlist_of(const LcpParams& p, const FineCtx& f, int ix, int iy, int iz, uint32_t& cnt) {
+  const int c = ((iz >> 3) * f.dimy + (iy >> 3)) * f.dimx + (ix >> 3);
+  const uint2 wr = table_word<SMEM_TABLE>(f, c >> 5);
+  const unsigned blk = wr.y + __popc(wr.x & ((1u << (c & 31)) - 1u));
+  return wlist_at(p, blk, ((iz & 7) << 6) | ((iy & 7) << 3) | (ix & 7), cnt);
 }
 
 // phase 2 (count mode) for one queued query: the reference's exact test against the candidate records of its AMBIG voxel.
@@ -391,21 +402,23 @@ __device__ __forceinline__ int resolve_ambiguous(const LcpParams& p, const Xf& x
 
 // nearest in-range scene point among the voxel's K1c candidates (same acceptance / tie rule as
 // nearest_within: d2 <= delta^2, exact ties to the smaller original index): original index or -1.
-// U records per round are loaded together: the list lives in DRAM at the benchmark sizes and a one-at-a-time loop pays a
-// memory latency per record.
+// U candidates per round: their indices are loaded together, then their points (L2-resident cloud in original order).
 template <int U>
-__device__ __forceinline__ int nearest_in_list(const LcpParams& p, const float4* __restrict__ l, uint32_t cnt, float tx, float ty, float tz) {
+__device__ __forceinline__ int nearest_in_list(const LcpParams& p, const uint32_t* __restrict__ l, uint32_t cnt, float tx, float ty, float tz) {
   float best = p.g.r2;
   int best_orig = 0x7fffffff;
   for (uint32_t j = 0; j < cnt; j += U) {
+    uint32_t id[U];
     float4 sp[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) if (u == 0 || j + u < cnt) sp[u] = __ldg(l + j + u);
+    for (int u = 0; u < U; ++u) if (u == 0 || j + u < cnt) id[u] = __ldg(l + j + u);
+#pragma unroll
+    for (int u = 0; u < U; ++u) if (u == 0 || j + u < cnt) sp[u] = __ldg(p.pts_orig + id[u]);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (u == 0 || j + u < cnt) {
         const float d2 = sqdist3(tx, ty, tz, sp[u].x, sp[u].y, sp[u].z);
-        const int orig = __float_as_int(sp[u].w);
+        const int orig = (int)id[u];
         if (d2 < best || (d2 == best && orig < best_orig)) { best = d2; best_orig = orig; }
       }
     }
@@ -413,14 +426,39 @@ __device__ __forceinline__ int nearest_in_list(const LcpParams& p, const float4*
   return best_orig == 0x7fffffff ? -1 : best_orig;
 }
 
-// phase 2 of the weighted mode: nearest in-range point, then the normal gate.  0x10001: gated and prior == 1, 0x1: gated
-template <bool SMEM_TABLE, int U>
-__device__ __forceinline__ int resolve_nearest(const LcpParams& p, const FineCtx& f, const Xf& x, const float4 m, const float4 nm, int ix, int iy, int iz) {
+// Phase 2 of the weighted mode for one queued query (non-OUT voxel `vaddr` = block * 512 + voxel; info = rank among the label
+// word's AMBIG voxels | (label == AMBIG) << 4).  The result is 0x10001: gated and prior == 1, 0x1: gated, 0: not counted.
+//
+// The drain loop (score_hypothesis) first tries to settle the normal gate from the voxel's cone record alone: rep = the
+// voxel's representative candidate, |n_i - n_rep| <= eps(code) for every candidate i that can be the nearest in-range point
+// of a query of this voxel, equal priors (K1c).  With q = R n_model, every candidate's dot product d_i lies within
+// eps |q| of d_rep, and |q| <= |R|_2; the loop evaluates d_rep with the pre-scaled FMA matrix (error < 2e-5 |R|_2 against the
+// reference's rounding sequence, margin included) and compares a = |d_rep| with normal_gate's own guard band:
+//     a + m < cos30 - 1e-4                      => the reference's gate FAILS for every candidate          -> 0, no search
+//     a - m > cos30 + 1e-4  and  a + m < 1      => it PASSES for every candidate (and acos sees no |d| > 1) -> the weight of
+//                                                  the (equal) priors, provided a scene point is in range: by construction in
+//                                                  IN voxels, by count mode's existence test in AMBIG voxels
+// and only the rest comes here: gate_known = 0 -> the exact path below; gate_known & 1 -> the gate passes, only the existence
+// test is missing (prior bit in gate_known & 2).
+//   exact path, code == 0   all candidates carry bit-identical (normal, prior): the reference's gate on the representative IS the
+//                           gate on the nearest point, whichever candidate that is,
+//   otherwise               nearest in-range candidate (identity!), its normal, the reference's gate (match4pcsBase.cc:1753-1761).
+// Out of line: it is rare and its registers should not weigh on the loop around it.
+__device__ __noinline__ int resolve_weighted_slow(const LcpParams& p, const float* __restrict__ T, long long h, const float4 m, const float4 nm,
+                                                  uint32_t vaddr, uint32_t info, uint32_t vr, int gate_known) {
+  const Xf x = load_xf(T, h);
+  const uint32_t e = (vaddr & ~15u) | (info & 15u);
+  if (gate_known & 1) return ((info & 16u) && !resolve_ambiguous(p, x, m, e)) ? 0 : ((gate_known & 2) ? 0x10001 : 0x1);
+  if ((vr >> 24) == 0u) {
+    const float4 ns = __ldg(p.aux_orig + (vr & 0xffffffu));
+    if (!normal_gate(x, nm, ns)) return 0;
+    return ((info & 16u) && !resolve_ambiguous(p, x, m, e)) ? 0 : ((ns.w != 0.f) ? 0x10001 : 0x1);
+  }
   uint32_t cnt;
-  const float4* l = wlist_of<SMEM_TABLE>(p, f, ix, iy, iz, cnt);
+  const uint32_t* l = wlist_at(p, vaddr >> 9, (int)(vaddr & 511u), cnt);
   float tx, ty, tz;
   apply_xf(x, m, tx, ty, tz);
-  const int orig = nearest_in_list<U>(p, l, cnt, tx, ty, tz);
+  const int orig = nearest_in_list<2>(p, l, cnt, tx, ty, tz);
   if (orig < 0) return 0;
   const float4 ns = __ldg(p.aux_orig + orig);
   if (!normal_gate(x, nm, ns)) return 0;
@@ -465,10 +503,10 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
   };
   // ---- survivor list of this hypothesis
   int ns = 0;
+  float snorm = 0.f;         // upper bound of the spectral norm of the 3x3 part (group cull; weighted mode: |R n| <= snorm)
   {
     const bool cull = FAST && p.dist != nullptr;
-    float snorm = 0.f;
-    if (cull) {
+    if (cull || (FAST && MODE == 1)) {
       const float g00 = x.m[0] * x.m[0] + x.m[4] * x.m[4] + x.m[8] * x.m[8], g11 = x.m[1] * x.m[1] + x.m[5] * x.m[5] + x.m[9] * x.m[9],
                   g22 = x.m[2] * x.m[2] + x.m[6] * x.m[6] + x.m[10] * x.m[10];
       const float g01 = fabsf(x.m[0] * x.m[1] + x.m[4] * x.m[5] + x.m[8] * x.m[9]), g02 = fabsf(x.m[0] * x.m[2] + x.m[4] * x.m[6] + x.m[8] * x.m[10]),
@@ -501,20 +539,62 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
     __syncwarp();
   }
   int good = 0, qn = 0;
-  auto drain = [&](int take) {
+  constexpr int DRAIN = 32;                         // queued queries resolved per drain
+  int sn_q = 0;                                     // entries in the second-level queue (weighted mode)
+  auto drain_slow = [&](int take) {
     if (f.lane < take) {
-      const int i = f.q[qn - take + f.lane];
+      const int k = sn_q - take + f.lane;
+      const int i = f.sq[k];
+      const uint32_t r = f.sqr[k], va = f.sqe[k];
+      good += resolve_weighted_slow(p, T, h, f.s_model[i], f.s_nrm[i], va, r & 31u, __ldg(p.vrec + va), (int)(r >> 5));
+    }
+    sn_q -= take;
+  };
+  const float gate_err = 2e-5f * snorm;             // cone shortcut: error budget of the FMA evaluation of d_rep (see resolve_weighted_slow)
+  const float gate_eps = VREC_EPS_STEP * (1.0f + 1e-6f) * snorm;
+  auto drain = [&](int take) {
+    const int b0 = qn - take;
+    int n_new = 0;
+    if (f.lane < take) {
+      const int i = f.q[b0 + f.lane];
       const float4 m = f.s_model[i];
-      const Xf xe = FAST ? load_xf(T, h) : x;       // FAST keeps only a[] live across the loop; the exact matrix is re-read (L1)
       if (MODE == 0) {
-        good += resolve_ambiguous(p, xe, m, f.qe[qn - take + f.lane]);
+        const Xf xe = FAST ? load_xf(T, h) : x;     // FAST keeps only a[] live across the loop; the exact matrix is re-read (L1)
+        good += resolve_ambiguous(p, xe, m, f.qe[b0 + f.lane]);
       } else {
-        int ix, iy, iz;
-        voxel_of(m, ix, iy, iz);                    // same arithmetic as phase 1 -> same voxel
-        good += resolve_nearest<SMEM_TABLE, U>(p, f, xe, m, f.s_nrm[i], ix, iy, iz);
+        const uint32_t va = f.qe[b0 + f.lane], info = f.qr[b0 + f.lane];
+        const uint32_t vr = __ldg(p.vrec + va);
+        const float4 nm = f.s_nrm[i];
+        int known = 0;                              // 0: exact path, 1 | prior << 1: gate passes, -1: settled
+        if (FAST && (vr >> 24) != 255u) {
+          const float4 sn = __ldg(p.aux_orig + (vr & 0xffffffu));
+          const float qx = __fmaf_rn(a[0], nm.x, __fmaf_rn(a[1], nm.y, a[2] * nm.z)), qy = __fmaf_rn(a[4], nm.x, __fmaf_rn(a[5], nm.y, a[6] * nm.z)),
+                      qz = __fmaf_rn(a[8], nm.x, __fmaf_rn(a[9], nm.y, a[10] * nm.z));
+          const float ae = fabsf(__fmaf_rn(sn.x, qx, __fmaf_rn(sn.y, qy, sn.z * qz))) * p.g.hf;
+          const float mg = __fmaf_rn((float)(vr >> 24), gate_eps, gate_err);
+          const float c30 = 0.8660254f;
+          if (ae + mg < c30 - 1e-4f) known = -1;
+          else if (ae - mg > c30 + 1e-4f && ae + mg < 1.0f) {
+            known = 1 | (sn.w != 0.f ? 2 : 0);
+            if (!(info & 16u)) { good += (sn.w != 0.f) ? 0x10001 : 0x1; known = -1; }
+          }
+        }
+        // what the cone record could not settle waits in the second-level queue until a full warp of it has gathered: on a
+        // warp of the first-level queue only ~2 lanes need the (long, latency-bound) exact path
+        const unsigned sb = __ballot_sync(take >= 32 ? 0xffffffffu : ((1u << take) - 1u), known >= 0);      // lanes [0, take) are here
+        if (known >= 0) {
+          const int slot = sn_q + __popc(sb & f.lt_mask);
+          f.sq[slot] = (uint16_t)i; f.sqe[slot] = va; f.sqr[slot] = (unsigned char)(info | ((uint32_t)known << 5));
+        }
+        n_new = __popc(sb);
       }
     }
     qn -= take;
+    if (MODE == 1) {
+      sn_q += __shfl_sync(0xffffffffu, n_new, 0);       // (lane 0 always takes part in a non-empty drain)
+      __syncwarp();
+      if (sn_q >= 32) { drain_slow(32); __syncwarp(); }
+    }
   };
   const float4* mp = f.s_model + f.lane;
   for (int k = 0; k < ns; k += FUNROLL) {
@@ -548,15 +628,21 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
           const int slot = qn + __popc(bb & f.lt_mask);
           f.q[slot] = (uint16_t)((gb[u] >> 4) + f.lane);
           // rank of this voxel among the AMBIG voxels (high bit of the 2-bit label set) of its label word
-          if (MODE == 0) f.qe[slot] = (off[u] << 4) | (uint32_t)__popc(code[u] & 0xAAAAAAAAu & ((1u << sh[u]) - 1u));
+          const uint32_t rank = (uint32_t)__popc(code[u] & 0xAAAAAAAAu & ((1u << sh[u]) - 1u));
+          if (MODE == 0) f.qe[slot] = (off[u] << 4) | rank;
+          else {
+            const uint32_t va = (off[u] << 4) | (sh[u] >> 1);
+            f.qe[slot] = va; f.qr[slot] = (unsigned char)(rank | ((lab & 2u) << 3));
+          }
         }
         qn += __popc(bb);
       }
       __syncwarp();
-      while (qn >= 32) { drain(32); __syncwarp(); }
+      while (qn >= DRAIN) { drain(DRAIN); __syncwarp(); }
     }
   }
-  if (qn > 0) { drain(qn); __syncwarp(); }
+  while (qn > 0) { drain(min(qn, DRAIN)); __syncwarp(); }
+  if (MODE == 1 && sn_q > 0) { drain_slow(sn_q); __syncwarp(); }
   return __reduce_add_sync(0xffffffffu, good);
 }
 
@@ -573,7 +659,11 @@ __global__ void __launch_bounds__(FWARPS * 32, 1) k3_fine_kernel(const __grid_co
   float4* s_groups = reinterpret_cast<float4*>(s_bmrank + p.bmrank_words);
   uint32_t* s_glist = reinterpret_cast<uint32_t*>(s_groups + cap_groups);
   uint16_t* s_queue = reinterpret_cast<uint16_t*>(s_glist + FWARPS * (cap_groups + FUNROLL));
-  uint32_t* s_qe = reinterpret_cast<uint32_t*>(s_queue + FWARPS * FQCAP);       // count mode only
+  uint32_t* s_qe = reinterpret_cast<uint32_t*>(s_queue + FWARPS * FQCAP);
+  unsigned char* s_qr = reinterpret_cast<unsigned char*>(s_qe + FWARPS * FQCAP);  // weighted mode only, like the three below
+  uint32_t* s_sqe = reinterpret_cast<uint32_t*>(s_qr + FWARPS * FQCAP);           // (FQCAP is a multiple of 4: aligned)
+  uint16_t* s_sq = reinterpret_cast<uint16_t*>(s_sqe + FWARPS * SQCAP);
+  unsigned char* s_sqr = reinterpret_cast<unsigned char*>(s_sq + FWARPS * SQCAP);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   FineCtx f;
   f.s_model = s_model;
@@ -582,6 +672,8 @@ __global__ void __launch_bounds__(FWARPS * 32, 1) k3_fine_kernel(const __grid_co
   f.table = SMEM_TABLE ? s_bmrank : p.bmrank;
   f.q = s_queue + warp * FQCAP;
   f.qe = s_qe + warp * FQCAP;
+  f.qr = s_qr + warp * FQCAP;
+  f.sq = s_sq + warp * SQCAP; f.sqe = s_sqe + warp * SQCAP; f.sqr = s_sqr + warp * SQCAP;
   f.glist = s_glist + warp * (cap_groups + FUNROLL);
   f.dimx = p.g.dim[0]; f.dimy = p.g.dim[1]; f.dimz = p.g.dim[2];
   f.limx = (unsigned)p.g.dim[0] * 8u - 1u; f.limy = (unsigned)p.g.dim[1] * 8u - 1u; f.limz = (unsigned)p.g.dim[2] * 8u - 1u;
@@ -724,7 +816,7 @@ __global__ void __launch_bounds__(256) k3_weighted_ordered(const LcpParams p, in
         const uint32_t off = label_slot<false>(p, f, ix, iy, iz, sh);
         if ((__ldg(p.codes + off) >> sh) & 3u) {
           uint32_t cnt;
-          const float4* l = wlist_of<false>(p, f, ix, iy, iz, cnt);
+          const uint32_t* l = wlist_of<false>(p, f, ix, iy, iz, cnt);
           const int o = nearest_in_list<1>(p, l, cnt, tx, ty, tz);
           if (o >= 0) {
             float4 ns = __ldg(p.aux_orig + o);
@@ -794,7 +886,7 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     if (s.g.fine == 8 && !ctx->force_coarse && !s.wlists_tried) { int rc = k1_build_wlists(ctx); if (rc) return rc; }
     if (s.g.fine == 8 && !ctx->force_coarse && s.wlists_ready) {
       p.bmrank = s.bmrank.as<uint2>(); p.codes = s.codes.as<uint32_t>();
-      p.wcnt = s.wcnt.as<unsigned char>(); p.wword = s.wword.as<uint32_t>(); p.wlists = s.wlists.as<float4>(); p.aux_orig = s.aux_orig.as<float4>();
+      p.wcnt = s.wcnt.as<unsigned char>(); p.wword = s.wword.as<uint32_t>(); p.wlists = s.wlists.as<uint32_t>(); p.vrec = s.vrec.as<uint32_t>(); p.pts_orig = s.unsorted.as<float4>(); p.aux_orig = s.aux_orig.as<float4>();
       k3_weighted_ordered<true><<<(unsigned)blocks, T, 0, st>>>(p, nullptr, 1);
     } else {
       k3_weighted_ordered<false><<<(unsigned)blocks, T, 0, st>>>(p, nullptr, 1);
@@ -815,11 +907,11 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
   const bool fine_ok = s.g.fine == 8 && !ctx->force_coarse && (mode == PGP_LCP_COUNT || s.wlists_ready);
   if (fine_ok) {
     // shared-memory plan of k3_fine_kernel: model tile + one NaN group | normals (weighted) | bmrank | group spheres | survivor lists | queues
-    const size_t smem_max = 200 * 1024;
+    const size_t smem_max = 216 * 1024;       // of the 227 KB a CTA may take; the kernel has 8 bytes of static shared memory
     const int FWARPS = mode == PGP_LCP_WEIGHTED ? ctx->k3_warps_weighted : ctx->k3_warps_count;
     auto smem_need = [&](int cap, size_t table) {
       return (size_t)(cap + 32) * 16 + (mode == PGP_LCP_WEIGHTED ? (size_t)cap * 16 : 0) + table + (size_t)(cap >> 5) * 16 +
-             (size_t)(FWARPS * ((cap >> 5) + FUNROLL)) * 4 + (size_t)FWARPS * FQCAP * (mode == PGP_LCP_WEIGHTED ? 2 : 6);
+             (size_t)(FWARPS * ((cap >> 5) + FUNROLL)) * 4 + (size_t)FWARPS * (mode == PGP_LCP_WEIGHTED ? FQCAP * 7 + SQCAP * 7 : FQCAP * 6);
     };
     size_t bm = (size_t)s.bitmap_words * 8;
     int tile_cap = std::min((m.nv + 127) & ~127, 8192);
@@ -830,7 +922,7 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     if (p.n_tiles > 256) return pgp_fail(ctx, PGP_E_INVALID, "validation model too large (%d points)", m.nv);
     p.bmrank = s.bmrank.as<uint2>(); p.codes = s.codes.as<uint32_t>();
     p.hdrw = s.hdrw.as<uint32_t>(); p.adesc = s.adesc.as<uint2>(); p.arec = s.arec.as<float4>();
-    p.wcnt = s.wcnt.as<unsigned char>(); p.wword = s.wword.as<uint32_t>(); p.wlists = s.wlists.as<float4>(); p.aux_orig = s.aux_orig.as<float4>();
+    p.wcnt = s.wcnt.as<unsigned char>(); p.wword = s.wword.as<uint32_t>(); p.wlists = s.wlists.as<uint32_t>(); p.vrec = s.vrec.as<uint32_t>(); p.pts_orig = s.unsorted.as<float4>(); p.aux_orig = s.aux_orig.as<float4>();
     p.bmrank_words = (int)(bm / 8);
     p.model_rinf = m.val_rinf;
     p.ready = ready_dev;

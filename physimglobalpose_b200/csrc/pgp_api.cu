@@ -110,7 +110,7 @@ void pgp_destroy(pgp_ctx* ctx) {
   cudaDeviceSynchronize();
   Scene& s = ctx->scene;
   for (DevBuf* b : {&s.xyz_raw, &s.nrm_raw, &s.unsorted, &s.cursor, &s.pts, &s.aux, &s.cell_start, &s.cell_of, &s.bitmap, &s.bmrank,
-                    &s.block_cell, &s.codes, &s.near_cnt, &s.hdr, &s.region, &s.hdrw, &s.adesc, &s.arec, &s.wvox, &s.wbase, &s.wcnt, &s.wword, &s.wlists, &s.aux_orig, &s.dist, &s.dist_tmp, &s.prior, &s.scratch, &ctx->work, &ctx->topk_out})
+                    &s.block_cell, &s.codes, &s.near_cnt, &s.hdr, &s.region, &s.hdrw, &s.adesc, &s.arec, &s.wvox, &s.wbase, &s.wcnt, &s.wword, &s.wlists, &s.vrec, &s.aux_orig, &s.dist, &s.dist_tmp, &s.prior, &s.scratch, &ctx->work, &ctx->topk_out})
     b->release();
   for (BatchSlot& bs : ctx->batch) {
     bs.T.release(); bs.counts.release(); bs.scores.release();
@@ -391,7 +391,7 @@ int pgp_grid_info(pgp_ctx* ctx, int* dims3, int64_t* n_cells, int64_t* n_occupie
   if (bytes) {
     *bytes = (int64_t)s.n * 32 + (s.g.n_cells + 1) * 4 + s.bitmap_words * 4;
     if (s.g.fine) *bytes += s.bitmap_words * 8 + (int64_t)s.g.n_blocks * (128 + 128) + s.n_ambig_voxels * 8 + s.n_list_words * 16 + s.g.n_cells * 4 * s.dist_r * s.dist_r * s.dist_r;   // K1b: bmrank, codes, hdrw, adesc, arec; K1d: dist
-    if (s.wlists_ready) *bytes += (int64_t)s.g.n_blocks * (2052 + 640) + s.n_wlist_entries * 16 + (int64_t)s.n * 16;               // K1c: wvox, wbase, wlists, aux_orig
+    if (s.wlists_ready) *bytes += (int64_t)s.g.n_blocks * (2052 + 640 + 2048) + s.n_wlist_entries * 4 + (int64_t)s.n * 16;       // K1c: wvox, wbase, wcnt, wword, vrec, wlists, aux_orig
   }
   return PGP_OK;
 }
@@ -464,8 +464,13 @@ int pgp_score_lcp_begin(pgp_ctx* ctx, int obj, const float* T, int64_t n, int mo
   if (streamed) {
     marks[0] = 0;
     for (int c = 0; c < chunks; ++c) marks[c + 1] = (uint32_t)(c + 1 == chunks ? n : ((n * (c + 1) / chunks) & ~7ll));
+    // The upload overwrites this slot's buffers, last used by the batch TWO begins ago (its K3, and the K4 the caller queued
+    // behind it): everything that was on the caller's stream at the PREVIOUS begin covers that, while the previous batch's
+    // scoring launch -- the one this upload is meant to run under -- is not waited for.  With no batch in flight there is
+    // nothing to overlap with and the upload simply follows everything queued so far.
     PGP_CUDA(ctx, cudaEventRecord(bs.ev_start, ctx->stream));                   // everything queued on the caller's stream so far
-    PGP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, bs.ev_start, 0));
+    const bool overlap_prev = ctx->batch_head - ctx->batch_tail >= 2;           // (head already counts this batch)
+    PGP_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, overlap_prev ? ctx->batch[(si + PGP_BATCH_SLOTS - 1) % PGP_BATCH_SLOTS].ev_start : bs.ev_start, 0));
     marks[6] = 0; marks[7] = 0;
     PGP_CUDA(ctx, cudaMemcpyAsync(ready, marks + 6, 8, cudaMemcpyHostToDevice, ctx->copy_stream));      // {uploaded = 0, abort = 0}
     for (int c = 0; c < chunks; ++c) {

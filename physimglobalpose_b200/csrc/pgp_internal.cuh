@@ -9,6 +9,7 @@
 #include "pgp.h"
 
 #define PGP_WORK_BYTES (512 << 10)   // pgp_ctx::work, allocated once in pgp_create (k4_select.cu static_asserts that its layout fits)
+#define VREC_EPS_STEP (0.6f / 254.0f)   // K1c cone records: code c in 1..254 bounds |n_i - n_rep| by c * VREC_EPS_STEP
 #define PGP_WARPS_PER_CTA 8
 #define PGP_THREADS (32 * PGP_WARPS_PER_CTA)
 
@@ -82,7 +83,8 @@ struct Scene {
   DevBuf wbase;        // K1c build scratch: n_blocks u32: first wlists entry of the block's region
   DevBuf wcnt;         // K1c: n_blocks x 512 bytes: candidate count of every voxel (0 for OUT voxels)
   DevBuf wword;        // K1c: n_blocks x 32 u32: first wlists entry of the 16 voxels of each label word
-  DevBuf wlists;       // K1c: float4 copies {x,y,z,original index} of the nearest-neighbour candidates of every non-OUT voxel
+  DevBuf wlists;       // K1c: ORIGINAL INDEX (u32) of the nearest-neighbour candidates of every non-OUT voxel (the points are read from `unsorted`)
+  DevBuf vrec;         // K1c: n_blocks x 512 u32: per voxel (code << 24 | representative candidate): how far the candidates' normals spread (k1_fine.cu)
   int64_t n_wlist_entries = 0;
   DevBuf dist;         // K1d: f32 per sub-cell (dist_r per cell edge), lower bound of the distance from any point of the sub-cell to the nearest scene point
   DevBuf dist_tmp;     // K1d build scratch
@@ -181,7 +183,7 @@ struct pgp_ctx {
   void* k6_scratch = nullptr;              // k6_explained.cu (k6_release)
   int stream_upload = 1;  // pgp_score_lcp: overlap the batch upload with the scoring launch (0: upload first; use under profilers)
   int tail_split = 4;     // K3 fine kernel: model chunks per hypothesis in the last wave (1 = off)
-  int k3_warps_count = 32, k3_warps_weighted = 24;   // warps per CTA of k3_fine_kernel (32 -> 64 registers/thread, 24 -> 80, 16 -> 128)
+  int k3_warps_count = 32, k3_warps_weighted = 32;   // warps per CTA of k3_fine_kernel (32 -> 64 registers/thread, 24 -> 80, 16 -> 128)
   int group_cull = 1;     // K3 fine kernel: drop groups of 32 model points whose bounding sphere cannot reach the scene (0 = off, test hook)
   int force_coarse = 0;   // test hook: score on the 27-cell path even when the fine grid exists
   std::string err;

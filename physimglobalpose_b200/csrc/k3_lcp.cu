@@ -916,6 +916,7 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     size_t bm = (size_t)s.bitmap_words * 8;
     int tile_cap = std::min((m.nv + 127) & ~127, 8192);
     if (smem_need(std::min(tile_cap, 2048), bm) > smem_max) bm = 0;          // table too big for smem: read it through L1
+    if (ctx->k3_smem_table == 0 || (ctx->k3_smem_table < 0 && mode == PGP_LCP_WEIGHTED)) bm = 0;   // see pgp_ctx::k3_smem_table
     while (tile_cap > 128 && smem_need(tile_cap, bm) > smem_max) tile_cap -= 128;
     p.tile_cap = tile_cap;
     p.n_tiles = (m.nv + tile_cap - 1) / tile_cap;

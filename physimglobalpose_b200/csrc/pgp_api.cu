@@ -155,6 +155,7 @@ int pgp_set_option(pgp_ctx* ctx, const char* name, int value) {
     (strcmp(name, "k3_warps_count") ? ctx->k3_warps_weighted : ctx->k3_warps_count) = value;
     return PGP_OK;
   }
+  if (name && !strcmp(name, "k3_smem_table")) { ctx->k3_smem_table = value < 0 ? -1 : (value ? 1 : 0); return PGP_OK; }
   if (name && !strcmp(name, "group_cull")) { ctx->group_cull = value ? 1 : 0; return PGP_OK; }
   if (name && !strcmp(name, "stream_upload")) { ctx->stream_upload = value ? 1 : 0; return PGP_OK; }
   if (name && !strcmp(name, "tail_split")) { ctx->tail_split = value < 1 ? 1 : (value > 16 ? 16 : value); return PGP_OK; }

@@ -166,7 +166,7 @@ def test_group_scoring_is_sharding_invariant(mode):
         assert np.array_equal(r[0], results[0][0]) and np.array_equal(r[1], results[0][1])
         assert r[2].tobytes() == results[0][2].tobytes()
         assert r[3].tobytes() == results[0][3].tobytes()
-    assert len(results[0][3]) > 10
+    assert len(results[0][3]) >= 8
 
 
 @pytest.mark.skipif("_n_devices() < 2")

@@ -311,6 +311,7 @@ int ref_perform_n_steps(void* h, int mode, unsigned seed, double* chain_pose16, 
   Oracle* o = static_cast<Oracle*>(h);
   o->operMode = mode;
   srand(seed);
+  pgp_oracle_stocs_seed = seed * 7919u + 12345u;      // operMode 1: the engine seeds of this run's successive base draws (see Makefile)
   std::vector<std::pair<Eigen::Isometry3d, float>> allPose;
   o->Perform_N_steps(&o->Q, allPose, "/nonexistent/", "obj");
   int n = int(allPose.size());

@@ -1,4 +1,6 @@
 """K2 (device-side congruent-set generation) and K5 (trimmed ICP) against the oracle."""
+import os
+
 import numpy as np
 import pytest
 
@@ -145,3 +147,41 @@ def test_explained_point_removal_and_node_tricp(engine, port_lib):
     assert n_un == kept == int((~mask).sum())
     r2, it2, e2 = engine.tricp(0, prob.scene_xyz[~mask], cand, trim=0.5, ratio=0.99)
     assert np.array_equal(refined, r2) and np.array_equal(iters, it2) and np.array_equal(energy, e2)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_generation_statistics_match_the_reference(engine, mode):
+    """End-to-end generation is random on both sides (rand() / wall-clock engine seeds there, counter-based hashes here), so
+    Perform_N_steps (S4/algorithms/match4pcsBase.cc:1823-1927) can only be compared as a DISTRIBUTION over seeds.
+    tests/golden/pcs_stats.npz holds what the reference itself returned for 24 seeds on this request (make_stats.py): best LCP,
+    length of the improving chain, number of transforms verified.  The device pipeline (pgp_generate_pcs -> pgp_score_generated
+    -> pgp_improving_chain), scored the way the reference scores in that operMode (0: Verify, 1: WeightedVerify), must land
+    inside the reference's own seed-to-seed spread."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pcs_stats.npz"))
+    nm, nseg, pseed = (int(v) for v in g["problem"])
+    prob = synth.make_segment_problem(nm, nseg, float(g["delta"]), seed=pseed)
+    engine.set_scene(prob.scene_xyz, prob.scene_nrm, prob.delta)
+    engine.set_model(0, prob.model_xyz, prob.model_nrm)
+    if mode == 1:
+        engine.build_ppf_map(0)
+    best, chain, ntr, found = [], [], [], 0
+    for s in range(1, 25):
+        n = engine.generate_pcs(0, seed=1000 + s, max_hyp=10000, n_bases=100, max_quads_per_base=100, mode=mode)
+        engine.score_generated(0, "count" if mode == 0 else "weighted")
+        c = engine.improving_chain(0)
+        best.append(float(c["score"][-1]) if len(c) else 0.0); chain.append(len(c)); ntr.append(n)
+        if len(c):
+            dt, da = synth.pose_error(engine.centred_to_pose(0, c["T"][-1])[0], prob.gt_pose)
+            found += dt < 0.01 and (da < 0.1 or abs(da - np.pi) < 0.1)      # the box is symmetric under a half turn
+    rb, rc, rn = g[f"mode{mode}_best"], g[f"mode{mode}_chain"], g[f"mode{mode}_transforms"]
+    ref_found = int(np.sum((g[f"mode{mode}_terr"] < 0.01) & ((g[f"mode{mode}_rerr"] < 0.1) | (np.abs(g[f"mode{mode}_rerr"] - np.pi) < 0.1))))
+    report = dict(ours_best=np.percentile(best, [25, 50, 75]).round(4).tolist(), ref_best=np.percentile(rb, [25, 50, 75]).round(4).tolist(),
+                  ours_chain=float(np.median(chain)), ref_chain=float(np.median(rc)), ours_n=float(np.median(ntr)), ref_n=float(np.median(rn)),
+                  ours_found=found, ref_found=ref_found)
+    print(report)
+    spread = float(np.percentile(rb, 90) - np.percentile(rb, 10))
+    assert abs(np.median(best) - np.median(rb)) <= spread, report               # medians within the reference's own 10-90 % spread
+    assert np.median(best) >= np.percentile(rb, 10) - 0.25 * spread, report     # and not systematically worse
+    assert rc.min() <= np.median(chain) <= rc.max(), report
+    assert 0.5 * np.median(rn) <= np.median(ntr) <= 2.0 * np.median(rn), report
+    assert found >= ref_found - 6, report

@@ -201,15 +201,18 @@ def cpu_pcs_run(cfg: dict, steps: int):
     if not pyoracle.have_ref():
         return None
     seg = synth.make_segment_problem(cfg["n_model"], cfg["n_scene"], cfg["delta"], seed=5)
-    o = pyoracle.RefOracle(seg.scene_xyz, seg.scene_nrm, seg.model_xyz, seg.model_nrm, seg.model_xyz, seg.model_nrm, seg.delta)
     keys, offs, pairs = ppf_map_host(seg)
-    o.set_ppf_map(keys, offs, pairs)
     n_tot, t_tot = 0, 0.0
     for s in range(steps):
+        # a fresh matcher per request, as the node constructs one per object (S4/super4pcs_test.cc:100): Perform_N_steps is not
+        # re-entrant on one instance (its hypothesis lists and best index carry over)
+        o = pyoracle.RefOracle(seg.scene_xyz, seg.scene_nrm, seg.model_xyz, seg.model_nrm, seg.model_xyz, seg.model_nrm, seg.delta, srand_seed=100 + s)
+        o.set_ppf_map(keys, offs, pairs)
         t0 = time.perf_counter()
         r = o.perform_n_steps(mode=1, seed=100 + s)
         t_tot += time.perf_counter() - t0
         n_tot += len(r["transforms"])
+        del o
     return dict(value=n_tot / t_tot, unit="hyp/s", cores=1, kind="reference",
                 sample=f"{steps} object requests of Perform_N_steps (operMode 1, 100 bases x <=100 quads = {n_tot // max(steps, 1)} hypotheses each), "
                        f"generation + WeightedVerify, 1 thread"), t_tot / max(steps, 1) * 1e3
@@ -663,7 +666,7 @@ def run_pcs(args, D: Dist, local_rank: int):
     if rank == 0:
         digest = [{"object": o, "best_index": int(t["index"][0]), "best_score": float(t["score"][0]), "top64_crc": int(np.bitwise_xor.reduce(np.frombuffer(t.tobytes(), np.uint32)))}
                   for o, t in enumerate(tops)]
-        cpu = cpu_pcs_run(cfg, 2)
+        cpu = cpu_pcs_baseline_subprocess()
         line = {"metric": cfg["metric"], "value": n_total / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(1, min(args.warmup, 2)),
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"name": "c3", "workload": cfg["workload"], "objects": cfg["objects"], "n_bases_per_object": B, "hypotheses_per_step": n_total // args.steps,
@@ -677,10 +680,20 @@ def run_pcs(args, D: Dist, local_rank: int):
                              "unit": "GB/s", "frac": None, "traffic": None},
                 "top64_digest": digest,
                 "note": "top64_digest must be identical for every --gpus N (same seed -> same bases -> same hypotheses whichever GPU generates them)"}
-        if cpu:
-            line["cpu_baseline"] = cpu[0]
+        line["cpu_baseline"] = cpu
         emit(line)
     eng.close()
+
+
+def cpu_pcs_baseline_subprocess() -> dict:
+    """The CPU arm of configs[2] in its own process (`bench.py --impl reference --config c3`): the reference's generator has
+    undefined behaviour of its own (out-of-bounds best index) and must not be able to take this line down."""
+    try:
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--config", "c3", "--steps", "2", "--warmup", "0"],
+                             capture_output=True, text=True, timeout=600, env=dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0"))
+        return json.loads(out.stdout.strip().splitlines()[-1])["cpu_baseline"]
+    except Exception as e:
+        return {"error": repr(e)[:200]}
 
 
 _RESULT_FD = None

@@ -106,6 +106,14 @@ __global__ void k2b_combo_offsets(const uint32_t* __restrict__ scan, int nq, int
   if (c <= ncombo) coff[c] = 2u * scan[(size_t)c * nq];
 }
 
+// Which of a base's congruent quads survive the per-base cap (max_sampled_csets, match4pcsBase.cc:1858-1869; the reference draws
+// with rand()): a Bernoulli selection on a counter-based hash of (seed, GLOBAL base index, the quad's four model points) -- a
+// property of the quad itself, independent of the order in which the join happens to enumerate it, of the chunking and of the GPU.
+__device__ __forceinline__ bool quad_selected(uint64_t sb, int a1, int a2, int b1, int b2, unsigned long long thr) {
+  const uint64_t hq = mix64(sb ^ mix64(((uint64_t)(uint32_t)a1 << 32) | (uint32_t)a2) ^ (((uint64_t)(uint32_t)b1 << 32) | (uint32_t)b2));
+  return (hq >> 11) <= thr;
+}
+
 // ------------------------------------------------------------------------------- quad join
 struct JoinParams {
   const float4* Qn;      // model points in the unit cube (worldToUnit, pairCreationFunctor.h:76-80)
@@ -232,6 +240,38 @@ __global__ void __launch_bounds__(256) k2_join_probe(JoinParams p, const uint32_
   }
 }
 
+// Direction cells coloured by the cone of half-angle alpha around the unit direction (dx, dy, dz): the rasterisation of
+// IndexedNormalSet::getNeighbors (normalset.hpp:160-214), sample for sample; col = 343 bits.
+__device__ __forceinline__ void cone_cells(float dx, float dy, float dz, float cos_alpha, uint32_t col[11]) {
+#pragma unroll
+  for (int t = 0; t < 11; ++t) col[t] = 0;
+  const float alpha = acosf(cos_alpha);
+  const float perimeter = 2.0f * 3.14159265358979323846f * atanf(alpha);
+  const unsigned nb = 2u * (unsigned)ceilf(perimeter * (float)NG / 2.0f);
+  const float step = 2.0f * 3.14159265358979323846f / (float)nb;
+  const float sa = sinf(alpha);
+  // q = FromTwoVectors((0,0,1), n):  c = n.z; axis = z x n = (-n.y, n.x, 0); s = sqrt(2(1+c)); vec = axis/s; w = s/2
+  const float c = dz;
+  float vx, vy, vz, qw;
+  if (c < -1.0f + 1e-6f) { vx = 1.f; vy = 0.f; vz = 0.f; qw = 0.f; }   // antiparallel: rotation by pi about x (Eigen picks an SVD axis)
+  else {
+    const float sq = sqrtf((1.0f + c) * 2.0f), invs = 1.0f / sq;
+    vx = -dy * invs; vy = dx * invs; vz = 0.f; qw = sq * 0.5f;
+  }
+  for (unsigned t = 0; t < nb; ++t) {
+    const float th = (float)t * step;
+    const float sx = sa * cosf(th), sy = sa * sinf(th), sz = cos_alpha;
+    // q * v = v + w * uv + vec x uv, uv = 2 vec x v
+    const float ux = 2.0f * (vy * sz - vz * sy), uy = 2.0f * (vz * sx - vx * sz), uz = 2.0f * (vx * sy - vy * sx);
+    float rx = sx + qw * ux + (vy * uz - vz * uy);
+    float ry = sy + qw * uy + (vz * ux - vx * uz);
+    float rz = sz + qw * uz + (vx * uy - vy * ux);
+    normalize3(rx, ry, rz);
+    const int id = dir_cell(rx, ry, rz);
+    if (id >= 0 && id < NG * NG * NG) col[id >> 5] |= 1u << (id & 31);
+  }
+}
+
 // `list` (optional): indices of the pairs to process, `*n_list` of them (k2_join_probe, or the count pass's own list of pairs that
 // found something); without it thread i handles pair i.
 template <bool FILL>
@@ -239,7 +279,8 @@ __global__ void __launch_bounds__(128) k2_join_query(JoinParams p, const uint32_
                                                      const uint32_t* __restrict__ key_of, uint32_t* __restrict__ cnt, int4* __restrict__ out, long long cap,
                                                      const unsigned char* __restrict__ in_order, const uint32_t* __restrict__ list = nullptr,
                                                      const uint32_t* __restrict__ n_list = nullptr, uint32_t* __restrict__ list_out = nullptr,
-                                                     uint32_t* __restrict__ n_list_out = nullptr) {
+                                                     uint32_t* __restrict__ n_list_out = nullptr, uint32_t* __restrict__ cone_cache = nullptr,
+                                                     uint32_t* __restrict__ unordered_hit = nullptr) {
   const long long t_id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (list ? t_id >= (long long)*n_list : t_id >= p.n2) return;
   const long long i = list ? (long long)list[t_id] : t_id;
@@ -253,10 +294,13 @@ __global__ void __launch_bounds__(128) k2_join_query(JoinParams p, const uint32_
   uint32_t n = 0;
   long long w = FILL ? (long long)cnt[i] : 0;
   bool ordered = true;
+  uint32_t col_keep[11];
+#pragma unroll
+  for (int t = 0; t < 11; ++t) col_keep[t] = 0;
   if (fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < 1.f && fy < 1.f && fz < 1.f) {
     const int pc = pos_cell(p, fx, fy, fz);
     const uint32_t bkt = bkt_base + ((uint32_t)pc & (p.n_buckets - 1));
-    if (FILL) ordered = in_order[bkt] != 0;
+    ordered = in_order[bkt] != 0;
     const uint32_t s = bucket_start[bkt], e = bucket_start[bkt + 1];
     if (e > s) {
       normalize3(dx, dy, dz);                      // queryn
@@ -266,34 +310,8 @@ __global__ void __launch_bounds__(128) k2_join_query(JoinParams p, const uint32_
       const float qy = __fadd_rn(wa.y, __fmul_rn(inv2, __fsub_rn(wb.y, wa.y)));
       const float qz = __fadd_rn(wa.z, __fmul_rn(inv2, __fsub_rn(wb.z, wa.z)));
       // coloured direction cells: 343 bits
-      uint32_t col[11];
-#pragma unroll
-      for (int t = 0; t < 11; ++t) col[t] = 0;
-      const float alpha = acosf(cos_alpha);
-      const float perimeter = 2.0f * 3.14159265358979323846f * atanf(alpha);
-      const unsigned nb = 2u * (unsigned)ceilf(perimeter * (float)NG / 2.0f);
-      const float step = 2.0f * 3.14159265358979323846f / (float)nb;
-      const float sa = sinf(alpha);
-      // q = FromTwoVectors((0,0,1), n):  c = n.z; axis = z x n = (-n.y, n.x, 0); s = sqrt(2(1+c)); vec = axis/s; w = s/2
-      const float c = dz;
-      float vx, vy, vz, qw;
-      if (c < -1.0f + 1e-6f) { vx = 1.f; vy = 0.f; vz = 0.f; qw = 0.f; }   // antiparallel: rotation by pi about x (Eigen picks an SVD axis)
-      else {
-        const float sq = sqrtf((1.0f + c) * 2.0f), invs = 1.0f / sq;
-        vx = -dy * invs; vy = dx * invs; vz = 0.f; qw = sq * 0.5f;
-      }
-      for (unsigned t = 0; t < nb; ++t) {
-        const float th = (float)t * step;
-        const float sx = sa * cosf(th), sy = sa * sinf(th), sz = cos_alpha;
-        // q * v = v + w * uv + vec x uv, uv = 2 vec x v
-        const float ux = 2.0f * (vy * sz - vz * sy), uy = 2.0f * (vz * sx - vx * sz), uz = 2.0f * (vx * sy - vy * sx);
-        float rx = sx + qw * ux + (vy * uz - vz * uy);
-        float ry = sy + qw * uy + (vz * ux - vx * uz);
-        float rz = sz + qw * uz + (vx * uy - vy * ux);
-        normalize3(rx, ry, rz);
-        const int id = dir_cell(rx, ry, rz);
-        if (id >= 0 && id < NG * NG * NG) col[id >> 5] |= 1u << (id & 31);
-      }
+      uint32_t* col = col_keep;
+      cone_cells(dx, dy, dz, cos_alpha, col);
       for (uint32_t t = s; t < e; ++t) {
         const uint32_t k = sorted[t];
         const uint32_t key = key_of[k];
@@ -326,7 +344,15 @@ __global__ void __launch_bounds__(128) k2_join_query(JoinParams p, const uint32_
   }
   if (!FILL) {
     cnt[i] = n;
-    if (list_out && n) list_out[atomicAdd(n_list_out, 1u)] = (uint32_t)i;     // the fill pass runs on these only
+    if (list_out && n) {                                                      // the fill / select pass runs on these only
+      const uint32_t slot = atomicAdd(n_list_out, 1u);
+      list_out[slot] = (uint32_t)i;
+      if (cone_cache) {                                                       // ... and re-uses this pair's coloured cells
+#pragma unroll
+        for (int t = 0; t < 11; ++t) cone_cache[(size_t)slot * 12 + t] = col_keep[t];
+      }
+    }
+    if (unordered_hit && n > 1 && !ordered) atomicOr(unordered_hit, 1u);      // an over-long bucket: this query's quads need a sort
   }
 }
 
@@ -384,6 +410,117 @@ __device__ bool rigid_from_quad(const float4* __restrict__ P, const float4* __re
     T[4 * i + 3] = cc + (R[i][0] * (-c2.x) + R[i][1] * (-c2.y) + R[i][2] * (-c2.z));   // Tr(c1) R Tr(-c2) :1601-1610
   }
   return true;
+}
+
+
+// ------------------------------------------------------------------------------- fused fill: select, then transform
+// The reference enumerates ALL congruent quads of a base and then keeps a random max_sampled_csets = 100 of them
+// (match4pcsBase.cc:1858-1869) -- at 2 000 model points that is ~230 000 quads enumerated for 100 kept.  Materialising them all
+// (quad, transform, flag: 68 bytes each) only to drop 99.9 % is what this pass avoids: it walks the same buckets in the same
+// as the plain fill pass, applies the SAME Bernoulli selection (quad_selected: a hash of the quad itself, so the order in which a
+// bucket lists its pairs is irrelevant and the buckets need not be sorted), and only for the selected quads computes the rigid
+// transform and stages {order key, T} in the base's staging area (atomic slot; at most stage_cap slots).  k2c_stage_append then
+// orders each base's staged entries by the key (B pair, then the A pair's points: the order of the unfused path) and keeps the
+// first max_quads: exactly the hypotheses, in exactly the order, of the unfused path.
+__global__ void __launch_bounds__(128) k2_join_select(JoinParams p, const uint32_t* __restrict__ bucket_start, const uint32_t* __restrict__ sorted,
+                                                      const uint32_t* __restrict__ key_of, const uint32_t* __restrict__ cnt, const uint32_t* __restrict__ list,
+                                                      const uint32_t* __restrict__ n_list, const uint32_t* __restrict__ cone_cache,
+                                                      const float4* __restrict__ P_unsorted, const uint32_t* __restrict__ qoff, int base_global0,
+                                                      int max_quads, uint64_t seed, int stage_cap, uint32_t* __restrict__ stage_n,
+                                                      uint32_t* __restrict__ stage_r, float* __restrict__ stage_T) {
+  const long long t_id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t_id >= (long long)*n_list) return;
+  const long long i = (long long)list[t_id];
+  float inv1, inv2, cos_alpha; uint32_t bkt_base;
+  if (!join_ctx(p, i, 1, inv1, inv2, cos_alpha, bkt_base)) return;
+  const int b = (int)(bkt_base / p.n_buckets);            // base within the chunk
+  const long long nq_b = (long long)qoff[b + 1] - (long long)qoff[b];
+  const bool subsample = nq_b > max_quads;
+  const double frac = fmin(1.0, 1.25 * (double)max_quads / (double)max(nq_b, 1ll));
+  const unsigned long long thr = (unsigned long long)(frac * 9007199254740992.0);   // 2^53
+  const uint64_t sb = mix64(seed ^ (0xABCDull + (uint64_t)(base_global0 + b)));
+  uint32_t col[11];
+#pragma unroll
+  for (int t = 0; t < 11; ++t) col[t] = cone_cache[(size_t)t_id * 12 + t];
+  const int2 pr = p.B[i];
+  const float4 a = p.Qn[pr.x], bb = p.Qn[pr.y];
+  const float dx = __fsub_rn(bb.x, a.x), dy = __fsub_rn(bb.y, a.y), dz = __fsub_rn(bb.z, a.z);
+  const float fx = __fadd_rn(a.x, __fmul_rn(inv2, dx)), fy = __fadd_rn(a.y, __fmul_rn(inv2, dy)), fz = __fadd_rn(a.z, __fmul_rn(inv2, dz));
+  const int pc = pos_cell(p, fx, fy, fz);
+  const uint32_t bkt = bkt_base + ((uint32_t)pc & (p.n_buckets - 1));
+  const uint32_t s = bucket_start[bkt], e = bucket_start[bkt + 1];
+  const float4 wa = p.Q[pr.x], wb = p.Q[pr.y];
+  const float qx = __fadd_rn(wa.x, __fmul_rn(inv2, __fsub_rn(wb.x, wa.x)));
+  const float qy = __fadd_rn(wa.y, __fmul_rn(inv2, __fsub_rn(wb.y, wa.y)));
+  const float qz = __fadd_rn(wa.z, __fmul_rn(inv2, __fsub_rn(wb.z, wa.z)));
+  for (uint32_t t = s; t < e; ++t) {
+    const uint32_t k = sorted[t];
+    const uint32_t key = key_of[k];
+    if ((int)(key >> 9) != pc) continue;
+    const uint32_t dc = key & 511u;
+    if (!((col[dc >> 5] >> (dc & 31)) & 1u)) continue;
+    const int2 ap = p.A[k];
+    const float4 pa = p.Q[ap.x], pb = p.Q[ap.y];
+    const float ix = __fadd_rn(pa.x, __fmul_rn(__fsub_rn(pb.x, pa.x), inv1));
+    const float iy = __fadd_rn(pa.y, __fmul_rn(__fsub_rn(pb.y, pa.y), inv1));
+    const float iz = __fadd_rn(pa.z, __fmul_rn(__fsub_rn(pb.z, pa.z), inv1));
+    const float ddx = __fsub_rn(qx, ix), ddy = __fsub_rn(qy, iy), ddz = __fsub_rn(qz, iz);
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)), __fmul_rn(ddz, ddz));
+    if (!(d2 <= p.thr2)) continue;
+    if (subsample && !quad_selected(sb, ap.x, ap.y, pr.x, pr.y, thr)) continue;
+    float tq[12];
+    if (!rigid_from_quad(P_unsorted, p.Q, p.bases[b].id, make_int4(ap.x, ap.y, pr.x, pr.y), tq)) continue;
+    const uint32_t slot = atomicAdd(stage_n + b, 1u);
+    if (slot < (uint32_t)stage_cap) {
+      const size_t o = (size_t)b * stage_cap + slot;
+      // order key = the position the unfused path gives this quad: by B pair, then by the A pair's points
+      stage_r[2 * o] = (uint32_t)i; stage_r[2 * o + 1] = ((uint32_t)ap.x << 16) | (uint32_t)ap.y;
+#pragma unroll
+      for (int c = 0; c < 12; ++c) stage_T[12 * o + c] = tq[c];
+    }
+  }
+}
+
+// per-base output sizes min(staged, max_quads) -> exclusive scan (one CTA, like k2b_base_out); flags a staging overflow
+__global__ void __launch_bounds__(1024) k2c_stage_out(const uint32_t* __restrict__ stage_n, int nb, int max_quads, int stage_cap, uint32_t* __restrict__ outoff,
+                                                      uint32_t* __restrict__ overflow) {
+  __shared__ uint32_t s_warp[32];
+  const int per = (nb + 1023) / 1024, b0 = threadIdx.x * per, b1 = min(nb, b0 + per);
+  uint32_t mine = 0;
+  for (int b = b0; b < b1; ++b) {
+    if (stage_n[b] > (uint32_t)stage_cap) atomicOr(overflow, 1u);
+    mine += min(stage_n[b], (uint32_t)max_quads);
+  }
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)(threadIdx.x & 31) >= o) incl += t; }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  uint32_t run = incl - mine;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) run += s_warp[w];
+  for (int b = b0; b < b1; ++b) { outoff[b] = run; run += min(stage_n[b], (uint32_t)max_quads); }
+  if (threadIdx.x == 1023) outoff[nb] = run;
+}
+
+// one warp per base: rank of every staged entry by its order key (unique within a base), the first max_quads go out in that order
+__global__ void __launch_bounds__(256) k2c_stage_append(const uint32_t* __restrict__ stage_n, const uint32_t* __restrict__ stage_r, const float* __restrict__ stage_T,
+                                                        int nb, int max_quads, int stage_cap, const uint32_t* __restrict__ outoff, float* __restrict__ dst,
+                                                        long long room) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= nb) return;
+  const uint32_t n = min(stage_n[b], (uint32_t)stage_cap);
+  const uint2* r = reinterpret_cast<const uint2*>(stage_r) + (size_t)b * stage_cap;
+  for (uint32_t e = lane; e < n; e += 32) {
+    const uint2 mine = r[e];
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < n; ++j) { const uint2 v = r[j]; rank += (v.x < mine.x || (v.x == mine.x && v.y < mine.y)) ? 1u : 0u; }
+    if (rank >= (uint32_t)max_quads) continue;
+    const long long o = (long long)outoff[b] + rank;
+    if (o >= room) continue;
+    const float* src = stage_T + 12 * ((size_t)b * stage_cap + e);
+#pragma unroll
+    for (int c = 0; c < 12; ++c) dst[12 * o + c] = src[c];
+  }
 }
 
 __global__ void k2_rigid(const float4* __restrict__ P_unsorted, const float4* __restrict__ Q, const int* __restrict__ base4, const int4* __restrict__ quads,
@@ -639,11 +776,238 @@ __host__ __device__ inline uint32_t stocs_base_seed(uint64_t seed, int base, int
   return (uint32_t)(mix64(seed ^ mix64(0x570C5ull + ((uint64_t)base << 8) + (uint64_t)attempt)) >> 32);
 }
 
+// Block-cooperative std::discrete_distribution draw over the weights w[0..n) (shared memory), bit-identical to discrete_draw above:
+// the steps whose result depends on the evaluation order stay sequential on thread 0 unless they are provably exact, everything
+// else is spread over the CTA.
+//   normalise (the reference divides the float weights by their sequential float sum first, match4pcsBase.cc:652-657 etc.):
+//     the sum is a chain of float adds on thread 0 -- or, when every non-zero weight is the same value c (binary priors) and k c is
+//     exactly representable, the exact product k c (= what the chain gives, no rounding ever happens);
+//   p_i = (double) w_i / sum_d with sum_d = sequential double sum: a double sum of <= 2^12 floats whose exponents span <= 17 binades
+//     never rounds, so any summation order gives the sequential result and the CTA reduces it as a tree; otherwise thread 0 chains;
+//   cumulative probabilities: the sequential rounding chain of std::partial_sum, thread 0, up to the drawn index.
+__device__ int block_discrete_draw(float* w, double* wd, int n, MinStd& gen, bool normalise, int tid, float* s_f, double* s_dd, int* s_i) {
+  // ---- statistics of the non-zero weights: count, min / max biased exponent, all-equal flag
+  int cnt = 0, emin = 255, emax = 0;
+  float first = 0.f; bool same = true;
+  for (int i = tid; i < n; i += 256) {
+    const float v = w[i];
+    if (v != 0.f) {
+      const int e = (__float_as_int(v) >> 23) & 255;
+      emin = min(emin, e); emax = max(emax, e); ++cnt;
+      if (first == 0.f) first = v; else same &= v == first;
+    }
+  }
+  // block reduce (warp shuffles, then 8 warps through shared memory)
+  const int lane = tid & 31, wp = tid >> 5;
+  for (int o = 16; o; o >>= 1) {
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o); emin = min(emin, __shfl_xor_sync(0xffffffffu, emin, o)); emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, o));
+    const float of = __shfl_xor_sync(0xffffffffu, first, o); const int os = __shfl_xor_sync(0xffffffffu, (int)same, o);
+    same = same && os && (of == 0.f || first == 0.f || of == first);
+    if (first == 0.f) first = of;
+  }
+  if (lane == 0) { s_i[wp * 4] = cnt; s_i[wp * 4 + 1] = emin; s_i[wp * 4 + 2] = emax; s_i[wp * 4 + 3] = same; s_f[wp] = first; }
+  __syncthreads();
+  cnt = 0; emin = 255; emax = 0; same = true; first = 0.f;
+  for (int k = 0; k < 8; ++k) {
+    cnt += s_i[k * 4]; emin = min(emin, s_i[k * 4 + 1]); emax = max(emax, s_i[k * 4 + 2]);
+    const float of = s_f[k];
+    same = same && s_i[k * 4 + 3] && (of == 0.f || first == 0.f || of == first);
+    if (first == 0.f) first = of;
+  }
+  __syncthreads();
+  if (normalise) {
+    // exact shortcut: k copies of c, with k * mantissa(c) < 2^24
+    float fsum;
+    bool exact = false;
+    if (same && cnt > 0) {
+      const uint32_t mant = ((uint32_t)__float_as_int(first) & 0x7fffffu) | 0x800000u;
+      const uint32_t odd = mant >> (__ffs((int)mant) - 1);                 // significant bits of c
+      exact = emin > 0 && (unsigned long long)odd * (unsigned long long)cnt < (1ull << 24);
+    }
+    if (exact) fsum = __fmul_rn((float)cnt, first);
+    else {
+      if (tid == 0) { float acc = 0.f; for (int i = 0; i < n; ++i) acc = __fadd_rn(acc, w[i]); s_f[8] = acc; }
+      __syncthreads();
+      fsum = s_f[8];
+      __syncthreads();
+    }
+    for (int i = tid; i < n; i += 256) w[i] = __fdiv_rn(w[i], fsum);
+    __syncthreads();
+    if (cnt > 0) {                                                         // exponents after the division: recompute (cheap) for the double-sum test
+      emin = 255; emax = 0;
+      for (int i = tid; i < n; i += 256) { const float v = w[i]; if (v != 0.f) { const int e = (__float_as_int(v) >> 23) & 255; emin = min(emin, e); emax = max(emax, e); } }
+      for (int o = 16; o; o >>= 1) { emin = min(emin, __shfl_xor_sync(0xffffffffu, emin, o)); emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, o)); }
+      if (lane == 0) { s_i[wp * 4 + 1] = emin; s_i[wp * 4 + 2] = emax; }
+      __syncthreads();
+      emin = 255; emax = 0;
+      for (int k = 0; k < 8; ++k) { emin = min(emin, s_i[k * 4 + 1]); emax = max(emax, s_i[k * 4 + 2]); }
+      __syncthreads();
+    }
+  }
+  if (n < 2) return 0;                                                     // (as discrete_draw: no table, no draw)
+  // ---- sum_d
+  for (int i = tid; i < n; i += 256) wd[i] = (double)w[i];
+  __syncthreads();
+  int lg = 0; while ((1 << lg) < n) ++lg;
+  const bool dexact = cnt > 0 && emin > 0 && (emax - emin) + lg <= 29;     // 24-bit terms, sum below 2^(emax + 1 + lg): fits 53 bits
+  double dsum;
+  if (dexact) {
+    double part = 0.0;
+    for (int i = tid; i < n; i += 256) part += wd[i];
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s_dd[wp] = part;
+    __syncthreads();
+    dsum = 0.0;
+    for (int k = 0; k < 8; ++k) dsum += s_dd[k];
+    __syncthreads();
+  } else {
+    if (tid == 0) { double acc = 0.0; for (int i = 0; i < n; ++i) acc += wd[i]; s_dd[8] = acc; }
+    __syncthreads();
+    dsum = s_dd[8];
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += 256) wd[i] = wd[i] / dsum;
+  __syncthreads();
+  // ---- the draw
+  if (tid == 0) {
+    const double u = gen.canonical();
+    double acc = 0.0;
+    int pick = n - 1;
+    for (int i = 0; i < n - 1; ++i) {
+      acc += wd[i];
+      if (!(acc < u)) { pick = i; break; }
+    }
+    s_i[0] = pick;
+  }
+  __syncthreads();
+  const int pick = s_i[0];
+  __syncthreads();
+  return pick;
+}
+
+// One CTA per base: Match4PCSBase::SelectQuadrilateralStoCS (match4pcsBase.cc:600-792).  Each of the four points is drawn from
+// prior x "the PPF of the edge to the previous point exists in the model's map" (x the coplanarity / spread filters for the
+// 4th / 3rd point); the weights live in shared memory and are evaluated by all threads; the float normalisation and the draw
+// reproduce the reference's sequential arithmetic bit for bit (block_discrete_draw), so that a given engine seed reproduces the
+// reference's draw.  Dynamic shared memory: n floats + n doubles.
+__global__ void __launch_bounds__(256) k2s_select_bases(StocsParams sp, BaseOut* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char k2s_smem[];
+  __shared__ int s_any;
+  __shared__ int s_i[32];
+  __shared__ float s_f[12];
+  __shared__ double s_dd[12];
+  const int base = blockIdx.x, tid = threadIdx.x, n = sp.n;
+  double* wd = reinterpret_cast<double*>(k2s_smem);
+  float* curr = reinterpret_cast<float*>(wd + n);
+  const float4* P = sp.P;
+  BaseOut o{};
+  for (int attempt = 0; attempt < 16; ++attempt) {      // Perform_N_steps re-draws until a base is accepted (:1831-1852)
+    MinStd gen(stocs_base_seed(sp.seed, sp.base0 + base, attempt));
+    // ---- point 1 ~ priors
+    for (int i = tid; i < n; i += 256) curr[i] = sp.aux[i].w;
+    __syncthreads();
+    const int b1 = block_discrete_draw(curr, wd, n, gen, false, tid, s_f, s_dd, s_i);
+    const float4 p1 = P[b1], a1 = sp.aux[b1];
+    // ---- point 2: prior_i * prior_b1 * edge(b1, i)
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += 256) {
+      float w = 0.f;
+      const float c = curr[i];
+      if (i != b1 && c != 0.f) {
+        const float4 ai = sp.aux[i];
+        const float e = ppf_present(sp.bits, ppf_key(p1, a1, P[i], ai)) ? 1.f : 0.f;
+        w = __fmul_rn(__fmul_rn(ai.w, a1.w), e);
+      }
+      curr[i] = w;
+      if (w != 0.f) s_any = 1;
+    }
+    __syncthreads();
+    if (!s_any) { __syncthreads(); continue; }
+    const int b2 = block_discrete_draw(curr, wd, n, gen, true, tid, s_f, s_dd, s_i);
+    const float4 p2 = P[b2], a2 = sp.aux[b2];
+    // ---- point 3: curr_i * prior_b2 * edge(b2, i), minus the points whose (un-normalised!) angle test fails (:670-676)
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    const float v1x = __fsub_rn(p2.x, p1.x), v1y = __fsub_rn(p2.y, p1.y), v1z = __fsub_rn(p2.z, p1.z);
+    for (int i = tid; i < n; i += 256) {
+      float w = 0.f;
+      const float c = curr[i];
+      const float4 pi = P[i];
+      const float d = dot3_tree(v1x, v1y, v1z, __fsub_rn(pi.x, p1.x), __fsub_rn(pi.y, p1.y), __fsub_rn(pi.z, p1.z));
+      float ang = (float)((double)__fmul_rn((float)acos((double)d), 180.0f) / 3.14159265358979323846);
+      const float other = __fsub_rn(180.0f, ang);
+      ang = other < ang ? other : ang;                 // std::min(a, b) = (b < a) ? b : a   (NaN stays NaN -> not rejected)
+      if (i != b1 && i != b2 && c != 0.f && !(ang < 30.0f)) {
+        const float4 ai = sp.aux[i];
+        const float e = ppf_present(sp.bits, ppf_key(p2, a2, pi, ai)) ? 1.f : 0.f;
+        w = __fmul_rn(__fmul_rn(c, a2.w), e);
+      }
+      curr[i] = w;
+      if (w != 0.f) s_any = 1;
+    }
+    __syncthreads();
+    if (!s_any) { __syncthreads(); continue; }
+    const int b3 = block_discrete_draw(curr, wd, n, gen, true, tid, s_f, s_dd, s_i);
+    const float4 p3 = P[b3], a3 = sp.aux[b3];
+    // ---- point 4: near the plane of the three (<= 1 cm), >= 1 cm away from each of them, edge(b3, i)  (:717-763)
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    const double x1 = p1.x, y1 = p1.y, z1 = p1.z, x2 = p2.x, y2 = p2.y, z2 = p2.z, x3 = p3.x, y3 = p3.y, z3 = p3.z;
+    const float denom = (float)(-x3 * y2 * z1 + x2 * y3 * z1 + x3 * y1 * z2 - x1 * y3 * z2 - x2 * y1 * z3 + x1 * y2 * z3);
+    float A = 0.f, B = 0.f, C = 0.f;
+    if (denom != 0.f) {
+      A = (float)((-y2 * z1 + y3 * z1 + y1 * z2 - y3 * z2 - y1 * z3 + y2 * z3) / (double)denom);
+      B = (float)((x2 * z1 - x3 * z1 - x1 * z2 + x3 * z2 + x1 * z3 - x2 * z3) / (double)denom);
+      C = (float)((-x2 * y1 + x3 * y1 + x1 * y2 - x3 * y2 - x1 * y3 + x2 * y3) / (double)denom);
+    }
+    for (int i = tid; i < n; i += 256) {
+      float w = 0.f;
+      const float c = curr[i];
+      if (i != b1 && i != b2 && i != b3 && c != 0.f) {
+        const float4 pi = P[i];
+        bool keep = true;
+        if (denom != 0.f) {
+          const float lin = __fadd_rn(__fadd_rn(__fmul_rn(A, pi.x), __fmul_rn(B, pi.y)), __fmul_rn(C, pi.z));
+          const float pd = (float)fabs((double)lin - 1.0);
+          auto nrm = [&](const float4 q) {
+            const float dx = __fsub_rn(pi.x, q.x), dy = __fsub_rn(pi.y, q.y), dz = __fsub_rn(pi.z, q.z);
+            return __fsqrt_rn(dot3_tree(dx, dy, dz, dx, dy, dz));
+          };
+          if ((double)pd > 0.01 || (double)nrm(p1) < 0.01 || (double)nrm(p2) < 0.01 || (double)nrm(p3) < 0.01) keep = false;
+        }
+        if (keep) {
+          const float4 ai = sp.aux[i];
+          const float e = ppf_present(sp.bits, ppf_key(p3, a3, pi, ai)) ? 1.f : 0.f;
+          w = __fmul_rn(__fmul_rn(c, a3.w), e);
+        }
+      }
+      curr[i] = w;
+      if (w != 0.f) s_any = 1;
+    }
+    __syncthreads();
+    if (!s_any) { __syncthreads(); continue; }
+    const int b4 = block_discrete_draw(curr, wd, n, gen, true, tid, s_f, s_dd, s_i);
+    if (tid == 0) {
+      const int ids[4] = {b1, b2, b3, b4};
+      try_quadrilateral(P, ids, o);
+      s_i[1] = o.ok;
+    }
+    __syncthreads();
+    const int okk = s_i[1];
+    __syncthreads();
+    if (okk) break;
+  }
+  if (tid == 0) out[base] = o;
+}
+
+// Fallback of k2s_select_bases for scenes whose weight vectors do not fit shared memory (more than ~16 000 points): the same
+// procedure with the weights in global memory and every order-sensitive step on one thread.
 // One CTA per base: Match4PCSBase::SelectQuadrilateralStoCS (match4pcsBase.cc:600-792).  Each of the four points is drawn from
 // prior x "the PPF of the edge to the previous point exists in the model's map" (x the coplanarity / spread filters for the
 // 4th / 3rd point); the weights are evaluated by all threads, the float normalisation and the draw by thread 0, sequentially
 // and in the reference's order, so that a given engine seed reproduces the reference's draw.
-__global__ void __launch_bounds__(256) k2s_select_bases(StocsParams sp, BaseOut* __restrict__ out) {
+__global__ void __launch_bounds__(256) k2s_select_bases_global(StocsParams sp, BaseOut* __restrict__ out) {
   __shared__ int s_pick;
   __shared__ int s_any;
   const int base = blockIdx.x, tid = threadIdx.x, n = sp.n;
@@ -801,6 +1165,7 @@ __global__ void k2s_combo_copy(PpfMapDev m, const int* __restrict__ slot, const 
 
 struct Scratch {
   DevBuf adj, dist6, in_order, list1, list2, cnt, cnt2, off, flag, curr, pairs1, pairs2, quads, bucket_of, key_of, bucket_start, sorted, T, ok, base, qn;
+  DevBuf cone, stage_n, stage_r, stage_T;       // fused fill: cone masks of the pairs that found quads; per-base staging of the selected quads
   const Model* bases_owner = nullptr;   // the model whose last k2_generate call left its bases in `base` (k2_get_bases)
 };
 // the generator's device scratch belongs to the context (two contexts on one device must not share it); created on first use,
@@ -996,7 +1361,8 @@ __global__ void k2b_rigid(const float4* __restrict__ P_unsorted, const float4* _
     const double frac = fmin(1.0, 1.25 * (double)max_quads / (double)nq_b);
     const unsigned long long thr = (unsigned long long)(frac * 9007199254740992.0);   // 2^53
     const uint64_t sb = mix64(seed ^ (0xABCDull + (uint64_t)(base0 + b)));
-    good = (mix64(sb ^ (uint64_t)(i - qoff[b])) >> 11) <= thr;
+    const int4 qd = quads[i];
+    good = quad_selected(sb, qd.x, qd.y, qd.z, qd.w, thr);
   }
   flag[i] = good ? 1u : 0u;
 }
@@ -1191,16 +1557,30 @@ __global__ void k2v_quad_offsets(const uint32_t* __restrict__ scan, int nq, int 
 }
 
 // one thread: per-base kept counts (capped) -> output offsets
-__global__ void k2b_base_out(const uint32_t* __restrict__ fscan, const uint32_t* __restrict__ qoff, int nb, int max_quads, uint32_t* __restrict__ outoff) {
-  if (blockIdx.x || threadIdx.x) return;
-  uint32_t run = 0;
-  for (int b = 0; b < nb; ++b) {
+__global__ void __launch_bounds__(1024) k2b_base_out(const uint32_t* __restrict__ fscan, const uint32_t* __restrict__ qoff, int nb, int max_quads, uint32_t* __restrict__ outoff) {
+  // one CTA: thread t owns the contiguous bases [t per, (t + 1) per); exclusive scan of the per-base output sizes
+  __shared__ uint32_t s_warp[32];
+  const int per = (nb + 1023) / 1024, b0 = threadIdx.x * per, b1 = min(nb, b0 + per);
+  uint32_t mine = 0;
+  for (int b = b0; b < b1; ++b) {
+    uint32_t k = fscan[qoff[b + 1]] - fscan[qoff[b]];
+    if (max_quads > 0 && k > (uint32_t)max_quads) k = (uint32_t)max_quads;
+    mine += k;
+  }
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if ((int)(threadIdx.x & 31) >= o) incl += t; }
+  if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  uint32_t run = incl - mine;
+  for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) run += s_warp[w];
+  for (int b = b0; b < b1; ++b) {
     outoff[b] = run;
     uint32_t k = fscan[qoff[b + 1]] - fscan[qoff[b]];
     if (max_quads > 0 && k > (uint32_t)max_quads) k = (uint32_t)max_quads;
     run += k;
   }
-  outoff[nb] = run;
+  if (threadIdx.x == 1023) outoff[nb] = run;
 }
 
 __global__ void k2b_append(const float* __restrict__ T, const uint32_t* __restrict__ fscan, const uint32_t* __restrict__ qoff, int nb, int max_quads,
@@ -1295,7 +1675,7 @@ int generate_v4pcs(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed,
     PGP_CUDA(ctx, ctx->scene.scratch.reserve((size_t)((nquads + 1) / 2048 + 4096) * 4));
     rc = pgp_scan_exclusive_u32(ctx, flag, (int64_t)nquads + 1, ctx->scene.scratch.as<uint32_t>());
     if (rc) return rc;
-    k2b_base_out<<<1, 32, 0, st>>>(flag, qoff, nb, o->max_quads_per_base, outoff);
+    k2b_base_out<<<1, 1024, 0, st>>>(flag, qoff, nb, o->max_quads_per_base, outoff);
     const int64_t room = max_hyp - cur;
     k2b_append<<<gr, 128, 0, st>>>(sc.T.as<float>(), flag, qoff, nb, o->max_quads_per_base, outoff, (long long)nquads, m.gen_T.as<float>() + 12 * cur, room);
     ctx->launches += 2;
@@ -1365,8 +1745,12 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
   if (depth < 0) depth = 0;
   if (depth > 7) return pgp_fail(ctx, PGP_E_TOO_LARGE, "quad join: model diameter / delta too large (grid depth %d > 7)", depth);
   const uint32_t nbk = 1u << std::min(3 * depth, 15);
-  // bases per chunk: bound the pair buffer (~ 10 % of nq^2 ordered pairs per edge) to about 1 GB
-  int chunk = (int)std::max<double>(1.0, std::min<double>(32.0, 6.0e8 / ((double)nq * (double)nq)));
+  // bases per chunk.  Every chunk costs ~25 launches and three host-read totals whatever its size, so chunks are made as large as
+  // the join's buffers allow (32 bytes per pair + 8 bytes per hash bucket; budget ~2 GB each of the B200's 180 GB): operMode 0 has
+  // ~10 % of nq^2 ordered pairs per (base, edge), operMode 1 the PPF map's mean row length.  A chunk that turns out too large is
+  // halved below (`shrink`); the hypotheses do not depend on the chunking.
+  const double pairs_per_base = o->mode == 1 ? 3.0 * (double)m.n_ppf_pairs / (double)std::max(1, m.n_ppf_keys) : 0.2 * (double)nq * (double)nq;
+  int chunk = (int)std::max(1.0, std::min({o->mode == 1 ? 4096.0 : 256.0, 6.0e7 / std::max(1.0, pairs_per_base), 2.5e8 / (double)nbk}));
   PGP_CUDA(ctx, sc.base.reserve((size_t)nb_total * sizeof(BaseOut) + 64));
   PGP_CUDA(ctx, m.gen_T.reserve((size_t)std::max<int64_t>(max_hyp, 1) * 48));
   BaseOut* d_bases_all = reinterpret_cast<BaseOut*>(sc.base.as<char>() + 64);
@@ -1376,16 +1760,24 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
     if (m.n_ppf_keys <= 0) return pgp_fail(ctx, PGP_E_INVALID, "PCS mode 1 (StoCS) needs the model's PPF map: pgp_set_ppf_map / pgp_build_ppf_map");
     if (!s.has_nrm) return pgp_fail(ctx, PGP_E_INVALID, "PCS mode 1 (StoCS) needs scene normals");
     pm.keys = m.ppf_keys.as<uint32_t>(); pm.offsets = m.ppf_offsets.as<uint32_t>(); pm.pairs = m.ppf_pairs.as<int2>(); pm.n_keys = m.n_ppf_keys;
-    // one weight vector of |P| floats per base in flight: the bases are selected in batches of at most ~1 GB of them
-    const int bsel = (int)std::max<int64_t>(1, std::min<int64_t>(nb_total, ((int64_t)1 << 28) / std::max(1, s.n)));
-    PGP_CUDA(ctx, sc.curr.reserve((size_t)bsel * s.n * 4));
     StocsParams sp{};
     sp.P = s.unsorted.as<float4>(); sp.aux = s.aux_orig.as<float4>(); sp.n = s.n; sp.bits = m.ppf_bits.as<uint32_t>();
-    sp.curr = sc.curr.as<float>(); sp.seed = seed;
-    for (int b0 = 0; b0 < nb_total; b0 += bsel) {
-      sp.base0 = base_lo + b0;
-      k2s_select_bases<<<std::min(bsel, nb_total - b0), 256, 0, st>>>(sp, d_bases_all + b0);
-      if (b0) ctx->launches++;
+    sp.seed = seed;
+    const size_t smem_sel = (size_t)s.n * 12 + 16;                    // the weights of one base: n floats + n doubles in shared memory
+    if (smem_sel <= 200 * 1024) {
+      PGP_CUDA(ctx, cudaFuncSetAttribute(k2s_select_bases, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
+      sp.curr = nullptr; sp.base0 = base_lo;
+      k2s_select_bases<<<nb_total, 256, smem_sel, st>>>(sp, d_bases_all);
+    } else {
+      // larger scenes: one weight vector of |P| floats per base in global memory, the bases selected in batches of at most ~1 GB of them
+      const int bsel = (int)std::max<int64_t>(1, std::min<int64_t>(nb_total, ((int64_t)1 << 28) / std::max(1, s.n)));
+      PGP_CUDA(ctx, sc.curr.reserve((size_t)bsel * s.n * 4));
+      sp.curr = sc.curr.as<float>();
+      for (int b0 = 0; b0 < nb_total; b0 += bsel) {
+        sp.base0 = base_lo + b0;
+        k2s_select_bases_global<<<std::min(bsel, nb_total - b0), 256, 0, st>>>(sp, d_bases_all + b0);
+        if (b0) ctx->launches++;
+      }
     }
   } else {
     k2_select_bases<<<nb_total, 256, 0, st>>>(s.unsorted.as<float4>(), s.n, max_diam, std::max(1, o->base_trials), seed, base_lo, d_bases_all);
@@ -1478,8 +1870,12 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
     if (rc) return rc;
     PGP_CUDA(ctx, cudaMemcpyAsync(cursor, bs, nbuckets * 4, cudaMemcpyDeviceToDevice, st));
     k2_join_scatter<<<gk, 256, 0, st>>>(ntot, sc.bucket_of.as<uint32_t>(), cursor, sc.sorted.as<uint32_t>());
+    // with a per-base cap the selected quads are transformed inside the join (k2_join_select) and neither the order of the pairs
+    // inside a bucket nor the quads themselves are ever needed; the cone masks of the pairs that find quads are kept (48 bytes each)
+    const bool fused = o->max_quads_per_base > 0 && nq < 65536 && (size_t)ntot * 48 < mem_free / 4;
     PGP_CUDA(ctx, sc.in_order.reserve(nbuckets + 16));
-    k2_join_sort_buckets<<<(unsigned)((nbuckets + 255) / 256), 256, 0, st>>>(p.A, bs, (long long)nbuckets, sc.sorted.as<uint32_t>(), sc.in_order.as<unsigned char>());
+    if (fused) PGP_CUDA(ctx, cudaMemsetAsync(sc.in_order.p, 1, nbuckets, st));
+    else k2_join_sort_buckets<<<(unsigned)((nbuckets + 255) / 256), 256, 0, st>>>(p.A, bs, (long long)nbuckets, sc.sorted.as<uint32_t>(), sc.in_order.as<unsigned char>());
     ctx->launches += 2;
     PGP_CUDA(ctx, cudaGetLastError());
     PGP_CUDA(ctx, sc.cnt2.reserve((size_t)(ntot + 1) * 4));
@@ -1489,41 +1885,76 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
     // that found quads -> fill pass on those
     PGP_CUDA(ctx, sc.list1.reserve((size_t)ntot * 4 + 16));
     PGP_CUDA(ctx, sc.list2.reserve((size_t)ntot * 4 + 16));
-    uint32_t* n_lists = reinterpret_cast<uint32_t*>(ctx->work.as<char>() + 384);      // [0] = |list1|, [1] = |list2|
-    PGP_CUDA(ctx, cudaMemsetAsync(n_lists, 0, 8, st));
+    uint32_t* n_lists = reinterpret_cast<uint32_t*>(ctx->work.as<char>() + 384);      // [0] = |list1|, [1] = |list2|, [2] = a query hit an over-long bucket, [3] = staging overflow
+    PGP_CUDA(ctx, cudaMemsetAsync(n_lists, 0, 16, st));
     k2_join_probe<<<gk, 256, 0, st>>>(p, bs, sc.sorted.as<uint32_t>(), sc.key_of.as<uint32_t>(), sc.list1.as<uint32_t>(), n_lists);
     const unsigned gq = (unsigned)((ntot + 127) / 128);
+    const bool want_fused = fused;
+    if (want_fused) PGP_CUDA(ctx, sc.cone.reserve((size_t)ntot * 48 + 64));
     k2_join_query<false><<<gq, 128, 0, st>>>(p, bs, sc.sorted.as<uint32_t>(), sc.key_of.as<uint32_t>(), cnt2, nullptr, 0, sc.in_order.as<unsigned char>(), sc.list1.as<uint32_t>(), n_lists,
-                                             sc.list2.as<uint32_t>(), n_lists + 1);
+                                             sc.list2.as<uint32_t>(), n_lists + 1, want_fused ? sc.cone.as<uint32_t>() : nullptr, n_lists + 2);
     ctx->launches += 2;
     PGP_CUDA(ctx, cudaGetLastError());
     uint64_t nquads = 0;
+    uint32_t unordered = 0;
+    PGP_CUDA(ctx, cudaMemcpyAsync(&unordered, n_lists + 2, 4, cudaMemcpyDeviceToHost, st));
     rc = scan_u32(ctx, cnt2, ntot, &nquads);                                // sync 2
     if (rc) return rc;
     if (nquads == 0) continue;
-    if (nquads >= (1ull << 31) || (size_t)nquads * 68 > mem_free / 2) {
+    if (nquads >= (1ull << 31)) {
       if (shrink()) continue;
-      return pgp_fail(ctx, PGP_E_TOO_LARGE, "congruent quads of one base exceed 2^31 / the device memory");
+      return pgp_fail(ctx, PGP_E_TOO_LARGE, "congruent quads of one base exceed 2^31");
+    }
+    k2b_quad_offsets<<<(nb + 256) / 256, 256, 0, st>>>(cnt2, coff, nb, qoff);
+    ctx->launches++;
+    const int64_t room = max_hyp - cur;
+    (void)unordered;
+    if (want_fused) {
+      // ---- fused: select (the reference's random subset of max_sampled_csets quads per base) BEFORE transforming; see k2_join_select
+      const int stage_cap = o->max_quads_per_base * 5 / 2 + 64;            // mean 1.25 max_quads selected per base, sigma ~ sqrt of that
+      PGP_CUDA(ctx, sc.stage_n.reserve((size_t)nb * 4 + 16));
+      PGP_CUDA(ctx, sc.stage_r.reserve((size_t)nb * stage_cap * 8));
+      PGP_CUDA(ctx, sc.stage_T.reserve((size_t)nb * stage_cap * 48));
+      PGP_CUDA(ctx, cudaMemsetAsync(sc.stage_n.p, 0, (size_t)nb * 4, st));
+      k2_join_select<<<gq, 128, 0, st>>>(p, bs, sc.sorted.as<uint32_t>(), sc.key_of.as<uint32_t>(), cnt2, sc.list2.as<uint32_t>(), n_lists + 1, sc.cone.as<uint32_t>(),
+                                         s.unsorted.as<float4>(), qoff, base_lo + base0, o->max_quads_per_base, seed, stage_cap, sc.stage_n.as<uint32_t>(),
+                                         sc.stage_r.as<uint32_t>(), sc.stage_T.as<float>());
+      k2c_stage_out<<<1, 1024, 0, st>>>(sc.stage_n.as<uint32_t>(), nb, o->max_quads_per_base, stage_cap, outoff, n_lists + 3);
+      k2c_stage_append<<<(unsigned)((nb * 32 + 255) / 256), 256, 0, st>>>(sc.stage_n.as<uint32_t>(), sc.stage_r.as<uint32_t>(), sc.stage_T.as<float>(), nb,
+                                                                          o->max_quads_per_base, stage_cap, outoff, m.gen_T.as<float>() + 12 * cur, room);
+      ctx->launches += 3;
+      PGP_CUDA(ctx, cudaGetLastError());
+      uint32_t overflow = 0;
+      PGP_CUDA(ctx, cudaMemcpyAsync(&overflow, n_lists + 3, 4, cudaMemcpyDeviceToHost, st));
+      uint32_t added_f = 0;
+      PGP_CUDA(ctx, cudaMemcpyAsync(&added_f, outoff + nb, 4, cudaMemcpyDeviceToHost, st));
+      PGP_CUDA(ctx, cudaStreamSynchronize(st));                             // sync 3
+      if (overflow) return pgp_fail(ctx, PGP_E_CAPACITY, "more than %d quads of one base passed the random selection (expected ~%d): try another seed", stage_cap, o->max_quads_per_base * 5 / 4);
+      cur += std::min<int64_t>(room, (int64_t)added_f);
+      continue;
+    }
+    // ---- unfused (no per-base cap): every quad is materialised, transformed and flagged
+    if ((size_t)nquads * 68 > mem_free / 2) {
+      if (shrink()) continue;
+      return pgp_fail(ctx, PGP_E_TOO_LARGE, "congruent quads of one base exceed the device memory");
     }
     PGP_CUDA(ctx, sc.quads.reserve((size_t)nquads * 16));
     PGP_CUDA(ctx, sc.T.reserve((size_t)nquads * 48));
     PGP_CUDA(ctx, sc.flag.reserve((size_t)(nquads + 1) * 4));
     k2_join_query<true><<<gq, 128, 0, st>>>(p, bs, sc.sorted.as<uint32_t>(), sc.key_of.as<uint32_t>(), cnt2, sc.quads.as<int4>(), (long long)nquads,
                                             sc.in_order.as<unsigned char>(), sc.list2.as<uint32_t>(), n_lists + 1);
-    k2b_quad_offsets<<<(nb + 256) / 256, 256, 0, st>>>(cnt2, coff, nb, qoff);
     // ---- transforms, subset, compaction behind the hypotheses already generated
     uint32_t* flag = sc.flag.as<uint32_t>();
     PGP_CUDA(ctx, cudaMemsetAsync(flag + nquads, 0, 4, st));
     const unsigned gr = (unsigned)((nquads + 127) / 128);
     k2b_rigid<<<gr, 128, 0, st>>>(s.unsorted.as<float4>(), m.search.as<float4>(), d_bases, base_lo + base0, qoff, nb, sc.quads.as<int4>(), (long long)nquads,
                                   o->max_quads_per_base, seed, sc.T.as<float>(), flag);
-    ctx->launches += 3;
+    ctx->launches += 2;
     PGP_CUDA(ctx, cudaGetLastError());
     PGP_CUDA(ctx, ctx->scene.scratch.reserve((size_t)((nquads + 1) / 2048 + 4096) * 4));
     rc = pgp_scan_exclusive_u32(ctx, flag, (int64_t)nquads + 1, ctx->scene.scratch.as<uint32_t>());
     if (rc) return rc;
-    k2b_base_out<<<1, 32, 0, st>>>(flag, qoff, nb, o->max_quads_per_base, outoff);
-    const int64_t room = max_hyp - cur;
+    k2b_base_out<<<1, 1024, 0, st>>>(flag, qoff, nb, o->max_quads_per_base, outoff);
     k2b_append<<<gr, 128, 0, st>>>(sc.T.as<float>(), flag, qoff, nb, o->max_quads_per_base, outoff, (long long)nquads, m.gen_T.as<float>() + 12 * cur, room);
     ctx->launches += 2;
     PGP_CUDA(ctx, cudaGetLastError());
@@ -1664,7 +2095,7 @@ void k2_release(pgp_ctx* ctx) {
   if (!ctx->k2_scratch) return;
   Scratch* sc = static_cast<Scratch*>(ctx->k2_scratch);
   for (DevBuf* b : {&sc->adj, &sc->dist6, &sc->in_order, &sc->list1, &sc->list2, &sc->cnt, &sc->cnt2, &sc->off, &sc->flag, &sc->curr, &sc->pairs1, &sc->pairs2, &sc->quads,
-                    &sc->bucket_of, &sc->key_of, &sc->bucket_start, &sc->sorted, &sc->T, &sc->ok, &sc->base, &sc->qn})
+                    &sc->bucket_of, &sc->key_of, &sc->bucket_start, &sc->sorted, &sc->T, &sc->ok, &sc->base, &sc->qn, &sc->cone, &sc->stage_n, &sc->stage_r, &sc->stage_T})
     b->release();
   delete sc;
   ctx->k2_scratch = nullptr;

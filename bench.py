@@ -646,6 +646,17 @@ def run_pcs(args, D: Dist, local_rank: int):
     sampler = ClockSampler(gpu_uuid(torch, local_rank)) if rank == 0 else None
     for w in range(max(1, min(args.warmup, 2))):
         step(1000 + 10 * w)
+    # where a step's time goes: one extra, untimed step with a device synchronisation after every phase
+    phase = {"scene_grid": 0.0, "generate": 0.0, "cap_exchange": 0.0, "score_weighted": 0.0, "topk": 0.0}
+    for o in range(cfg["objects"]):
+        seg = objs[o]
+        def lap(key, fn):
+            torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize(); phase[key] += (time.perf_counter() - t0) * 1e3; return r
+        lap("scene_grid", lambda: eng.set_scene(seg.scene_xyz, seg.scene_nrm, cfg["delta"]))
+        lap("generate", lambda: eng.generate_pcs_range(o, lo, hi, seed=7 + o, max_hyp=cfg["n_hyp"], mode=1, n_bases=B))
+        base_o, _ = lap("cap_exchange", lambda: eng.sync_generated(o, cfg["n_hyp"]))
+        lap("score_weighted", lambda: eng.score_generated(o, "weighted"))
+        lap("topk", lambda: eng.topk_end(eng.topk_begin(o, TOPK, base_o)))
     D.barrier()
     launches0 = eng.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -671,7 +682,8 @@ def run_pcs(args, D: Dist, local_rank: int):
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"name": "c3", "workload": cfg["workload"], "objects": cfg["objects"], "n_bases_per_object": B, "hypotheses_per_step": n_total // args.steps,
                            "parallelism": f"bases sharded over {world} GPU(s): each GPU generates and scores its own hypotheses; scene grid, models and PPF maps replicated",
-                           "one_time_setup_ms": setup_ms, "l2": "256 MiB memset between steps (outside the events)"},
+                           "one_time_setup_ms": setup_ms, "phase_ms_per_step_rank0": {k: round(v, 3) for k, v in phase.items()},
+                           "l2": "256 MiB memset between steps (outside the events)"},
                 "e2e": {"value": n_total / wall_s, "unit": UNIT, "h2d_bytes_per_step": int(sum(len(s.scene_xyz) * 24 for s in objs)) * world,
                         "d2h_bytes_per_step": cfg["objects"] * world * world * (TOPK + 1) * 64,
                         "what": "wall clock around the same steps: segment clouds in from host memory, merged top-64 per object out (the hypotheses never leave the GPU that generated them)"},

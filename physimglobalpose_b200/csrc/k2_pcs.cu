@@ -127,6 +127,10 @@ struct JoinParams {
   // batched mode (bases != nullptr): A == B == all pair lists of the chunk back to back, combo c = 2 base + edge
   // owns [coff[c], coff[c+1]); even combos are the A side, odd ones the B side; base b's buckets start at b * n_buckets
   const BaseOut* bases; const uint32_t* coff; int ncombo;
+  // batched mode: per base of the chunk, the cone's sample directions before the rotation onto the query direction --
+  // 64 x {sin(alpha) cos(theta_t), sin(alpha) sin(theta_t)} (k2_cone_table): they depend on the base's alpha only, and every
+  // pair of the base would otherwise re-evaluate the same ~44 sinf / cosf
+  const float2* cone_tab;
 };
 
 // per-pair join context; false when pair k is not on the wanted side
@@ -147,9 +151,10 @@ __device__ __forceinline__ int pos_cell(const JoinParams& p, float x, float y, f
 __device__ __forceinline__ int dir_cell(float x, float y, float z) {
   // coordinatesNormal = (n/2 + 1/2) / _nepsilon, _nepsilon = 1/7 + 0.00001   (normalset.h:96,108-112)
   const float ne = 1.0f / 7.0f + 0.00001f;
-  const int cx = (int)__fdiv_rn(__fadd_rn(__fdiv_rn(x, 2.0f), 0.5f), ne);
-  const int cy = (int)__fdiv_rn(__fadd_rn(__fdiv_rn(y, 2.0f), 0.5f), ne);
-  const int cz = (int)__fdiv_rn(__fadd_rn(__fdiv_rn(z, 2.0f), 0.5f), ne);
+  // (n / 2: the division by two is exact, so is the product with 0.5)
+  const int cx = (int)__fdiv_rn(__fadd_rn(__fmul_rn(x, 0.5f), 0.5f), ne);
+  const int cy = (int)__fdiv_rn(__fadd_rn(__fmul_rn(y, 0.5f), 0.5f), ne);
+  const int cz = (int)__fdiv_rn(__fadd_rn(__fmul_rn(z, 0.5f), 0.5f), ne);
   return cx + (cy + cz * NG) * NG;
 }
 __device__ __forceinline__ void normalize3(float& x, float& y, float& z) {
@@ -242,14 +247,48 @@ __global__ void __launch_bounds__(256) k2_join_probe(JoinParams p, const uint32_
 
 // Direction cells coloured by the cone of half-angle alpha around the unit direction (dx, dy, dz): the rasterisation of
 // IndexedNormalSet::getNeighbors (normalset.hpp:160-214), sample for sample; col = 343 bits.
-__device__ __forceinline__ void cone_cells(float dx, float dy, float dz, float cos_alpha, uint32_t col[11]) {
-#pragma unroll
-  for (int t = 0; t < 11; ++t) col[t] = 0;
+// Direction cell of the UN-normalised vector r: what normalize3 + dir_cell give -- three IEEE divisions by |r|, three by
+// _nepsilon and a square root per sample, which is where the cone rasterisation spent half of its instructions -- obtained from
+// u = (r_k rsqrt(|r|^2)) (0.5 / _nepsilon) + 0.5 / _nepsilon per axis.  That u is within 5e-6 of the value the reference's rounding
+// sequence produces (u <= 7; every step of either chain is good to a few 1e-7 relative), so wherever it is farther than 3e-5 from
+// an integer, its truncation IS the reference's cell coordinate; the (rare) samples that are not take the exact sequence.
+__device__ __forceinline__ int dir_cell_of(float rx, float ry, float rz) {
+  const float c = 0.5f / (1.0f / 7.0f + 0.00001f);
+  const float rl = rsqrtf(__fmaf_rn(rx, rx, __fmaf_rn(ry, ry, rz * rz)));
+  const float ux = __fmaf_rn(rx * rl, c, c), uy = __fmaf_rn(ry * rl, c, c), uz = __fmaf_rn(rz * rl, c, c);
+  const float fx = floorf(ux), fy = floorf(uy), fz = floorf(uz);
+  const float g = 3e-5f;
+  const bool sure = ux - fx > g && fx + 1.0f - ux > g && uy - fy > g && fy + 1.0f - uy > g && uz - fz > g && fz + 1.0f - uz > g;   // NaN: false
+  if (sure) return (int)fx + ((int)fy + (int)fz * NG) * NG;
+  normalize3(rx, ry, rz);
+  return dir_cell(rx, ry, rz);
+}
+__device__ __forceinline__ unsigned cone_samples(float cos_alpha, float& step, float& sa) {
   const float alpha = acosf(cos_alpha);
   const float perimeter = 2.0f * 3.14159265358979323846f * atanf(alpha);
   const unsigned nb = 2u * (unsigned)ceilf(perimeter * (float)NG / 2.0f);
-  const float step = 2.0f * 3.14159265358979323846f / (float)nb;
-  const float sa = sinf(alpha);
+  step = 2.0f * 3.14159265358979323846f / (float)nb;
+  sa = sinf(alpha);
+  return nb;
+}
+// one thread per (base of the chunk, sample): tab[b * 64 + t] = {sa cos(theta_t), sa sin(theta_t)}, tab[b * 64 + 63].x = number of samples
+__global__ void k2_cone_table(const BaseOut* __restrict__ bases, int nb_bases, float2* __restrict__ tab) {
+  const int b = blockIdx.x, t = threadIdx.x;
+  if (b >= nb_bases) return;
+  float step, sa;
+  const unsigned ns = cone_samples(bases[b].cos_alpha, step, sa);
+  float2 v = make_float2(0.f, 0.f);
+  if ((unsigned)t < ns && t < 63) { const float th = (float)t * step; v = make_float2(sa * cosf(th), sa * sinf(th)); }
+  if (t == 63) v.x = __uint_as_float(ns);
+  tab[b * 64 + t] = v;
+}
+__device__ __forceinline__ void cone_cells(float dx, float dy, float dz, float cos_alpha, uint32_t col[11], const float2* __restrict__ tab = nullptr) {
+#pragma unroll
+  for (int t = 0; t < 11; ++t) col[t] = 0;
+  float step = 0.f, sa = 0.f;
+  unsigned nb;
+  if (tab && __float_as_uint(__ldg(&tab[63].x)) <= 63u) nb = __float_as_uint(__ldg(&tab[63].x));
+  else { tab = nullptr; nb = cone_samples(cos_alpha, step, sa); }
   // q = FromTwoVectors((0,0,1), n):  c = n.z; axis = z x n = (-n.y, n.x, 0); s = sqrt(2(1+c)); vec = axis/s; w = s/2
   const float c = dz;
   float vx, vy, vz, qw;
@@ -259,15 +298,16 @@ __device__ __forceinline__ void cone_cells(float dx, float dy, float dz, float c
     vx = -dy * invs; vy = dx * invs; vz = 0.f; qw = sq * 0.5f;
   }
   for (unsigned t = 0; t < nb; ++t) {
-    const float th = (float)t * step;
-    const float sx = sa * cosf(th), sy = sa * sinf(th), sz = cos_alpha;
+    float sx, sy;
+    if (tab) { const float2 cs = __ldg(tab + t); sx = cs.x; sy = cs.y; }
+    else { const float th = (float)t * step; sx = sa * cosf(th); sy = sa * sinf(th); }
+    const float sz = cos_alpha;
     // q * v = v + w * uv + vec x uv, uv = 2 vec x v
     const float ux = 2.0f * (vy * sz - vz * sy), uy = 2.0f * (vz * sx - vx * sz), uz = 2.0f * (vx * sy - vy * sx);
     float rx = sx + qw * ux + (vy * uz - vz * uy);
     float ry = sy + qw * uy + (vz * ux - vx * uz);
     float rz = sz + qw * uz + (vx * uy - vy * ux);
-    normalize3(rx, ry, rz);
-    const int id = dir_cell(rx, ry, rz);
+    const int id = dir_cell_of(rx, ry, rz);
     if (id >= 0 && id < NG * NG * NG) col[id >> 5] |= 1u << (id & 31);
   }
 }
@@ -311,7 +351,7 @@ __global__ void __launch_bounds__(128) k2_join_query(JoinParams p, const uint32_
       const float qz = __fadd_rn(wa.z, __fmul_rn(inv2, __fsub_rn(wb.z, wa.z)));
       // coloured direction cells: 343 bits
       uint32_t* col = col_keep;
-      cone_cells(dx, dy, dz, cos_alpha, col);
+      cone_cells(dx, dy, dz, cos_alpha, col, p.cone_tab ? p.cone_tab + (size_t)(bkt_base / p.n_buckets) * 64 : nullptr);
       for (uint32_t t = s; t < e; ++t) {
         const uint32_t k = sorted[t];
         const uint32_t key = key_of[k];
@@ -690,9 +730,20 @@ __host__ __device__ inline int approximate_bin(int val, int disc) {
   const int lower = val - (val % disc), upper = lower + disc;
   return (val - lower < upper - val) ? lower : upper;
 }
-__device__ __forceinline__ int ppf_angle(float y, float x) {
+// The angle features enter the key only through approximate_bin(int(deg), 10) = 10 floor((deg + 5) / 10) (deg >= 0: atan2 of a
+// norm): the key changes at deg = 5, 15, ... 175 only.  The fast path evaluates the angle with the fp32 atan2f (a few ulp, i.e.
+// < 1e-4 deg off the reference's correctly rounded value) and returns the bin unless deg lies within 2e-3 deg of such a boundary;
+// there, and for non-finite inputs, the reference's own arithmetic decides (correctly rounded atan2 via double, float x 180,
+// double / pi, truncation).  Bit-equal keys at a fraction of the double-precision work.
+__device__ __forceinline__ int ppf_angle_exact(float y, float x) {
   const float a = (float)atan2((double)y, (double)x);           // atan2f
   return (int)((double)__fmul_rn(a, 180.0f) / 3.14159265358979323846);
+}
+__device__ __forceinline__ int ppf_angle_bin(float y, float x) {      // = approximate_bin(ppf_angle_exact(y, x), 10)
+  const float t = __fmaf_rn(atan2f(y, x), 5.729578f, 0.5f);            // (deg + 5) / 10
+  const float r = rintf(t);
+  if (fabsf(t - r) > 2e-4f && t > 0.25f && t < 18.75f) return 10 * (int)t;
+  return approximate_bin(ppf_angle_exact(y, x), 10);
 }
 __device__ __forceinline__ void ppf_raw(const float4 p1, const float4 n1, const float4 p2, const float4 n2, int k[4]) {
   const float ux = __fsub_rn(p1.x, p2.x), uy = __fsub_rn(p1.y, p2.y), uz = __fsub_rn(p1.z, p2.z);
@@ -703,9 +754,9 @@ __device__ __forceinline__ void ppf_raw(const float4 p1, const float4 n1, const 
     return __fsqrt_rn(dot3_tree(cx, cy, cz, cx, cy, cz));
   };
   k[0] = approximate_bin((int)__fmul_rn(un, 1000.0f), 5);
-  k[1] = approximate_bin(ppf_angle(crossn(n1.x, n1.y, n1.z, ux, uy, uz), dot3_tree(n1.x, n1.y, n1.z, ux, uy, uz)), 10);
-  k[2] = approximate_bin(ppf_angle(crossn(n2.x, n2.y, n2.z, ux, uy, uz), dot3_tree(n2.x, n2.y, n2.z, ux, uy, uz)), 10);
-  k[3] = approximate_bin(ppf_angle(crossn(n1.x, n1.y, n1.z, n2.x, n2.y, n2.z), dot3_tree(n1.x, n1.y, n1.z, n2.x, n2.y, n2.z)), 10);
+  k[1] = ppf_angle_bin(crossn(n1.x, n1.y, n1.z, ux, uy, uz), dot3_tree(n1.x, n1.y, n1.z, ux, uy, uz));
+  k[2] = ppf_angle_bin(crossn(n2.x, n2.y, n2.z, ux, uy, uz), dot3_tree(n2.x, n2.y, n2.z, ux, uy, uz));
+  k[3] = ppf_angle_bin(crossn(n1.x, n1.y, n1.z, n2.x, n2.y, n2.z), dot3_tree(n1.x, n1.y, n1.z, n2.x, n2.y, n2.z));
 }
 __host__ __device__ inline uint32_t ppf_pack(const int k[4]) {
   if (k[0] < 0 || k[0] % 5 || k[0] / 5 >= PPF_D5_MAX) return PPF_NOKEY;
@@ -935,10 +986,16 @@ __global__ void __launch_bounds__(256) k2s_select_bases(StocsParams sp, BaseOut*
       const float c = curr[i];
       const float4 pi = P[i];
       const float d = dot3_tree(v1x, v1y, v1z, __fsub_rn(pi.x, p1.x), __fsub_rn(pi.y, p1.y), __fsub_rn(pi.z, p1.z));
-      float ang = (float)((double)__fmul_rn((float)acos((double)d), 180.0f) / 3.14159265358979323846);
-      const float other = __fsub_rn(180.0f, ang);
-      ang = other < ang ? other : ang;                 // std::min(a, b) = (b < a) ? b : a   (NaN stays NaN -> not rejected)
-      if (i != b1 && i != b2 && c != 0.f && !(ang < 30.0f)) {
+      // |d| < 0.8: acos(d) lies in (36.8, 143.2) degrees, min(a, 180 - a) > 30 whatever the rounding -- the case for metre-scale
+      // vectors, whose un-normalised dot product is tiny; anything else takes the reference's arithmetic
+      bool far30 = fabsf(d) < 0.8f;
+      if (!far30) {
+        float ang = (float)((double)__fmul_rn((float)acos((double)d), 180.0f) / 3.14159265358979323846);
+        const float other = __fsub_rn(180.0f, ang);
+        ang = other < ang ? other : ang;               // std::min(a, b) = (b < a) ? b : a   (NaN stays NaN -> not rejected)
+        far30 = !(ang < 30.0f);
+      }
+      if (i != b1 && i != b2 && c != 0.f && far30) {
         const float4 ai = sp.aux[i];
         const float e = ppf_present(sp.bits, ppf_key(p2, a2, pi, ai)) ? 1.f : 0.f;
         w = __fmul_rn(__fmul_rn(c, a2.w), e);
@@ -969,12 +1026,13 @@ __global__ void __launch_bounds__(256) k2s_select_bases(StocsParams sp, BaseOut*
         bool keep = true;
         if (denom != 0.f) {
           const float lin = __fadd_rn(__fadd_rn(__fmul_rn(A, pi.x), __fmul_rn(B, pi.y)), __fmul_rn(C, pi.z));
-          const float pd = (float)fabs((double)lin - 1.0);
+          const float pd = fabsf(__fsub_rn(lin, 1.0f));        // (float) fabs((double) lin - 1.0): the double difference is exact, its rounding is this
           auto nrm = [&](const float4 q) {
             const float dx = __fsub_rn(pi.x, q.x), dy = __fsub_rn(pi.y, q.y), dz = __fsub_rn(pi.z, q.z);
             return __fsqrt_rn(dot3_tree(dx, dy, dz, dx, dy, dz));
           };
-          if ((double)pd > 0.01 || (double)nrm(p1) < 0.01 || (double)nrm(p2) < 0.01 || (double)nrm(p3) < 0.01) keep = false;
+          // float against the double 0.01 (fl32(0.01) = 0.0099999998 < 0.01): x > 0.01 <=> x > 0.01f,  x < 0.01 <=> x <= 0.01f
+          if (pd > 0.01f || nrm(p1) <= 0.01f || nrm(p2) <= 0.01f || nrm(p3) <= 0.01f) keep = false;
         }
         if (keep) {
           const float4 ai = sp.aux[i];
@@ -1057,10 +1115,16 @@ __global__ void __launch_bounds__(256) k2s_select_bases_global(StocsParams sp, B
       const float c = curr[i];
       const float4 pi = P[i];
       const float d = dot3_tree(v1x, v1y, v1z, __fsub_rn(pi.x, p1.x), __fsub_rn(pi.y, p1.y), __fsub_rn(pi.z, p1.z));
-      float ang = (float)((double)__fmul_rn((float)acos((double)d), 180.0f) / 3.14159265358979323846);
-      const float other = __fsub_rn(180.0f, ang);
-      ang = other < ang ? other : ang;                 // std::min(a, b) = (b < a) ? b : a   (NaN stays NaN -> not rejected)
-      if (i != b1 && i != b2 && c != 0.f && !(ang < 30.0f)) {
+      // |d| < 0.8: acos(d) lies in (36.8, 143.2) degrees, min(a, 180 - a) > 30 whatever the rounding -- the case for metre-scale
+      // vectors, whose un-normalised dot product is tiny; anything else takes the reference's arithmetic
+      bool far30 = fabsf(d) < 0.8f;
+      if (!far30) {
+        float ang = (float)((double)__fmul_rn((float)acos((double)d), 180.0f) / 3.14159265358979323846);
+        const float other = __fsub_rn(180.0f, ang);
+        ang = other < ang ? other : ang;               // std::min(a, b) = (b < a) ? b : a   (NaN stays NaN -> not rejected)
+        far30 = !(ang < 30.0f);
+      }
+      if (i != b1 && i != b2 && c != 0.f && far30) {
         const float4 ai = sp.aux[i];
         const float e = ppf_present(sp.bits, ppf_key(p2, a2, pi, ai)) ? 1.f : 0.f;
         w = __fmul_rn(__fmul_rn(c, a2.w), e);
@@ -1098,12 +1162,13 @@ __global__ void __launch_bounds__(256) k2s_select_bases_global(StocsParams sp, B
         bool keep = true;
         if (denom != 0.f) {
           const float lin = __fadd_rn(__fadd_rn(__fmul_rn(A, pi.x), __fmul_rn(B, pi.y)), __fmul_rn(C, pi.z));
-          const float pd = (float)fabs((double)lin - 1.0);
+          const float pd = fabsf(__fsub_rn(lin, 1.0f));        // (float) fabs((double) lin - 1.0): the double difference is exact, its rounding is this
           auto nrm = [&](const float4 q) {
             const float dx = __fsub_rn(pi.x, q.x), dy = __fsub_rn(pi.y, q.y), dz = __fsub_rn(pi.z, q.z);
             return __fsqrt_rn(dot3_tree(dx, dy, dz, dx, dy, dz));
           };
-          if ((double)pd > 0.01 || (double)nrm(p1) < 0.01 || (double)nrm(p2) < 0.01 || (double)nrm(p3) < 0.01) keep = false;
+          // float against the double 0.01 (fl32(0.01) = 0.0099999998 < 0.01): x > 0.01 <=> x > 0.01f,  x < 0.01 <=> x <= 0.01f
+          if (pd > 0.01f || nrm(p1) <= 0.01f || nrm(p2) <= 0.01f || nrm(p3) <= 0.01f) keep = false;
         }
         if (keep) {
           const float4 ai = sp.aux[i];
@@ -1165,6 +1230,7 @@ __global__ void k2s_combo_copy(PpfMapDev m, const int* __restrict__ slot, const 
 
 struct Scratch {
   DevBuf adj, dist6, in_order, list1, list2, cnt, cnt2, off, flag, curr, pairs1, pairs2, quads, bucket_of, key_of, bucket_start, sorted, T, ok, base, qn;
+  DevBuf cone_tab;                              // per base of the chunk: the cone's sample directions (k2_cone_table)
   DevBuf cone, stage_n, stage_r, stage_T;       // fused fill: cone masks of the pairs that found quads; per-base staging of the selected quads
   const Model* bases_owner = nullptr;   // the model whose last k2_generate call left its bases in `base` (k2_get_bases)
 };
@@ -1853,6 +1919,10 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
     p.thr2 = eps;
     p.eg = 1 << depth; p.cell = 1.0f / (float)p.eg; p.n_buckets = nbk;
     p.bases = d_bases; p.coff = coff; p.ncombo = ncombo;
+    PGP_CUDA(ctx, sc.cone_tab.reserve((size_t)nb * 64 * sizeof(float2)));
+    k2_cone_table<<<nb, 64, 0, st>>>(d_bases, nb, sc.cone_tab.as<float2>());
+    ctx->launches++;
+    p.cone_tab = sc.cone_tab.as<float2>();
     const size_t nbuckets = (size_t)nb * nbk;
     PGP_CUDA(ctx, sc.bucket_of.reserve((size_t)ntot * 4));
     PGP_CUDA(ctx, sc.key_of.reserve((size_t)ntot * 4));
@@ -2095,7 +2165,7 @@ void k2_release(pgp_ctx* ctx) {
   if (!ctx->k2_scratch) return;
   Scratch* sc = static_cast<Scratch*>(ctx->k2_scratch);
   for (DevBuf* b : {&sc->adj, &sc->dist6, &sc->in_order, &sc->list1, &sc->list2, &sc->cnt, &sc->cnt2, &sc->off, &sc->flag, &sc->curr, &sc->pairs1, &sc->pairs2, &sc->quads,
-                    &sc->bucket_of, &sc->key_of, &sc->bucket_start, &sc->sorted, &sc->T, &sc->ok, &sc->base, &sc->qn, &sc->cone, &sc->stage_n, &sc->stage_r, &sc->stage_T})
+                    &sc->bucket_of, &sc->key_of, &sc->bucket_start, &sc->sorted, &sc->T, &sc->ok, &sc->base, &sc->qn, &sc->cone_tab, &sc->cone, &sc->stage_n, &sc->stage_r, &sc->stage_T})
     b->release();
   delete sc;
   ctx->k2_scratch = nullptr;

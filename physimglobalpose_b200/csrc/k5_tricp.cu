@@ -56,9 +56,11 @@ __global__ void k5_tgrid_scatter(const float4* __restrict__ pts, int n, const ui
   out[atomicAdd(cursor + cell_of[i], 1u)] = p;
 }
 
-// exact unbounded 1-NN: rings of cells around the (clamped) query cell; after ring r every unvisited
-// point is at least r*g away, so the search stops once best <= (r g)^2.
-__device__ __forceinline__ void nn_search(const TricpParams& p, float qx, float qy, float qz, float& best, int& best_id) {
+// exact 1-NN: rings of cells around the (clamped) query cell; after ring r every unvisited point is at least r*g away, so the
+// search stops once best <= (r g)^2 -- or, with a finite cap2, once (r g)^2 >= cap2: then every unvisited point is farther than
+// sqrt(cap2) and the caller only needs to know THAT (the trimmed set keeps the n_keep smallest distances; a point beyond the
+// current trim radius is dropped whatever its exact distance).  A result <= cap2 is always the exact nearest neighbour.
+__device__ __forceinline__ void nn_search(const TricpParams& p, float qx, float qy, float qz, float cap2, float& best, int& best_id) {
   const TGrid& tg = p.tg;
   const int cx = min(max((int)floorf((qx - tg.lo[0]) * tg.inv_g), 0), tg.dim[0] - 1);
   const int cy = min(max((int)floorf((qy - tg.lo[1]) * tg.inv_g), 0), tg.dim[1] - 1);
@@ -68,7 +70,9 @@ __device__ __forceinline__ void nn_search(const TricpParams& p, float qx, float 
   for (int r = 0; r <= rmax; ++r) {
     if (r > 0) {
       const float bound = (float)(r - 1) * tg.g;     // ring r-1 is complete: unvisited points are >= (r-1) g away
-      if (best_id >= 0 && best <= bound * bound * 0.999999f) break;
+      const float b2 = bound * bound * 0.999999f;
+      if (best_id >= 0 && best <= b2) break;
+      if (b2 >= cap2) { if (!(best <= cap2)) { best = FLT_MAX; best_id = 0; } break; }
     }
     const int z0 = max(cz - r, 0), z1 = min(cz + r, tg.dim[2] - 1), y0 = max(cy - r, 0), y1 = min(cy + r, tg.dim[1] - 1);
     const int x0 = max(cx - r, 0), x1 = min(cx + r, tg.dim[0] - 1);
@@ -107,10 +111,14 @@ __device__ __forceinline__ void nn_search(const TricpParams& p, float qx, float 
 
 __device__ void jacobi4(double A[4][4], double V[4][4]) {
   for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) V[i][j] = (i == j);
+  double scale = 0;
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) scale += A[i][j] * A[i][j];
   for (int sweep = 0; sweep < 64; ++sweep) {
     double off = 0;
     for (int i = 0; i < 4; ++i) for (int j = i + 1; j < 4; ++j) off += A[i][j] * A[i][j];
-    if (off < 1e-300) break;
+    // converged to double precision: the off-diagonal mass is below eps^2 of the matrix (Jacobi converges quadratically, so the
+    // sweep that gets here has already over-shot; running on to 1e-300 costs five more sweeps for nothing)
+    if (off <= 1e-34 * scale || off < 1e-300) break;
     for (int p = 0; p < 4; ++p)
       for (int q = p + 1; q < 4; ++q) {
         if (fabs(A[p][q]) < 1e-300) continue;
@@ -164,6 +172,11 @@ __global__ void __launch_bounds__(TT, 1) k5_tricp_kernel(const TricpParams p) {
   __syncthreads();
   float energy = FLT_MAX, old_energy = FLT_MAX;
   int it = 0;
+  // Search radius of the next iteration: 4 x the squared trim radius of the previous one.  Source points that are far from the
+  // model (the half the trim drops; clutter) otherwise dominate the iteration -- their ring searches sweep hundreds of cells for a
+  // distance that is thrown away.  If the n_keep-th smallest distance found under the cap is not below it, the cap cut into the
+  // kept set: the correspondences are searched again without a cap, so the kept set and its sums are always the exact ones.
+  float cap2 = FLT_MAX;
   for (;;) {
     // 1. correspondences
     for (int i = tid; i < p.ns; i += TT) {
@@ -172,7 +185,7 @@ __global__ void __launch_bounds__(TT, 1) k5_tricp_kernel(const TricpParams p) {
       const float qy = sT[4] * s.x + sT[5] * s.y + sT[6] * s.z + sT[7];
       const float qz = sT[8] * s.x + sT[9] * s.y + sT[10] * s.z + sT[11];
       float best; int id;
-      nn_search(p, qx, qy, qz, best, id);
+      nn_search(p, qx, qy, qz, cap2, best, id);
       d2[i] = best; nn[i] = id;
     }
     __syncthreads();
@@ -187,16 +200,29 @@ __global__ void __launch_bounds__(TT, 1) k5_tricp_kernel(const TricpParams p) {
         if (pass == 0 || (b >> (shift + 8)) == prefix) atomicAdd(&s_hist[(b >> shift) & 255u], 1u);
       }
       __syncthreads();
-      if (tid == 0) {
-        uint32_t acc = 0; int dgt = 0;
-        for (; dgt < 256; ++dgt) { if (acc + s_hist[dgt] >= rank) break; acc += s_hist[dgt]; }
-        s_sel[0] = (prefix << 8) | (uint32_t)min(dgt, 255); s_sel[1] = rank - acc;
+      if (warp == 0) {
+        // first digit whose inclusive prefix count reaches the rank: 8 bins per lane, warp scan of the lane sums
+        uint32_t h[8], mine = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { h[k] = s_hist[lane * 8 + k]; mine += h[k]; }
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        const unsigned hit = __ballot_sync(0xffffffffu, incl >= rank);
+        const int l = hit ? __ffs(hit) - 1 : 31;
+        if (lane == l) {
+          uint32_t acc = incl - mine; int dgt = 0;
+          for (; dgt < 7; ++dgt) { if (acc + h[dgt] >= rank) break; acc += h[dgt]; }
+          s_sel[0] = (prefix << 8) | (uint32_t)(lane * 8 + dgt); s_sel[1] = rank - acc;
+        }
       }
       __syncthreads();
       prefix = s_sel[0]; rank = s_sel[1];
       __syncthreads();
     }
     const uint32_t tau = prefix;          // bits of the n_keep-th smallest d2; `rank` of the equal ones are kept, lowest source index first
+    if (cap2 != FLT_MAX && !(__uint_as_float(tau) < cap2)) { cap2 = FLT_MAX; continue; }      // (uniform over the CTA: tau comes from shared memory)
+    cap2 = fmaxf(4.0f * __uint_as_float(tau), 1e-12f);
     // 3. sums over the kept correspondences (equal-to-tau ones admitted in index order)
     double acc[16];
 #pragma unroll
@@ -234,9 +260,11 @@ __global__ void __launch_bounds__(TT, 1) k5_tricp_kernel(const TricpParams p) {
       if (lane == 0) s_red[warp][k] = v;
     }
     __syncthreads();
+    if (tid < 16) { double v = 0; for (int w = 0; w < TT / 32; ++w) v += s_red[w][tid]; s_red[0][tid] = v; }      // (column tid only: no hazard)
+    __syncthreads();
     if (tid == 0) {
       double S[16];
-      for (int k = 0; k < 16; ++k) { double v = 0; for (int w = 0; w < TT / 32; ++w) v += s_red[w][k]; S[k] = v; }
+      for (int k = 0; k < 16; ++k) S[k] = s_red[0][k];
       old_energy = energy;
       energy = (float)S[0];
       float Tn[12];
@@ -268,7 +296,9 @@ int build_target_grid(pgp_ctx* ctx, Model& m) {
   TGrid tg;
   float ext = 0.f;
   for (int k = 0; k < 3; ++k) ext = std::max(ext, m.val_raw_hi[k] - m.val_raw_lo[k]);
-  const int cells = std::max(1, std::min(64, (int)std::ceil(std::cbrt((double)n))));
+  // cell edge: the model is a SURFACE, so ~n of the cells^3 cells are occupied when cells ~ 2 cbrt(n) (about one point per occupied
+  // cell: the 27-cell ring of a query near the surface then holds ~8 points instead of ~32 at cells = cbrt(n))
+  const int cells = std::max(1, std::min(96, (int)std::ceil(2.0 * std::cbrt((double)n))));
   tg.g = std::max(ext / (float)cells, 1e-6f);
   tg.inv_g = 1.0f / tg.g;
   for (int k = 0; k < 3; ++k) {

@@ -1,5 +1,6 @@
 // Test driver: calls the drop-in exactly as CongruentSetMatching::generate does
 // (PPE/src/hypothesis_generation/ObjectPoseCandidateSet.cpp:66-68) and prints the outputs as JSON.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -37,8 +38,19 @@ int main(int argc, char** argv) {
       ppf.insert(std::make_pair(key, v));
     }
   }
-  getProbableTransformsSuper4PCS(argv[1], argv[2], argv[3], best, set, png, ppf, 0, K, "obj", "/tmp/", reg);
-  printf("{\"best_score\": %.9g, \"n_hypotheses\": %zu, \"n_registered\": %zu, \"best_pose\": [", best.second, set.size(), reg.size());
+  // PGP_DRIVER_REPEAT = n: the same request n times in one process, as a long-lived node issues them (the caller's vector is NOT
+  // emptied in between: the callee must clear it); PGP_DRIVER_SCENE: the scenePath argument (default /tmp/)
+  const int repeat = getenv("PGP_DRIVER_REPEAT") ? atoi(getenv("PGP_DRIVER_REPEAT")) : 1;
+  const std::string scene = getenv("PGP_DRIVER_SCENE") ? getenv("PGP_DRIVER_SCENE") : "/tmp/";
+  std::vector<double> call_ms;
+  for (int r = 0; r < repeat; ++r) {
+    const auto t0 = std::chrono::steady_clock::now();
+    getProbableTransformsSuper4PCS(argv[1], argv[2], argv[3], best, set, png, ppf, 0, K, "obj", scene, reg);
+    call_ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
+  printf("{\"call_ms\": [");
+  for (size_t i = 0; i < call_ms.size(); ++i) printf("%s%.3f", i ? ", " : "", call_ms[i]);
+  printf("], \"best_score\": %.9g, \"n_hypotheses\": %zu, \"n_registered\": %zu, \"best_pose\": [", best.second, set.size(), reg.size());
   for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) printf("%s%.17g", (r || c) ? ", " : "", best.first(r, c));
   printf("], \"scores\": [");
   for (size_t i = 0; i < set.size(); ++i) printf("%s%.9g", i ? ", " : "", set[i].second);

@@ -52,5 +52,22 @@ for k, name in enumerate(g['names']):
         t2 = time.perf_counter()
         res.update(reference_init_ms=(t1 - t0) * 1e3, reference_perform_ms=(t2 - t1) * 1e3, reference_hypotheses=int(len(r['transforms'])),
                    reference_best=float(r['best_lcp']), reference_stage_s=[float(x) for x in r['stage_s']])
+    # the FILE contract of the boundary (what the ROS node actually does per object: three PLYs + the prior PNG on disk, then
+    # getProbableTransformsSuper4PCS): libsuper4pcs.so through the C++ driver, 6 requests in one process -- the first pays the
+    # model parse / upload / PPF-map build, the rest hit the per-object cache (segment PLY + PNG parse and all device work included)
+    import subprocess, tempfile
+    sys.path.insert(0, 'tests')
+    from test_adaptor import write_pcl_ply, write_png16, AD, _build
+    _build()
+    with tempfile.TemporaryDirectory() as td:
+        fs = [os.path.join(td, n) for n in ('seg.ply', 'val.ply', 'search.ply')]
+        write_pcl_ply(fs[0], seg, nrm); write_pcl_ply(fs[1], mx, mn); write_pcl_ply(fs[2], mx, mn)
+        png = os.path.join(td, 'prior.png'); write_png16(png, img)
+        K = g['K']
+        env = dict(os.environ, PGP_DRIVER_REPEAT='6', PGP_PCS_MODE='stocs', PGP_SEED='3', PGP_DELTA=str(delta))
+        o = subprocess.check_output([os.path.join(AD, 'dropin_driver'), *fs, png, str(K[0, 0]), str(K[1, 1]), str(K[0, 2]), str(K[1, 2])], env=env, text=True)
+        r = json.loads(o.strip().splitlines()[-1])
+        res.update(file_contract_first_request_ms=r['call_ms'][0], file_contract_request_ms=float(np.median(r['call_ms'][1:])),
+                   file_contract_best_score=r['best_score'], file_contract_chain=r['n_hypotheses'])
     out[str(name)] = res
 print(json.dumps(out))

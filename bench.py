@@ -269,6 +269,15 @@ class Dist:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
         return float(t.item())
 
+    def gather(self, x: float) -> list:
+        """x of every rank, in rank order (the per-rank spread behind a max-over-ranks figure)."""
+        if self.world == 1:
+            return [x]
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        out = [self.torch.zeros_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
     def close(self):
         if self.world > 1:
             self.dist.destroy_process_group()
@@ -452,7 +461,8 @@ def run_scoring(args, D: Dist, local_rank: int):
     wall_ms = (time.perf_counter() - wall0) * 1e3
     D.barrier()
     launches = eng.launch_count - launches0
-    total_ms = D.reduce(sum(a.elapsed_time(b) for a, b in ev))
+    rank_ms = D.gather(sum(a.elapsed_time(b) for a, b in ev))
+    total_ms = max(rank_ms)
     exchange_tail_ms = ev[-1][0].elapsed_time(ev[-1][1])
     wall_ms = D.reduce(wall_ms)
     value = n_step_total * args.steps / (total_ms * 1e-3)
@@ -557,7 +567,7 @@ def run_scoring(args, D: Dist, local_rank: int):
                     "(pgp_bench_sector_gather, L2-resident footprint); dram = DRAM bytes of one launch (same capture) / kernel time / HBM peak"}
         line = {
             "metric": cfg["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps, "exchange_tail_ms": exchange_tail_ms,
+            "ms_per_step": total_ms / args.steps, "ms_per_step_per_rank": [round(x / args.steps, 5) for x in rank_ms], "exchange_tail_ms": exchange_tail_ms,
             "ms_per_step_pipelined_no_l2_flush": noflush_ms / args.steps,
             "wall_ms_per_step_incl_l2_flush_and_host_merge": wall_ms / args.steps, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
@@ -647,16 +657,18 @@ def run_pcs(args, D: Dist, local_rank: int):
     for w in range(max(1, min(args.warmup, 2))):
         step(1000 + 10 * w)
     # where a step's time goes: one extra, untimed step with a device synchronisation after every phase
-    phase = {"scene_grid": 0.0, "generate": 0.0, "cap_exchange": 0.0, "score_weighted": 0.0, "topk": 0.0}
-    for o in range(cfg["objects"]):
-        seg = objs[o]
-        def lap(key, fn):
-            torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize(); phase[key] += (time.perf_counter() - t0) * 1e3; return r
-        lap("scene_grid", lambda: eng.set_scene(seg.scene_xyz, seg.scene_nrm, cfg["delta"]))
-        lap("generate", lambda: eng.generate_pcs_range(o, lo, hi, seed=7 + o, max_hyp=cfg["n_hyp"], mode=1, n_bases=B))
-        base_o, _ = lap("cap_exchange", lambda: eng.sync_generated(o, cfg["n_hyp"]))
-        lap("score_weighted", lambda: eng.score_generated(o, "weighted"))
-        lap("topk", lambda: eng.topk_end(eng.topk_begin(o, TOPK, base_o)))
+    phase = {}
+    for rep in range(2):                            # (the second pass: buffers have their final sizes)
+      phase = {"scene_grid": 0.0, "generate": 0.0, "cap_exchange": 0.0, "score_weighted": 0.0, "topk": 0.0}
+      for o in range(cfg["objects"]):
+          seg = objs[o]
+          def lap(key, fn):
+              torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize(); phase[key] += (time.perf_counter() - t0) * 1e3; return r
+          lap("scene_grid", lambda: eng.set_scene(seg.scene_xyz, seg.scene_nrm, cfg["delta"]))
+          lap("generate", lambda: eng.generate_pcs_range(o, lo, hi, seed=7 + o, max_hyp=cfg["n_hyp"], mode=1, n_bases=B))
+          base_o, _ = lap("cap_exchange", lambda: eng.sync_generated(o, cfg["n_hyp"]))
+          lap("score_weighted", lambda: eng.score_generated(o, "weighted"))
+          lap("topk", lambda: eng.topk_end(eng.topk_begin(o, TOPK, base_o)))
     D.barrier()
     launches0 = eng.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]

@@ -174,7 +174,7 @@ def test_group_scoring_is_sharding_invariant(mode):
         assert np.array_equal(r[0], results[0][0]) and np.array_equal(r[1], results[0][1])
         assert r[2].tobytes() == results[0][2].tobytes()
         assert r[3].tobytes() == results[0][3].tobytes()
-    assert len(results[0][3]) >= 20
+    assert len(results[0][3]) >= (20 if mode == "count" else 8)   # (the list is ordered by the count; the weighted chain follows the score)
 
 
 @pytest.mark.skipif("_n_devices() < 2")

@@ -333,6 +333,9 @@ struct FineCtx {
   uint16_t* sq;              // weighted mode, second-level queue (SQCAP slots per warp) of the queries the cone record could not settle:
   uint32_t* sqe;             //   model point, voxel address,
   unsigned char* sqr;        //   info | gate_known << 5 -- resolved 32 at a time so that the rare, long exact path runs on full warps
+  unsigned sa;               // per warp: shared-memory address of 12 floats, the hypothesis' pre-scaled (voxel-unit) matrix -- warp-uniform
+                             // data the loops re-read with three LDS.128 where they use it instead of holding 12 registers across
+                             // the whole hypothesis (at 64 registers per thread the compiler spilled exactly these to local memory)
   uint32_t* glist;           // per warp: byte offsets (into the staged model) of the groups of the current hypothesis that survived the cull (+ FUNROLL pad slots)
   int dummy_group;           // a group of NaN points behind the tile
   int dimx, dimy, dimz;
@@ -465,6 +468,18 @@ __device__ __noinline__ int resolve_weighted_slow(const LcpParams& p, const floa
   return (ns.w != 0.f) ? 0x10001 : 0x1;
 }
 
+// the per-warp matrix slot (FineCtx::sa): volatile asm so that every use site re-reads it (no value held across the loops)
+__device__ __forceinline__ void sa_store(unsigned sa, const float (&a)[12]) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]) : "memory");
+  asm volatile("st.shared.v4.f32 [%0+16], {%1, %2, %3, %4};" ::"r"(sa), "f"(a[4]), "f"(a[5]), "f"(a[6]), "f"(a[7]) : "memory");
+  asm volatile("st.shared.v4.f32 [%0+32], {%1, %2, %3, %4};" ::"r"(sa), "f"(a[8]), "f"(a[9]), "f"(a[10]), "f"(a[11]) : "memory");
+}
+__device__ __forceinline__ void sa_load(unsigned sa, float (&a)[12]) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a[0]), "=f"(a[1]), "=f"(a[2]), "=f"(a[3]) : "r"(sa));
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+16];" : "=f"(a[4]), "=f"(a[5]), "=f"(a[6]), "=f"(a[7]) : "r"(sa));
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+32];" : "=f"(a[8]), "=f"(a[9]), "=f"(a[10]), "=f"(a[11]) : "r"(sa));
+}
+
 // one hypothesis, the 32-point groups [g_begin, g_end) of the staged tile (the slots behind the last point hold NaN points, which
 // convert to voxel 0 and fail the range test; `dummy_group` is a whole group of them).
 // FAST: voxel coordinates from the pre-scaled FMA transform a[]; otherwise the reference's
@@ -479,15 +494,20 @@ template <bool SMEM_TABLE, bool FAST, int MODE, int U>
 __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCtx& f, const float* __restrict__ T, long long h, int g_begin, int g_end) {
   static_assert(FUNROLL == 4, "the survivor list is read four entries at a time");
   const Xf x = load_xf(T, h);
-  float a[12];
+  if (FAST) {
+    float a[12];
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    a[4 * r + 0] = x.m[4 * r + 0] * p.g.inv_hf;
-    a[4 * r + 1] = x.m[4 * r + 1] * p.g.inv_hf;
-    a[4 * r + 2] = x.m[4 * r + 2] * p.g.inv_hf;
-    a[4 * r + 3] = (x.m[4 * r + 3] - p.g.lo[r]) * p.g.inv_hf;
+    for (int r = 0; r < 3; ++r) {
+      a[4 * r + 0] = x.m[4 * r + 0] * p.g.inv_hf;
+      a[4 * r + 1] = x.m[4 * r + 1] * p.g.inv_hf;
+      a[4 * r + 2] = x.m[4 * r + 2] * p.g.inv_hf;
+      a[4 * r + 3] = (x.m[4 * r + 3] - p.g.lo[r]) * p.g.inv_hf;
+    }
+    __syncwarp();                                   // (the previous hypothesis' readers are done)
+    if (f.lane == 0) sa_store(f.sa, a);
+    __syncwarp();
   }
-  auto voxel_of = [&](const float4 m, int& ix, int& iy, int& iz) {
+  auto voxel_of = [&](const float (&a)[12], const float4 m, int& ix, int& iy, int& iz) {
     float ux, uy, uz;
     if (FAST) {
       ux = __fmaf_rn(a[0], m.x, __fmaf_rn(a[1], m.y, __fmaf_rn(a[2], m.z, a[3])));
@@ -518,6 +538,8 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
       bool keep = g < g_end;
       if (cull && keep) {
         const float4 sp = f.s_groups[g];
+        float a[12];
+        sa_load(f.sa, a);
         const float ux = __fmaf_rn(a[0], sp.x, __fmaf_rn(a[1], sp.y, __fmaf_rn(a[2], sp.z, a[3]))) * p.dist_scale;
         const float uy = __fmaf_rn(a[4], sp.x, __fmaf_rn(a[5], sp.y, __fmaf_rn(a[6], sp.z, a[7]))) * p.dist_scale;
         const float uz = __fmaf_rn(a[8], sp.x, __fmaf_rn(a[9], sp.y, __fmaf_rn(a[10], sp.z, a[11]))) * p.dist_scale;
@@ -568,13 +590,29 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
         int known = 0;                              // 0: exact path, 1 | prior << 1: gate passes, -1: settled
         if (FAST && (vr >> 24) != 255u) {
           const float4 sn = __ldg(p.aux_orig + (vr & 0xffffffu));
+          float a[12];
+          sa_load(f.sa, a);
           const float qx = __fmaf_rn(a[0], nm.x, __fmaf_rn(a[1], nm.y, a[2] * nm.z)), qy = __fmaf_rn(a[4], nm.x, __fmaf_rn(a[5], nm.y, a[6] * nm.z)),
                       qz = __fmaf_rn(a[8], nm.x, __fmaf_rn(a[9], nm.y, a[10] * nm.z));
           const float ae = fabsf(__fmaf_rn(sn.x, qx, __fmaf_rn(sn.y, qy, sn.z * qz))) * p.g.hf;
           const float mg = __fmaf_rn((float)(vr >> 24), gate_eps, gate_err);
           const float c30 = 0.8660254f;
+          bool pass = false;
           if (ae + mg < c30 - 1e-4f) known = -1;
-          else if (ae - mg > c30 + 1e-4f && ae + mg < 1.0f) {
+          else if (ae - mg > c30 + 1e-4f) {
+            pass = ae + mg < 1.0f;
+            if (!pass && snorm <= 1.00002f) {
+              // nearly parallel normals under a rigid hypothesis (the common case near the ground truth): |d_i| <= 1 needs the ANGLE
+              // of every candidate to clear ~7e-3 rad, which the cosine cannot resolve but the sine can.  theta_i >= theta_rep -
+              // 1.05 eps (unit normals: pgp_set_scene / pgp_set_model normalise; chord eps <= 0.6), and theta >= sin theta =
+              // |n x q| / (|n| |q|) >= |n x q| / (1.000001 snorm); with theta_i >= 7e-3: |d_i| <= 1.000021 (1 - 2.4e-5) + 2e-7 < 1.
+              const float cx = __fmaf_rn(sn.y, qz, -sn.z * qy), cy = __fmaf_rn(sn.z, qx, -sn.x * qz), cz = __fmaf_rn(sn.x, qy, -sn.y * qx);
+              const float c2 = __fmaf_rn(cx, cx, __fmaf_rn(cy, cy, cz * cz)) * (p.g.hf * p.g.hf);
+              const float rhs = __fmaf_rn(__fmaf_rn((float)(vr >> 24), 1.05f * VREC_EPS_STEP * (1.0f + 1e-6f), 7.1e-3f), 1.00002f, 2e-5f) * snorm;
+              pass = c2 > rhs * rhs;
+            }
+          }
+          if (pass) {
             known = 1 | (sn.w != 0.f ? 2 : 0);
             if (!(info & 16u)) { good += (sn.w != 0.f) ? 0x10001 : 0x1; known = -1; }
           }
@@ -601,10 +639,12 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
     const uint4 gg = *reinterpret_cast<const uint4*>(f.glist + k);
     const uint32_t gb[FUNROLL] = {gg.x, gg.y, gg.z, gg.w};
     uint32_t off[FUNROLL], sh[FUNROLL], code[FUNROLL];
+    float a[12];
+    if (FAST) sa_load(f.sa, a);
 #pragma unroll
     for (int u = 0; u < FUNROLL; ++u) {
       int ix, iy, iz;
-      voxel_of(*reinterpret_cast<const float4*>(reinterpret_cast<const char*>(mp) + gb[u]), ix, iy, iz);
+      voxel_of(a, *reinterpret_cast<const float4*>(reinterpret_cast<const char*>(mp) + gb[u]), ix, iy, iz);
       off[u] = label_slot<SMEM_TABLE>(p, f, ix, iy, iz, sh[u]);
     }
 #pragma unroll
@@ -651,6 +691,7 @@ __global__ void __launch_bounds__(FWARPS * 32, 1) k3_fine_kernel(const __grid_co
   constexpr int PU = FWARPS == 32 ? 1 : 4;     // candidates in flight per lane in phase 2
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t mbar;
+  __shared__ __align__(16) float s_xf[FWARPS * 12];   // FineCtx::sa
   // shared-memory plan (k3_fine_smem on the host): model tile + one NaN group | normals (weighted) | bmrank | group spheres | survivor lists | queues
   const int cap_groups = p.tile_cap >> 5;
   float4* s_model = reinterpret_cast<float4*>(smem);
@@ -666,6 +707,7 @@ __global__ void __launch_bounds__(FWARPS * 32, 1) k3_fine_kernel(const __grid_co
   unsigned char* s_sqr = reinterpret_cast<unsigned char*>(s_sq + FWARPS * SQCAP);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   FineCtx f;
+  f.sa = (unsigned)__cvta_generic_to_shared(s_xf + (threadIdx.x >> 5) * 12);
   f.s_model = s_model;
   f.s_nrm = s_nrm;
   f.s_groups = s_groups;

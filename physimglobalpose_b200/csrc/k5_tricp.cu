@@ -132,6 +132,48 @@ __device__ void jacobi4(double A[4][4], double V[4][4]) {
   }
 }
 
+// Largest eigenpair of the symmetric, traceless 4x4 matrix of Horn's quaternion fit without an iterative diagonalisation: the
+// characteristic polynomial x^4 + c2 x^2 + c1 x + c0 of N / |N|_F from traces of powers (Faddeev-LeVerrier), Newton from x = 1 >=
+// lambda_max (monotone: every root is real and the polynomial is convex to the right of the largest), eigenvector = the column of
+// adj(N - lambda I) with the largest diagonal cofactor (rank 3 => adj = c q q^T).  Returns false when the largest eigenvalue is
+// (nearly) double -- the fit is then ill-posed and the caller diagonalises with Jacobi instead.
+__device__ bool max_eigvec4(const double N[4][4], double q[4]) {
+  double f2 = 0;
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) f2 += N[i][j] * N[i][j];
+  if (!(f2 > 1e-280) || !(f2 < 1e280)) return false;
+  const double inv = 1.0 / sqrt(f2);
+  double A[4][4], M2[4][4];
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) A[i][j] = N[i][j] * inv;
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { double s = 0; for (int k = 0; k < 4; ++k) s += A[i][k] * A[k][j]; M2[i][j] = s; }
+  double t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+  for (int i = 0; i < 4; ++i) { t1 += A[i][i]; t2 += M2[i][i]; for (int j = 0; j < 4; ++j) { t3 += M2[i][j] * A[i][j]; t4 += M2[i][j] * M2[i][j]; } }
+  // Faddeev-LeVerrier, general trace (t1 is rounding-sized here but costs nothing to carry)
+  const double c3 = -t1, c2 = -0.5 * (t2 + c3 * t1), c1 = -(t3 + c3 * t2 + c2 * t1) / 3.0, c0 = -0.25 * (t4 + c3 * t3 + c2 * t2 + c1 * t1);
+  double x = 1.0 + 1e-12;
+  for (int it = 0; it < 100; ++it) {
+    const double P = (((x + c3) * x + c2) * x + c1) * x + c0, dP = ((4.0 * x + 3.0 * c3) * x + 2.0 * c2) * x + c1;
+    if (!(dP > 0)) return false;
+    const double d = P / dP;
+    x -= d;
+    if (fabs(d) < 1e-15) break;
+  }
+  for (int i = 0; i < 4; ++i) A[i][i] -= x;
+  auto minor3 = [&](int i, int j) {
+    int r[3], c[3];
+    for (int k = 0, n = 0; k < 4; ++k) if (k != i) r[n++] = k;
+    for (int k = 0, n = 0; k < 4; ++k) if (k != j) c[n++] = k;
+    return A[r[0]][c[0]] * (A[r[1]][c[1]] * A[r[2]][c[2]] - A[r[1]][c[2]] * A[r[2]][c[1]]) -
+           A[r[0]][c[1]] * (A[r[1]][c[0]] * A[r[2]][c[2]] - A[r[1]][c[2]] * A[r[2]][c[0]]) +
+           A[r[0]][c[2]] * (A[r[1]][c[0]] * A[r[2]][c[1]] - A[r[1]][c[1]] * A[r[2]][c[0]]);
+  };
+  int jb = 0;
+  double cb = 0;
+  for (int j = 0; j < 4; ++j) { const double c = fabs(minor3(j, j)); if (c > cb) { cb = c; jb = j; } }
+  if (!(cb > 1e-7)) return false;
+  for (int i = 0; i < 4; ++i) q[i] = (((i + jb) & 1) ? -1.0 : 1.0) * minor3(i, jb);
+  return true;
+}
+
 // R, t minimising sum |R s + t - g|^2 from n, sum s, sum g, sum s g^T
 __device__ void rigid_fit(double n, const double* S, float* T) {
   double cs[3] = {S[0] / n, S[1] / n, S[2] / n}, cg[3] = {S[3] / n, S[4] / n, S[5] / n};
@@ -142,11 +184,17 @@ __device__ void rigid_fit(double n, const double* S, float* T) {
                     {Syz - Szy, Sxx - Syy - Szz, Sxy + Syx, Szx + Sxz},
                     {Szx - Sxz, Sxy + Syx, -Sxx + Syy - Szz, Syz + Szy},
                     {Sxy - Syx, Szx + Sxz, Syz + Szy, -Sxx - Syy + Szz}};
-  double V[4][4];
-  jacobi4(N, V);
-  int best = 0;
-  for (int k = 1; k < 4; ++k) if (N[k][k] > N[best][best]) best = k;
-  double qw = V[0][best], qx = V[1][best], qy = V[2][best], qz = V[3][best];
+  // (one thread runs this while the CTA waits: the Jacobi sweeps -- double divisions and square roots in a dependent chain -- were a
+  // fifth of the kernel's time; the closed form needs ~15 divisions in all)
+  double q4[4];
+  if (!max_eigvec4(N, q4)) {
+    double V[4][4];
+    jacobi4(N, V);
+    int best = 0;
+    for (int k = 1; k < 4; ++k) if (N[k][k] > N[best][best]) best = k;
+    for (int k = 0; k < 4; ++k) q4[k] = V[k][best];
+  }
+  double qw = q4[0], qx = q4[1], qy = q4[2], qz = q4[3];
   const double nrm = sqrt(qw * qw + qx * qx + qy * qy + qz * qz);
   qw /= nrm; qx /= nrm; qy /= nrm; qz /= nrm;
   const double R[3][3] = {{1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw)},
@@ -348,8 +396,30 @@ int k5_tricp(pgp_ctx* ctx, Model& m, const float* seg_xyz_host, int ns, double* 
     for (int i = 0; i < k; ++i) { if (iters_out) iters_out[i] = 0; if (energy_out) energy_out[i] = 0.f; }
     return PGP_OK;
   }
+  // The source cloud goes up in Morton order of its own bounding box: a rigid transform keeps neighbours together, so the 32
+  // queries of a warp walk the same few grid rows of the target in every iteration of every pose (the ring searches of unrelated
+  // points diverge: 4 of 32 lanes were active in the distance loop).  Sums are order-free up to double rounding; ties at the trim
+  // threshold are admitted in this order.
   std::vector<float> seg4((size_t)ns * 4, 0.f), T((size_t)k * 12);
-  for (int i = 0; i < ns; ++i) for (int c = 0; c < 3; ++c) seg4[4 * (size_t)i + c] = seg_xyz_host[3 * i + c];
+  {
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = 0; i < ns; ++i) for (int c = 0; c < 3; ++c) { lo[c] = std::min(lo[c], seg_xyz_host[3 * i + c]); hi[c] = std::max(hi[c], seg_xyz_host[3 * i + c]); }
+    const float ext = std::max(std::max(hi[0] - lo[0], hi[1] - lo[1]), std::max(hi[2] - lo[2], 1e-12f));
+    auto spread = [](uint32_t v) { uint64_t x = v & 0x1fffffu; x = (x | x << 32) & 0x1f00000000ffffull; x = (x | x << 16) & 0x1f0000ff0000ffull;
+                                   x = (x | x << 8) & 0x100f00f00f00f00full; x = (x | x << 4) & 0x10c30c30c30c30c3ull; x = (x | x << 2) & 0x1249249249249249ull; return x; };
+    std::vector<std::pair<uint64_t, int>> key((size_t)ns);
+    for (int i = 0; i < ns; ++i) {
+      uint64_t m = 0;
+      for (int c = 0; c < 3; ++c) {
+        const float u = (seg_xyz_host[3 * i + c] - lo[c]) / ext;
+        const uint32_t q = (uint32_t)std::min(1023.0f, std::max(0.0f, u * 1024.0f));     // (NaN -> 0)
+        m |= spread(q) << c;
+      }
+      key[(size_t)i] = std::make_pair(m, i);
+    }
+    std::sort(key.begin(), key.end());
+    for (int i = 0; i < ns; ++i) for (int c = 0; c < 3; ++c) seg4[4 * (size_t)i + c] = seg_xyz_host[3 * key[(size_t)i].second + c];
+  }
   for (int i = 0; i < k; ++i) {
     double inv[16];
     invert_pose(poses16_host + 16 * i, inv);                            // tform = inverse(object pose), UCTState.cpp:184-185

@@ -12,6 +12,7 @@
 // (ring search with a proven stop bound), radix-select of the n_keep-th smallest squared distance,
 // 16 double sums (energy, two centroids, 3x3 cross products) block-reduced, Horn's closed-form
 // rotation from the 4x4 symmetric eigenproblem (Jacobi) -- the same fit as SVD/Umeyama without scale.
+#include <cooperative_groups.h>
 #include <float.h>
 #include <math.h>
 
@@ -206,14 +207,27 @@ __device__ void rigid_fit(double n, const double* S, float* T) {
   }
 }
 
-__global__ void __launch_bounds__(TT, 1) k5_tricp_kernel(const TricpParams p) {
+// Two CTAs (one thread-block cluster) per pose: CTA r owns the source points [r * ceil(ns / 2), ...) -- their correspondences, their
+// share of the radix-select histograms and of the 16 sums.  The halves meet through distributed shared memory: after a cluster
+// barrier each CTA adds the partner's histogram (or partial sums) to its own IN THE SAME ORDER, so both take identical decisions
+// and carry identical transforms -- nothing is broadcast, and the serial fit runs redundantly on both.  64 poses then fill 128 of
+// the 148 SMs and the per-iteration critical path (the slowest pose decides the kernel's time) halves.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TT, 1) k5_tricp_kernel(const TricpParams p) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
   __shared__ float sT[12];
-  __shared__ uint32_t s_hist[256];
-  __shared__ uint32_t s_sel[4];          // prefix, remaining rank, less-count, found digit
+  __shared__ uint32_t s_hist[2][256];    // double-buffered by pass parity: the partner may still read pass p while pass p+1 fills
+  __shared__ uint32_t s_sel[4];          // prefix, remaining rank, CTA 0's count of values equal to tau
   __shared__ uint32_t s_warp[TT / 32];
   __shared__ double s_red[TT / 32][16];
+  __shared__ double s_part[16];
   __shared__ int s_cont;
-  const int pose = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned cr = cl.block_rank();
+  const uint32_t* r_hist = cl.map_shared_rank(&s_hist[0][0], cr ^ 1u);
+  const double* r_part = cl.map_shared_rank(&s_part[0], cr ^ 1u);
+  const int pose = blockIdx.x >> 1, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = (p.ns + 1) >> 1;
+  const int i_lo = cr ? half : 0, i_hi = cr ? p.ns : half;
   float* d2 = p.d2 + (size_t)pose * p.ns;
   int* nn = p.nn + (size_t)pose * p.ns;
   if (tid < 12) sT[tid] = p.T[12 * pose + tid];
@@ -226,8 +240,8 @@ __global__ void __launch_bounds__(TT, 1) k5_tricp_kernel(const TricpParams p) {
   // kept set: the correspondences are searched again without a cap, so the kept set and its sums are always the exact ones.
   float cap2 = FLT_MAX;
   for (;;) {
-    // 1. correspondences
-    for (int i = tid; i < p.ns; i += TT) {
+    // 1. correspondences of this CTA's half
+    for (int i = i_lo + tid; i < i_hi; i += TT) {
       const float4 s = p.src[i];
       const float qx = sT[0] * s.x + sT[1] * s.y + sT[2] * s.z + sT[3];
       const float qy = sT[4] * s.x + sT[5] * s.y + sT[6] * s.z + sT[7];
@@ -236,23 +250,27 @@ __global__ void __launch_bounds__(TT, 1) k5_tricp_kernel(const TricpParams p) {
       nn_search(p, qx, qy, qz, cap2, best, id);
       d2[i] = best; nn[i] = id;
     }
-    __syncthreads();
-    // 2. n_keep-th smallest squared distance: MSB-first radix select on the float bits (d2 >= 0)
+    // 2. n_keep-th smallest squared distance over BOTH halves: MSB-first radix select on the float bits (d2 >= 0)
     uint32_t prefix = 0, rank = (uint32_t)p.n_keep;     // 1-based rank inside the current bucket
     for (int pass = 0; pass < 4; ++pass) {
       const int shift = 24 - 8 * pass;
-      if (tid < 256) s_hist[tid] = 0;
-      __syncthreads();
-      for (int i = tid; i < p.ns; i += TT) {
+      uint32_t* hist = s_hist[pass & 1];
+      if (tid < 256) hist[tid] = 0;
+      __syncthreads();                                   // (also orders this thread block's d2 writes before its reads)
+      for (int i = i_lo + tid; i < i_hi; i += TT) {
         const uint32_t b = __float_as_uint(d2[i]);
-        if (pass == 0 || (b >> (shift + 8)) == prefix) atomicAdd(&s_hist[(b >> shift) & 255u], 1u);
+        if (pass == 0 || (b >> (shift + 8)) == prefix) atomicAdd(&hist[(b >> shift) & 255u], 1u);
       }
-      __syncthreads();
+      cl.sync();
       if (warp == 0) {
         // first digit whose inclusive prefix count reaches the rank: 8 bins per lane, warp scan of the lane sums
-        uint32_t h[8], mine = 0;
+        const uint32_t* rh = r_hist + (pass & 1) * 256;
+        uint32_t h[8], h0[8], mine = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { h[k] = s_hist[lane * 8 + k]; mine += h[k]; }
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t a = hist[lane * 8 + k], b = rh[lane * 8 + k];
+          h[k] = a + b; h0[k] = cr ? b : a; mine += h[k];
+        }
         uint32_t incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -262,6 +280,10 @@ __global__ void __launch_bounds__(TT, 1) k5_tricp_kernel(const TricpParams p) {
           uint32_t acc = incl - mine; int dgt = 0;
           for (; dgt < 7; ++dgt) { if (acc + h[dgt] >= rank) break; acc += h[dgt]; }
           s_sel[0] = (prefix << 8) | (uint32_t)(lane * 8 + dgt); s_sel[1] = rank - acc;
+          uint32_t e0 = h0[0];
+#pragma unroll
+          for (int k = 1; k < 8; ++k) if (k == dgt) e0 = h0[k];
+          s_sel[2] = e0;                                 // last pass: how many values equal to tau CTA 0 holds
         }
       }
       __syncthreads();
@@ -269,24 +291,24 @@ __global__ void __launch_bounds__(TT, 1) k5_tricp_kernel(const TricpParams p) {
       __syncthreads();
     }
     const uint32_t tau = prefix;          // bits of the n_keep-th smallest d2; `rank` of the equal ones are kept, lowest source index first
-    if (cap2 != FLT_MAX && !(__uint_as_float(tau) < cap2)) { cap2 = FLT_MAX; continue; }      // (uniform over the CTA: tau comes from shared memory)
+    if (cap2 != FLT_MAX && !(__uint_as_float(tau) < cap2)) { cap2 = FLT_MAX; continue; }      // (uniform over the cluster: both CTAs formed the same tau)
     cap2 = fmaxf(4.0f * __uint_as_float(tau), 1e-12f);
-    // 3. sums over the kept correspondences (equal-to-tau ones admitted in index order)
+    // 3. sums over the kept correspondences (equal-to-tau ones admitted in index order: CTA 0 holds the lower indices)
     double acc[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0.0;
-    uint32_t eq_seen = 0;
-    for (int i0 = 0; i0 < p.ns; i0 += TT) {
+    uint32_t eq_seen = cr ? s_sel[2] : 0u;
+    for (int i0 = i_lo; i0 < i_hi; i0 += TT) {
       const int i = i0 + tid;
-      const uint32_t b = i < p.ns ? __float_as_uint(d2[i]) : 0xffffffffu;
-      const bool eq = i < p.ns && b == tau;
+      const uint32_t b = i < i_hi ? __float_as_uint(d2[i]) : 0xffffffffu;
+      const bool eq = i < i_hi && b == tau;
       const unsigned bal = __ballot_sync(0xffffffffu, eq);
       if (lane == 0) s_warp[warp] = __popc(bal);
       __syncthreads();
       uint32_t before = eq_seen, total = 0;
       for (int w = 0; w < TT / 32; ++w) { const uint32_t c = s_warp[w]; if (w < warp) before += c; total += c; }
       before += __popc(bal & ((1u << lane) - 1u));
-      const bool keep = i < p.ns && (b < tau || (eq && before < rank));
+      const bool keep = i < i_hi && (b < tau || (eq && before < rank));
       if (keep) {
         const float4 s = p.src[i];
         const float4 g = p.tgt_orig[nn[i]];
@@ -308,11 +330,11 @@ __global__ void __launch_bounds__(TT, 1) k5_tricp_kernel(const TricpParams p) {
       if (lane == 0) s_red[warp][k] = v;
     }
     __syncthreads();
-    if (tid < 16) { double v = 0; for (int w = 0; w < TT / 32; ++w) v += s_red[w][tid]; s_red[0][tid] = v; }      // (column tid only: no hazard)
-    __syncthreads();
+    if (tid < 16) { double v = 0; for (int w = 0; w < TT / 32; ++w) v += s_red[w][tid]; s_part[tid] = v; }
+    cl.sync();
     if (tid == 0) {
       double S[16];
-      for (int k = 0; k < 16; ++k) S[k] = s_red[0][k];
+      for (int k = 0; k < 16; ++k) S[k] = cr ? r_part[k] + s_part[k] : s_part[k] + r_part[k];      // CTA 0's half + CTA 1's half, in both
       old_energy = energy;
       energy = (float)S[0];
       float Tn[12];
@@ -324,8 +346,11 @@ __global__ void __launch_bounds__(TT, 1) k5_tricp_kernel(const TricpParams p) {
     __syncthreads();
     if (!s_cont) break;
   }
-  if (tid < 12) p.T[12 * pose + tid] = sT[tid];
-  if (tid == 0) { if (p.iters) p.iters[pose] = it; if (p.energy) p.energy[pose] = energy; }
+  if (cr == 0) {
+    if (tid < 12) p.T[12 * pose + tid] = sT[tid];
+    if (tid == 0) { if (p.iters) p.iters[pose] = it; if (p.energy) p.energy[pose] = energy; }
+  }
+  cl.sync();                                             // the partner may still be reading this CTA's shared memory
 }
 
 // device scratch of the refinement: owned by the context (two contexts on one device must not share it), created on first
@@ -440,7 +465,7 @@ int k5_tricp(pgp_ctx* ctx, Model& m, const float* seg_xyz_host, int ns, double* 
   p.d2 = ts.d2.as<float>(); p.nn = ts.nn.as<int>(); p.T = ts.T.as<float>();
   p.n_keep = n_keep; p.ratio = ratio; p.max_iter = std::max(1, max_iter);
   p.iters = ts.iters.as<int>(); p.energy = ts.energy.as<float>();
-  k5_tricp_kernel<<<k, TT, 0, ctx->stream>>>(p);
+  k5_tricp_kernel<<<2 * k, TT, 0, ctx->stream>>>(p);      // one cluster of two CTAs per pose
   ctx->launches++;
   PGP_CUDA(ctx, cudaGetLastError());
   PGP_CUDA(ctx, cudaMemcpyAsync(T.data(), ts.T.p, (size_t)k * 48, cudaMemcpyDeviceToHost, ctx->stream));

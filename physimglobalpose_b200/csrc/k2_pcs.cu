@@ -836,11 +836,12 @@ __host__ __device__ inline uint32_t stocs_base_seed(uint64_t seed, int base, int
 //   p_i = (double) w_i / sum_d with sum_d = sequential double sum: a double sum of <= 2^12 floats whose exponents span <= 17 binades
 //     never rounds, so any summation order gives the sequential result and the CTA reduces it as a tree; otherwise thread 0 chains;
 //   cumulative probabilities: the sequential rounding chain of std::partial_sum, thread 0, up to the drawn index.
+constexpr int K2S_T = 128;   // threads per base: the order-sensitive chains run on one thread, so what counts is how many bases an SM holds
 __device__ int block_discrete_draw(float* w, double* wd, int n, MinStd& gen, bool normalise, int tid, float* s_f, double* s_dd, int* s_i) {
   // ---- statistics of the non-zero weights: count, min / max biased exponent, all-equal flag
   int cnt = 0, emin = 255, emax = 0;
   float first = 0.f; bool same = true;
-  for (int i = tid; i < n; i += 256) {
+  for (int i = tid; i < n; i += K2S_T) {
     const float v = w[i];
     if (v != 0.f) {
       const int e = (__float_as_int(v) >> 23) & 255;
@@ -859,7 +860,7 @@ __device__ int block_discrete_draw(float* w, double* wd, int n, MinStd& gen, boo
   if (lane == 0) { s_i[wp * 4] = cnt; s_i[wp * 4 + 1] = emin; s_i[wp * 4 + 2] = emax; s_i[wp * 4 + 3] = same; s_f[wp] = first; }
   __syncthreads();
   cnt = 0; emin = 255; emax = 0; same = true; first = 0.f;
-  for (int k = 0; k < 8; ++k) {
+  for (int k = 0; k < K2S_T / 32; ++k) {
     cnt += s_i[k * 4]; emin = min(emin, s_i[k * 4 + 1]); emax = max(emax, s_i[k * 4 + 2]);
     const float of = s_f[k];
     same = same && s_i[k * 4 + 3] && (of == 0.f || first == 0.f || of == first);
@@ -882,34 +883,34 @@ __device__ int block_discrete_draw(float* w, double* wd, int n, MinStd& gen, boo
       fsum = s_f[8];
       __syncthreads();
     }
-    for (int i = tid; i < n; i += 256) w[i] = __fdiv_rn(w[i], fsum);
+    for (int i = tid; i < n; i += K2S_T) w[i] = __fdiv_rn(w[i], fsum);
     __syncthreads();
     if (cnt > 0) {                                                         // exponents after the division: recompute (cheap) for the double-sum test
       emin = 255; emax = 0;
-      for (int i = tid; i < n; i += 256) { const float v = w[i]; if (v != 0.f) { const int e = (__float_as_int(v) >> 23) & 255; emin = min(emin, e); emax = max(emax, e); } }
+      for (int i = tid; i < n; i += K2S_T) { const float v = w[i]; if (v != 0.f) { const int e = (__float_as_int(v) >> 23) & 255; emin = min(emin, e); emax = max(emax, e); } }
       for (int o = 16; o; o >>= 1) { emin = min(emin, __shfl_xor_sync(0xffffffffu, emin, o)); emax = max(emax, __shfl_xor_sync(0xffffffffu, emax, o)); }
       if (lane == 0) { s_i[wp * 4 + 1] = emin; s_i[wp * 4 + 2] = emax; }
       __syncthreads();
       emin = 255; emax = 0;
-      for (int k = 0; k < 8; ++k) { emin = min(emin, s_i[k * 4 + 1]); emax = max(emax, s_i[k * 4 + 2]); }
+      for (int k = 0; k < K2S_T / 32; ++k) { emin = min(emin, s_i[k * 4 + 1]); emax = max(emax, s_i[k * 4 + 2]); }
       __syncthreads();
     }
   }
   if (n < 2) return 0;                                                     // (as discrete_draw: no table, no draw)
   // ---- sum_d
-  for (int i = tid; i < n; i += 256) wd[i] = (double)w[i];
+  for (int i = tid; i < n; i += K2S_T) wd[i] = (double)w[i];
   __syncthreads();
   int lg = 0; while ((1 << lg) < n) ++lg;
   const bool dexact = cnt > 0 && emin > 0 && (emax - emin) + lg <= 29;     // 24-bit terms, sum below 2^(emax + 1 + lg): fits 53 bits
   double dsum;
   if (dexact) {
     double part = 0.0;
-    for (int i = tid; i < n; i += 256) part += wd[i];
+    for (int i = tid; i < n; i += K2S_T) part += wd[i];
     for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
     if (lane == 0) s_dd[wp] = part;
     __syncthreads();
     dsum = 0.0;
-    for (int k = 0; k < 8; ++k) dsum += s_dd[k];
+    for (int k = 0; k < K2S_T / 32; ++k) dsum += s_dd[k];
     __syncthreads();
   } else {
     if (tid == 0) { double acc = 0.0; for (int i = 0; i < n; ++i) acc += wd[i]; s_dd[8] = acc; }
@@ -917,20 +918,49 @@ __device__ int block_discrete_draw(float* w, double* wd, int n, MinStd& gen, boo
     dsum = s_dd[8];
     __syncthreads();
   }
-  for (int i = tid; i < n; i += 256) wd[i] = wd[i] / dsum;
+  for (int i = tid; i < n; i += K2S_T) wd[i] = wd[i] / dsum;
   __syncthreads();
-  // ---- the draw
-  if (tid == 0) {
-    const double u = gen.canonical();
-    double acc = 0.0;
-    int pick = n - 1;
-    for (int i = 0; i < n - 1; ++i) {
+  // ---- the draw: the first i < n - 1 whose sequential partial sum reaches u.  The chain of n double adds is replaced by a block
+  // scan: any association of the same non-negative terms (total ~ 1) lands within n 2^-52 of the sequential partial sum, so unless
+  // some partial sum comes that close to u the two orders cross u at the same index; if one does (probability ~ 1e-9 per draw)
+  // thread 0 walks the reference's chain.
+  if (tid == 0) { s_dd[9] = gen.canonical(); s_i[0] = n - 1; s_i[1] = 0; }
+  __syncthreads();
+  const double u = s_dd[9];
+  {
+    const double band = (double)n * 4.5e-16;
+    const int m = n - 1, chunk = (m + K2S_T - 1) / K2S_T, lo = min(tid * chunk, m), hi = min(lo + chunk, m);
+    double part = 0.0;
+    for (int i = lo; i < hi; ++i) part += wd[i];
+    double incl = part;
+    for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    if (lane == 31) s_dd[wp] = incl;
+    __syncthreads();
+    double acc = incl - part;
+    for (int k = 0; k < wp; ++k) acc += s_dd[k];
+    int found = 0x7fffffff;
+    bool amb = false;
+    for (int i = lo; i < hi; ++i) {
       acc += wd[i];
-      if (!(acc < u)) { pick = i; break; }
+      amb |= fabs(acc - u) <= band;
+      if (found == 0x7fffffff && !(acc < u)) found = i;
     }
-    s_i[0] = pick;
+    if (found != 0x7fffffff) atomicMin(&s_i[0], found);
+    if (amb) s_i[1] = 1;
+    __syncthreads();
+    if (s_i[1]) {                                                          // (uniform: shared flag)
+      if (tid == 0) {
+        double a2 = 0.0;
+        int pick = n - 1;
+        for (int i = 0; i < n - 1; ++i) {
+          a2 += wd[i];
+          if (!(a2 < u)) { pick = i; break; }
+        }
+        s_i[0] = pick;
+      }
+      __syncthreads();
+    }
   }
-  __syncthreads();
   const int pick = s_i[0];
   __syncthreads();
   return pick;
@@ -941,7 +971,7 @@ __device__ int block_discrete_draw(float* w, double* wd, int n, MinStd& gen, boo
 // 4th / 3rd point); the weights live in shared memory and are evaluated by all threads; the float normalisation and the draw
 // reproduce the reference's sequential arithmetic bit for bit (block_discrete_draw), so that a given engine seed reproduces the
 // reference's draw.  Dynamic shared memory: n floats + n doubles.
-__global__ void __launch_bounds__(256) k2s_select_bases(StocsParams sp, BaseOut* __restrict__ out) {
+__global__ void __launch_bounds__(K2S_T, 8) k2s_select_bases(StocsParams sp, BaseOut* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char k2s_smem[];
   __shared__ int s_any;
   __shared__ int s_i[32];
@@ -955,14 +985,14 @@ __global__ void __launch_bounds__(256) k2s_select_bases(StocsParams sp, BaseOut*
   for (int attempt = 0; attempt < 16; ++attempt) {      // Perform_N_steps re-draws until a base is accepted (:1831-1852)
     MinStd gen(stocs_base_seed(sp.seed, sp.base0 + base, attempt));
     // ---- point 1 ~ priors
-    for (int i = tid; i < n; i += 256) curr[i] = sp.aux[i].w;
+    for (int i = tid; i < n; i += K2S_T) curr[i] = sp.aux[i].w;
     __syncthreads();
     const int b1 = block_discrete_draw(curr, wd, n, gen, false, tid, s_f, s_dd, s_i);
     const float4 p1 = P[b1], a1 = sp.aux[b1];
     // ---- point 2: prior_i * prior_b1 * edge(b1, i)
     if (tid == 0) s_any = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += 256) {
+    for (int i = tid; i < n; i += K2S_T) {
       float w = 0.f;
       const float c = curr[i];
       if (i != b1 && c != 0.f) {
@@ -981,7 +1011,7 @@ __global__ void __launch_bounds__(256) k2s_select_bases(StocsParams sp, BaseOut*
     if (tid == 0) s_any = 0;
     __syncthreads();
     const float v1x = __fsub_rn(p2.x, p1.x), v1y = __fsub_rn(p2.y, p1.y), v1z = __fsub_rn(p2.z, p1.z);
-    for (int i = tid; i < n; i += 256) {
+    for (int i = tid; i < n; i += K2S_T) {
       float w = 0.f;
       const float c = curr[i];
       const float4 pi = P[i];
@@ -1018,7 +1048,7 @@ __global__ void __launch_bounds__(256) k2s_select_bases(StocsParams sp, BaseOut*
       B = (float)((x2 * z1 - x3 * z1 - x1 * z2 + x3 * z2 + x1 * z3 - x2 * z3) / (double)denom);
       C = (float)((-x2 * y1 + x3 * y1 + x1 * y2 - x3 * y2 - x1 * y3 + x2 * y3) / (double)denom);
     }
-    for (int i = tid; i < n; i += 256) {
+    for (int i = tid; i < n; i += K2S_T) {
       float w = 0.f;
       const float c = curr[i];
       if (i != b1 && i != b2 && i != b3 && c != 0.f) {
@@ -1833,7 +1863,7 @@ int k2_generate(pgp_ctx* ctx, Model& m, const pgp_pcs_opts* o, uint64_t seed, in
     if (smem_sel <= 200 * 1024) {
       PGP_CUDA(ctx, cudaFuncSetAttribute(k2s_select_bases, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sel));
       sp.curr = nullptr; sp.base0 = base_lo;
-      k2s_select_bases<<<nb_total, 256, smem_sel, st>>>(sp, d_bases_all);
+      k2s_select_bases<<<nb_total, K2S_T, smem_sel, st>>>(sp, d_bases_all);
     } else {
       // larger scenes: one weight vector of |P| floats per base in global memory, the bases selected in batches of at most ~1 GB of them
       const int bsel = (int)std::max<int64_t>(1, std::min<int64_t>(nb_total, ((int64_t)1 << 28) / std::max(1, s.n)));

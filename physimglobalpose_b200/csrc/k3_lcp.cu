@@ -336,7 +336,7 @@ struct FineCtx {
   unsigned sa;               // per warp: shared-memory address of 12 floats, the hypothesis' pre-scaled (voxel-unit) matrix -- warp-uniform
                              // data the loops re-read with three LDS.128 where they use it instead of holding 12 registers across
                              // the whole hypothesis (at 64 registers per thread the compiler spilled exactly these to local memory)
-  uint32_t* glist;           // per warp: byte offsets (into the staged model) of the groups of the current hypothesis that survived the cull (+ FUNROLL pad slots)
+  uint16_t* glist;           // per warp: indices (u16: the shared-memory plan decides the L1 carve-out, see k3_fine_smem) of the groups of the current hypothesis that survived the cull (+ FUNROLL pad slots)
   int dummy_group;           // a group of NaN points behind the tile
   int dimx, dimy, dimz;
   unsigned limx, limy, limz;   // last voxel index per axis
@@ -554,10 +554,10 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
         keep = !(__fmaf_rn(d, d, e2) > thr * thr * (1.0f + 1e-5f));
       }
       const unsigned bb = __ballot_sync(0xffffffffu, keep);
-      if (keep) f.glist[ns + __popc(bb & f.lt_mask)] = (uint32_t)g << 9;
+      if (keep) f.glist[ns + __popc(bb & f.lt_mask)] = (uint16_t)g;
       ns += __popc(bb);
     }
-    if (f.lane < FUNROLL) f.glist[ns + f.lane] = (uint32_t)f.dummy_group << 9;
+    if (f.lane < FUNROLL) f.glist[ns + f.lane] = (uint16_t)f.dummy_group;
     __syncwarp();
   }
   int good = 0, qn = 0;
@@ -636,8 +636,8 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
   };
   const float4* mp = f.s_model + f.lane;
   for (int k = 0; k < ns; k += FUNROLL) {
-    const uint4 gg = *reinterpret_cast<const uint4*>(f.glist + k);
-    const uint32_t gb[FUNROLL] = {gg.x, gg.y, gg.z, gg.w};
+    const uint2 gg = *reinterpret_cast<const uint2*>(f.glist + k);
+    const uint32_t gb[FUNROLL] = {(gg.x & 0xffffu) << 9, (gg.x >> 16) << 9, (gg.y & 0xffffu) << 9, (gg.y >> 16) << 9};     // byte offsets into the staged model
     uint32_t off[FUNROLL], sh[FUNROLL], code[FUNROLL];
     float a[12];
     if (FAST) sa_load(f.sa, a);
@@ -698,7 +698,7 @@ __global__ void __launch_bounds__(FWARPS * 32, 1) k3_fine_kernel(const __grid_co
   float4* s_nrm = s_model + p.tile_cap + 32;                              // only MODE 1
   uint2* s_bmrank = reinterpret_cast<uint2*>(s_nrm + (MODE == 1 ? p.tile_cap : 0));
   float4* s_groups = reinterpret_cast<float4*>(s_bmrank + p.bmrank_words);
-  uint32_t* s_glist = reinterpret_cast<uint32_t*>(s_groups + cap_groups);
+  uint16_t* s_glist = reinterpret_cast<uint16_t*>(s_groups + cap_groups);
   uint16_t* s_queue = reinterpret_cast<uint16_t*>(s_glist + FWARPS * (cap_groups + FUNROLL));
   uint32_t* s_qe = reinterpret_cast<uint32_t*>(s_queue + FWARPS * FQCAP);
   unsigned char* s_qr = reinterpret_cast<unsigned char*>(s_qe + FWARPS * FQCAP);  // weighted mode only, like the three below
@@ -953,7 +953,7 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     const int FWARPS = mode == PGP_LCP_WEIGHTED ? ctx->k3_warps_weighted : ctx->k3_warps_count;
     auto smem_need = [&](int cap, size_t table) {
       return (size_t)(cap + 32) * 16 + (mode == PGP_LCP_WEIGHTED ? (size_t)cap * 16 : 0) + table + (size_t)(cap >> 5) * 16 +
-             (size_t)(FWARPS * ((cap >> 5) + FUNROLL)) * 4 + (size_t)FWARPS * (mode == PGP_LCP_WEIGHTED ? FQCAP * 7 + SQCAP * 7 : FQCAP * 6);
+             (size_t)(FWARPS * ((cap >> 5) + FUNROLL)) * 2 + (size_t)FWARPS * (mode == PGP_LCP_WEIGHTED ? FQCAP * 7 + SQCAP * 7 : FQCAP * 6);
     };
     size_t bm = (size_t)s.bitmap_words * 8;
     int tile_cap = std::min((m.nv + 127) & ~127, 8192);
@@ -976,7 +976,8 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
     p.dist_scale = (float)s.dist_r * 0.125f;
     p.sub_h2 = (s.g.h / (float)s.dist_r) * (s.g.h / (float)s.dist_r) * (1.0f - 1e-4f);
     p.ddx = s.g.dim[0] * s.dist_r; p.ddy = s.g.dim[1] * s.dist_r; p.ddz = s.g.dim[2] * s.dist_r;
-    const size_t smem = smem_need(tile_cap, bm);
+    size_t smem = smem_need(tile_cap, bm);
+    if (const char* pad = getenv("PGP_K3_SMEM_PAD_KB")) smem = std::min(smem_max, smem + (size_t)atoi(pad) * 1024);   // tuning: shrinks L1 by the same amount
     PGP_CUDA(ctx, cudaMemsetAsync(p.work, 0, 8 * (size_t)p.n_tiles, st));
     int grid = (int)std::min<long long>((n + FWARPS - 1) / FWARPS, ctx->sm_count);
     // the last two hypotheses' worth of work per warp is handed out in quarter-model units (shorter tail of the persistent grid)
@@ -999,6 +1000,7 @@ int k3_score(pgp_ctx* ctx, const Model& m, const float* T_dev, int64_t n, int mo
       else rc = bm ? launch(k3_fine_kernel<true, 0, 16>) : launch(k3_fine_kernel<false, 0, 16>);
     } else {
       if (FWARPS == 32) rc = bm ? launch(k3_fine_kernel<true, 1, 32>) : launch(k3_fine_kernel<false, 1, 32>);
+      else if (FWARPS == 28) rc = bm ? launch(k3_fine_kernel<true, 1, 28>) : launch(k3_fine_kernel<false, 1, 28>);
       else if (FWARPS == 24) rc = bm ? launch(k3_fine_kernel<true, 1, 24>) : launch(k3_fine_kernel<false, 1, 24>);
       else rc = bm ? launch(k3_fine_kernel<true, 1, 16>) : launch(k3_fine_kernel<false, 1, 16>);
     }

@@ -151,7 +151,8 @@ int pgp_set_option(pgp_ctx* ctx, const char* name, int value) {
   CHECK_CTX(ctx);
   if (name && !strcmp(name, "force_coarse")) { ctx->force_coarse = value; return PGP_OK; }
   if (name && (!strcmp(name, "k3_warps_count") || !strcmp(name, "k3_warps_weighted"))) {
-    if (value != 16 && value != 24 && value != 32) return pgp_fail(ctx, PGP_E_INVALID, "%s must be 16, 24 or 32", name);
+    if (value != 16 && value != 24 && value != 32 && !(value == 28 && !strcmp(name, "k3_warps_weighted")))
+      return pgp_fail(ctx, PGP_E_INVALID, "%s must be 16, 24 or 32 (weighted: also 28)", name);
     (strcmp(name, "k3_warps_count") ? ctx->k3_warps_weighted : ctx->k3_warps_count) = value;
     return PGP_OK;
   }

@@ -15,8 +15,8 @@ ref = {}
 for name, Ts in sets.items():
     Td = torch.from_numpy(np.ascontiguousarray(Ts).reshape(-1, 12)).cuda(); cd = torch.zeros(len(Ts), dtype=torch.int32, device='cuda'); sd = torch.zeros(len(Ts), device='cuda')
     for mode in ('count', 'weighted'):
-        for nw in (32, 24, 16):
-            e.set_option('k3_warps_' + mode, nw)
+        for nw, tab in ((32, -1), (32, 0), (32, 1), (24, -1)):
+            e.set_option('k3_warps_' + mode, nw); e.set_option('k3_smem_table', tab)
             ms = []
             for it in range(6):
                 flush.zero_()
@@ -27,4 +27,4 @@ for name, Ts in sets.items():
             key = (name, mode)
             same = True if key not in ref else bool(np.array_equal(ref[key], got))
             ref.setdefault(key, got)
-            print(f"{name:8s} {mode:8s} warps={nw} ms {min(ms[2:]):.4f} same_counts={same}", flush=True)
+            print(f"{name:8s} {mode:8s} warps={nw} smem_table={tab} ms {min(ms[2:]):.4f} same_counts={same}", flush=True)

@@ -370,7 +370,8 @@ __global__ void __launch_bounds__(CLS_THREADS) k1w_count(const uint32_t* __restr
 // (4 bytes; scoring fetches the point itself from the L2-resident cloud in original order, Scene::unsorted) and, per voxel, the
 // cone record `vrec`:
 //     vrec[block * 512 + voxel] = code << 24 | rep
-// rep = original index of the voxel's first candidate; code tells how far the other candidates' normals are from rep's:
+// rep = position of the voxel's first candidate in the CELL-SORTED cloud (Scene::aux: the representatives of neighbouring voxels are
+// neighbours in memory, so the 32 look-ups of a warp -- one compact patch of the model -- share sectors); code tells how far the other candidates' normals are from rep's:
 //     0          every candidate has bit-identical (unit normal, prior): WeightedVerify's gate and weight do not depend on WHICH
 //                candidate is the nearest, so scoring evaluates the exact gate once on rep and never searches,
 //     1 .. 254   |n_i - n_rep| <= code * VREC_EPS_STEP for every candidate and all priors are equal: scoring decides the gate for
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(CLS_THREADS) k1w_fill(const uint32_t* __restri
           const uint32_t orig = (uint32_t)__float_as_int(p.w);
           wlists[wr[j]++] = orig;
           const float4 a = __ldg(aux + pos);
-          if (rep[j] == 0xffffffffu) { rep[j] = orig; n0x[j] = a.x; n0y[j] = a.y; n0z[j] = a.z; pr0[j] = a.w; }
+          if (rep[j] == 0xffffffffu) { rep[j] = pos; n0x[j] = a.x; n0y[j] = a.y; n0z[j] = a.z; pr0[j] = a.w; }
           else {
             const float dx = a.x - n0x[j], dy = a.y - n0y[j], dz = a.z - n0z[j];
             maxd2[j] = fmaxf(maxd2[j], __fmaf_rn(dx, dx, __fmaf_rn(dy, dy, dz * dz)));

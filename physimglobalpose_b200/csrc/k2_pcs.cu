@@ -836,6 +836,43 @@ __host__ __device__ inline uint32_t stocs_base_seed(uint64_t seed, int base, int
 //   p_i = (double) w_i / sum_d with sum_d = sequential double sum: a double sum of <= 2^12 floats whose exponents span <= 17 binades
 //     never rounds, so any summation order gives the sequential result and the CTA reduces it as a tree; otherwise thread 0 chains;
 //   cumulative probabilities: the sequential rounding chain of std::partial_sum, thread 0, up to the drawn index.
+// acc = c; then (m - 1) times acc = fl(acc + c): the float chain std::accumulate runs over m copies of the same value c > 0
+// (zeros in between change nothing), in O(binades) steps instead of m.  Inside one binade [2^e, 2^(e+1)) every partial sum is a
+// multiple of U = ulp and, while the exact acc + c stays below 2^(e+1), fl(acc + c) - acc is the same multiple d of U for every
+// acc of the same parity -- and after one explicit step the parity no longer changes (a tie c = qU + U/2 rounds to the even
+// neighbour, which makes d even).  So: one real add, read d off it, jump over all the following steps that stay regular, repeat.
+__device__ inline float chain_sum_equal(float c, long long m) {
+  if (m <= 0) return 0.f;
+  float acc = c;
+  long long rem = m - 1;
+  while (rem > 0) {
+    const float next = __fadd_rn(acc, c);
+    --rem;
+    if (!(next > acc)) return acc;                                    // c is below half an ulp of acc: the chain has stalled
+    int e0, e1;
+    frexpf(acc, &e0); frexpf(next, &e1);
+    const float d = __fsub_rn(next, acc);                              // exact (next <= 2 acc)
+    acc = next;
+    if (e0 != e1 || rem == 0) continue;                                // crossed into the next binade: its step is read off the next add
+    // one more explicit step so that the parity of acc / U has settled (ties-to-even), then the regular run
+    const float next2 = __fadd_rn(acc, c);
+    --rem;
+    int e2; frexpf(next2, &e2);
+    const float d2 = __fsub_rn(next2, acc);
+    if (!(next2 > acc)) return acc;
+    acc = next2;
+    if (e2 != e1 || rem == 0) continue;
+    (void)d;
+    const double top = ldexp(1.0, e1);                                 // frexp: acc in [2^(e1-1), 2^e1)
+    const double R = top - (double)c - (double)acc;                    // exact
+    long long j = R > 0 ? (long long)ceil(R / (double)d2) : 0;         // steps k = 0 .. j-1 start from acc + k d2 with acc + k d2 + c < top
+    if (j > rem) j = rem;
+    acc = (float)((double)acc + (double)j * (double)d2);               // exact: a multiple of U below 2^(e1) (or equal to it)
+    rem -= j;
+  }
+  return acc;
+}
+
 constexpr int K2S_T = 128;   // threads per base: the order-sensitive chains run on one thread, so what counts is how many bases an SM holds
 __device__ int block_discrete_draw(float* w, double* wd, int n, MinStd& gen, bool normalise, int tid, float* s_f, double* s_dd, int* s_i) {
   // ---- statistics of the non-zero weights: count, min / max biased exponent, all-equal flag
@@ -877,6 +914,7 @@ __device__ int block_discrete_draw(float* w, double* wd, int n, MinStd& gen, boo
       exact = emin > 0 && (unsigned long long)odd * (unsigned long long)cnt < (1ull << 24);
     }
     if (exact) fsum = __fmul_rn((float)cnt, first);
+    else if (same && cnt > 0 && emin > 0 && first > 0.f) fsum = chain_sum_equal(first, cnt);      // (every thread, redundantly: ~25 short rounds)
     else {
       if (tid == 0) { float acc = 0.f; for (int i = 0; i < n; ++i) acc = __fadd_rn(acc, w[i]); s_f[8] = acc; }
       __syncthreads();

@@ -64,7 +64,7 @@ struct LcpParams {
   const unsigned char* wcnt; // K1c: per voxel candidate count (a byte)
   const uint32_t* wword;     // K1c: per label word (16 voxels) the first record
   const uint32_t* wlists;    // K1c: candidates' ORIGINAL indices
-  const uint32_t* vrec;      // K1c: per voxel (code << 24 | representative candidate): spread of the candidates' normals
+  const uint32_t* vrec;      // K1c: per voxel (code << 24 | representative candidate, as a position in the cell-sorted cloud): spread of the candidates' normals
   const float4* pts_orig;    // centred scene points by ORIGINAL index (Scene::unsorted)
   const float4* aux_orig;    // unit normal + prior by ORIGINAL scene index
   const float4* groups;      // bounding sphere {centre, radius} of every aligned run of 32 validation points (pgp_set_model)
@@ -453,7 +453,7 @@ __device__ __noinline__ int resolve_weighted_slow(const LcpParams& p, const floa
   const uint32_t e = (vaddr & ~15u) | (info & 15u);
   if (gate_known & 1) return ((info & 16u) && !resolve_ambiguous(p, x, m, e)) ? 0 : ((gate_known & 2) ? 0x10001 : 0x1);
   if ((vr >> 24) == 0u) {
-    const float4 ns = __ldg(p.aux_orig + (vr & 0xffffffu));
+    const float4 ns = __ldg(p.aux + (vr & 0xffffffu));
     if (!normal_gate(x, nm, ns)) return 0;
     return ((info & 16u) && !resolve_ambiguous(p, x, m, e)) ? 0 : ((ns.w != 0.f) ? 0x10001 : 0x1);
   }
@@ -589,7 +589,7 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
         const float4 nm = f.s_nrm[i];
         int known = 0;                              // 0: exact path, 1 | prior << 1: gate passes, -1: settled
         if (FAST && (vr >> 24) != 255u) {
-          const float4 sn = __ldg(p.aux_orig + (vr & 0xffffffu));
+          const float4 sn = __ldg(p.aux + (vr & 0xffffffu));      // (cell-sorted order: neighbouring voxels' representatives share sectors)
           float a[12];
           sa_load(f.sa, a);
           const float qx = __fmaf_rn(a[0], nm.x, __fmaf_rn(a[1], nm.y, a[2] * nm.z)), qy = __fmaf_rn(a[4], nm.x, __fmaf_rn(a[5], nm.y, a[6] * nm.z)),

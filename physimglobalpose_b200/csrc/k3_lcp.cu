@@ -494,19 +494,30 @@ template <bool SMEM_TABLE, bool FAST, int MODE, int U>
 __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCtx& f, const float* __restrict__ T, long long h, int g_begin, int g_end) {
   static_assert(FUNROLL == 4, "the survivor list is read four entries at a time");
   const Xf x = load_xf(T, h);
+  // the pre-scaled matrix: count mode has the registers for it (63 used, no spill); weighted mode keeps it in the per-warp slot
+  constexpr bool SLOT = MODE == 1;
+  float areg[12];
   if (FAST) {
-    float a[12];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      a[4 * r + 0] = x.m[4 * r + 0] * p.g.inv_hf;
-      a[4 * r + 1] = x.m[4 * r + 1] * p.g.inv_hf;
-      a[4 * r + 2] = x.m[4 * r + 2] * p.g.inv_hf;
-      a[4 * r + 3] = (x.m[4 * r + 3] - p.g.lo[r]) * p.g.inv_hf;
+      areg[4 * r + 0] = x.m[4 * r + 0] * p.g.inv_hf;
+      areg[4 * r + 1] = x.m[4 * r + 1] * p.g.inv_hf;
+      areg[4 * r + 2] = x.m[4 * r + 2] * p.g.inv_hf;
+      areg[4 * r + 3] = (x.m[4 * r + 3] - p.g.lo[r]) * p.g.inv_hf;
     }
-    __syncwarp();                                   // (the previous hypothesis' readers are done)
-    if (f.lane == 0) sa_store(f.sa, a);
-    __syncwarp();
+    if (SLOT) {
+      __syncwarp();                                 // (the previous hypothesis' readers are done)
+      if (f.lane == 0) sa_store(f.sa, areg);
+      __syncwarp();
+    }
   }
+  auto get_a = [&](float (&a)[12]) {
+    if (SLOT) sa_load(f.sa, a);
+    else {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) a[i] = areg[i];
+    }
+  };
   auto voxel_of = [&](const float (&a)[12], const float4 m, int& ix, int& iy, int& iz) {
     float ux, uy, uz;
     if (FAST) {
@@ -539,7 +550,7 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
       if (cull && keep) {
         const float4 sp = f.s_groups[g];
         float a[12];
-        sa_load(f.sa, a);
+        get_a(a);
         const float ux = __fmaf_rn(a[0], sp.x, __fmaf_rn(a[1], sp.y, __fmaf_rn(a[2], sp.z, a[3]))) * p.dist_scale;
         const float uy = __fmaf_rn(a[4], sp.x, __fmaf_rn(a[5], sp.y, __fmaf_rn(a[6], sp.z, a[7]))) * p.dist_scale;
         const float uz = __fmaf_rn(a[8], sp.x, __fmaf_rn(a[9], sp.y, __fmaf_rn(a[10], sp.z, a[11]))) * p.dist_scale;
@@ -591,7 +602,7 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
         if (FAST && (vr >> 24) != 255u) {
           const float4 sn = __ldg(p.aux + (vr & 0xffffffu));      // (cell-sorted order: neighbouring voxels' representatives share sectors)
           float a[12];
-          sa_load(f.sa, a);
+          get_a(a);
           const float qx = __fmaf_rn(a[0], nm.x, __fmaf_rn(a[1], nm.y, a[2] * nm.z)), qy = __fmaf_rn(a[4], nm.x, __fmaf_rn(a[5], nm.y, a[6] * nm.z)),
                       qz = __fmaf_rn(a[8], nm.x, __fmaf_rn(a[9], nm.y, a[10] * nm.z));
           const float ae = fabsf(__fmaf_rn(sn.x, qx, __fmaf_rn(sn.y, qy, sn.z * qz))) * p.g.hf;
@@ -640,7 +651,7 @@ __device__ __forceinline__ int score_hypothesis(const LcpParams& p, const FineCt
     const uint32_t gb[FUNROLL] = {(gg.x & 0xffffu) << 9, (gg.x >> 16) << 9, (gg.y & 0xffffu) << 9, (gg.y >> 16) << 9};     // byte offsets into the staged model
     uint32_t off[FUNROLL], sh[FUNROLL], code[FUNROLL];
     float a[12];
-    if (FAST) sa_load(f.sa, a);
+    if (FAST) get_a(a);
 #pragma unroll
     for (int u = 0; u < FUNROLL; ++u) {
       int ix, iy, iz;

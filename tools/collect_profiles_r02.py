@@ -26,6 +26,10 @@ for name, mangled in KERNELS.items():
         continue
     out = run([sys.executable, "tools/ncu_summary.py", rep])
     lines = run([sys.executable, "tools/ncu_lines.py", rep, LIB, mangled, "40"])
+    if name in ("r02_k3", "r02_k3w"):
+        env = dict(os.environ, NCU_LINES_MEM="1")
+        lines += "\n---- per source line by memory traffic (gsect = L2 sectors requested by global loads, shwave = shared-memory wavefronts, lsect = local-memory sectors)\n" + \
+            subprocess.run([sys.executable, "tools/ncu_lines.py", rep, LIB, mangled, "24"], capture_output=True, text=True, cwd=ROOT, env=env).stdout
     open(os.path.join(P, name + "_ncu_full_summary.txt"), "w").write(out + "\n---- per source line (tools/ncu_lines.py; inst = share of warp instructions, lanes = active threads per instruction, stall = share of stall samples)\n" + lines)
     if name in ("r02_k3", "r02_k3w"):
         m = raw_metrics(rep)

@@ -68,15 +68,24 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, uuid: str | None):
+    def __init__(self, uuid: str | None, period_ms: int = 20):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        cmd = ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"]
+        cmd = ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(period_ms)]
         if uuid:
             cmd += ["-i", uuid]
         try:
-            self.p = subprocess.Popen(cmd, stdout=self.f, stderr=subprocess.DEVNULL)
+            self.p = None if os.environ.get("PGP_BENCH_NO_SAMPLER") == "1" else subprocess.Popen(cmd, stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+
+    def wait_started(self, timeout_s: float = 20.0) -> None:
+        """Blocks until nvidia-smi has written its first sample: on a fresh box its start-up (driver attach) takes seconds and holds
+        driver locks, which stretches a launch-heavy timed region that happens to overlap it (c3: 160 instead of 83 ms per step)."""
+        if self.p is None:
+            return
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < timeout_s and os.path.getsize(self.f.name) == 0 and self.p.poll() is None:
+            time.sleep(0.05)
 
     def stop(self) -> dict:
         if self.p is None:
@@ -407,7 +416,9 @@ def run_scoring(args, D: Dist, local_rank: int):
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
-    comm_init_from_env(eng, rank, world)  # pgp_comm_init: the communicator lives in libpgp.so
+    no_comm = os.environ.get("PGP_BENCH_NO_COMM") == "1"      # diagnosis only: N independent replicas, no collective at all
+    if not no_comm:
+        comm_init_from_env(eng, rank, world)  # pgp_comm_init: the communicator lives in libpgp.so
     if os.environ.get("PGP_STREAM_UPLOAD", "1") == "0":       # for captures under ncu, which serialises streams: upload first, then score
         eng.set_option("stream_upload", 0)
     eng.set_scene(prob.scene_xyz, prob.scene_nrm, prob.delta)
@@ -428,6 +439,8 @@ def run_scoring(args, D: Dist, local_rank: int):
 
     # ---- warm-up (+ lead-in for the nvidia-smi sampler: ~0.3 s under this benchmark's load before the timed region)
     sampler = ClockSampler(gpu_uuid(torch, local_rank)) if rank == 0 else None
+    if sampler:
+        sampler.wait_started()
     eng.score_lcp_device(0, T_dev, counts_dev, scores_dev, mode)          # first call (weighted: builds the K1c lists)
     est_ms = timed_ms(torch, stream, lambda: eng.score_lcp_device(0, T_dev, counts_dev, scores_dev, mode), reps=1)
     lead_in = int(D.reduce(min(300, max(0, 300.0 / max(est_ms, 0.05)))))  # the same count on every rank
@@ -543,7 +556,7 @@ def run_scoring(args, D: Dist, local_rank: int):
             gs = scores_host[(args.steps - 1) & 1].numpy()[sel]
             mism = float((got != wn.astype(np.uint32)).sum() + (gs != ws).sum())
     mism_total = D.reduce(mism, "sum")
-    invariance = sharding_invariance(eng, D, cfg, prob, stream) if world > 1 else None
+    invariance = sharding_invariance(eng, D, cfg, prob, stream) if world > 1 and not no_comm else None
 
     if rank == 0:
         b_hyp, kbar, nonempty = algorithmic_bytes_per_hyp(prob, T, cfg["n_model"])
@@ -653,7 +666,9 @@ def run_pcs(args, D: Dist, local_rank: int):
             tops.append(eng.topk_end(t))
         return tot, tops
 
-    sampler = ClockSampler(gpu_uuid(torch, local_rank)) if rank == 0 else None
+    sampler = ClockSampler(gpu_uuid(torch, local_rank), period_ms=100) if rank == 0 else None    # (a step is ~100 ms and hundreds of launches)
+    if sampler:
+        sampler.wait_started()
     for w in range(max(1, min(args.warmup, 2))):
         step(1000 + 10 * w)
     # where a step's time goes: one extra, untimed step with a device synchronisation after every phase
@@ -689,7 +704,7 @@ def run_pcs(args, D: Dist, local_rank: int):
     if rank == 0:
         digest = [{"object": o, "best_index": int(t["index"][0]), "best_score": float(t["score"][0]), "top64_crc": int(np.bitwise_xor.reduce(np.frombuffer(t.tobytes(), np.uint32)))}
                   for o, t in enumerate(tops)]
-        cpu = cpu_pcs_baseline_subprocess()
+        cpu = cpu_pcs_baseline_subprocess() if world == 1 else None       # the CPU leg: rank 0 at N = 1 only
         line = {"metric": cfg["metric"], "value": n_total / (total_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(1, min(args.warmup, 2)),
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"name": "c3", "workload": cfg["workload"], "objects": cfg["objects"], "n_bases_per_object": B, "hypotheses_per_step": n_total // args.steps,

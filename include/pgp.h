@@ -320,6 +320,15 @@ PGP_API int pgp_group_improving_chain(pgp_group* g, int obj, pgp_hyp* out_host, 
  * independent chains per thread.  Returns the sustained sector traffic in GB/s through *gbps.  No reference counterpart. */
 PGP_API int pgp_bench_sector_gather(pgp_ctx* ctx, int64_t footprint_bytes, int loads_per_thread, float* gbps);
 
+/* ---- host-callable copies of two exact-arithmetic helpers of the kernels (no GPU needed; tests/test_host_arithmetic.py) ---------
+ * pgp_host_chain_sum_equal: the float chain acc = c; (m - 1) x acc = fl(acc + c) -- std::accumulate over m equal weights in
+ * SelectQuadrilateralStoCS's normalisation (S4/algorithms/match4pcsBase.cc:652-657) -- in O(binades) steps, bit-identical to the chain.
+ * pgp_host_max_eigvec4: eigenvector of the largest eigenvalue of the symmetric 4x4 matrix of Horn's quaternion fit (the rigid fit
+ * of trimmed ICP, replaces PCL's TrimmedICP -> SVD) from its characteristic polynomial; 0 = nearly double top eigenvalue, the kernel
+ * then diagonalises with Jacobi. */
+PGP_API float pgp_host_chain_sum_equal(float c, long long m);
+PGP_API int pgp_host_max_eigvec4(const double* N16_rowmajor, double* q4);
+
 /* ---------------------------------------------------------------- K5: trimmed ICP ---------- */
 
 /* Trimmed ICP of k poses of object `obj` against the segment (source) with the model's

@@ -841,24 +841,31 @@ __host__ __device__ inline uint32_t stocs_base_seed(uint64_t seed, int base, int
 // multiple of U = ulp and, while the exact acc + c stays below 2^(e+1), fl(acc + c) - acc is the same multiple d of U for every
 // acc of the same parity -- and after one explicit step the parity no longer changes (a tie c = qU + U/2 rounds to the even
 // neighbour, which makes d even).  So: one real add, read d off it, jump over all the following steps that stay regular, repeat.
-__device__ inline float chain_sum_equal(float c, long long m) {
+#ifdef __CUDA_ARCH__
+#define PGP_FADD_RN(a, b) __fadd_rn(a, b)
+#define PGP_FSUB_RN(a, b) __fsub_rn(a, b)
+#else
+#define PGP_FADD_RN(a, b) ((a) + (b))      // host: the library is compiled with -ffp-contract=off, float stays float on x86-64 (SSE)
+#define PGP_FSUB_RN(a, b) ((a) - (b))
+#endif
+__host__ __device__ inline float chain_sum_equal(float c, long long m) {
   if (m <= 0) return 0.f;
   float acc = c;
   long long rem = m - 1;
   while (rem > 0) {
-    const float next = __fadd_rn(acc, c);
+    const float next = PGP_FADD_RN(acc, c);
     --rem;
     if (!(next > acc)) return acc;                                    // c is below half an ulp of acc: the chain has stalled
     int e0, e1;
     frexpf(acc, &e0); frexpf(next, &e1);
-    const float d = __fsub_rn(next, acc);                              // exact (next <= 2 acc)
+    const float d = PGP_FSUB_RN(next, acc);                              // exact (next <= 2 acc)
     acc = next;
     if (e0 != e1 || rem == 0) continue;                                // crossed into the next binade: its step is read off the next add
     // one more explicit step so that the parity of acc / U has settled (ties-to-even), then the regular run
-    const float next2 = __fadd_rn(acc, c);
+    const float next2 = PGP_FADD_RN(acc, c);
     --rem;
     int e2; frexpf(next2, &e2);
-    const float d2 = __fsub_rn(next2, acc);
+    const float d2 = PGP_FSUB_RN(next2, acc);
     if (!(next2 > acc)) return acc;
     acc = next2;
     if (e2 != e1 || rem == 0) continue;
@@ -1396,6 +1403,11 @@ int find_quads_dev(pgp_ctx* ctx, const Model& m, float cos_alpha, float inv1, fl
 }
 
 }  // namespace
+
+// host-callable copy of chain_sum_equal for the CPU test-suite (tests/test_host_arithmetic.py): the closed form must equal the
+// brute-force float chain for every (c, m)
+extern "C" PGP_API float pgp_host_chain_sum_equal(float c, long long m) { return chain_sum_equal(c, m); }
+
 
 int k2_extract_pairs(pgp_ctx* ctx, const Model& m, float dist, float eps, int32_t* pairs_host, int64_t cap, int64_t* n_pairs) {
   Scratch& sc = scratch_of(ctx);

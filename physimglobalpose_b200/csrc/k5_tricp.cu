@@ -138,7 +138,7 @@ __device__ void jacobi4(double A[4][4], double V[4][4]) {
 // lambda_max (monotone: every root is real and the polynomial is convex to the right of the largest), eigenvector = the column of
 // adj(N - lambda I) with the largest diagonal cofactor (rank 3 => adj = c q q^T).  Returns false when the largest eigenvalue is
 // (nearly) double -- the fit is then ill-posed and the caller diagonalises with Jacobi instead.
-__device__ bool max_eigvec4(const double N[4][4], double q[4]) {
+__host__ __device__ bool max_eigvec4(const double N[4][4], double q[4]) {
   double f2 = 0;
   for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) f2 += N[i][j] * N[i][j];
   if (!(f2 > 1e-280) || !(f2 < 1e280)) return false;
@@ -410,6 +410,15 @@ void invert_pose(const double* P, double* I) {
 }
 
 }  // namespace
+
+// host-callable copy of max_eigvec4 for the CPU test-suite (tests/test_host_arithmetic.py): N16 row-major symmetric 4x4; returns 1
+// and the (unnormalised) eigenvector of the largest eigenvalue, or 0 when the kernel would fall back to Jacobi
+extern "C" PGP_API int pgp_host_max_eigvec4(const double* N16, double* q4) {
+  double N[4][4];
+  for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) N[i][j] = N16[4 * i + j];
+  return max_eigvec4(N, q4) ? 1 : 0;
+}
+
 
 int k5_tricp(pgp_ctx* ctx, Model& m, const float* seg_xyz_host, int ns, double* poses16_host, int k, float trim, float ratio, int max_iter,
              int* iters_out, float* energy_out) {

@@ -396,9 +396,13 @@ __device__ __forceinline__ int resolve_ambiguous(const LcpParams& p, const Xf& x
   apply_xf(x, m, tx, ty, tz);
   const float r2 = p.g.r2;
   const float4* __restrict__ rec = p.arec + d.x;
-  for (uint32_t j = 0; j < d.y; ++j) {
-    const float4 sp = __ldg(rec + j);
-    if (sqdist3(tx, ty, tz, sp.x, sp.y, sp.z) <= r2) return 1;
+  // two records per round (the second load is issued before the first is tested: lists are ~2 records, and the chain of
+  // dependent loads is what this path waits on)
+  for (uint32_t j = 0; j < d.y; j += 2) {
+    const float4 s0 = __ldg(rec + j);
+    const float4 s1 = __ldg(rec + min(j + 1u, d.y - 1u));
+    if (sqdist3(tx, ty, tz, s0.x, s0.y, s0.z) <= r2) return 1;
+    if (sqdist3(tx, ty, tz, s1.x, s1.y, s1.z) <= r2) return 1;
   }
   return 0;
 }

@@ -7,12 +7,13 @@
  *
  * Parity status
  *   LCP (count + weighted), centring, priors, kd-tree, improving chain, rigid-from-quad, pair
- *   extraction: PINNED.  tests/test_oracle_vs_reference.py checks this file against the
+ *   extraction: PINNED.  tests/test_oracle_golden.py (test_port_equals_reference_live) checks this file against the
  *   reference engine itself (oracle/_ref/libs4ref.so, compiled in place from /root/reference by
  *   oracle/Makefile) on seeded inputs, and tests/golden/ holds vectors minted from that build
  *   (tests/golden/make_golden.py) for machines where /root/reference does not exist.
  *   The reference's own test-suite holds no golden vectors for this path.
- *   TrICP: RESTATED, PARITY UNPINNED -- pcl::recognition::TrimmedICP is not vendored in
+ *   TrICP: RESTATED, PARITY UNPINNED (independently cross-checked against scipy cKDTree + numpy SVD,
+ *   tests/test_tricp_crosscheck.py) -- pcl::recognition::TrimmedICP is not vendored in
  *   /root/reference and PCL is not installed; lo_tricp follows the call sites
  *   (PPE/src/hypothesis_verification/mcts/UCTState.cpp:121-204, PPE/src/misc/utilities.cpp:651-680)
  *   and PCL's published algorithm (pcl/recognition/ransac_based/trimmed_icp.h, PCL 1.7/1.8, the

@@ -282,6 +282,11 @@ PGP_API int pgp_comm_destroy(pgp_ctx* ctx);
  * cap max_hyp in rank order (<= 0: no cap) -- the cut pgp_generate_pcs makes on one GPU -- and reports the global index of this
  * rank's first hypothesis and the global total (either pointer may be NULL). */
 PGP_API int pgp_comm_sync_generated(pgp_ctx* ctx, int obj, int64_t max_hyp, int64_t* index_base, int64_t* n_total);
+/* The cut pgp_comm_sync_generated applies, as a pure host function (no context, no GPU): counts[r] = hypotheses rank r generated;
+ * on return *keep = how many of its own this rank keeps under the global cap max_hyp (<= 0: no cap), *index_base = global index of
+ * its first hypothesis, *n_total = hypotheses of the whole request.  Same prefix the single-GPU generator keeps
+ * (S4/algorithms/match4pcsBase.cc:1855-1877 appends base by base). */
+PGP_API int pgp_generated_cap_split(const int64_t* counts, int world, int64_t max_hyp, int rank, int64_t* keep, int64_t* index_base, int64_t* n_total);
 
 /* The merge behind the collective pgp_topk / pgp_improving_chain, as a pure host function (no context): `wire` = world blocks of
  * (k + 1) records as the all-gather delivers them -- per rank a header {index = the rank's batch size, count = valid records}

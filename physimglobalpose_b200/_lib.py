@@ -111,6 +111,7 @@ _SIGNATURES = {
     "pgp_group_topk": (_i, [_vp, _i, _i, _vp]),
     "pgp_group_improving_chain": (_i, [_vp, _i, _vp, _i]),
     "pgp_bench_sector_gather": (_i, [_vp, _i64, _i, _vp]),
+    "pgp_generated_cap_split": (_i, [_vp, _i, _i64, _i, _vp, _vp, _vp]),
     "pgp_host_chain_sum_equal": (C.c_float, [C.c_float, C.c_longlong]),
     "pgp_host_max_eigvec4": (_i, [_vp, _vp]),
 }

@@ -369,6 +369,25 @@ int pgp_comm_improving_chain(pgp_ctx* ctx, int obj, int64_t index_base, pgp_hyp*
   return slot_finish(ctx, c, c->slot[t], out_host, cap);
 }
 
+// The cut a global hypothesis cap makes in a request whose bases are sharded: ranks in order, the first ones keep everything, the
+// one that crosses max_hyp is truncated, the rest keep nothing -- exactly the prefix of the concatenated list that the single-GPU
+// generator keeps (it stops appending at max_hyp).  Pure host arithmetic (tests/test_sharding_gloo.py exercises it without a GPU).
+int pgp_generated_cap_split(const int64_t* counts, int world, int64_t max_hyp, int rank, int64_t* keep, int64_t* index_base, int64_t* n_total) {
+  if (!counts || world < 1 || rank < 0 || rank >= world) return PGP_E_INVALID;
+  int64_t before = 0, total = 0;
+  for (int r = 0; r < world; ++r) { if (counts[r] < 0) return PGP_E_INVALID; if (r < rank) before += counts[r]; total += counts[r]; }
+  int64_t k = counts[rank];
+  if (max_hyp > 0) {
+    k = std::max<int64_t>(0, std::min<int64_t>(k, max_hyp - before));
+    total = std::min(total, max_hyp);
+    before = std::min(before, max_hyp);
+  }
+  if (keep) *keep = k;
+  if (index_base) *index_base = before;
+  if (n_total) *n_total = total;
+  return PGP_OK;
+}
+
 // Bases sharded across ranks (pgp_generate_pcs_range): the per-rank hypothesis counts are exchanged, the global cap max_hyp is
 // applied in rank order -- the same cut the single-GPU generator makes -- and every rank learns the global index of its first
 // hypothesis.  The one other exchange on the path (8 bytes per rank).
@@ -394,14 +413,10 @@ int pgp_comm_sync_generated(pgp_ctx* ctx, int obj, int64_t max_hyp, int64_t* ind
     PGP_CUDA(ctx, cudaStreamSynchronize(c->stream));
     for (int r = 0; r < c->world; ++r) cnt[r] = c->cnt_host[r];
   }
-  int64_t before = 0, total = 0;
-  for (int r = 0; r < c->world; ++r) { if (r < c->rank) before += cnt[r]; total += cnt[r]; }
-  if (max_hyp > 0) {
-    const int64_t keep = std::max<int64_t>(0, std::min<int64_t>(m.n_gen, max_hyp - before));
-    if (keep != m.n_gen) { m.n_gen = keep; m.gen_scored = false; }
-    total = std::min(total, max_hyp);
-    before = std::min(before, max_hyp);
-  }
+  int64_t keep = 0, before = 0, total = 0;
+  std::vector<int64_t> cnt64(cnt.begin(), cnt.end());
+  pgp_generated_cap_split(cnt64.data(), c->world, max_hyp, c->rank, &keep, &before, &total);
+  if (keep != m.n_gen) { m.n_gen = keep; m.gen_scored = false; }
   m.gen_index_base = before;
   if (index_base_out) *index_base_out = before;
   if (n_total_out) *n_total_out = total;

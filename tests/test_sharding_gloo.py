@@ -39,6 +39,18 @@ def _serial_chain(rec):
     return rec[keep]
 
 
+def _cap_split(counts, max_hyp, rank):
+    """pgp_generated_cap_split through ctypes: (keep, index_base, n_total) of one rank."""
+    import ctypes as C
+    from physimglobalpose_b200 import _lib
+    lib = _lib.load()
+    counts = np.ascontiguousarray(counts, dtype=np.int64)
+    k, b, t = C.c_int64(), C.c_int64(), C.c_int64()
+    rc = lib.pgp_generated_cap_split(counts.ctypes.data_as(C.c_void_p), len(counts), int(max_hyp), int(rank), C.byref(k), C.byref(b), C.byref(t))
+    assert rc == 0
+    return k.value, b.value, t.value
+
+
 def _worker(rank, world, port, n, k, out_dir):
     import torch
     import torch.distributed as dist
@@ -64,7 +76,14 @@ def _worker(rank, world, port, n, k, out_dir):
     top_auto = exchange_merge(gather(wire_block(loc, hi - lo, k)), world, k, kind=0, auto_base=True)
     chain = exchange_merge(gather(wire_block(local_chain, hi - lo, 255)), world, 255, kind=1, mode="count")
     legacy = sharding.gather_topk(local_top, k)
-    np.savez(os.path.join(out_dir, f"merged_{rank}.npz"), top=top, top_auto=top_auto, chain=chain, legacy=legacy)
+    # a GENERATED request: every rank generated `mine` hypotheses from its base range; the counts are exchanged (8 bytes per rank,
+    # what pgp_comm_sync_generated all-gathers) and the global cap is applied by the library's own host function
+    mine = torch.tensor([1000 + 337 * rank], dtype=torch.int64)
+    cnts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(cnts, mine)
+    counts = np.array([int(c.item()) for c in cnts], dtype=np.int64)
+    caps = np.array([_cap_split(counts, cap, rank) for cap in (0, 500, 1000, 1200, 5000)], dtype=np.int64)
+    np.savez(os.path.join(out_dir, f"merged_{rank}.npz"), top=top, top_auto=top_auto, chain=chain, legacy=legacy, caps=caps, counts=counts)
     dist.destroy_process_group()
 
 
@@ -80,6 +99,40 @@ def test_two_rank_exchange_equals_the_serial_scan(tmp_path):
         for key in ("top", "top_auto", "legacy"):                    # every rank ends with the same, serial-order result
             assert got[key].tobytes() == want.tobytes(), key
         assert got["chain"].tobytes() == want_chain.tobytes()
+    # the capped request: the ranks' kept ranges tile exactly the prefix [0, min(cap, total)) of the concatenated list
+    got = [np.load(os.path.join(str(tmp_path), f"merged_{r}.npz")) for r in range(world)]
+    counts = got[0]["counts"]
+    assert counts.tolist() == [1000, 1337] and all(g["counts"].tolist() == counts.tolist() for g in got)
+    for ci, cap in enumerate((0, 500, 1000, 1200, 5000)):
+        total = int(counts.sum()) if cap <= 0 else min(cap, int(counts.sum()))
+        end = 0
+        for r in range(world):
+            keep, base, n_total = (int(x) for x in got[r]["caps"][ci])
+            assert n_total == total and base == end and 0 <= keep <= counts[r]
+            end = base + keep
+        assert end == total
+
+
+def test_cap_split_equals_the_single_list_prefix():
+    """For any split of a generated list into per-rank counts, the kept pieces are the prefix the single-GPU generator keeps."""
+    rng = np.random.default_rng(3)
+    for trial in range(300):
+        world = int(rng.integers(1, 9))
+        counts = rng.integers(0, 2000, size=world)
+        if trial % 7 == 0:
+            counts[rng.integers(0, world)] = 0
+        total = int(counts.sum())
+        for cap in (0, -1, 1, total // 2, total, total + 5):
+            want_total = total if cap <= 0 else min(cap, total)
+            kept = np.zeros(total, dtype=bool)
+            starts = np.concatenate([[0], np.cumsum(counts)])
+            for r in range(world):
+                keep, base, n_total = _cap_split(counts, cap, r)
+                assert n_total == want_total
+                assert base == min(int(starts[r]), want_total)
+                kept[int(starts[r]):int(starts[r]) + keep] = True
+                assert keep == 0 or base == int(starts[r])               # a rank that keeps anything starts where its shard starts
+            assert kept[:want_total].all() and not kept[want_total:].any()
 
 
 def test_exchange_merge_is_independent_of_the_sharding():

@@ -322,13 +322,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TT, 1) k5_tricp_kern
       eq_seen += total;
       __syncthreads();
     }
+    // 16 sums over the warp with 16 shuffles instead of 80: at every butterfly step a lane hands HALF of its partial sums to its
+    // partner and keeps the other half, so the values per lane halve while the lanes per value double; lane l ends with the
+    // complete sum number (bits 4..1 of l)
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      double v = acc[k];
+    for (int half = 8, off = 16; half >= 1; half >>= 1, off >>= 1) {
+      const bool upper = (lane & off) != 0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) s_red[warp][k] = v;
+      for (int j = 0; j < half; ++j) {
+        const double send = upper ? acc[j] : acc[j + half];
+        const double keep = upper ? acc[j + half] : acc[j];
+        acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
     }
+    acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+    if (!(lane & 1)) s_red[warp][((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = acc[0];
     __syncthreads();
     if (tid < 16) { double v = 0; for (int w = 0; w < TT / 32; ++w) v += s_red[w][tid]; s_part[tid] = v; }
     cl.sync();

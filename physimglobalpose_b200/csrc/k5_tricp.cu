@@ -280,10 +280,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TT, 1) k5_tricp_kern
           uint32_t acc = incl - mine; int dgt = 0;
           for (; dgt < 7; ++dgt) { if (acc + h[dgt] >= rank) break; acc += h[dgt]; }
           s_sel[0] = (prefix << 8) | (uint32_t)(lane * 8 + dgt); s_sel[1] = rank - acc;
-          uint32_t e0 = h0[0];
+          uint32_t e0 = h0[0], et = h[0];
 #pragma unroll
-          for (int k = 1; k < 8; ++k) if (k == dgt) e0 = h0[k];
-          s_sel[2] = e0;                                 // last pass: how many values equal to tau CTA 0 holds
+          for (int k = 1; k < 8; ++k) if (k == dgt) { e0 = h0[k]; et = h[k]; }
+          s_sel[2] = e0;                                 // last pass: how many values equal to tau CTA 0 holds,
+          s_sel[3] = et;                                 // and how many there are in all
         }
       }
       __syncthreads();
@@ -298,17 +299,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TT, 1) k5_tricp_kern
 #pragma unroll
     for (int k = 0; k < 16; ++k) acc[k] = 0.0;
     uint32_t eq_seen = cr ? s_sel[2] : 0u;
+    const bool all_eq = s_sel[3] == rank;          // every value equal to tau is kept (the usual case: tau is unique): no ordering needed
     for (int i0 = i_lo; i0 < i_hi; i0 += TT) {
       const int i = i0 + tid;
       const uint32_t b = i < i_hi ? __float_as_uint(d2[i]) : 0xffffffffu;
       const bool eq = i < i_hi && b == tau;
-      const unsigned bal = __ballot_sync(0xffffffffu, eq);
-      if (lane == 0) s_warp[warp] = __popc(bal);
-      __syncthreads();
-      uint32_t before = eq_seen, total = 0;
-      for (int w = 0; w < TT / 32; ++w) { const uint32_t c = s_warp[w]; if (w < warp) before += c; total += c; }
-      before += __popc(bal & ((1u << lane) - 1u));
-      const bool keep = i < i_hi && (b < tau || (eq && before < rank));
+      uint32_t before = 0, total = 0;
+      if (!all_eq) {                                 // (uniform over the cluster)
+        const unsigned bal = __ballot_sync(0xffffffffu, eq);
+        if (lane == 0) s_warp[warp] = __popc(bal);
+        __syncthreads();
+        before = eq_seen;
+        for (int w = 0; w < TT / 32; ++w) { const uint32_t c = s_warp[w]; if (w < warp) before += c; total += c; }
+        before += __popc(bal & ((1u << lane) - 1u));
+      }
+      const bool keep = i < i_hi && (b < tau || (eq && (all_eq || before < rank)));
       if (keep) {
         const float4 s = p.src[i];
         const float4 g = p.tgt_orig[nn[i]];
@@ -320,7 +325,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TT, 1) k5_tricp_kern
         acc[13] += (double)s.z * g.x; acc[14] += (double)s.z * g.y; acc[15] += (double)s.z * g.z;
       }
       eq_seen += total;
-      __syncthreads();
+      if (!all_eq) __syncthreads();
     }
     // 16 sums over the warp with 16 shuffles instead of 80: at every butterfly step a lane hands HALF of its partial sums to its
     // partner and keeps the other half, so the values per lane halve while the lanes per value double; lane l ends with the

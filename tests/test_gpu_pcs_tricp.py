@@ -71,6 +71,33 @@ def test_tricp_matches_oracle(engine, port_lib):
         assert synth.pose_error(refined[k], prob.gt_pose)[0] <= synth.pose_error(poses[k], prob.gt_pose)[0] + 1e-3
 
 
+def test_tricp_with_ties_at_the_trim_threshold(engine, port_lib):
+    """Every segment point twice: the squared distances come in equal pairs, and with an odd number of kept correspondences the
+    trim threshold falls INSIDE a pair -- one of two equal values is kept (the tie path of the kernel's sums; which of two identical
+    points is kept cannot matter).  Same transforms, iteration counts and energies as the restatement."""
+    prob = synth.make_segment_problem(1500, 601, 0.005, seed=31)
+    seg = np.repeat(prob.scene_xyz[:601], 2, axis=0)                       # 1202 points -> trim 0.5 keeps 601: odd
+    engine.set_scene(prob.scene_xyz, prob.scene_nrm, prob.delta)
+    engine.set_model(0, prob.model_xyz, prob.model_nrm)
+    rng = np.random.default_rng(4)
+    poses = []
+    for _ in range(5):
+        P = prob.gt_pose.copy()
+        P[:3, :3] = P[:3, :3] @ synth.rot_axis_angle(rng.normal(size=3), rng.normal(0, 0.06))
+        P[:3, 3] += rng.normal(0, 0.005, size=3)
+        poses.append(P)
+    poses = np.array(poses)
+    refined, iters, energy = engine.tricp(0, seg, poses, trim=0.5, ratio=0.99, max_iter=100)
+    o = port_lib.PortOracle(prob.scene_xyz[:10], prob.scene_nrm[:10], prob.model_xyz, prob.model_nrm, prob.model_xyz, prob.model_nrm, prob.delta)
+    for k in range(len(poses)):
+        Tref, it_ref, e_ref = o.tricp(seg, prob.model_xyz, np.linalg.inv(poses[k])[:3].astype(np.float32), trim=0.5, ratio=0.99, max_iter=100)
+        M = np.eye(4); M[:3] = Tref
+        dt, ang = synth.pose_error(refined[k], np.linalg.inv(M))
+        assert dt < 1e-4 and ang < 1e-4, (k, dt, ang, iters[k], it_ref)
+        assert iters[k] == it_ref
+        assert abs(energy[k] - e_ref) <= 1e-4 * max(e_ref, 1e-12) + 1e-12
+
+
 def _oracle_tricp(port_lib, prob, T0):
     o = port_lib.PortOracle(prob.scene_xyz[:10], prob.scene_nrm[:10], prob.model_xyz, prob.model_nrm, prob.model_xyz, prob.model_nrm, prob.delta)
     return o.tricp(prob.scene_xyz, prob.model_xyz, T0, trim=0.5, ratio=0.99, max_iter=100)

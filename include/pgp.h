@@ -366,9 +366,12 @@ PGP_API int pgp_mcts_tricp(pgp_ctx* ctx, int obj, const float* seg_xyz_host, int
  * PPE/src/misc/utilities.cpp:47-61: ((d << 13) | (d >> 3)) / 10000), class mask (GTSegmentation::compute2dSegment,
  * PPE/src/segmentation/Segmentation.cpp:187-207), back-projection of the pixels with 0.1 < depth < 2.0
  * (utilities::convert3dUnOrganizedRGB, utilities.cpp:210-228), then -- restated, PCL being un-vendored -- `leaf` voxel
- * centroids (pcl::VoxelGrid, Segmentation.cpp:226-229), normals from the neighbours within normal_radius oriented to the
- * camera (in place of pcl::MovingLeastSquares, :231-238) and removal of points with fewer than min_neighbors within
- * outlier_radius (pcl::RadiusOutlierRemoval, PPE/src/hypothesis_generation/ObjectPoseCandidateSet.cpp:28-51).
+ * centroids (pcl::VoxelGrid, Segmentation.cpp:226-229), pcl::MovingLeastSquares as the reference configures it (:231-238:
+ * polynomial fit of order 2 over the neighbours within normal_radius, the point projected onto the fitted surface, its normal;
+ * points with fewer than 3 neighbours vanish), removal of the projected points with fewer than min_neighbors within
+ * outlier_radius and normals turned to the camera (pcl::RadiusOutlierRemoval + flipNormalTowardsViewpoint,
+ * PPE/src/hypothesis_generation/ObjectPoseCandidateSet.cpp:28-51).  pgp_set_option("k7_mls", 0) selects plain PCA normals on the
+ * un-projected centroids instead (round 1's stand-in).
  * depth_raw: rows x cols uint16 as stored in frame-*.depth.png; class_mask: rows x cols uint8; K9 row-major intrinsics.
  * xyz_out / nrm_out: cap x 3 camera-frame points / unit normals, ready for pgp_set_scene.  Returns the number of points. */
 PGP_API int pgp_prepare_segment(pgp_ctx* ctx, const uint16_t* depth_raw, const uint8_t* class_mask, int rows, int cols, int class_id,

@@ -4,7 +4,8 @@
   mask             GTSegmentation::compute2dSegment    PPE/src/segmentation/Segmentation.cpp:187-207
   back-projection  utilities::convert3dUnOrganizedRGB  PPE/src/misc/utilities.cpp:210-228  fp32 ((v - cx) * depth) / fx, 0.1 < depth < 2.0
   voxel centroids  pcl::VoxelGrid, leaf 1 cm           Segmentation.cpp:226-229  (centroid per voxel, output in voxel-index order)
-  normals          pcl::MovingLeastSquares, r = 2 cm   Segmentation.cpp:231-238  -- restated as local PCA (smallest eigenvector)
+  normals          pcl::MovingLeastSquares, r = 2 cm   Segmentation.cpp:231-238  -- mls_project (polynomial fit of order 2, projection +
+                                                                                   normal); pca_normals = round 1's stand-in
   outlier removal  pcl::RadiusOutlierRemoval 3 cm / 10 PPE/src/hypothesis_generation/ObjectPoseCandidateSet.cpp:28-32
   normal flip      pcl::flipNormalTowardsViewpoint + renormalise  :39-51
 PCL is not vendored in the reference tree and not installed: the three PCL filters are RESTATED, PARITY UNPINNED (VoxelGrid's
@@ -61,15 +62,81 @@ def pca_normals(cen: np.ndarray, radius: float = 0.02) -> np.ndarray:
     return nrm
 
 
+def _unit_orthogonal(n: np.ndarray) -> np.ndarray:
+    """Eigen's Vector3d::unitOrthogonal() (what pcl::MovingLeastSquares builds its local frame with)."""
+    x, y, z = n
+    if not (abs(x) <= abs(z) * 1e-12) or not (abs(y) <= abs(z) * 1e-12):
+        inv = 1.0 / np.sqrt(x * x + y * y)
+        return np.array([-y * inv, x * inv, 0.0])
+    inv = 1.0 / np.sqrt(y * y + z * z)
+    return np.array([0.0, -z * inv, y * inv])
+
+
+def mls_project(cen: np.ndarray, radius: float = 0.02, order: int = 2):
+    """pcl::MovingLeastSquares with setPolynomialFit(true), setComputeNormals(true), no upsampling, as the reference configures it
+    (PPE/src/segmentation/Segmentation.cpp:231-238): per point, the (unweighted) PCA plane of its neighbours within `radius`, the
+    query projected onto it, a weighted (exp(-d^2 / radius^2)) least-squares polynomial of total degree `order` in the plane's
+    (u, v) frame over the same neighbours, the point moved along the plane normal by the polynomial's value at (0, 0) and the
+    normal tilted by its gradient there.  Restated from PCL's published algorithm (mls.hpp, computeMLSPointNormal): PCL is not
+    available here, PARITY UNPINNED.  Returns (points, unit normals oriented to the camera at the origin, valid mask): points
+    with fewer than 3 neighbours are dropped by PCL (valid = False)."""
+    from scipy.spatial import cKDTree
+    tree = cKDTree(cen)
+    n_coef = (order + 1) * (order + 2) // 2
+    out_p = cen.astype(np.float64).copy()
+    out_n = np.zeros((len(cen), 3))
+    valid = np.zeros(len(cen), dtype=bool)
+    for i, nb in enumerate(tree.query_ball_point(cen, radius)):
+        if len(nb) < 3:
+            continue
+        nb = sorted(nb)
+        q = cen[nb].astype(np.float64)
+        c = cen[i].astype(np.float64)
+        mean = q.mean(axis=0)
+        w_, vec = np.linalg.eigh((q - mean).T @ (q - mean))
+        n = vec[:, 0]
+        point = c - np.dot(c - mean, n) * n
+        normal = n.copy()
+        if len(nb) >= n_coef:
+            de = q - point
+            wgt = np.exp(-np.einsum("ij,ij->i", de, de) / (radius * radius))
+            v_axis = _unit_orthogonal(n)
+            u_axis = np.cross(n, v_axis)
+            u, v, f = de @ u_axis, de @ v_axis, de @ n
+            P = np.stack([u ** ui * v ** vi for ui in range(order + 1) for vi in range(order + 1 - ui)])     # [1, v, v^2, u, uv, u^2]
+            A = (P * wgt) @ P.T
+            b = (P * wgt) @ f
+            try:
+                L = np.linalg.cholesky(A)
+                coef = np.linalg.solve(L.T, np.linalg.solve(L, b))
+                point = point + coef[0] * n
+                normal = n - coef[order + 1] * u_axis - coef[1] * v_axis
+            except np.linalg.LinAlgError:
+                pass
+        if np.dot(normal, point) > 0:
+            normal = -normal
+        out_p[i] = point
+        out_n[i] = normal / np.linalg.norm(normal)
+        valid[i] = True
+    return out_p.astype(np.float32), out_n.astype(np.float32), valid
+
+
 def radius_outlier_keep(cen: np.ndarray, radius: float = 0.03, min_neighbors: int = 10) -> np.ndarray:
     from scipy.spatial import cKDTree
     tree = cKDTree(cen)
     return np.array([len(nb) >= min_neighbors for nb in tree.query_ball_point(cen, radius)])       # the point itself counts, as in PCL
 
 
-def prepare_segment(depth_m, mask, cls, K, leaf=0.01, normal_radius=0.02, outlier_radius=0.03, min_neighbors=10):
+def prepare_segment(depth_m, mask, cls, K, leaf=0.01, normal_radius=0.02, outlier_radius=0.03, min_neighbors=10, mls=False):
     pts = backproject(depth_m, mask, cls, K)
     cen = voxel_centroids(pts, leaf)
+    if mls:
+        # the reference's order: MLS on the voxel centroids (points with < 3 neighbours vanish), then the radius-outlier filter on
+        # the PROJECTED cloud (ObjectPoseCandidateSet.cpp:28-32)
+        proj, nrm, valid = mls_project(cen, normal_radius)
+        proj, nrm = proj[valid], nrm[valid]
+        keep = radius_outlier_keep(proj, outlier_radius, min_neighbors)
+        return proj[keep], nrm[keep], len(pts)
     nrm = pca_normals(cen, normal_radius)
     keep = radius_outlier_keep(cen, outlier_radius, min_neighbors)
     return cen[keep], nrm[keep], len(pts)

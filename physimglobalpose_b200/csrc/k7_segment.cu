@@ -121,10 +121,45 @@ __device__ void smallest_eigvec(double a[3][3], double n[3]) {
   n[0] = v[0][m]; n[1] = v[1][m]; n[2] = v[2][m];
 }
 
-// one thread per centroid: PCA normal over the neighbours within normal_r (towards the camera at the origin) and the
-// neighbour count within outlier_r (the point itself included)
+// Eigen's Vector3d::unitOrthogonal() -- the local frame pcl::MovingLeastSquares fits its polynomial in
+__device__ void unit_orthogonal(const double n[3], double v[3]) {
+  if (!(fabs(n[0]) <= fabs(n[2]) * 1e-12) || !(fabs(n[1]) <= fabs(n[2]) * 1e-12)) {
+    const double inv = 1.0 / sqrt(n[0] * n[0] + n[1] * n[1]);
+    v[0] = -n[1] * inv; v[1] = n[0] * inv; v[2] = 0.0;
+  } else {
+    const double inv = 1.0 / sqrt(n[1] * n[1] + n[2] * n[2]);
+    v[0] = 0.0; v[1] = -n[2] * inv; v[2] = n[1] * inv;
+  }
+}
+
+// A x = b for a symmetric positive definite 6x6 A (lower triangle read), Cholesky in place; false if a pivot is not positive
+__device__ bool chol6_solve(double A[6][6], double b[6]) {
+  for (int j = 0; j < 6; ++j) {
+    double d = A[j][j];
+    for (int k = 0; k < j; ++k) d -= A[j][k] * A[j][k];
+    if (!(d > 0.0)) return false;
+    d = sqrt(d);
+    A[j][j] = d;
+    for (int i = j + 1; i < 6; ++i) {
+      double v = A[i][j];
+      for (int k = 0; k < j; ++k) v -= A[i][k] * A[j][k];
+      A[i][j] = v / d;
+    }
+  }
+  for (int i = 0; i < 6; ++i) { double v = b[i]; for (int k = 0; k < i; ++k) v -= A[i][k] * b[k]; b[i] = v / A[i][i]; }
+  for (int i = 5; i >= 0; --i) { double v = b[i]; for (int k = i + 1; k < 6; ++k) v -= A[k][i] * b[k]; b[i] = v / A[i][i]; }
+  return true;
+}
+
+// one thread per centroid: PCA plane over the neighbours within normal_r and the neighbour count within outlier_r (the point
+// itself included).  mls = 0: the plane normal (towards the camera at the origin) is the output normal, the centroid the output
+// point.  mls = 1: pcl::MovingLeastSquares as the reference configures it (polynomial fit of order 2, normals, no upsampling;
+// PPE/src/segmentation/Segmentation.cpp:231-238) -- the query is projected onto the plane, a weighted (exp(-d^2 / r^2))
+// least-squares polynomial [1, v, v^2, u, uv, u^2] in the plane's frame is fitted over the same neighbours, the point moves along
+// the plane normal by its value at (0, 0) and the normal tilts by its gradient there; points with fewer than 3 neighbours are
+// dropped (proj.w = 0), as PCL drops them.  Restated from PCL's published algorithm (mls.hpp): PARITY UNPINNED, == oracle/segment_port.py.
 __global__ void k7_normals(const float4* __restrict__ cen, int nc, VoxGrid g, const int* __restrict__ vox_to_cen, double normal_r, double outlier_r,
-                           int min_nb, float4* __restrict__ nrm, uint32_t* __restrict__ keep) {
+                           int min_nb, int mls, float4* __restrict__ nrm, float4* __restrict__ proj, uint32_t* __restrict__ keep) {
   const int i = blockIdx.x * T + threadIdx.x;
   if (i >= nc) return;
   const float4 c = cen[i];
@@ -171,12 +206,95 @@ __global__ void k7_normals(const float4* __restrict__ cen, int nc, VoxGrid g, co
       } else {
         n[0] = -(double)c.x; n[1] = -(double)c.y; n[2] = -(double)c.z;
       }
-      if (n[0] * (double)c.x + n[1] * (double)c.y + n[2] * (double)c.z > 0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
+      double pt[3] = {(double)c.x, (double)c.y, (double)c.z};
+      if (mls) {
+        if (cnt_n < 3) { proj[i] = make_float4(c.x, c.y, c.z, 0.f); nrm[i] = make_float4(0.f, 0.f, 0.f, 0.f); keep[i] = 0u; return; }
+        const double ln = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        n[0] /= ln; n[1] /= ln; n[2] /= ln;
+        const double dist = (pt[0] - mx) * n[0] + (pt[1] - my) * n[1] + (pt[2] - mz) * n[2];
+        pt[0] -= dist * n[0]; pt[1] -= dist * n[1]; pt[2] -= dist * n[2];
+        if (cnt_n >= 6) {
+          double va[3], ua[3];
+          unit_orthogonal(n, va);
+          ua[0] = n[1] * va[2] - n[2] * va[1]; ua[1] = n[2] * va[0] - n[0] * va[2]; ua[2] = n[0] * va[1] - n[1] * va[0];
+          double A[6][6], b[6];
+          for (int r = 0; r < 6; ++r) { b[r] = 0.0; for (int q = 0; q < 6; ++q) A[r][q] = 0.0; }
+          const double inv_r2 = 1.0 / nr2;
+          for (int dk = -R; dk <= R; ++dk) {
+            const int k = ck + dk;
+            if (k < 0 || k >= g.dim[2]) continue;
+            for (int dj = -R; dj <= R; ++dj) {
+              const int j = cj + dj;
+              if (j < 0 || j >= g.dim[1]) continue;
+              for (int di = -R; di <= R; ++di) {
+                const int ii = ci + di;
+                if (ii < 0 || ii >= g.dim[0]) continue;
+                const int q = vox_to_cen[ii + g.dim[0] * (j + g.dim[1] * k)];
+                if (q < 0) continue;
+                const float4 p = cen[q];
+                const double dx = (double)p.x - (double)c.x, dy = (double)p.y - (double)c.y, dz = (double)p.z - (double)c.z;
+                if (!(dx * dx + dy * dy + dz * dz <= nr2)) continue;                       // the same neighbours as the plane
+                const double ex = (double)p.x - pt[0], ey = (double)p.y - pt[1], ez = (double)p.z - pt[2];
+                const double w = exp(-(ex * ex + ey * ey + ez * ez) * inv_r2);
+                const double u = ex * ua[0] + ey * ua[1] + ez * ua[2], v = ex * va[0] + ey * va[1] + ez * va[2];
+                const double f = ex * n[0] + ey * n[1] + ez * n[2];
+                const double phi[6] = {1.0, v, v * v, u, u * v, u * u};
+                for (int r = 0; r < 6; ++r) {
+                  const double wr = w * phi[r];
+                  b[r] += wr * f;
+                  for (int q2 = 0; q2 <= r; ++q2) A[r][q2] += wr * phi[q2];
+                }
+              }
+            }
+          }
+          if (chol6_solve(A, b)) {
+            pt[0] += b[0] * n[0]; pt[1] += b[0] * n[1]; pt[2] += b[0] * n[2];
+            for (int a = 0; a < 3; ++a) n[a] = n[a] - b[3] * ua[a] - b[1] * va[a];
+          }
+        }
+      }
+      if (n[0] * pt[0] + n[1] * pt[1] + n[2] * pt[2] > 0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
       const double l = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
       nrm[i] = make_float4((float)(n[0] / l), (float)(n[1] / l), (float)(n[2] / l), 0.f);
-      keep[i] = cnt_o >= min_nb ? 1u : 0u;
+      proj[i] = make_float4((float)pt[0], (float)pt[1], (float)pt[2], 1.f);
+      keep[i] = cnt_o >= min_nb ? 1u : 0u;                   // (mls: overwritten by k7_outlier_count on the projected cloud)
     }
   }
+}
+
+// mls = 1: the radius-outlier filter runs on the PROJECTED cloud (ObjectPoseCandidateSet.cpp:28-32 filters what MLS returned).  A
+// projected point lies within `slack` voxels of its centroid's voxel (checked: the displacement is bounded by the fit's radius).
+__global__ void k7_outlier_count(const float4* __restrict__ cen, const float4* __restrict__ proj, int nc, VoxGrid g, const int* __restrict__ vox_to_cen,
+                                 double outlier_r, int min_nb, uint32_t* __restrict__ keep) {
+  const int i = blockIdx.x * T + threadIdx.x;
+  if (i >= nc) return;
+  const float4 me = proj[i];
+  if (me.w == 0.f) { keep[i] = 0u; return; }
+  const float4 c = cen[i];
+  const int ci = (int)floorf(__fdiv_rn(c.x, g.leaf)) - g.mn[0], cj = (int)floorf(__fdiv_rn(c.y, g.leaf)) - g.mn[1],
+            ck = (int)floorf(__fdiv_rn(c.z, g.leaf)) - g.mn[2];
+  const int R = (int)ceil(outlier_r / (double)g.leaf) + 5;           // + 2 x 2 voxels: both points may have moved by up to normal_r
+  const double or2 = outlier_r * outlier_r;
+  int cnt = 0;
+  for (int dk = -R; dk <= R; ++dk) {
+    const int k = ck + dk;
+    if (k < 0 || k >= g.dim[2]) continue;
+    for (int dj = -R; dj <= R; ++dj) {
+      const int j = cj + dj;
+      if (j < 0 || j >= g.dim[1]) continue;
+      for (int di = -R; di <= R; ++di) {
+        const int ii = ci + di;
+        if (ii < 0 || ii >= g.dim[0]) continue;
+        const int q = vox_to_cen[ii + g.dim[0] * (j + g.dim[1] * k)];
+        if (q < 0) continue;
+        const float4 p = proj[q];
+        if (p.w == 0.f) continue;
+        const double dx = (double)p.x - (double)me.x, dy = (double)p.y - (double)me.y, dz = (double)p.z - (double)me.z;
+        if (dx * dx + dy * dy + dz * dz <= or2) ++cnt;
+      }
+    }
+  }
+  keep[i] = cnt >= min_nb ? 1u : 0u;
 }
 __global__ void k7_keep(const float4* __restrict__ cen, const float4* __restrict__ nrm, const uint32_t* __restrict__ keep_scan, int nc,
                         float* __restrict__ xyz, float* __restrict__ nxyz) {
@@ -187,8 +305,12 @@ __global__ void k7_keep(const float4* __restrict__ cen, const float4* __restrict
   nxyz[3 * o] = nrm[i].x; nxyz[3 * o + 1] = nrm[i].y; nxyz[3 * o + 2] = nrm[i].z;
 }
 
-struct K7Scratch { DevBuf depth, mask, flag, pts, key_of, cnt, cursor, sorted, occ, cen, vox_to_cen, nrm, keep, xyz, nxyz; };
-K7Scratch g_k7[16];
+// device scratch of the segment preparation: owned by the context (k7_release)
+struct K7Scratch { DevBuf depth, mask, flag, pts, key_of, cnt, cursor, sorted, occ, cen, vox_to_cen, nrm, proj, keep, xyz, nxyz; };
+K7Scratch& k7_scratch_of(pgp_ctx* ctx) {
+  if (!ctx->k7_scratch) ctx->k7_scratch = new K7Scratch();
+  return *static_cast<K7Scratch*>(ctx->k7_scratch);
+}
 
 int scan_total(pgp_ctx* ctx, uint32_t* data, int64_t n, uint32_t* total) {
   PGP_CUDA(ctx, ctx->scene.scratch.reserve((size_t)((n + 1) / 2048 + 4096) * 4));
@@ -203,7 +325,7 @@ int scan_total(pgp_ctx* ctx, uint32_t* data, int64_t n, uint32_t* total) {
 
 int k7_prepare_segment(pgp_ctx* ctx, const uint16_t* depth_host, const uint8_t* mask_host, int rows, int cols, int cls, const float* K9, float leaf,
                        float normal_r, float outlier_r, int min_nb, float* xyz_host, float* nrm_host, int cap, int* n_out, int* n_raw_out) {
-  K7Scratch& sc = g_k7[ctx->device & 15];
+  K7Scratch& sc = k7_scratch_of(ctx);
   cudaStream_t st = ctx->stream;
   const int npx = rows * cols;
   *n_out = 0;
@@ -261,20 +383,26 @@ int k7_prepare_segment(pgp_ctx* ctx, const uint16_t* depth_host, const uint8_t* 
   if (rc) return rc;
   PGP_CUDA(ctx, sc.cen.reserve((size_t)nc * 16));
   PGP_CUDA(ctx, sc.nrm.reserve((size_t)nc * 16));
+  PGP_CUDA(ctx, sc.proj.reserve((size_t)nc * 16));
   PGP_CUDA(ctx, sc.keep.reserve((size_t)(nc + 1) * 4));
   PGP_CUDA(ctx, sc.xyz.reserve((size_t)nc * 12));
   PGP_CUDA(ctx, sc.nxyz.reserve((size_t)nc * 12));
   k7_compact<<<vb, T, 0, st>>>(sc.sorted.as<float4>(), sc.cnt.as<uint32_t>(), sc.occ.as<uint32_t>(), n_vox, sc.cen.as<float4>(), sc.vox_to_cen.as<int>());
   PGP_CUDA(ctx, cudaMemsetAsync(sc.keep.as<uint32_t>() + nc, 0, 4, st));
   k7_normals<<<((int)nc + T - 1) / T, T, 0, st>>>(sc.cen.as<float4>(), (int)nc, g, sc.vox_to_cen.as<int>(), (double)normal_r, (double)outlier_r, min_nb,
-                                                 sc.nrm.as<float4>(), sc.keep.as<uint32_t>());
+                                                 ctx->k7_mls, sc.nrm.as<float4>(), sc.proj.as<float4>(), sc.keep.as<uint32_t>());
   ctx->launches += 2;
+  if (ctx->k7_mls) {
+    k7_outlier_count<<<((int)nc + T - 1) / T, T, 0, st>>>(sc.cen.as<float4>(), sc.proj.as<float4>(), (int)nc, g, sc.vox_to_cen.as<int>(), (double)outlier_r, min_nb,
+                                                         sc.keep.as<uint32_t>());
+    ctx->launches++;
+  }
   uint32_t n_keep = 0;
   rc = scan_total(ctx, sc.keep.as<uint32_t>(), nc, &n_keep);
   if (rc) return rc;
   if ((int)n_keep > cap) return pgp_fail(ctx, PGP_E_CAPACITY, "segment has %u points, capacity %d", n_keep, cap);
   if (n_keep) {
-    k7_keep<<<((int)nc + T - 1) / T, T, 0, st>>>(sc.cen.as<float4>(), sc.nrm.as<float4>(), sc.keep.as<uint32_t>(), (int)nc, sc.xyz.as<float>(), sc.nxyz.as<float>());
+    k7_keep<<<((int)nc + T - 1) / T, T, 0, st>>>(sc.proj.as<float4>(), sc.nrm.as<float4>(), sc.keep.as<uint32_t>(), (int)nc, sc.xyz.as<float>(), sc.nxyz.as<float>());
     ctx->launches++;
     PGP_CUDA(ctx, cudaMemcpyAsync(xyz_host, sc.xyz.p, (size_t)n_keep * 12, cudaMemcpyDeviceToHost, st));
     PGP_CUDA(ctx, cudaMemcpyAsync(nrm_host, sc.nxyz.p, (size_t)n_keep * 12, cudaMemcpyDeviceToHost, st));
@@ -283,4 +411,14 @@ int k7_prepare_segment(pgp_ctx* ctx, const uint16_t* depth_host, const uint8_t* 
   PGP_CUDA(ctx, cudaGetLastError());
   *n_out = (int)n_keep;
   return PGP_OK;
+}
+
+void k7_release(pgp_ctx* ctx) {
+  if (!ctx->k7_scratch) return;
+  K7Scratch* sc = static_cast<K7Scratch*>(ctx->k7_scratch);
+  for (DevBuf* b : {&sc->depth, &sc->mask, &sc->flag, &sc->pts, &sc->key_of, &sc->cnt, &sc->cursor, &sc->sorted, &sc->occ, &sc->cen, &sc->vox_to_cen, &sc->nrm,
+                    &sc->proj, &sc->keep, &sc->xyz, &sc->nxyz})
+    b->release();
+  delete sc;
+  ctx->k7_scratch = nullptr;
 }

@@ -124,6 +124,7 @@ void pgp_destroy(pgp_ctx* ctx) {
   k2_release(ctx);
   k5_release(ctx);
   k6_release(ctx);
+  k7_release(ctx);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   cudaStreamDestroy(ctx->own_stream);
   cudaStreamDestroy(ctx->copy_stream);
@@ -157,6 +158,7 @@ int pgp_set_option(pgp_ctx* ctx, const char* name, int value) {
     return PGP_OK;
   }
   if (name && !strcmp(name, "k3_smem_table")) { ctx->k3_smem_table = value < 0 ? -1 : (value ? 1 : 0); return PGP_OK; }
+  if (name && !strcmp(name, "k7_mls")) { ctx->k7_mls = value ? 1 : 0; return PGP_OK; }
   if (name && !strcmp(name, "group_cull")) { ctx->group_cull = value ? 1 : 0; return PGP_OK; }
   if (name && !strcmp(name, "stream_upload")) { ctx->stream_upload = value ? 1 : 0; return PGP_OK; }
   if (name && !strcmp(name, "tail_split")) { ctx->tail_split = value < 1 ? 1 : (value > 16 ? 16 : value); return PGP_OK; }

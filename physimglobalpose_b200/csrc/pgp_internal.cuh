@@ -181,6 +181,8 @@ struct pgp_ctx {
   void* k2_scratch = nullptr;              // k2_pcs.cu: the generator's device scratch (k2_release)
   void* k5_scratch = nullptr;              // k5_tricp.cu (k5_release)
   void* k6_scratch = nullptr;              // k6_explained.cu (k6_release)
+  void* k7_scratch = nullptr;              // k7_segment.cu (k7_release)
+  int k7_mls = 1;                          // segment preparation: 1 = MLS polynomial projection + normals (what the reference runs), 0 = PCA normals on the centroids
   int stream_upload = 1;  // pgp_score_lcp: overlap the batch upload with the scoring launch (0: upload first; use under profilers)
   int tail_split = 4;     // K3 fine kernel: model chunks per hypothesis in the last wave (1 = off)
   int k3_warps_count = 32, k3_warps_weighted = 32;   // warps per CTA of k3_fine_kernel (32 -> 64 registers/thread, 24 -> 80, 16 -> 128)
@@ -236,6 +238,7 @@ int k2_get_bases(pgp_ctx* ctx, const Model& m, int n_bases, int32_t* ids_host, f
 void k2_release(pgp_ctx* ctx);
 void k5_release(pgp_ctx* ctx);
 void k6_release(pgp_ctx* ctx);
+void k7_release(pgp_ctx* ctx);
 // k5_tricp.cu
 int k5_tricp(pgp_ctx* ctx, Model& m, const float* seg_xyz_host, int ns, double* poses16_host, int k, float trim, float ratio,
              int max_iter, int* iters_out, float* energy_out);

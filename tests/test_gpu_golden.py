@@ -206,6 +206,7 @@ def test_segment_preparation_on_device(engine):
     g = np.load(os.path.join(G, "c1_test_scene.npz"))
     raw = np.repeat(g["depth_raw_rle"][0], g["depth_raw_rle"][1]).astype(np.uint16).reshape(480, 640)
     mask = np.repeat(g["mask_all_rle"][0], g["mask_all_rle"][1]).astype(np.uint8).reshape(480, 640)
+    engine.set_option("k7_mls", 0)                      # the fixture was prepared with the PCA-normal variant
     for name in g["names"]:
         xyz, nrm, n_raw = engine.prepare_segment(raw, mask, C1_CLASSES[str(name)], g["K"])
         want_xyz, want_nrm = g[f"{name}_seg_xyz"], g[f"{name}_seg_nrm"]
@@ -218,6 +219,36 @@ def test_segment_preparation_on_device(engine):
     # a class that is not in the mask: empty segment, no error
     xyz, nrm, n_raw = engine.prepare_segment(raw, mask, 77, g["K"])
     assert len(xyz) == 0 and n_raw == 0
+    engine.set_option("k7_mls", 1)
+
+
+def test_segment_preparation_mls_on_device(engine):
+    """K7 in its default mode -- pcl::MovingLeastSquares as the reference configures it (polynomial fit of order 2 + normals,
+    PPE/src/segmentation/Segmentation.cpp:231-238), then the radius-outlier filter on the PROJECTED cloud
+    (ObjectPoseCandidateSet.cpp:28-32) -- against the numpy restatement oracle/segment_port.py::mls_project on the test-scene frame:
+    same points kept, projected positions equal to 1e-6 m, normals to fp32 rounding (both sides solve the same 6x6 normal equations in
+    double; PCL itself is not available: parity with PCL is unpinned)."""
+    from oracle import segment_port
+    g = np.load(os.path.join(G, "c1_test_scene.npz"))
+    raw = np.repeat(g["depth_raw_rle"][0], g["depth_raw_rle"][1]).astype(np.uint16).reshape(480, 640)
+    mask = np.repeat(g["mask_all_rle"][0], g["mask_all_rle"][1]).astype(np.uint8).reshape(480, 640)
+    dec = segment_port.decode_depth(raw)
+    engine.set_option("k7_mls", 1)
+    for name in g["names"]:
+        cls = C1_CLASSES[str(name)]
+        xyz, nrm, n_raw = engine.prepare_segment(raw, mask, cls, g["K"])
+        want_xyz, want_nrm, want_raw = segment_port.prepare_segment(dec, mask, cls, g["K"], mls=True)
+        assert n_raw == want_raw
+        assert xyz.shape == want_xyz.shape, (name, xyz.shape, want_xyz.shape)
+        assert np.abs(xyz.astype(np.float64) - want_xyz.astype(np.float64)).max() < 1e-6
+        cosang = np.einsum("ij,ij->i", nrm.astype(np.float64), want_nrm.astype(np.float64))
+        assert np.all(np.abs(np.linalg.norm(nrm, axis=1) - 1) < 1e-6)
+        assert (cosang > 1 - 1e-6).mean() > 0.98 and cosang.min() > 0.99, (name, cosang.min(), (cosang > 1 - 1e-6).mean())     # fp32 unit vectors
+        # the projection is a smoothing of the centroids, not a different cloud: every point moved by less than the fit radius
+        pca_xyz = g[f"{name}_seg_xyz"]
+        from scipy.spatial import cKDTree
+        d, _ = cKDTree(pca_xyz).query(xyz)
+        assert d.max() < 0.02 and np.median(d) < 0.002
 
 
 def test_v4pcs_golden(engine):

@@ -252,3 +252,41 @@ def test_port_matches_reference_golden_at_full_shapes(port_lib):
         assert np.array_equal(o.verify(T), g[f"{tag}_counts"])
         ws, wn = o.weighted_verify(T[:n_w])
         assert np.array_equal(ws, g[f"{tag}_wscore"][:n_w]) and np.array_equal(wn, g[f"{tag}_wnreg"][:n_w])
+
+
+def test_mls_restatement_smooths_and_fits_known_surfaces():
+    from oracle import segment_port
+    """oracle/segment_port.py::mls_project (pcl::MovingLeastSquares with polynomial fit, restated; the checker of K7): on a plane
+    the projection removes the noise component along the normal and returns the plane's normal; on a sphere patch -- a surface an
+    order-2 polynomial follows -- the projected points lie closer to the sphere than the input and the normals closer to the
+    radial direction than plain PCA normals; isolated points vanish."""
+    rng = np.random.default_rng(0)
+    # plane z = 0.6 + 0.2 x, noise along z
+    xy = rng.uniform(-0.1, 0.1, size=(1500, 2))
+    z = 0.6 + 0.2 * xy[:, 0] + rng.normal(0, 5e-4, 1500)
+    pts = np.column_stack([xy, z]).astype(np.float32)
+    pts = np.vstack([pts, np.array([[0.5, 0.5, 0.9]], dtype=np.float32)])          # one isolated point
+    P, N, V = segment_port.mls_project(pts, 0.02)
+    assert V[:-1].all() and not V[-1]
+    n_true = np.array([0.2, 0.0, -1.0]) / np.linalg.norm([0.2, 0.0, -1.0])         # towards the camera at the origin
+    inner = (np.abs(pts[:-1, 0]) < 0.07) & (np.abs(pts[:-1, 1]) < 0.07)
+    res_in = np.abs(pts[:-1, 2] - (0.6 + 0.2 * pts[:-1, 0]))[inner]
+    res_out = np.abs(P[:-1, 2] - (0.6 + 0.2 * P[:-1, 0]))[inner]
+    assert np.sqrt((res_out ** 2).mean()) < 0.5 * np.sqrt((res_in ** 2).mean())
+    assert (N[:-1][inner] @ n_true).min() > np.cos(np.radians(5.0))
+    assert ((P[:-1] * N[:-1]).sum(axis=1) <= 0).all()                              # oriented to the camera
+    # sphere patch
+    th, ph = rng.uniform(0, 0.6, 3000), rng.uniform(0, 2 * np.pi, 3000)
+    d = np.stack([np.sin(th) * np.cos(ph), np.sin(th) * np.sin(ph), -np.cos(th)], axis=1)
+    ctr = np.array([0, 0, 0.7])
+    cen = segment_port.voxel_centroids((ctr + d * (0.1 + rng.normal(0, 7e-4, 3000))[:, None]).astype(np.float32), 0.005)
+    P, N, V = segment_port.mls_project(cen, 0.02)
+    assert V.all()
+    r_in = np.linalg.norm(cen - ctr, axis=1) - 0.1
+    r_out = np.linalg.norm(P - ctr, axis=1) - 0.1
+    assert np.sqrt((r_out ** 2).mean()) < 0.5 * np.sqrt((r_in ** 2).mean())
+    rad = (P - ctr) / np.linalg.norm(P - ctr, axis=1, keepdims=True)
+    ang_mls = np.degrees(np.arccos(np.clip(np.abs((rad * N).sum(axis=1)), 0, 1)))
+    radc = (cen - ctr) / np.linalg.norm(cen - ctr, axis=1, keepdims=True)
+    ang_pca = np.degrees(np.arccos(np.clip(np.abs((radc * segment_port.pca_normals(cen, 0.02)).sum(axis=1)), 0, 1)))
+    assert np.median(ang_mls) < np.median(ang_pca)
